@@ -1,0 +1,234 @@
+// AFA-U k-prediction module: fused mixed-score cross attention, add + InstanceNorm, k head.
+//
+// Replaces /root/reference/src/model/afau.py:231-300 (CrossSet_MultiHeadAttention, which materialises
+// [B, n, 16, n, 16] fp32 intermediates = 2.6 GB per block at B=256, n=100), afau.py:145-176
+// (AddAndInstanceNormalization) and the max-pool + MLP + sigmoid head of
+// /root/reference/src/model/ngm.py:402-412.  The q/k/v, combine and feed-forward projections are plain
+// dense GEMMs and go through gemm_*.cu.
+#include "common.cuh"
+
+namespace fpm {
+
+constexpr int kHeads = 16, kQkv = 16, kMs = 16;
+
+// One CTA per (row tile of 128, head, pair); thread = one query row.  k_h / v_h of the pair are staged in
+// shared memory ([nc][16] each); scores are recomputed in the second pass instead of being stored, so the
+// [n, n] score tile never leaves registers.  No masking: softmax runs over all nc columns (afau.py:288).
+// cost is addressed as cost[b*cs_b + i*cs_r + j*cs_c] so the column block can pass cost^T without a copy.
+__global__ void __launch_bounds__(128)
+afau_attention_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                      const float* __restrict__ cost, long long cs_b, long long cs_r, long long cs_c,
+                      const float* __restrict__ mix1_w, const float* __restrict__ mix1_b,
+                      const float* __restrict__ mix2_w, const float* __restrict__ mix2_b,
+                      float* __restrict__ out, int nr, int nc) {
+  extern __shared__ float sm[];
+  float* ks = sm;                    // [nc][16]
+  float* vs = sm + (size_t)nc * kQkv;
+  __shared__ float w1a[kMs], w1b[kMs], b1[kMs], w2[kMs];
+  __shared__ float b2s;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int E = kHeads * kQkv;
+  for (int idx = threadIdx.x; idx < nc * kQkv; idx += blockDim.x) {
+    const int j = idx / kQkv, d = idx - j * kQkv;
+    const size_t g = ((size_t)b * nc + j) * E + h * kQkv + d;
+    ks[idx] = k[g];
+    vs[idx] = v[g];
+  }
+  if (threadIdx.x < kMs) {
+    w1a[threadIdx.x] = mix1_w[(h * 2 + 0) * kMs + threadIdx.x];
+    w1b[threadIdx.x] = mix1_w[(h * 2 + 1) * kMs + threadIdx.x];
+    b1[threadIdx.x] = mix1_b[h * kMs + threadIdx.x];
+    w2[threadIdx.x] = mix2_w[h * kMs + threadIdx.x];
+  }
+  if (threadIdx.x == 0) b2s = mix2_b[h];
+  __syncthreads();
+  if (i >= nr) return;
+
+  float qv[kQkv];
+  {
+    const float4* qp = (const float4*)(q + ((size_t)b * nr + i) * E + h * kQkv);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float4 x = qp[t];
+      qv[t * 4] = x.x; qv[t * 4 + 1] = x.y; qv[t * 4 + 2] = x.z; qv[t * 4 + 3] = x.w;
+    }
+  }
+  const float* crow = cost + (size_t)b * cs_b + (size_t)i * cs_r;
+
+  auto score = [&](int j) -> float {
+    float dot = 0.f;
+#pragma unroll
+    for (int d = 0; d < kQkv; ++d) dot = fmaf(qv[d], ks[j * kQkv + d], dot);
+    dot = dot / 4.0f;                                        // / sqrt(qkv_dim)
+    const float c = crow[(size_t)j * cs_c];
+    float s = 0.f;
+#pragma unroll
+    for (int m = 0; m < kMs; ++m) {
+      const float h1 = fmaxf(fmaf(c, w1b[m], dot * w1a[m]) + b1[m], 0.f);
+      s = fmaf(h1, w2[m], s);
+    }
+    return s + b2s;
+  };
+
+  float mx = kNegInf;
+  for (int j = 0; j < nc; ++j) mx = fmaxf(mx, score(j));
+  float den = 0.f;
+  float acc[kQkv];
+#pragma unroll
+  for (int d = 0; d < kQkv; ++d) acc[d] = 0.f;
+  for (int j = 0; j < nc; ++j) {
+    const float e = expf(score(j) - mx);
+    den += e;
+#pragma unroll
+    for (int d = 0; d < kQkv; ++d) acc[d] = fmaf(e, vs[j * kQkv + d], acc[d]);
+  }
+  float4* op = (float4*)(out + ((size_t)b * nr + i) * E + h * kQkv);
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+    op[t] = make_float4(acc[t * 4] / den, acc[t * 4 + 1] / den, acc[t * 4 + 2] / den, acc[t * 4 + 3] / den);
+}
+
+// out[b, r, e] = InstanceNorm over r of (a + other)[b, :, e] * gamma[e] + beta[e]; other_mode: 0 none,
+// 1 tensor [B, n, E], 2 row vector [E].  Optionally rowmax[b, e] = max_r out[b, r, e] (the
+// "pad to 600 rows with -inf, MaxPool1d(600)" of ngm.py:402-405).  Thread per channel, coalesced along E.
+__global__ void __launch_bounds__(128)
+add_instnorm_kernel(const float* __restrict__ a, const float* __restrict__ other, int other_mode,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
+                    float* __restrict__ rowmax, int n, int E, float eps) {
+  const int b = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const float* ab = a + (size_t)b * n * E + e;
+  const float* ob = other_mode == 1 ? other + (size_t)b * n * E + e : nullptr;
+  const float ov = other_mode == 2 ? other[e] : 0.f;
+  float sum = 0.f;
+  for (int r = 0; r < n; ++r) {
+    const float x = ab[(size_t)r * E] + (ob ? ob[(size_t)r * E] : ov);
+    sum += x;
+  }
+  const float mean = sum / (float)n;
+  float vs = 0.f;
+  for (int r = 0; r < n; ++r) {
+    const float x = ab[(size_t)r * E] + (ob ? ob[(size_t)r * E] : ov);
+    const float d = x - mean;
+    vs = fmaf(d, d, vs);
+  }
+  const float inv = 1.0f / sqrtf(vs / (float)n + eps);
+  const float g = gamma[e], bt = beta[e];
+  float mxv = kNegInf;
+  float* outb = out + (size_t)b * n * E + e;
+  for (int r = 0; r < n; ++r) {
+    const float x = ab[(size_t)r * E] + (ob ? ob[(size_t)r * E] : ov);
+    const float y = (x - mean) * inv * g + bt;
+    outb[(size_t)r * E] = y;
+    mxv = fmaxf(mxv, y);
+  }
+  if (rowmax) rowmax[(size_t)b * E + e] = mxv;
+}
+
+// k[b, j, o] = j < n[b] ? W[o, j] : 0 : the projection of a one-hot embedding (ngm.py:396-399) is a
+// column gather of the weight, exact because the remaining terms are products with 0.
+__global__ void onehot_proj_kernel(const float* __restrict__ W, const int64_t* __restrict__ n,
+                                   float* __restrict__ out, int nmax, int OUT, int IN) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nmax * OUT) return;
+  const int j = idx / OUT, o = idx - j * OUT;
+  out[(size_t)b * nmax * OUT + idx] = (j < (int)n[b] && j < IN) ? W[(size_t)o * IN + j] : 0.f;
+}
+
+// ks[b] = sigmoid((final_row(g_row[b]) + final_col(g_col[b])) / 2);  k_scaled[b] = ks[b] * min(n1_b, n2_b)
+__global__ void __launch_bounds__(256)
+k_head_kernel(const float* __restrict__ g_row, const float* __restrict__ g_col,
+              const float* __restrict__ r0w, const float* __restrict__ r0b, const float* __restrict__ r2w,
+              const float* __restrict__ r2b, const float* __restrict__ c0w, const float* __restrict__ c0b,
+              const float* __restrict__ c2w, const float* __restrict__ c2b, const int64_t* __restrict__ n1,
+              const int64_t* __restrict__ n2, float* __restrict__ ks, float* __restrict__ k_scaled, int E,
+              int Hd, int mean_k) {
+  __shared__ float hid[2][32];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int u = warp; u < 2 * Hd; u += nw) {
+    const int net = u / Hd, o = u - net * Hd;
+    const float* g = (net ? g_col : g_row) + (size_t)b * E;
+    const float* w = (net ? c0w : r0w) + (size_t)o * E;
+    float acc = 0.f;
+    for (int i = lane; i < E; i += 32) acc = fmaf(w[i], g[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) hid[net][o] = fmaxf(acc + (net ? c0b : r0b)[o], 0.f);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float kr = r2b[0], kc = c2b[0];
+    for (int o = 0; o < Hd; ++o) { kr = fmaf(r2w[o], hid[0][o], kr); kc = fmaf(c2w[o], hid[1][o], kc); }
+    const float logit = mean_k ? (kr + kc) / 2.f : kr;
+    const float kv = 1.f / (1.f + expf(-logit));
+    ks[b] = kv;
+    if (k_scaled) {
+      const long long m = n1[b] < n2[b] ? n1[b] : n2[b];
+      k_scaled[b] = kv * (float)m;
+    }
+  }
+}
+
+}  // namespace fpm
+
+extern "C" int fpm_afau_attention(const float* q, const float* k, const float* v, const float* cost,
+                                  long long cs_b, long long cs_r, long long cs_c, const float* mix1_w,
+                                  const float* mix1_b, const float* mix2_w, const float* mix2_b, float* out,
+                                  int B, int nr, int nc, void* stream) {
+  FPM_CHECK_ARG(q && k && v && cost && mix1_w && mix1_b && mix2_w && mix2_b && out, "fpm_afau_attention: null tensor");
+  FPM_CHECK_ARG(B >= 0 && nr > 0 && nc > 0, "fpm_afau_attention: bad sizes");
+  if (B == 0) return FPM_OK;
+  FPM_CHECK_ARG(B <= 65535, "fpm_afau_attention: batch too large");
+  const size_t smem = (size_t)2 * nc * fpm::kQkv * sizeof(float);
+  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_afau_attention: too many columns");
+  FPM_CUDA(cudaFuncSetAttribute(fpm::afau_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  dim3 grid(fpm_cdiv(nr, 128), fpm::kHeads, B);
+  fpm::afau_attention_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(
+      q, k, v, cost, cs_b, cs_r, cs_c, mix1_w, mix1_b, mix2_w, mix2_b, out, nr, nc);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_add_instnorm(const float* a, const float* other, int other_mode, const float* gamma,
+                                const float* beta, float* out, float* rowmax, int B, int n, int E, float eps,
+                                void* stream) {
+  FPM_CHECK_ARG(a && gamma && beta && out, "fpm_add_instnorm: null tensor");
+  FPM_CHECK_ARG(other_mode == 0 || other, "fpm_add_instnorm: other tensor missing");
+  FPM_CHECK_ARG(other_mode >= 0 && other_mode <= 2, "fpm_add_instnorm: bad mode");
+  FPM_CHECK_ARG(B >= 0 && n > 0 && E > 0, "fpm_add_instnorm: bad sizes");
+  if (B == 0) return FPM_OK;
+  FPM_CHECK_ARG(B <= 65535, "fpm_add_instnorm: batch too large");
+  dim3 grid(fpm_cdiv(E, 128), B);
+  fpm::add_instnorm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, other, other_mode, gamma, beta, out,
+                                                                    rowmax, n, E, eps);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_onehot_proj(const float* W, const long long* n, float* out, int B, int nmax, int OUT,
+                               int IN, void* stream) {
+  FPM_CHECK_ARG(W && n && out, "fpm_onehot_proj: null tensor");
+  if (B == 0) return FPM_OK;
+  FPM_CHECK_ARG(B <= 65535, "fpm_onehot_proj: batch too large");
+  dim3 grid(fpm_cdiv((long long)nmax * OUT, 256), B);
+  fpm::onehot_proj_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, (const int64_t*)n, out, nmax, OUT, IN);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_k_head(const float* g_row, const float* g_col, const float* const* weights,
+                          const long long* n1, const long long* n2, float* ks, float* k_scaled, int B, int E,
+                          int Hd, int mean_k, void* stream) {
+  FPM_CHECK_ARG(g_row && g_col && weights && ks, "fpm_k_head: null tensor");
+  FPM_CHECK_ARG(!k_scaled || (n1 && n2), "fpm_k_head: k_scaled needs n1, n2");
+  FPM_CHECK_ARG(Hd > 0 && Hd <= 32, "fpm_k_head: hidden width must be <= 32");
+  for (int i = 0; i < 8; ++i) FPM_CHECK_ARG(weights[i], "fpm_k_head: null weight");
+  if (B == 0) return FPM_OK;
+  fpm::k_head_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(
+      g_row, g_col, weights[0], weights[1], weights[2], weights[3], weights[4], weights[5], weights[6],
+      weights[7], (const int64_t*)n1, (const int64_t*)n2, ks, k_scaled, E, Hd, mean_k);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}

@@ -1,0 +1,264 @@
+// Keypoint feature gather: bilinear feature_align over the backbone feature maps.
+//
+// Replaces /root/reference/utils/feature_align.py:5-125 (a python loop of ~40 tiny ops per keypoint)
+// and, in the fused head path, normalize_over_channels + concat_features + torch.cat of
+// /root/reference/src/model/ngm.py:241-251.  HBM-bound: per pair it reads the two feature maps once
+// and writes [n, 768] node features once (1.56 MB/pair at n = 100).
+//
+//   fpm_feature_align        drop-in for utils.feature_align.feature_align ([B,C,H,W] -> [B,C,nmax]),
+//                            bit-exact: products and sums are rounded separately, left to right,
+//                            exactly as  Ia*wa + Ib*wb + Ic*wc + Id*wd  evaluates in torch.
+//   fpm_fmap_prep            NCHW -> channels-last with the per-position L2 norm divided out, so the
+//                            gather below reads 128-bit vectors along C.
+//   fpm_node_features        one warp per keypoint: 4 taps x (256 + 512) channels, float4 loads,
+//                            writes row [768] of the concatenated node-feature matrix.
+#include "common.cuh"
+
+namespace fpm {
+
+struct Taps {
+  int y0, y1, x0, x1;       // clamped tap coordinates (fetch positions)
+  float wa, wb, wc, wd;     // weights after the post-fetch edge adjustment
+};
+
+// feature_align.py:55-62 (coordinate transform with the (W,H)/(Hf,Wf) mix-up kept) and :79-118.
+__device__ __forceinline__ Taps make_taps(float px, float py, float ori_w, float ori_h, int Hf, int Wf,
+                                          bool feat_coords = false) {
+  // ori_size = (ori_w, ori_h); feat_size = (Hf, Wf)  [sic]; step = ori / feat
+  const float f0 = (float)Hf, f1 = (float)Wf;
+  const float step0 = __fdiv_rn(ori_w, f0), step1 = __fdiv_rn(ori_h, f1);
+  float x = __fmul_rn(__fdiv_rn(__fsub_rn(px, __fdiv_rn(step0, 2.f)), ori_w), f0);
+  float y = __fmul_rn(__fdiv_rn(__fsub_rn(py, __fdiv_rn(step1, 2.f)), ori_h), f1);
+  if (feat_coords) { x = px; y = py; }     // bilinear_interpolate(im, x, y): already feature-space
+  float x0 = floorf(x), x1 = x0 + 1.f, y0 = floorf(y), y1 = y0 + 1.f;
+  x0 = fminf(fmaxf(x0, 0.f), (float)(Wf - 1)); x1 = fminf(fmaxf(x1, 0.f), (float)(Wf - 1));
+  y0 = fminf(fmaxf(y0, 0.f), (float)(Hf - 1)); y1 = fminf(fmaxf(y1, 0.f), (float)(Hf - 1));
+  Taps t;
+  t.x0 = (int)x0; t.x1 = (int)x1; t.y0 = (int)y0; t.y1 = (int)y1;
+  int ax0 = t.x0, ax1 = t.x1, ay0 = t.y0, ay1 = t.y1;
+  if (ax0 == ax1) { if (ax0 == 0) ax0 -= 1; else ax1 += 1; }
+  if (ay0 == ay1) { if (ay0 == 0) ay0 -= 1; else ay1 += 1; }
+  const float fx0 = (float)ax0, fx1 = (float)ax1, fy0 = (float)ay0, fy1 = (float)ay1;
+  t.wa = __fmul_rn(__fsub_rn(fx1, x), __fsub_rn(fy1, y));
+  t.wb = __fmul_rn(__fsub_rn(fx1, x), __fsub_rn(y, fy0));
+  t.wc = __fmul_rn(__fsub_rn(x, fx0), __fsub_rn(fy1, y));
+  t.wd = __fmul_rn(__fsub_rn(x, fx0), __fsub_rn(y, fy0));
+  return t;
+}
+
+__device__ __forceinline__ float blend(float a, float b, float c, float d, const Taps& t) {
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, t.wa), __fmul_rn(b, t.wb)), __fmul_rn(c, t.wc)),
+                   __fmul_rn(d, t.wd));
+}
+
+// Drop-in op.  grid (ceil(nmax/32), ceil(C/8), B), block (32, 8): lanes over points (coalesced
+// stores along n), y over channels.
+__global__ void feature_align_kernel(const float* __restrict__ fmap, const float* __restrict__ P,
+                                     const int64_t* __restrict__ ns, float* __restrict__ out, int C,
+                                     int Hf, int Wf, int nmax, float ori_w, float ori_h, int feat_coords) {
+  const int b = blockIdx.z;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.y * 8 + threadIdx.y;
+  if (i >= nmax || c >= C) return;
+  const int n = (int)ns[b];
+  float v = 0.f;
+  if (i < n) {
+    const Taps t = make_taps(P[((size_t)b * nmax + i) * 2], P[((size_t)b * nmax + i) * 2 + 1], ori_w,
+                             ori_h, Hf, Wf, feat_coords != 0);
+    const float* im = fmap + ((size_t)b * C + c) * Hf * Wf;
+    v = blend(im[t.y0 * Wf + t.x0], im[t.y1 * Wf + t.x0], im[t.y0 * Wf + t.x1], im[t.y1 * Wf + t.x1], t);
+  }
+  out[((size_t)b * C + c) * nmax + i] = v;
+}
+
+// NCHW raw -> NHWC divided by the channel L2 norm (normalize_over_channels, ngm.py:65-67).
+// One CTA per (32-position tile, image); 256 threads; the tile [C][33] is staged in shared memory.
+// Optionally also reduces the per-channel max over positions of the RAW map (AdaptiveMaxPool2d(1,1),
+// feature_extractor.py:54) through ordered-int atomics into gmax_bits (pre-filled with INT_MIN).
+__global__ void __launch_bounds__(256)
+fmap_prep_kernel(const float* __restrict__ fmap, float* __restrict__ out, int C, int HW) {
+  extern __shared__ float tile[];              // [C][33]
+  __shared__ float part[8][33];
+  __shared__ float norm[32];
+  const int b = blockIdx.y, p0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = p0 + lane;
+  const float* src = fmap + (size_t)b * C * HW;
+  float ss = 0.f;
+  for (int c = warp; c < C; c += 8) {
+    const float v = (p < HW) ? src[(size_t)c * HW + p] : 0.f;
+    tile[c * 33 + lane] = v;
+    ss = fmaf(v, v, ss);
+  }
+  part[warp][lane] = ss;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    norm[lane] = sqrtf(t);
+  }
+  __syncthreads();
+  float* dst = out + ((size_t)b * HW + p0) * C;
+  const int npos = min(32, HW - p0);
+  for (int q = 0; q < npos; ++q) {
+    const float nq = norm[q];
+    for (int c = threadIdx.x; c < C; c += 256) dst[(size_t)q * C + c] = tile[c * 33 + q] / nq;
+  }
+}
+
+// global[b, c] = max over positions of the raw map; one warp per (b, c).
+__global__ void global_max_kernel(const float* __restrict__ fmap, float* __restrict__ out, int BC, int HW,
+                                  int out_stride, int out_offset, int C) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= BC) return;
+  const float* src = fmap + (size_t)w * HW;
+  float m = kNegInf;
+  for (int i = lane; i < HW; i += 32) m = fmaxf(m, src[i]);
+  m = warp_max(m);
+  if (lane == 0) out[(size_t)(w / C) * out_stride + out_offset + (w % C)] = m;
+}
+
+// Fused gather: X[ptr[b] + i, 0:C1] = align(nodes_nhwc), X[.., C1:C1+C2] = align(edges_nhwc).
+// One warp per keypoint, float4 lanes along channels.
+__global__ void __launch_bounds__(256)
+node_features_kernel(const float* __restrict__ nodes, const float* __restrict__ edges,
+                     const float* __restrict__ P, const int64_t* __restrict__ ns,
+                     const int64_t* __restrict__ ptr, float* __restrict__ X, int B, int nmax, int C1,
+                     int H1, int W1, int C2, int H2, int W2, float ori_w, float ori_h) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B * nmax) return;
+  const int b = gw / nmax, i = gw - b * nmax;
+  if (i >= (int)ns[b]) return;
+  const float px = P[((size_t)b * nmax + i) * 2], py = P[((size_t)b * nmax + i) * 2 + 1];
+  float* xrow = X + ((size_t)ptr[b] + i) * (C1 + C2);
+  {
+    const Taps t = make_taps(px, py, ori_w, ori_h, H1, W1);
+    const float* base = nodes + (size_t)b * H1 * W1 * C1;
+    const float4* a = (const float4*)(base + (size_t)(t.y0 * W1 + t.x0) * C1);
+    const float4* bq = (const float4*)(base + (size_t)(t.y1 * W1 + t.x0) * C1);
+    const float4* c = (const float4*)(base + (size_t)(t.y0 * W1 + t.x1) * C1);
+    const float4* d = (const float4*)(base + (size_t)(t.y1 * W1 + t.x1) * C1);
+    float4* o = (float4*)xrow;
+    for (int v = lane; v < C1 / 4; v += 32) {
+      const float4 A = a[v], Bv = bq[v], Cv = c[v], Dv = d[v];
+      float4 r;
+      r.x = blend(A.x, Bv.x, Cv.x, Dv.x, t); r.y = blend(A.y, Bv.y, Cv.y, Dv.y, t);
+      r.z = blend(A.z, Bv.z, Cv.z, Dv.z, t); r.w = blend(A.w, Bv.w, Cv.w, Dv.w, t);
+      o[v] = r;
+    }
+  }
+  {
+    const Taps t = make_taps(px, py, ori_w, ori_h, H2, W2);
+    const float* base = edges + (size_t)b * H2 * W2 * C2;
+    const float4* a = (const float4*)(base + (size_t)(t.y0 * W2 + t.x0) * C2);
+    const float4* bq = (const float4*)(base + (size_t)(t.y1 * W2 + t.x0) * C2);
+    const float4* c = (const float4*)(base + (size_t)(t.y0 * W2 + t.x1) * C2);
+    const float4* d = (const float4*)(base + (size_t)(t.y1 * W2 + t.x1) * C2);
+    float4* o = (float4*)(xrow + C1);
+    for (int v = lane; v < C2 / 4; v += 32) {
+      const float4 A = a[v], Bv = bq[v], Cv = c[v], Dv = d[v];
+      float4 r;
+      r.x = blend(A.x, Bv.x, Cv.x, Dv.x, t); r.y = blend(A.y, Bv.y, Cv.y, Dv.y, t);
+      r.z = blend(A.z, Bv.z, Cv.z, Dv.z, t); r.w = blend(A.w, Bv.w, Cv.w, Dv.w, t);
+      o[v] = r;
+    }
+  }
+}
+
+// coeff[b, :] = tanh(A * normalize([g_src[b]; g_tgt[b]]) + a)   (ngm.py:262-268, affinity_layer.py:13)
+// One CTA per pair; the 2*G-vector sits in shared memory; one warp per output row of A.
+__global__ void __launch_bounds__(256)
+affinity_coeff_kernel(const float* __restrict__ gcat, const float* __restrict__ W,
+                      const float* __restrict__ bias, float* __restrict__ coeff, int IN, int OUT) {
+  extern __shared__ float g[];
+  __shared__ float red[32];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < IN; i += blockDim.x) {
+    const float v = gcat[(size_t)b * IN + i];
+    g[i] = v;
+    ss = fmaf(v, v, ss);
+  }
+  ss = block_sum(ss, red);
+  const float nrm = sqrtf(ss);
+  __syncthreads();
+  for (int i = threadIdx.x; i < IN; i += blockDim.x) g[i] = g[i] / nrm;
+  __syncthreads();
+  for (int o = warp; o < OUT; o += (blockDim.x >> 5)) {
+    const float* w = W + (size_t)o * IN;
+    float acc = 0.f;
+    for (int i = lane; i < IN; i += 32) acc = fmaf(w[i], g[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) coeff[(size_t)b * OUT + o] = tanhf(acc + bias[o]);
+  }
+}
+
+}  // namespace fpm
+
+extern "C" int fpm_feature_align(const float* fmap, const float* P, const long long* ns, float* out,
+                                 int B, int C, int Hf, int Wf, int nmax, float ori_w, float ori_h,
+                                 int feat_coords, void* stream) {
+  FPM_CHECK_ARG(fmap && P && ns && out, "fpm_feature_align: null tensor");
+  FPM_CHECK_ARG(B >= 0 && C > 0 && Hf > 0 && Wf > 0 && nmax >= 0, "fpm_feature_align: bad sizes");
+  if (B == 0 || nmax == 0) return FPM_OK;
+  dim3 grid(fpm_cdiv(nmax, 32), fpm_cdiv(C, 8), B), block(32, 8);
+  FPM_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "fpm_feature_align: batch or channel count too large");
+  fpm::feature_align_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+      fmap, P, (const int64_t*)ns, out, C, Hf, Wf, nmax, ori_w, ori_h, feat_coords);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_fmap_prep(const float* fmap, float* out_nhwc, int B, int C, int Hf, int Wf,
+                             void* stream) {
+  FPM_CHECK_ARG(fmap && out_nhwc, "fpm_fmap_prep: null tensor");
+  FPM_CHECK_ARG(B >= 0 && C > 0 && Hf > 0 && Wf > 0, "fpm_fmap_prep: bad sizes");
+  if (B == 0) return FPM_OK;
+  const int HW = Hf * Wf;
+  const size_t smem = (size_t)C * 33 * sizeof(float);
+  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_fmap_prep: channel count too large");
+  FPM_CHECK_ARG(B <= 65535, "fpm_fmap_prep: batch too large");
+  FPM_CUDA(cudaFuncSetAttribute(fpm::fmap_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  dim3 grid(fpm_cdiv(HW, 32), B);
+  fpm::fmap_prep_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(fmap, out_nhwc, C, HW);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_global_max(const float* fmap, float* out, int B, int C, int HW, int out_stride,
+                              int out_offset, void* stream) {
+  FPM_CHECK_ARG(fmap && out, "fpm_global_max: null tensor");
+  if (B == 0) return FPM_OK;
+  const long long warps = (long long)B * C;
+  fpm::global_max_kernel<<<fpm_cdiv(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      fmap, out, (int)warps, HW, out_stride, out_offset, C);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_node_features(const float* nodes_nhwc, const float* edges_nhwc, const float* P,
+                                 const long long* ns, const long long* ptr, float* X, int B, int nmax,
+                                 int C1, int H1, int W1, int C2, int H2, int W2, float ori_w, float ori_h,
+                                 void* stream) {
+  FPM_CHECK_ARG(nodes_nhwc && edges_nhwc && P && ns && ptr && X, "fpm_node_features: null tensor");
+  FPM_CHECK_ARG(C1 % 4 == 0 && C2 % 4 == 0, "fpm_node_features: channels must be multiples of 4");
+  if (B == 0 || nmax == 0) return FPM_OK;
+  const long long warps = (long long)B * nmax;
+  fpm::node_features_kernel<<<fpm_cdiv(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      nodes_nhwc, edges_nhwc, P, (const int64_t*)ns, (const int64_t*)ptr, X, B, nmax, C1, H1, W1, C2, H2,
+      W2, ori_w, ori_h);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_affinity_coeff(const float* gcat, const float* W, const float* bias, float* coeff,
+                                  int B, int IN, int OUT, void* stream) {
+  FPM_CHECK_ARG(gcat && W && bias && coeff, "fpm_affinity_coeff: null tensor");
+  if (B == 0) return FPM_OK;
+  fpm::affinity_coeff_kernel<<<B, 256, (size_t)IN * sizeof(float), (cudaStream_t)stream>>>(
+      gcat, W, bias, coeff, IN, OUT);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}

@@ -1,0 +1,254 @@
+// fp32 CUDA-core GEMMs: the reference-precision path.
+//
+//   fpm_gemm_nt_f32     C[M,N] = act(A[M,K] * Bt[N,K]^T + bias)   (nn.Linear convention)
+//                       used for every dense contraction of the head when the tensor-core kernel
+//                       (gemm_tcgen05.cu) is switched off, and as the on-device checker for it.
+//   fpm_affinity        ragged batched  softplus((X1_b (.) c_b) X2_b^T) - 0.5  with optional edge
+//                       rows  x[src] - x[dst]  formed on the fly; replaces
+//                       /root/reference/src/model/affinity_layer.py:11-22 as used for Kp / Ke at
+//                       /root/reference/src/model/ngm.py:277-287 (+ the zero padding of :317-318).
+#include "common.cuh"
+
+namespace fpm {
+
+constexpr int GM = 128, GN = 128, GK = 16;
+
+template <int ACT>   // 0 none, 1 relu
+__global__ void __launch_bounds__(256)
+gemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ Bt, const float* __restrict__ bias,
+               float* __restrict__ Cm, int M, int N, int K, int lda, int ldb, int ldc) {
+  __shared__ __align__(16) float As[2][GK][GM + 4];
+  __shared__ __align__(16) float Bs[2][GK][GN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  const int lrow = tid >> 2, lk = (tid & 3) << 2;        // loader: row 0..63 (+64), k quad
+  const int ty = tid >> 4, tx = tid & 15;                // compute: 16 x 16 threads, 8 x 8 each
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float4 ra[2], rb[2];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = lrow + h * 64;
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + lk;
+      ra[h] = (gm < M && gk < K) ? *(const float4*)(A + (size_t)gm * lda + gk) : make_float4(0, 0, 0, 0);
+      rb[h] = (gn < N && gk < K) ? *(const float4*)(Bt + (size_t)gn * ldb + gk) : make_float4(0, 0, 0, 0);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = lrow + h * 64;
+      As[buf][lk + 0][r] = ra[h].x; As[buf][lk + 1][r] = ra[h].y;
+      As[buf][lk + 2][r] = ra[h].z; As[buf][lk + 3][r] = ra[h].w;
+      Bs[buf][lk + 0][r] = rb[h].x; Bs[buf][lk + 1][r] = rb[h].y;
+      Bs[buf][lk + 2][r] = rb[h].z; Bs[buf][lk + 3][r] = rb[h].w;
+    }
+  };
+
+  const int nk = (K + GK - 1) / GK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kb = 0; kb < nk; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < nk) gload((kb + 1) * GK);
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a0 = *(const float4*)&As[buf][k][ty * 4];
+      const float4 a1 = *(const float4*)&As[buf][k][64 + ty * 4];
+      const float4 b0 = *(const float4*)&Bs[buf][k][tx * 4];
+      const float4 b1 = *(const float4*)&Bs[buf][k][64 + tx * 4];
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kb + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int gn = n0 + jh * 64 + tx * 4;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x = acc[i][jh * 4 + j];
+        if (bias && gn + j < N) x += bias[gn + j];
+        if (ACT == 1) x = fmaxf(x, 0.f);
+        v[j] = x;
+      }
+      float* dst = Cm + (size_t)gm * ldc + gn;
+      if (gn + 3 < N && ((ldc & 3) == 0) && ((((size_t)Cm) & 15) == 0)) {
+        *(float4*)dst = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gn + j < N) dst[j] = v[j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Ragged affinity.  Row r of pair b's left operand is
+//     X[ptrA[b] + r]                                   (idxA0 == nullptr: node features), or
+//     X[ptrA[b] + idxA0[eA[b] + r]] - X[ptrA[b] + idxA1[eA[b] + r]]   (edge features, spline_conv.py:73-81)
+// scaled by coeff[b, :]; same for the right operand without the scaling.
+// out[b, i, j] = scale * (softplus(dot) - 0.5) inside [nA_b, nB_b], 0 in the padding.
+// ------------------------------------------------------------------------------------------
+constexpr int AM = 64, AN = 64, AK = 16;
+
+__global__ void __launch_bounds__(256)
+affinity_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const float* __restrict__ coeff,
+                const int64_t* __restrict__ ptrA, const int64_t* __restrict__ ptrB,
+                const int64_t* __restrict__ eptrA, const int64_t* __restrict__ eptrB,
+                const int64_t* __restrict__ eidxA, const int64_t* __restrict__ eidxB, int EA, int EB,
+                float* __restrict__ out, float* __restrict__ out_t, int Rmax, int Cmax, int Kdim,
+                float scale) {
+  __shared__ __align__(16) float As[AK][AM + 4];
+  __shared__ __align__(16) float Bs[AK][AN + 4];
+  const int b = blockIdx.z, tid = threadIdx.x;
+  const int i0 = blockIdx.y * AM, j0 = blockIdx.x * AN;
+  const bool edge_mode = eidxA != nullptr;
+  const int nA = edge_mode ? (int)(eptrA[b + 1] - eptrA[b]) : (int)(ptrA[b + 1] - ptrA[b]);
+  const int nB = edge_mode ? (int)(eptrB[b + 1] - eptrB[b]) : (int)(ptrB[b + 1] - ptrB[b]);
+  const int lrow = tid >> 2, lk = (tid & 3) << 2;
+  const int ty = tid >> 4, tx = tid & 15;
+  const float* cb = coeff + (size_t)b * Kdim;
+
+  // resolve this thread's operand rows once
+  const float *pa0 = nullptr, *pa1 = nullptr, *pb0 = nullptr, *pb1 = nullptr;
+  if (i0 + lrow < nA) {
+    if (edge_mode) {
+      // edge_index holds GLOBAL node ids (PyG batch), so no ptr offset is added
+      pa0 = XA + (size_t)eidxA[eptrA[b] + i0 + lrow] * Kdim;
+      pa1 = XA + (size_t)eidxA[(size_t)EA + eptrA[b] + i0 + lrow] * Kdim;
+    } else {
+      pa0 = XA + (size_t)(ptrA[b] + i0 + lrow) * Kdim;
+    }
+  }
+  if (j0 + lrow < nB) {
+    if (edge_mode) {
+      pb0 = XB + (size_t)eidxB[eptrB[b] + j0 + lrow] * Kdim;
+      pb1 = XB + (size_t)eidxB[(size_t)EB + eptrB[b] + j0 + lrow] * Kdim;
+    } else {
+      pb0 = XB + (size_t)(ptrB[b] + j0 + lrow) * Kdim;
+    }
+  }
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  if (i0 < nA && j0 < nB) {
+    for (int k0 = 0; k0 < Kdim; k0 += AK) {
+      const int gk = k0 + lk;
+      float4 a = make_float4(0, 0, 0, 0), bb = make_float4(0, 0, 0, 0);
+      if (gk < Kdim) {
+        if (pa0) {
+          a = *(const float4*)(pa0 + gk);
+          if (pa1) {
+            const float4 a2 = *(const float4*)(pa1 + gk);
+            a.x -= a2.x; a.y -= a2.y; a.z -= a2.z; a.w -= a2.w;
+          }
+          const float4 c4 = *(const float4*)(cb + gk);
+          a.x = __fmul_rn(a.x, c4.x); a.y = __fmul_rn(a.y, c4.y);
+          a.z = __fmul_rn(a.z, c4.z); a.w = __fmul_rn(a.w, c4.w);
+        }
+        if (pb0) {
+          bb = *(const float4*)(pb0 + gk);
+          if (pb1) {
+            const float4 b2 = *(const float4*)(pb1 + gk);
+            bb.x -= b2.x; bb.y -= b2.y; bb.z -= b2.z; bb.w -= b2.w;
+          }
+        }
+      }
+      __syncthreads();
+      As[lk + 0][lrow] = a.x; As[lk + 1][lrow] = a.y; As[lk + 2][lrow] = a.z; As[lk + 3][lrow] = a.w;
+      Bs[lk + 0][lrow] = bb.x; Bs[lk + 1][lrow] = bb.y; Bs[lk + 2][lrow] = bb.z; Bs[lk + 3][lrow] = bb.w;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < AK; ++k) {
+        const float4 av = *(const float4*)&As[k][ty * 4];
+        const float4 bv = *(const float4*)&Bs[k][tx * 4];
+        const float a4[4] = {av.x, av.y, av.z, av.w};
+        const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = i0 + ty * 4 + i;
+    if (gi >= Rmax) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gj = j0 + tx * 4 + j;
+      if (gj >= Cmax) continue;
+      float v = 0.f;
+      if (gi < nA && gj < nB) v = scale * (softplus_torch(acc[i][j]) - 0.5f);
+      out[((size_t)b * Rmax + gi) * Cmax + gj] = v;
+      if (out_t) out_t[((size_t)b * Cmax + gj) * Rmax + gi] = v;
+    }
+  }
+}
+
+}  // namespace fpm
+
+extern "C" int fpm_gemm_nt_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N,
+                               int K, int lda, int ldb, int ldc, int act, void* stream) {
+  FPM_CHECK_ARG(A && Bt && C, "fpm_gemm_nt_f32: null tensor");
+  FPM_CHECK_ARG(M >= 0 && N > 0 && K > 0, "fpm_gemm_nt_f32: bad sizes");
+  FPM_CHECK_ARG((K & 3) == 0 && (lda & 3) == 0 && (ldb & 3) == 0, "fpm_gemm_nt_f32: K, lda, ldb must be multiples of 4");
+  FPM_CHECK_ARG((((size_t)A) & 15) == 0 && (((size_t)Bt) & 15) == 0, "fpm_gemm_nt_f32: operands must be 16-byte aligned");
+  FPM_CHECK_ARG(act == 0 || act == 1, "fpm_gemm_nt_f32: unknown activation");
+  if (M == 0) return FPM_OK;
+  dim3 grid(fpm_cdiv(N, fpm::GN), fpm_cdiv(M, fpm::GM));
+  FPM_CHECK_ARG(grid.y <= 65535, "fpm_gemm_nt_f32: M too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act == 0) fpm::gemm_nt_kernel<0><<<grid, 256, 0, st>>>(A, Bt, bias, C, M, N, K, lda, ldb, ldc);
+  else fpm::gemm_nt_kernel<1><<<grid, 256, 0, st>>>(A, Bt, bias, C, M, N, K, lda, ldb, ldc);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_affinity(const float* XA, const float* XB, const float* coeff, const long long* ptrA,
+                            const long long* ptrB, const long long* eptrA, const long long* eptrB,
+                            const long long* eidxA, const long long* eidxB, int EA, int EB, float* out,
+                            float* out_t, int B, int Rmax, int Cmax, int Kdim, float scale, void* stream) {
+  FPM_CHECK_ARG(XA && XB && coeff && out, "fpm_affinity: null tensor");
+  FPM_CHECK_ARG((eidxA == nullptr) == (eidxB == nullptr), "fpm_affinity: edge indices must be given for both sides");
+  FPM_CHECK_ARG(eidxA ? (eptrA && eptrB) : (ptrA && ptrB), "fpm_affinity: missing offsets");
+  FPM_CHECK_ARG((Kdim & 3) == 0, "fpm_affinity: feature dim must be a multiple of 4");
+  FPM_CHECK_ARG(B >= 0 && Rmax > 0 && Cmax > 0, "fpm_affinity: bad sizes");
+  if (B == 0) return FPM_OK;
+  FPM_CHECK_ARG(B <= 65535, "fpm_affinity: batch too large");
+  dim3 grid(fpm_cdiv(Cmax, fpm::AN), fpm_cdiv(Rmax, fpm::AM), B);
+  fpm::affinity_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      XA, XB, coeff, (const int64_t*)ptrA, (const int64_t*)ptrB, (const int64_t*)eptrA,
+      (const int64_t*)eptrB, (const int64_t*)eidxA, (const int64_t*)eidxB, EA, EB, out, out_t, Rmax, Cmax,
+      Kdim, scale);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}

@@ -1,0 +1,323 @@
+// Exact GPU linear assignment + greedy top-k selection: one warp per fingerprint pair.
+//
+// Replaces /root/reference/utils/hungarian.py:8-65 (D2H copy -> scipy.optimize.linear_sum_assignment
+// per pair -> H2D) and the argsort + greedy_perm tail of /root/reference/src/model/ngm.py:444-449
+// (src/model/soft_topk.py:56-77).  Bit-exact permutations require scipy's exact traversal, because
+// soft-top-k matrices are full of ties (exact zeros / ones): this kernel re-states scipy's
+// rectangular_lsap.cpp (shortest augmenting path, Crouse 2016) in fp64 with the same
+//   * row order, transposition rule (nc < nr), `remaining` list with swap-removal,
+//   * left-to-right evaluation of  minVal + cost - u[i] - v[j],
+//   * tie rule: last minimum whose column is unassigned, else first minimum (in `remaining` order),
+// and replaces the serial inner scan by a warp-wide scan + 4 redux operations.
+// Latency-bound, not bandwidth-bound: algorithmic traffic is one read of ds_mat and one write of
+// perm_mat per pair.
+#include "common.cuh"
+#include <limits.h>
+
+namespace fpm {
+
+__device__ __forceinline__ unsigned long long ordered_key(double v) {
+  v = v + 0.0;   // -0.0 -> +0.0 so that equal values map to equal keys
+  unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  return (bits & 0x8000000000000000ull) ? ~bits : (bits | 0x8000000000000000ull);
+}
+
+struct LapSmem {
+  double* u; double* v; double* spc;
+  int* path; int* col4row; int* row4col; int* remaining;
+  unsigned char* SR; unsigned char* SC;
+  float* cost;
+};
+
+__host__ __device__ inline size_t lap_smem_bytes(int D, int cost_elems) {
+  size_t s = (size_t)D * (3 * sizeof(double) + 4 * sizeof(int)) + 2 * (size_t)((D + 15) / 16 * 16);
+  s = (s + 15) / 16 * 16;
+  return s + (size_t)cost_elems * sizeof(float);
+}
+
+// ds: [B, R, C] scores (maximised).  hung_out / perm_out: [B, R, C] or null.  ks: [B] floats or null.
+template <bool kCostSmem>
+__global__ void __launch_bounds__(32)
+lap_topk_kernel(const float* __restrict__ ds, const int64_t* __restrict__ n1,
+                const int64_t* __restrict__ n2, const float* __restrict__ ks,
+                float* __restrict__ hung_out, float* __restrict__ perm_out,
+                int* __restrict__ status, int R, int C) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const unsigned full = 0xffffffffu;
+  const int D = R > C ? R : C;
+
+  LapSmem sm;
+  {
+    unsigned char* p = raw;
+    sm.u = (double*)p; p += sizeof(double) * D;
+    sm.v = (double*)p; p += sizeof(double) * D;
+    sm.spc = (double*)p; p += sizeof(double) * D;
+    sm.path = (int*)p; p += sizeof(int) * D;
+    sm.col4row = (int*)p; p += sizeof(int) * D;
+    sm.row4col = (int*)p; p += sizeof(int) * D;
+    sm.remaining = (int*)p; p += sizeof(int) * D;
+    const int Dp = (D + 15) / 16 * 16;
+    sm.SR = p; p += Dp;
+    sm.SC = p; p += Dp;
+    p = raw + ((size_t)(p - raw) + 15) / 16 * 16;
+    sm.cost = (float*)p;
+  }
+
+  int n1b = n1 ? (int)n1[b] : R;
+  int n2b = n2 ? (int)n2[b] : C;
+  n1b = min(max(n1b, 0), R);
+  n2b = min(max(n2b, 0), C);
+  const bool tr = n2b < n1b;                 // scipy transposes when nc < nr
+  const int nr = tr ? n2b : n1b;
+  const int nc = tr ? n1b : n2b;
+  const float* dsb = ds + (size_t)b * R * C;
+
+  // zero the outputs for this pair
+  {
+    const int total = R * C;
+    if (hung_out) for (int i = lane; i < total; i += 32) hung_out[(size_t)b * total + i] = 0.f;
+    if (perm_out) for (int i = lane; i < total; i += 32) perm_out[(size_t)b * total + i] = 0.f;
+  }
+
+  if (kCostSmem) {
+    // working-frame cost (un-negated scores), row-major nr x nc
+    for (int idx = lane; idx < nr * nc; idx += 32) {
+      const int i = idx / nc, j = idx - i * nc;
+      sm.cost[idx] = tr ? dsb[(size_t)j * C + i] : dsb[(size_t)i * C + j];
+    }
+  }
+  for (int i = lane; i < D; i += 32) {
+    sm.u[i] = 0.0; sm.v[i] = 0.0;
+    sm.col4row[i] = -1; sm.row4col[i] = -1; sm.path[i] = -1;
+  }
+  __syncwarp();
+
+  bool infeasible = false;
+  if (nr > 0 && nc > 0) {
+    for (int curRow = 0; curRow < nr && !infeasible; ++curRow) {
+      double minVal = 0.0;
+      int num_remaining = nc;
+      for (int it = lane; it < nc; it += 32) {
+        sm.remaining[it] = nc - it - 1;
+        sm.SC[it] = 0;
+        sm.spc[it] = INFINITY;
+      }
+      for (int i = lane; i < nr; i += 32) sm.SR[i] = 0;
+      __syncwarp();
+
+      int sink = -1;
+      int i = curRow;
+      while (sink == -1) {
+        if (lane == 0) sm.SR[i] = 1;
+        const double ui = sm.u[i];
+        // lane-local sequential scan over it = lane, lane+32, ...
+        double best = INFINITY;
+        int upos = -1;          // last position at `best` whose column is unassigned
+        int fpos = INT_MAX;     // first position at `best`
+        for (int it = lane; it < num_remaining; it += 32) {
+          const int j = sm.remaining[it];
+          const float sc = kCostSmem ? sm.cost[(size_t)i * nc + j]
+                                     : (tr ? dsb[(size_t)j * C + i] : dsb[(size_t)i * C + j]);
+          const double c = -(double)sc;
+          double r = minVal + c;
+          r = r - ui;
+          r = r - sm.v[j];
+          double cur = sm.spc[j];
+          if (r < cur) {
+            sm.path[j] = i;
+            sm.spc[j] = r;
+            cur = r;
+          }
+          const bool unassigned = sm.row4col[j] == -1;
+          if (cur < best) {
+            best = cur; fpos = it; upos = unassigned ? it : -1;
+          } else if (cur == best) {
+            if (unassigned) upos = it;
+          }
+        }
+        // warp-wide: global minimum value, then last-unassigned / first position at that value
+        const unsigned long long key = ordered_key(best);
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned mhi = __reduce_min_sync(full, hi);
+        const unsigned mlo = __reduce_min_sync(full, hi == mhi ? lo : 0xffffffffu);
+        const bool is_min = (hi == mhi) && (lo == mlo);
+        const int gu = __reduce_max_sync(full, is_min ? upos : -1);
+        const int gf = __reduce_min_sync(full, is_min ? fpos : INT_MAX);
+        // every lane whose key equals the minimum holds the same double; broadcast it
+        const int src_lane = __ffs(__ballot_sync(full, is_min)) - 1;
+        const double lowest = __shfl_sync(full, best, src_lane);
+        if (lowest == INFINITY) { infeasible = true; break; }
+        const int index = gu >= 0 ? gu : gf;
+        minVal = lowest;
+        const int j = sm.remaining[index];
+        const int owner = sm.row4col[j];
+        __syncwarp();
+        if (owner == -1) sink = j; else i = owner;
+        if (lane == 0) {
+          sm.SC[j] = 1;
+          sm.remaining[index] = sm.remaining[num_remaining - 1];
+        }
+        --num_remaining;
+        __syncwarp();
+      }
+      if (infeasible) break;
+
+      // dual update
+      if (lane == 0) sm.u[curRow] += minVal;
+      for (int r = lane; r < nr; r += 32)
+        if (sm.SR[r] && r != curRow) sm.u[r] += minVal - sm.spc[sm.col4row[r]];
+      for (int j = lane; j < nc; j += 32)
+        if (sm.SC[j]) sm.v[j] -= minVal - sm.spc[j];
+      __syncwarp();
+      // augment along the alternating path (serial, short)
+      if (lane == 0) {
+        int j = sink;
+        while (true) {
+          const int r = sm.path[j];
+          sm.row4col[j] = r;
+          const int tmp = sm.col4row[r];
+          sm.col4row[r] = j;
+          j = tmp;
+          if (r == curRow) break;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (status && lane == 0) status[b] = infeasible ? 1 : 0;
+  if (infeasible) return;
+
+  // ---- hungarian() output: 1 at every assigned (row, col) of the original orientation
+  if (hung_out) {
+    for (int r = lane; r < nr; r += 32) {
+      const int c = sm.col4row[r];
+      if (c >= 0) {
+        const int a = tr ? c : r, cc = tr ? r : c;
+        hung_out[(size_t)b * R * C + (size_t)a * C + cc] = 1.f;
+      }
+    }
+  }
+  if (!perm_out) return;
+
+  // ---- greedy_perm(zeros, argsort(x * ds, descending, stable), ks): see SURVEY.md A.7
+  // Positive assigned entries never conflict (x is a partial permutation), so the first
+  // min(K, #positive) of them in (value desc, flat index asc) order are accepted; a larger K
+  // continues in raster order over zero-valued cells of the PADDED matrix.
+  const float kf = ks[b];
+  long long K = 0;
+  if (kf == kf) K = (long long)rint((double)kf);      // python round(): half to even
+  if (K <= 0) return;
+  // reuse: path[] = flat index, spc[] = value (as double), SR/SC = row/col used flags
+  int* flat = sm.path;
+  double* val = sm.spc;
+  __syncwarp();
+  for (int r = lane; r < D; r += 32) { sm.SR[r] = 0; sm.SC[r] = 0; }
+  for (int r = lane; r < nr; r += 32) {
+    const int c = sm.col4row[r];
+    const int a = tr ? c : r, cc = tr ? r : c;
+    flat[r] = a * C + cc;
+    val[r] = (double)dsb[(size_t)a * C + cc];
+  }
+  __syncwarp();
+  int accepted_local = 0, npos_local = 0;
+  for (int t = lane; t < nr; t += 32) {
+    const double vt = val[t];
+    if (vt > 0.0) {
+      ++npos_local;
+      int rank = 0;
+      const int ft = flat[t];
+      for (int q = 0; q < nr; ++q) {
+        const double vq = val[q];
+        rank += (vq > vt) || (vq == vt && flat[q] < ft);
+      }
+      if ((long long)rank < K) {
+        const int a = ft / C, cc = ft - a * C;
+        perm_out[(size_t)b * R * C + ft] = 1.f;
+        sm.SR[a] = 1; sm.SC[cc] = 1;
+        ++accepted_local;
+      }
+    }
+  }
+  const int npos = warp_sum_int(npos_local);
+  const int accepted = warp_sum_int(accepted_local);
+  __syncwarp();
+  if ((long long)npos < K && lane == 0) {
+    long long matched = accepted;
+    int cptr = 0;
+    for (int a = 0; a < R && matched < K; ++a) {
+      if (sm.SR[a]) continue;
+      while (cptr < C && sm.SC[cptr]) ++cptr;
+      if (cptr >= C) break;
+      perm_out[(size_t)b * R * C + (size_t)a * C + cptr] = 1.f;
+      sm.SC[cptr] = 1;
+      ++matched;
+    }
+  }
+}
+
+// Generic greedy_perm(x, top_indices, ks) (soft_topk.py:56-77) for callers that bring their own
+// candidate order: one thread per pair walks the list with row/column occupancy bitmaps in global
+// scratch (x itself: a row/col is occupied when its sum >= 1, exactly as the reference tests it).
+__global__ void greedy_perm_kernel(float* __restrict__ x, const int64_t* __restrict__ top,
+                                   const float* __restrict__ ks, int B, int R, int C, int L) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float kf = ks[b];
+  long long K = 0;
+  if (kf == kf) K = (long long)rint((double)kf);
+  float* xb = x + (size_t)b * R * C;
+  long long matched = 0;
+  for (int cur = 0; cur < L && matched < K; ++cur) {
+    const long long idx = top[(size_t)b * L + cur];
+    const int r = (int)(idx / C), c = (int)(idx % C);
+    float cs = 0.f, rs = 0.f;
+    for (int i = 0; i < R; ++i) cs += xb[(size_t)i * C + c];
+    for (int j = 0; j < C; ++j) rs += xb[(size_t)r * C + j];
+    if (cs < 1.f && rs < 1.f) {
+      xb[(size_t)r * C + c] = 1.f;
+      ++matched;
+    }
+  }
+}
+
+}  // namespace fpm
+
+extern "C" int fpm_lap_topk(const float* ds, const long long* n1, const long long* n2, const float* ks,
+                            float* hung_out, float* perm_out, int* status, int B, int R, int C,
+                            void* stream) {
+  FPM_CHECK_ARG(ds, "fpm_lap_topk: null score tensor");
+  FPM_CHECK_ARG(hung_out || perm_out, "fpm_lap_topk: no output requested");
+  FPM_CHECK_ARG(!perm_out || ks, "fpm_lap_topk: perm_out needs ks");
+  FPM_CHECK_ARG(B >= 0 && R > 0 && C > 0, "fpm_lap_topk: bad sizes");
+  if (B == 0) return FPM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = R > C ? R : C;
+  const size_t with_cost = fpm::lap_smem_bytes(D, R * C);
+  if (with_cost <= 100 * 1024) {
+    FPM_CUDA(cudaFuncSetAttribute(fpm::lap_topk_kernel<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_cost));
+    fpm::lap_topk_kernel<true><<<B, 32, with_cost, st>>>(ds, (const int64_t*)n1, (const int64_t*)n2, ks,
+                                                         hung_out, perm_out, status, R, C);
+  } else {
+    const size_t base = fpm::lap_smem_bytes(D, 0);
+    FPM_CHECK_ARG(base <= 200 * 1024, "fpm_lap_topk: matrix dimension too large");
+    FPM_CUDA(cudaFuncSetAttribute(fpm::lap_topk_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
+    fpm::lap_topk_kernel<false><<<B, 32, base, st>>>(ds, (const int64_t*)n1, (const int64_t*)n2, ks,
+                                                     hung_out, perm_out, status, R, C);
+  }
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_greedy_perm(float* x, const long long* top_indices, const float* ks, int B, int R,
+                               int C, int L, void* stream) {
+  FPM_CHECK_ARG(x && top_indices && ks, "fpm_greedy_perm: null tensor");
+  FPM_CHECK_ARG(B >= 0 && R > 0 && C > 0 && L >= 0, "fpm_greedy_perm: bad sizes");
+  if (B == 0) return FPM_OK;
+  fpm::greedy_perm_kernel<<<fpm_cdiv(B, 64), 64, 0, (cudaStream_t)stream>>>(
+      x, (const int64_t*)top_indices, ks, B, R, C, L);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}

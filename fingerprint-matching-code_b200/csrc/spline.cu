@@ -1,0 +1,159 @@
+// SplineConv node refinement, restructured for dense tensor-core work.
+//
+// Replaces torch_geometric.nn.SplineConv(768, 768, dim=2, kernel_size=5, aggr='max') as used by
+// /root/reference/src/model/spline_conv.py:7-58 (torch_spline_conv basis + weighting, torch_scatter max).
+//
+// The reference evaluates, per edge, sum_s basis_s * (x_src @ W[wi_s]): a gather-GEMM of shape
+// [4e, 768] x [768, 768] with a different weight slab per row.  Because every source node is used by
+// ~6 edges touching almost all 25 slabs, the same FLOPs buy a plain dense GEMM instead:
+//     Y[j, k, :] = x_j @ W[k]    for all 25 kernels (+ slab 25 = root weight)        -> gemm_*.cu
+// and the per-edge work collapses to a 4-row blend of Y plus a max over in-edges (this file):
+//     out_i = max_{e: j->i} sum_s basis_s(e) * Y[j, wi_s(e), :]  (0 if no in-edge) + Y[i, 25, :] + bias
+// fused with ReLU (layer 0) or the residual x + 0.1 * out (layer 1, spline_conv.py:56).
+#include "common.cuh"
+
+namespace fpm {
+
+// In-edge lists of a PyG-style batch graph: for every node, the ids of the edges that end in it, in
+// ascending edge order (deterministic).  One CTA per pair; one thread per destination node scans the
+// pair's edges.  in_ptr has [total_nodes + 1] entries (global offsets into in_eid).
+__global__ void csr_by_dst_kernel(const int64_t* __restrict__ edge_dst, const int64_t* __restrict__ ptr,
+                                  const int64_t* __restrict__ eptr, int* __restrict__ in_ptr,
+                                  int* __restrict__ in_eid, int total_nodes) {
+  extern __shared__ int sdst[];
+  __shared__ int wsum[32];
+  const int b = blockIdx.x;
+  const int n0 = (int)ptr[b], n = (int)ptr[b + 1] - n0;
+  const int e0 = (int)eptr[b], e = (int)eptr[b + 1] - e0;
+  for (int k = threadIdx.x; k < e; k += blockDim.x) sdst[k] = (int)edge_dst[e0 + k] - n0;
+  __syncthreads();
+  // count, then exclusive scan over nodes (nodes are processed in chunks of blockDim)
+  int base = 0;
+  for (int c0 = 0; c0 < n; c0 += blockDim.x) {
+    const int j = c0 + threadIdx.x;
+    int cnt = 0;
+    if (j < n)
+      for (int k = 0; k < e; ++k) cnt += (sdst[k] == j);
+    // block exclusive scan of cnt
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      int w = (lane < (int)(blockDim.x >> 5)) ? wsum[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const int woff = wid ? wsum[wid - 1] : 0;
+    const int excl = base + woff + inc - cnt;
+    if (j < n) {
+      in_ptr[n0 + j] = e0 + excl;
+      int w = e0 + excl;
+      for (int k = 0; k < e; ++k)
+        if (sdst[k] == j) in_eid[w++] = e0 + k;
+    }
+    base += wsum[(blockDim.x >> 5) - 1];
+    __syncthreads();
+  }
+  if (b == (int)gridDim.x - 1 && threadIdx.x == 0) in_ptr[total_nodes] = e0 + e;
+}
+
+// open B-spline basis, degree 1, 2-d pseudo coordinates, kernel 5x5 (torch_spline_conv basis_cpu.cpp)
+__device__ __forceinline__ void spline_basis4(float u0, float u1, int KS, float* bas, int* wi) {
+  const float v0 = u0 * (float)(KS - 1), v1 = u1 * (float)(KS - 1);
+  const float fl0 = floorf(v0), fl1 = floorf(v1);
+  const float f0 = v0 - fl0, f1 = v1 - fl1;
+  const int i0 = (int)fl0, i1 = (int)fl1;
+  const float g0 = (float)(1.0 - (double)f0), g1 = (float)(1.0 - (double)f1);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int k0 = s & 1, k1 = s >> 1;
+    bas[s] = __fmul_rn(k0 ? f0 : g0, k1 ? f1 : g1);
+    wi[s] = ((i0 + k0) % KS) + ((i1 + k1) % KS) * KS;
+  }
+}
+
+// One CTA (192 threads x float4 = 768 channels) per destination node.
+// Y: [total_nodes, NS, C] with NS = KS*KS + 1 slabs.  mode 0: out = relu(conv); mode 1: out = x + 0.1*conv.
+__global__ void __launch_bounds__(192)
+spline_gather_max_kernel(const float* __restrict__ Y, const float* __restrict__ xin,
+                         const int64_t* __restrict__ edge_src, const float* __restrict__ pseudo,
+                         const int* __restrict__ in_ptr, const int* __restrict__ in_eid,
+                         const float* __restrict__ bias, float* __restrict__ out, int C, int KS, int mode) {
+  const int i = blockIdx.x;
+  const int NS = KS * KS + 1;
+  const int e_beg = in_ptr[i], e_end = in_ptr[i + 1];
+  const int c4 = threadIdx.x;                 // float4 index along channels
+  if (c4 * 4 >= C) return;
+  float4 best = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+  for (int q = e_beg; q < e_end; ++q) {
+    const int e = in_eid[q];
+    const int j = (int)edge_src[e];
+    float bas[4]; int wi[4];
+    spline_basis4(pseudo[(size_t)e * 2], pseudo[(size_t)e * 2 + 1], KS, bas, wi);
+    const float* yj = Y + (size_t)j * NS * C;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const float4 y = *(const float4*)(yj + (size_t)wi[s] * C + c4 * 4);
+      m.x = fmaf(bas[s], y.x, m.x); m.y = fmaf(bas[s], y.y, m.y);
+      m.z = fmaf(bas[s], y.z, m.z); m.w = fmaf(bas[s], y.w, m.w);
+    }
+    best.x = fmaxf(best.x, m.x); best.y = fmaxf(best.y, m.y);
+    best.z = fmaxf(best.z, m.z); best.w = fmaxf(best.w, m.w);
+  }
+  if (e_beg == e_end) best = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 r = *(const float4*)(Y + ((size_t)i * NS + (NS - 1)) * C + c4 * 4);
+  const float4 bi = *(const float4*)(bias + c4 * 4);
+  float4 v;
+  v.x = best.x + r.x + bi.x; v.y = best.y + r.y + bi.y;
+  v.z = best.z + r.z + bi.z; v.w = best.w + r.w + bi.w;
+  if (mode == 0) {
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  } else if (mode == 1) {
+    const float4 x0 = *(const float4*)(xin + (size_t)i * C + c4 * 4);
+    v.x = x0.x + 0.1f * v.x; v.y = x0.y + 0.1f * v.y; v.z = x0.z + 0.1f * v.z; v.w = x0.w + 0.1f * v.w;
+  }
+  *(float4*)(out + (size_t)i * C + c4 * 4) = v;
+}
+
+}  // namespace fpm
+
+extern "C" int fpm_csr_by_dst(const long long* edge_dst, const long long* ptr, const long long* eptr,
+                              int* in_ptr, int* in_eid, int B, int total_nodes, int max_edges_per_graph,
+                              void* stream) {
+  FPM_CHECK_ARG(edge_dst && ptr && eptr && in_ptr && in_eid, "fpm_csr_by_dst: null tensor");
+  FPM_CHECK_ARG(B > 0 && max_edges_per_graph >= 0, "fpm_csr_by_dst: bad sizes");
+  const size_t smem = (size_t)(max_edges_per_graph + 1) * sizeof(int);
+  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_csr_by_dst: too many edges per graph");
+  FPM_CUDA(cudaFuncSetAttribute(fpm::csr_by_dst_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  fpm::csr_by_dst_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(
+      (const int64_t*)edge_dst, (const int64_t*)ptr, (const int64_t*)eptr, in_ptr, in_eid, total_nodes);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_spline_gather_max(const float* Y, const float* xin, const long long* edge_src,
+                                     const float* pseudo, const int* in_ptr, const int* in_eid,
+                                     const float* bias, float* out, int total_nodes, int C,
+                                     int kernel_size, int mode, void* stream) {
+  FPM_CHECK_ARG(Y && edge_src && pseudo && in_ptr && in_eid && bias && out, "fpm_spline_gather_max: null tensor");
+  FPM_CHECK_ARG(mode == 0 || mode == 2 || (mode == 1 && xin), "fpm_spline_gather_max: bad mode / residual mode needs xin");
+  FPM_CHECK_ARG(C % 4 == 0 && C <= 768, "fpm_spline_gather_max: C must be a multiple of 4, at most 768");
+  if (total_nodes == 0) return FPM_OK;
+  fpm::spline_gather_max_kernel<<<total_nodes, 192, 0, (cudaStream_t)stream>>>(
+      Y, xin, (const int64_t*)edge_src, pseudo, in_ptr, in_eid, bias, out, C, kernel_size, mode);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}

@@ -1,0 +1,80 @@
+"""ctypes binding of ``libfpmatch_b200.so`` (the C ABI of ``include/fpmatch.h``).
+
+There is no fallback: if the shared library is missing it is built in-tree with nvcc, and if that is
+impossible the import of any op raises.  Calls fail loudly (``RuntimeError`` with the library's message)
+on a non-zero return code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+from . import build as _build
+
+_LIB = None
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+_LL = C.c_longlong
+
+# name -> (restype, argtypes); kept in the order of include/fpmatch.h
+SIGNATURES = {
+    "fpm_abi_version": (_I, []),
+    "fpm_device_ok": (_I, []),
+    "fpm_last_error": (C.c_char_p, []),
+    "fpm_set_error": (None, [C.c_char_p]),
+    "fpm_feature_align": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _I, _P]),
+    "fpm_fmap_prep": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "fpm_global_max": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "fpm_node_features": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
+    "fpm_affinity_coeff": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_gemm_nt_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fpm_gemm_nt_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _P]),
+    "fpm_gemm_nt_tc_workspace_bytes": (_LL, [_I, _I, _I, _I]),
+    "fpm_csr_by_dst": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_spline_gather_max": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fpm_affinity": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "fpm_assoc_in_csr": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "fpm_gnn_layer": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "fpm_final_classifier": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_sinkhorn_workspace_bytes": (_LL, [_I, _I, _I, _I]),
+    "fpm_sinkhorn_log": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "fpm_soft_topk_workspace_bytes": (_LL, [_I, _I, _I]),
+    "fpm_soft_topk": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "fpm_afau_attention": (_I, [_P, _P, _P, _P, _LL, _LL, _LL, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_add_instnorm": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "fpm_onehot_proj": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "fpm_k_head": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fpm_lap_topk": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_greedy_perm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+}
+
+
+def header_symbols() -> list:
+    """Function names declared in include/fpmatch.h (used by the ABI test)."""
+    hdr = (Path(__file__).resolve().parents[2] / "include" / "fpmatch.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(fpm_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB_PATH
+        if not path.exists():
+            _build.build()
+        handle = C.CDLL(str(path))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError = the library is stale: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().fpm_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

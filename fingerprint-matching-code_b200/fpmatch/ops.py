@@ -1,0 +1,377 @@
+"""torch-tensor wrappers over the C ABI (``include/fpmatch.h``).
+
+PyTorch is plumbing here: it owns device memory (caching allocator) and the current stream.  Every op
+takes contiguous CUDA tensors, launches on ``torch.cuda.current_stream()``, never synchronises the
+host and raises ``RuntimeError`` for CPU tensors - there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+
+# dense-contraction engine: "fp32" (CUDA cores), "3xtf32" (tcgen05, fp32-faithful), "tf32" (tcgen05, 1 pass)
+_GEMM_MODE = os.environ.get("FPMATCH_GEMM", "fp32")
+_LAUNCHES = 0          # kernels launched through this module (bench.py reports it)
+
+
+def set_gemm_mode(mode: str) -> None:
+    global _GEMM_MODE
+    if mode not in ("fp32", "3xtf32", "tf32"):
+        raise ValueError(f"unknown GEMM mode {mode!r}")
+    _GEMM_MODE = mode
+
+
+def gemm_mode() -> str:
+    return _GEMM_MODE
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def _count(n: int = 1) -> None:
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: Optional[Tensor], name: str, dtype=torch.float32) -> Optional[int]:
+    if t is None:
+        return None
+    if not isinstance(t, Tensor) or not t.is_cuda:
+        raise RuntimeError(f"fpmatch: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"fpmatch: {name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"fpmatch: {name} must be contiguous")
+    return t.data_ptr()
+
+
+def _ptr_array(ts: Sequence[Tensor]):
+    arr = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    return arr
+
+
+def _i64(t: Tensor) -> Tensor:
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------
+# feature_align family
+# ---------------------------------------------------------------------------------------------------
+def feature_align(raw_feature: Tensor, P: Tensor, ns: Tensor, ori_size, feat_coords: bool = False) -> Tensor:
+    B, Cc, Hf, Wf = raw_feature.shape
+    nmax = P.shape[1]
+    ns = _i64(ns)
+    out = torch.empty((B, Cc, nmax), dtype=torch.float32, device=raw_feature.device)
+    rc = _lib.lib().fpm_feature_align(_chk(raw_feature, "raw_feature"), _chk(P, "P"), _chk(ns, "ns", torch.int64),
+                                      out.data_ptr(), B, Cc, Hf, Wf, nmax, float(ori_size[0]), float(ori_size[1]),
+                                      int(feat_coords), _stream())
+    _lib.check(rc, "fpm_feature_align"); _count()
+    return out
+
+
+def fmap_prep(fmap: Tensor) -> Tensor:
+    """NCHW raw map -> [B, H*W, C] channels-last, divided by the channel L2 norm."""
+    B, Cc, Hf, Wf = fmap.shape
+    out = torch.empty((B, Hf * Wf, Cc), dtype=torch.float32, device=fmap.device)
+    rc = _lib.lib().fpm_fmap_prep(_chk(fmap, "fmap"), out.data_ptr(), B, Cc, Hf, Wf, _stream())
+    _lib.check(rc, "fpm_fmap_prep"); _count()
+    return out
+
+
+def global_max_into(fmap: Tensor, out: Tensor, offset: int) -> None:
+    B, Cc, Hf, Wf = fmap.shape
+    rc = _lib.lib().fpm_global_max(_chk(fmap, "fmap"), _chk(out, "out"), B, Cc, Hf * Wf, out.shape[1], offset,
+                                   _stream())
+    _lib.check(rc, "fpm_global_max"); _count()
+
+
+def node_features(nodes_nhwc: Tensor, edges_nhwc: Tensor, hw1, hw2, P: Tensor, ns: Tensor, ptr: Tensor,
+                  total_nodes: int, ori_size) -> Tensor:
+    B = P.shape[0]
+    nmax = P.shape[1]
+    C1, C2 = nodes_nhwc.shape[2], edges_nhwc.shape[2]
+    X = torch.empty((total_nodes, C1 + C2), dtype=torch.float32, device=P.device)
+    rc = _lib.lib().fpm_node_features(_chk(nodes_nhwc, "nodes"), _chk(edges_nhwc, "edges"), _chk(P, "P"),
+                                      _chk(ns, "ns", torch.int64), _chk(ptr, "ptr", torch.int64), X.data_ptr(),
+                                      B, nmax, C1, hw1[0], hw1[1], C2, hw2[0], hw2[1],
+                                      float(ori_size[0]), float(ori_size[1]), _stream())
+    _lib.check(rc, "fpm_node_features"); _count()
+    return X
+
+
+def affinity_coeff(gcat: Tensor, W: Tensor, bias: Tensor) -> Tensor:
+    B, IN = gcat.shape
+    OUT = W.shape[0]
+    out = torch.empty((B, OUT), dtype=torch.float32, device=gcat.device)
+    rc = _lib.lib().fpm_affinity_coeff(_chk(gcat, "gcat"), _chk(W, "W"), _chk(bias, "bias"), out.data_ptr(),
+                                       B, IN, OUT, _stream())
+    _lib.check(rc, "fpm_affinity_coeff"); _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------------
+def gemm_nt(A: Tensor, Bt: Tensor, bias: Optional[Tensor] = None, act: int = 0, out: Optional[Tensor] = None,
+            mode: Optional[str] = None) -> Tensor:
+    """out[M,N] = act(A[M,K] @ Bt[N,K]^T + bias)."""
+    mode = mode or _GEMM_MODE
+    M, K = A.shape
+    N = Bt.shape[0]
+    assert Bt.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    a, b, c = _chk(A, "A"), _chk(Bt, "Bt"), _chk(out, "out")
+    bp = _chk(bias, "bias")
+    L = _lib.lib()
+    if mode == "fp32":
+        rc = L.fpm_gemm_nt_f32(a, b, bp, c, M, N, K, K, K, N, act, _stream())
+        _lib.check(rc, "fpm_gemm_nt_f32"); _count()
+    else:
+        passes = 3 if mode == "3xtf32" else 1
+        wsb = L.fpm_gemm_nt_tc_workspace_bytes(M, N, K, passes)
+        ws = torch.empty((max(int(wsb), 16),), dtype=torch.uint8, device=A.device)
+        rc = L.fpm_gemm_nt_tc(a, b, bp, c, M, N, K, K, K, N, act, passes, ws.data_ptr(), int(wsb), _stream())
+        _lib.check(rc, "fpm_gemm_nt_tc"); _count(3 if passes == 3 else 1)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# SplineConv
+# ---------------------------------------------------------------------------------------------------
+def csr_by_dst(edge_index: Tensor, ptr: Tensor, eptr: Tensor, total_nodes: int, max_edges: int):
+    E = edge_index.shape[1]
+    dev = edge_index.device
+    in_ptr = torch.empty((total_nodes + 1,), dtype=torch.int32, device=dev)
+    in_eid = torch.empty((max(E, 1),), dtype=torch.int32, device=dev)
+    dst = edge_index[1]
+    rc = _lib.lib().fpm_csr_by_dst(_chk(dst, "edge_index[1]", torch.int64), _chk(ptr, "ptr", torch.int64),
+                                   _chk(eptr, "eptr", torch.int64), in_ptr.data_ptr(), in_eid.data_ptr(),
+                                   ptr.numel() - 1, total_nodes, max_edges, _stream())
+    _lib.check(rc, "fpm_csr_by_dst"); _count()
+    return in_ptr, in_eid
+
+
+def spline_gather_max(Y: Tensor, xin: Optional[Tensor], edge_index: Tensor, pseudo: Tensor, in_ptr: Tensor,
+                      in_eid: Tensor, bias: Tensor, mode: int, kernel_size: int = 5) -> Tensor:
+    total, Cc = Y.shape[0], bias.shape[0]
+    out = torch.empty((total, Cc), dtype=torch.float32, device=Y.device)
+    rc = _lib.lib().fpm_spline_gather_max(_chk(Y, "Y"), _chk(xin, "xin"), _chk(edge_index[0], "edge_index[0]", torch.int64),
+                                          _chk(pseudo, "pseudo"), _chk(in_ptr, "in_ptr", torch.int32),
+                                          _chk(in_eid, "in_eid", torch.int32), _chk(bias, "bias"), out.data_ptr(),
+                                          total, Cc, kernel_size, mode, _stream())
+    _lib.check(rc, "fpm_spline_gather_max"); _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# affinities
+# ---------------------------------------------------------------------------------------------------
+def affinity_nodes(XA: Tensor, XB: Tensor, coeff: Tensor, ptrA: Tensor, ptrB: Tensor, Rmax: int, Cmax: int,
+                   scale: float = 1.0, want_t: bool = True):
+    B = coeff.shape[0]
+    out = torch.empty((B, Rmax, Cmax), dtype=torch.float32, device=XA.device)
+    out_t = torch.empty((B, Cmax, Rmax), dtype=torch.float32, device=XA.device) if want_t else None
+    rc = _lib.lib().fpm_affinity(_chk(XA, "XA"), _chk(XB, "XB"), _chk(coeff, "coeff"),
+                                 _chk(ptrA, "ptrA", torch.int64), _chk(ptrB, "ptrB", torch.int64),
+                                 None, None, None, None, 0, 0, out.data_ptr(),
+                                 out_t.data_ptr() if want_t else None, B, Rmax, Cmax, XA.shape[1], scale, _stream())
+    _lib.check(rc, "fpm_affinity"); _count()
+    return out, out_t
+
+
+def affinity_edges(XA: Tensor, XB: Tensor, coeff: Tensor, eptrA: Tensor, eptrB: Tensor, eidxA: Tensor,
+                   eidxB: Tensor, Rmax: int, Cmax: int, scale: float = 0.5) -> Tensor:
+    B = coeff.shape[0]
+    out = torch.empty((B, Rmax, Cmax), dtype=torch.float32, device=XA.device)
+    rc = _lib.lib().fpm_affinity(_chk(XA, "XA"), _chk(XB, "XB"), _chk(coeff, "coeff"), None, None,
+                                 _chk(eptrA, "eptrA", torch.int64), _chk(eptrB, "eptrB", torch.int64),
+                                 _chk(eidxA, "edge_index A", torch.int64), _chk(eidxB, "edge_index B", torch.int64),
+                                 eidxA.shape[1], eidxB.shape[1], out.data_ptr(), None, B, Rmax, Cmax, XA.shape[1],
+                                 scale, _stream())
+    _lib.check(rc, "fpm_affinity"); _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# association-graph GNN
+# ---------------------------------------------------------------------------------------------------
+def assoc_in_csr(edges: Tensor, nmax: int):
+    B, _, emax = edges.shape
+    in_ptr = torch.empty((B, nmax + 1), dtype=torch.int32, device=edges.device)
+    in_src = torch.empty((B, max(emax, 1)), dtype=torch.int32, device=edges.device)
+    rc = _lib.lib().fpm_assoc_in_csr(_chk(edges, "edges", torch.int32), in_ptr.data_ptr(), in_src.data_ptr(),
+                                     B, nmax, emax, _stream())
+    _lib.check(rc, "fpm_assoc_in_csr"); _count()
+    return in_ptr, in_src
+
+
+def gnn_layer(xprev: Optional[Tensor], mprev_t: Tensor, csr1, csr2, n1: Tensor, n2: Tensor, weights,
+              n1max: int, n2max: int, e1max: int, e2max: int):
+    B = mprev_t.shape[0]
+    N = n1max * n2max
+    dev = mprev_t.device
+    xout = torch.empty((B, N, 16), dtype=torch.float32, device=dev)
+    score = torch.empty((B, n1max, n2max), dtype=torch.float32, device=dev)
+    for i, w in enumerate(weights):
+        _chk(w, f"gnn weight {i}")
+    wp = _ptr_array(weights)
+    rc = _lib.lib().fpm_gnn_layer(_chk(xprev, "xprev"), _chk(mprev_t, "mprev_t"),
+                                  _chk(csr1[0], "in_ptr1", torch.int32), _chk(csr1[1], "in_src1", torch.int32),
+                                  _chk(csr2[0], "in_ptr2", torch.int32), _chk(csr2[1], "in_src2", torch.int32),
+                                  _chk(n1, "n1", torch.int64), _chk(n2, "n2", torch.int64), wp,
+                                  xout.data_ptr(), score.data_ptr(), B, n1max, n2max, e1max, e2max,
+                                  1 if xprev is None else 17, _stream())
+    _lib.check(rc, "fpm_gnn_layer"); _count()
+    return xout, score
+
+
+def final_classifier(x1: Tensor, sk_t: Tensor, cw: Tensor, cb: Tensor, n1max: int, n2max: int) -> Tensor:
+    B = x1.shape[0]
+    s = torch.empty((B, n1max, n2max), dtype=torch.float32, device=x1.device)
+    rc = _lib.lib().fpm_final_classifier(_chk(x1, "x1"), _chk(sk_t, "sk_t"), _chk(cw, "classifier.weight"),
+                                         _chk(cb, "classifier.bias"), s.data_ptr(), B, n1max, n2max, _stream())
+    _lib.check(rc, "fpm_final_classifier"); _count()
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------
+# Sinkhorn / soft-top-k
+# ---------------------------------------------------------------------------------------------------
+def sinkhorn_log(s: Tensor, n1: Optional[Tensor], n2: Optional[Tensor], max_iter: int, tau: float,
+                 dummy_row: bool, want_t: bool = False):
+    B, R, Cc = s.shape
+    L = _lib.lib()
+    out = torch.empty_like(s)
+    out_t = torch.empty((B, Cc, R), dtype=torch.float32, device=s.device) if want_t else None
+    wsb = int(L.fpm_sinkhorn_workspace_bytes(B, R, Cc, int(dummy_row)))
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=s.device) if wsb else None
+    n1 = _i64(n1) if n1 is not None else None
+    n2 = _i64(n2) if n2 is not None else None
+    rc = L.fpm_sinkhorn_log(_chk(s, "s"), _chk(n1, "nrows", torch.int64), _chk(n2, "ncols", torch.int64),
+                            out.data_ptr(), out_t.data_ptr() if want_t else None,
+                            ws.data_ptr() if ws is not None else None, B, R, Cc, int(max_iter), float(tau),
+                            int(bool(dummy_row)), _stream())
+    _lib.check(rc, "fpm_sinkhorn_log"); _count()
+    return (out, out_t) if want_t else out
+
+
+def soft_topk(scores: Tensor, ks: Tensor, n1: Optional[Tensor], n2: Optional[Tensor], max_iter: int,
+              tau: float) -> Tensor:
+    B, R, Cc = scores.shape
+    L = _lib.lib()
+    out = torch.empty_like(scores)
+    wsb = int(L.fpm_soft_topk_workspace_bytes(B, R, Cc))
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=scores.device) if wsb else None
+    n1 = _i64(n1) if n1 is not None else None
+    n2 = _i64(n2) if n2 is not None else None
+    ks = ks.to(torch.float32).contiguous()
+    rc = L.fpm_soft_topk(_chk(scores, "scores"), _chk(ks, "ks"), _chk(n1, "nrows", torch.int64),
+                         _chk(n2, "ncols", torch.int64), out.data_ptr(), ws.data_ptr() if ws is not None else None,
+                         B, R, Cc, int(max_iter), float(tau), _stream())
+    _lib.check(rc, "fpm_soft_topk"); _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# AFA-U
+# ---------------------------------------------------------------------------------------------------
+def afau_attention(q: Tensor, k: Tensor, v: Tensor, cost: Tensor, transposed_cost: bool, mix1_w: Tensor,
+                   mix1_b: Tensor, mix2_w: Tensor, mix2_b: Tensor) -> Tensor:
+    """cost is the ORIGINAL [B, n1, n2] matrix; ``transposed_cost`` makes the kernel read cost^T."""
+    B, nr, E = q.shape
+    nc = k.shape[1]
+    out = torch.empty((B, nr, E), dtype=torch.float32, device=q.device)
+    R, Cc = cost.shape[1], cost.shape[2]
+    if transposed_cost:
+        assert (nr, nc) == (Cc, R)
+        cs_b, cs_r, cs_c = R * Cc, 1, Cc
+    else:
+        assert (nr, nc) == (R, Cc)
+        cs_b, cs_r, cs_c = R * Cc, Cc, 1
+    rc = _lib.lib().fpm_afau_attention(_chk(q, "q"), _chk(k, "k"), _chk(v, "v"), _chk(cost, "cost"), cs_b, cs_r, cs_c,
+                                       _chk(mix1_w, "mix1_weight"), _chk(mix1_b, "mix1_bias"),
+                                       _chk(mix2_w, "mix2_weight"), _chk(mix2_b, "mix2_bias"), out.data_ptr(),
+                                       B, nr, nc, _stream())
+    _lib.check(rc, "fpm_afau_attention"); _count()
+    return out
+
+
+def add_instnorm(a: Tensor, other: Optional[Tensor], gamma: Tensor, beta: Tensor, want_rowmax: bool = False,
+                 eps: float = 1e-5):
+    B, n, E = a.shape
+    out = torch.empty_like(a)
+    rowmax = torch.empty((B, E), dtype=torch.float32, device=a.device) if want_rowmax else None
+    mode = 0 if other is None else (2 if other.dim() == 1 else 1)
+    rc = _lib.lib().fpm_add_instnorm(_chk(a, "a"), _chk(other, "other"), mode, _chk(gamma, "norm.weight"),
+                                     _chk(beta, "norm.bias"), out.data_ptr(),
+                                     rowmax.data_ptr() if want_rowmax else None, B, n, E, float(eps), _stream())
+    _lib.check(rc, "fpm_add_instnorm"); _count()
+    return (out, rowmax) if want_rowmax else out
+
+
+def onehot_proj(W: Tensor, n: Tensor, nmax: int) -> Tensor:
+    B = n.shape[0]
+    OUT, IN = W.shape
+    out = torch.empty((B, nmax, OUT), dtype=torch.float32, device=W.device)
+    rc = _lib.lib().fpm_onehot_proj(_chk(W, "W"), _chk(n, "n", torch.int64), out.data_ptr(), B, nmax, OUT, IN,
+                                    _stream())
+    _lib.check(rc, "fpm_onehot_proj"); _count()
+    return out
+
+
+def k_head(g_row: Tensor, g_col: Tensor, weights, n1: Tensor, n2: Tensor, mean_k: bool = True):
+    B, E = g_row.shape
+    Hd = weights[0].shape[0]
+    ks = torch.empty((B,), dtype=torch.float32, device=g_row.device)
+    kscaled = torch.empty((B,), dtype=torch.float32, device=g_row.device)
+    for i, w in enumerate(weights):
+        _chk(w, f"k-head weight {i}")
+    rc = _lib.lib().fpm_k_head(_chk(g_row, "g_row"), _chk(g_col, "g_col"), _ptr_array(weights),
+                               _chk(n1, "n1", torch.int64), _chk(n2, "n2", torch.int64), ks.data_ptr(),
+                               kscaled.data_ptr(), B, E, Hd, int(mean_k), _stream())
+    _lib.check(rc, "fpm_k_head"); _count()
+    return ks, kscaled
+
+
+# ---------------------------------------------------------------------------------------------------
+# LAP + greedy
+# ---------------------------------------------------------------------------------------------------
+def lap_topk(ds: Tensor, n1: Optional[Tensor], n2: Optional[Tensor], ks: Optional[Tensor] = None,
+             want_hungarian: bool = True, want_perm: bool = False):
+    B, R, Cc = ds.shape
+    hung = torch.empty_like(ds) if want_hungarian else None
+    perm = torch.empty_like(ds) if want_perm else None
+    n1 = _i64(n1) if n1 is not None else None
+    n2 = _i64(n2) if n2 is not None else None
+    if ks is not None:
+        ks = ks.to(torch.float32).contiguous()
+    rc = _lib.lib().fpm_lap_topk(_chk(ds, "s"), _chk(n1, "n1", torch.int64), _chk(n2, "n2", torch.int64),
+                                 _chk(ks, "ks"), hung.data_ptr() if want_hungarian else None,
+                                 perm.data_ptr() if want_perm else None, None, B, R, Cc, _stream())
+    _lib.check(rc, "fpm_lap_topk"); _count()
+    return hung, perm
+
+
+def greedy_perm(x: Tensor, top_indices: Tensor, ks: Tensor) -> Tensor:
+    B, R, Cc = x.shape
+    top_indices = _i64(top_indices)
+    ks = ks.to(torch.float32).contiguous()
+    rc = _lib.lib().fpm_greedy_perm(_chk(x, "x"), _chk(top_indices, "top_indices", torch.int64), _chk(ks, "ks"),
+                                    B, R, Cc, top_indices.shape[1], _stream())
+    _lib.check(rc, "fpm_greedy_perm"); _count()
+    return x

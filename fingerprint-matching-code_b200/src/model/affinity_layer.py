@@ -1,0 +1,49 @@
+"""Drop-in for ``/root/reference/src/model/affinity_layer.py`` (``InnerProductWithWeightsAffinity``).
+
+``forward(Xs, Ys, Ws)`` keeps the reference's list-in / list-out contract; all pairs run in one ragged
+batched launch (``csrc/gemm_simt.cu::affinity_kernel``) with the ``tanh(A w)`` scaling, softplus and
+``- 0.5`` fused.  ``Net.forward`` calls the packed form directly and never builds python lists.
+"""
+import torch
+import torch.nn as nn
+
+from fpmatch import ops
+
+
+class InnerProductWithWeightsAffinity(nn.Module):
+    def __init__(self, input_dim, output_dim):
+        super(InnerProductWithWeightsAffinity, self).__init__()
+        self.d = output_dim
+        self.A = torch.nn.Linear(input_dim, output_dim)
+
+    def fused_coefficients(self, global_cat: torch.Tensor) -> torch.Tensor:
+        """tanh(A (g / ||g||) + a) for UN-normalised ``global_cat [B, input_dim]`` in one launch
+        (normalize_over_channels of ngm.py:268 + affinity_layer.py:13)."""
+        return ops.affinity_coeff(global_cat.detach().contiguous(), self.A.weight.detach().contiguous(),
+                                  self.A.bias.detach().contiguous())
+
+    def _forward(self, X, Y, weights, use_global):
+        return self.forward([X], [Y], weights.unsqueeze(0), use_global)[0]
+
+    def forward(self, Xs, Ys, Ws, use_global=True):
+        Xs, Ys = list(Xs), list(Ys)
+        B = len(Xs)
+        for X, Y in zip(Xs, Ys):
+            assert X.shape[1] == Y.shape[1] == self.d, (X.shape[1], Y.shape[1], self.d)
+        dev = Xs[0].device
+        Ws = Ws if isinstance(Ws, torch.Tensor) else torch.stack(list(Ws), 0)
+        if use_global:
+            W32 = Ws.detach().to(torch.float32)
+            coeff = torch.tanh(torch.nn.functional.linear(W32, self.A.weight.detach(), self.A.bias.detach()))
+        else:
+            coeff = torch.ones((B, self.d), dtype=torch.float32, device=dev)
+        nA = torch.tensor([x.shape[0] for x in Xs], dtype=torch.int64)
+        nB = torch.tensor([y.shape[0] for y in Ys], dtype=torch.int64)
+        ptrA = torch.zeros(B + 1, dtype=torch.int64); ptrA[1:] = torch.cumsum(nA, 0)
+        ptrB = torch.zeros(B + 1, dtype=torch.int64); ptrB[1:] = torch.cumsum(nB, 0)
+        XA = torch.cat([x.detach().to(torch.float32) for x in Xs], 0).contiguous()
+        XB = torch.cat([y.detach().to(torch.float32) for y in Ys], 0).contiguous()
+        Rmax, Cmax = int(nA.max()), int(nB.max())
+        out, _ = ops.affinity_nodes(XA, XB, coeff.contiguous(), ptrA.to(dev), ptrB.to(dev), Rmax, Cmax,
+                                    scale=1.0, want_t=False)
+        return [out[b, :int(nA[b]), :int(nB[b])] for b in range(B)]

@@ -1,0 +1,56 @@
+"""Drop-in for ``/root/reference/src/model/sinkhorn.py`` (``Sinkhorn``; same constructor and forward).
+
+The reference forwards to ``pygmtools.sinkhorn(..., backend='pytorch')`` (``sinkhorn.py:85-87``), a python
+loop over pairs and iterations.  Here one CTA per pair keeps the pair's matrix in shared memory for all
+iterations (``csrc/sinkhorn.cu``).
+"""
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from fpmatch import ops
+
+
+class Sinkhorn(nn.Module):
+    r"""
+    Sinkhorn algorithm turns the input matrix into a bi-stochastic matrix (log-domain, temperature ``tau``).
+
+    :param max_iter: maximum iterations (default: ``10``)
+    :param tau: temperature (default: ``1``)
+    :param epsilon: kept for signature compatibility (unused by the log-domain path, as in the reference)
+    :param log_forward: only ``True`` is supported (the reference's ``forward_ori`` is deprecated)
+    :param batched_operation: accepted and ignored - every pair is always processed concurrently and the
+     result equals the reference's ``batched_operation=False`` arithmetic
+    """
+    def __init__(self, max_iter: int = 10, tau: float = 1., epsilon: float = 1e-4,
+                 log_forward: bool = True, batched_operation: bool = False):
+        super(Sinkhorn, self).__init__()
+        self.max_iter = max_iter
+        self.tau = tau
+        self.epsilon = epsilon
+        self.log_forward = log_forward
+        if not log_forward:
+            print('Warning: Sinkhorn algorithm without log forward is deprecated because log_forward is more stable.')
+        self.batched_operation = batched_operation
+
+    def forward(self, s: Tensor, nrows: Tensor = None, ncols: Tensor = None, dummy_row: bool = False) -> Tensor:
+        if not self.log_forward:
+            raise NotImplementedError('only the log-domain Sinkhorn (log_forward=True) is implemented')
+        return self.forward_log(s, nrows, ncols, dummy_row)
+
+    def forward_log(self, s, nrows=None, ncols=None, dummy_row=False):
+        """Compute sinkhorn with row/column normalization in the log space."""
+        if len(s.shape) == 2:
+            s = s.unsqueeze(0)
+            matrix_input = True
+        elif len(s.shape) == 3:
+            matrix_input = False
+        else:
+            raise ValueError('input data shape not understood.')
+        x = s.detach().to(torch.float32).contiguous()
+        nrows = nrows.to(x.device) if nrows is not None else None
+        ncols = ncols.to(x.device) if ncols is not None else None
+        out = ops.sinkhorn_log(x, nrows, ncols, self.max_iter, self.tau, dummy_row)
+        if matrix_input:
+            out = out.squeeze(0)
+        return out

@@ -1,0 +1,136 @@
+"""Drop-in for ``/root/reference/src/model/spline_conv.py`` (``SConv``, ``SiameseSConvOnNodes``,
+``SiameseNodeFeaturesToEdgeFeatures``) with its own ``SplineConv`` (torch_geometric is not required).
+
+``SplineConv`` keeps torch_geometric 1.6.3's parameters (``weight [25, in, out]``, ``root [in, out]``,
+``bias [out]``) and initialisation, so reference checkpoints load; a PyG 2.x checkpoint's ``lin.weight``
+is accepted as ``root``.  Forward = one dense GEMM against all 26 weight slabs + one gather/max kernel
+(``csrc/spline.cu``) instead of a per-edge weighting kernel and a scatter.
+"""
+import math
+
+import torch
+import torch.nn
+import torch.nn.functional as F
+
+from fpmatch import ops
+from fpmatch.graph import GraphData, graph_offsets
+
+
+class SplineConv(torch.nn.Module):
+    """SplineConv(in, out, dim=2, kernel_size=5, is_open_spline=True, degree=1, aggr='max',
+    root_weight=True, bias=True): the configuration of ``spline_conv.py:17``; others are rejected."""
+
+    def __init__(self, in_channels, out_channels, dim=2, kernel_size=5, is_open_spline=True, degree=1,
+                 aggr="max", root_weight=True, bias=True):
+        super().__init__()
+        if dim != 2 or degree != 1 or not is_open_spline or aggr != "max" or not root_weight or not bias:
+            raise NotImplementedError("only the configuration used by the matching head is implemented")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.dim, self.degree, self.kernel_size = dim, degree, kernel_size
+        K = kernel_size ** dim
+        self.weight = torch.nn.Parameter(torch.empty(K, in_channels, out_channels))
+        self.root = torch.nn.Parameter(torch.empty(in_channels, out_channels))
+        self.bias = torch.nn.Parameter(torch.empty(out_channels))
+        self._packed = None      # (key, [K+1)*out, in] slab matrix)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = 1.0 / math.sqrt(self.in_channels * self.weight.size(0))
+        torch.nn.init.uniform_(self.weight, -bound, bound)
+        torch.nn.init.uniform_(self.root, -bound, bound)
+        torch.nn.init.zeros_(self.bias)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        k2 = prefix + "lin.weight"                       # torch_geometric 2.x name of the root weight
+        if k2 in state_dict and prefix + "root" not in state_dict:
+            state_dict[prefix + "root"] = state_dict.pop(k2).t()
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def packed_weight(self) -> torch.Tensor:
+        """[(K+1)*out, in]: row k*out + o holds W[k][:, o]; slab K is the root weight."""
+        key = (self.weight.data_ptr(), self.weight._version, self.root.data_ptr(), self.root._version,
+               self.weight.device)
+        if self._packed is None or self._packed[0] != key:
+            w = torch.cat([self.weight.detach(), self.root.detach().unsqueeze(0)], 0)
+            self._packed = (key, w.permute(0, 2, 1).reshape(-1, self.in_channels).contiguous())
+        return self._packed[1]
+
+    def forward(self, x, edge_index, pseudo, csr=None, ptr=None, eptr=None, mode=None, residual=None):
+        """``csr`` = in-edge lists from ``ops.csr_by_dst``; built on the fly when missing.  ``mode``:
+        None / 2 = plain conv output, 0 = relu(out), 1 = residual + 0.1 * out."""
+        total = x.shape[0]
+        if csr is None:
+            if ptr is None:
+                ptr = torch.tensor([0, total], dtype=torch.int64, device=x.device)
+                eptr = torch.tensor([0, edge_index.shape[1]], dtype=torch.int64, device=x.device)
+            max_e = int((eptr[1:] - eptr[:-1]).max())
+            csr = ops.csr_by_dst(edge_index.contiguous(), ptr, eptr, total, max_e)
+        Y = ops.gemm_nt(x.detach().contiguous(), self.packed_weight())
+        bias = self.bias.detach().contiguous()
+        mode = 2 if mode is None else mode
+        return ops.spline_gather_max(Y, residual, edge_index, pseudo.contiguous(), csr[0], csr[1], bias, mode,
+                                     self.kernel_size)
+
+
+class SConv(torch.nn.Module):
+    def __init__(self, input_features, output_features):
+        super(SConv, self).__init__()
+        self.in_channels = input_features
+        self.num_layers = 2
+        self.convs = torch.nn.ModuleList()
+        for _ in range(self.num_layers):
+            self.convs.append(SplineConv(input_features, output_features, dim=2, kernel_size=5, aggr="max"))
+            input_features = output_features
+        self.out_channels = input_features
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+
+    def forward(self, data, residual_scale_input=None):
+        """relu(conv0(x)) -> conv1; with ``residual_scale_input`` the x + 0.1 * result of
+        SiameseSConvOnNodes is fused into the second gather kernel."""
+        x = data.x
+        edge_index = data.edge_index.to(x.device).contiguous()
+        edge_attr = data.edge_attr.to(x.device, torch.float32).contiguous()
+        ptr, eptr = graph_offsets(data)
+        csr = getattr(data, "_fpm_csr", None)
+        if csr is None:
+            max_e = int((eptr[1:] - eptr[:-1]).max()) if eptr.numel() > 1 else 0
+            csr = ops.csr_by_dst(edge_index.contiguous(), ptr.to(x.device), eptr.to(x.device), x.shape[0], max_e)
+            data._fpm_csr = csr
+        h = self.convs[0](x, edge_index, edge_attr, csr=csr, mode=0)
+        if residual_scale_input is not None:
+            return self.convs[1](h, edge_index, edge_attr, csr=csr, mode=1, residual=residual_scale_input)
+        return self.convs[1](h, edge_index, edge_attr, csr=csr, mode=2)
+
+
+class SiameseSConvOnNodes(torch.nn.Module):
+    def __init__(self, input_node_dim):
+        super(SiameseSConvOnNodes, self).__init__()
+        self.num_node_features = input_node_dim
+        self.mp_network = SConv(input_features=self.num_node_features, output_features=self.num_node_features)
+
+    def forward(self, graph):
+        old_features = graph.x.detach().contiguous()
+        graph.x = self.mp_network(graph, residual_scale_input=old_features)
+        return graph
+
+
+class SiameseNodeFeaturesToEdgeFeatures(torch.nn.Module):
+    def __init__(self, total_num_nodes):
+        super(SiameseNodeFeaturesToEdgeFeatures, self).__init__()
+        self.num_edge_features = total_num_nodes
+
+    def forward(self, graph, hyperedge=False):
+        if hyperedge:
+            raise NotImplementedError("hyperedge attributes are not on the matching head's path")
+        orig_graphs = graph.to_data_list()
+        return [self.vertex_attr_to_edge_attr(g) for g in orig_graphs]
+
+    def vertex_attr_to_edge_attr(self, graph):
+        """Assigns the difference of node features to each edge (spline_conv.py:73-81).  Net.forward does
+        not call this: the affinity kernel forms x[src] - x[dst] on the fly."""
+        graph.edge_attr = graph.x[graph.edge_index[0]] - graph.x[graph.edge_index[1]]
+        return graph

@@ -1,0 +1,42 @@
+"""Drop-in for ``/root/reference/utils/hungarian.py`` - same signature, no host round trip.
+
+The reference copies the scores to the host, negates them and calls scipy's
+``linear_sum_assignment`` per pair (``utils/hungarian.py:34-51,58-65``).  Here one warp per pair runs
+the same shortest-augmenting-path algorithm in fp64 on the GPU with scipy's exact traversal and
+tie-break rule (``csrc/lap.cu``), so the returned permutation matrices are bit-identical to scipy's.
+"""
+import torch
+from torch import Tensor
+
+from fpmatch import ops
+
+
+def hungarian(s: Tensor, n1: Tensor = None, n2: Tensor = None, nproc: int = 1) -> Tensor:
+    r"""
+    Solve optimal LAP permutation by the Hungarian (shortest augmenting path) algorithm.
+
+    :param s: :math:`(b\times n_1 \times n_2)` input 3d tensor (or a single 2d matrix)
+    :param n1: :math:`(b)` number of objects in dim1
+    :param n2: :math:`(b)` number of objects in dim2
+    :param nproc: kept for signature compatibility; the GPU solver always runs all pairs concurrently
+    :return: :math:`(b\times n_1 \times n_2)` optimal permutation matrix (float32, padded shape)
+    """
+    if len(s.shape) == 2:
+        s = s.unsqueeze(0)
+        matrix_input = True
+    elif len(s.shape) == 3:
+        matrix_input = False
+    else:
+        raise ValueError('input data shape not understood: {}'.format(s.shape))
+
+    x = s.detach()
+    if x.dtype != torch.float32:
+        x = x.to(torch.float32)
+    x = x.contiguous()
+    dev = x.device
+    n1 = n1.to(dev) if n1 is not None else None
+    n2 = n2.to(dev) if n2 is not None else None
+    perm_mat, _ = ops.lap_topk(x, n1, n2, want_hungarian=True, want_perm=False)
+    if matrix_input:
+        perm_mat = perm_mat.squeeze(0)
+    return perm_mat

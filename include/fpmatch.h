@@ -1,0 +1,163 @@
+/*
+ * fpmatch.h - C ABI of libfpmatch_b200.so, the sm_100a matching-head kernels.
+ *
+ * This is the drop-in boundary for the reference's graph-matching hot path
+ * (/root/reference/src/model/ngm.py:205-491 and the ops it calls).  The reference has no C ABI of its
+ * own: its natives are pybind11 functions over at::Tensor (src/extension/sparse_dot/sparse_dot.cpp:322-331,
+ * src/extension/bilinear_diag/bilinear_diag.cpp:324-326) and its hot ops are python functions.  Every entry
+ * point below therefore names the PYTHON interface it replaces (file:line); INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add at each site.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every tensor pointer is a DEVICE pointer to a contiguous fp32 /
+ *     int64 / int32 array in the row-major layout given in the comment; `stream` is a cudaStream_t
+ *     passed as void* (0 = legacy default stream).  Nothing synchronises the host.
+ *   - keypoint counts n1/n2/ns and graph offsets ptr/eptr are int64 (`long long`), exactly the dtype the
+ *     reference's data_dict carries (src/gmdataset.py:563-672), so no conversion launch is needed.
+ *   - return value: 0 on success, a negative FPM_ERR_* for rejected arguments, a positive cudaError_t
+ *     for launch failures; fpm_last_error() returns the message of the last failure on this thread.
+ *     This mirrors the reference's behaviour of raising on bad shapes/devices
+ *     (sparse_dot.cpp:42-45 CHECK_INPUT, utils/hungarian.py:29 ValueError).
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef FPMATCH_H_
+#define FPMATCH_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPM_OK 0
+#define FPM_ERR_ARG (-1)
+#define FPM_ERR_UNSUPPORTED (-2)
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int fpm_abi_version(void);
+int fpm_device_ok(void);                 /* 1 iff the current device is compute capability 10.x */
+const char* fpm_last_error(void);
+void fpm_set_error(const char* msg);
+
+/* ---- (1) feature_align ----------------------------------------------------------------------------
+ * fpm_feature_align replaces utils.feature_align.feature_align (utils/feature_align.py:5-37):
+ *   fmap [B,C,Hf,Wf], P [B,nmax,2] (x,y), ns [B] -> out [B,C,nmax], zero beyond ns[b]; bit-exact,
+ *   including the (W,H)/(Hf,Wf) scaling mix-up and the post-fetch edge rule (:55-62, :98-118).
+ *   feat_coords = 1: P already holds feature-space (x,y) = bilinear_interpolate(im, x, y) (:67-125).
+ * fpm_fmap_prep + fpm_node_features are the fused form used by Net.forward (ngm.py:241-251):
+ *   raw NCHW map -> channels-last map divided by its channel L2 norm; then one warp per keypoint writes
+ *   X[ptr[b]+i, 0:C1+C2] = [align(nodes), align(edges)].
+ * fpm_global_max replaces final_layers = AdaptiveMaxPool2d(1,1) (feature_extractor.py:54, ngm.py:238):
+ *   out[b*out_stride + out_offset + c] = max_hw fmap[b,c,:].
+ * fpm_affinity_coeff: coeff[b,:] = tanh(A * (g[b]/||g[b]||) + a)  (ngm.py:262-268, affinity_layer.py:13).
+ */
+int fpm_feature_align(const float* fmap, const float* P, const long long* ns, float* out, int B, int C,
+                      int Hf, int Wf, int nmax, float ori_w, float ori_h, int feat_coords, void* stream);
+int fpm_fmap_prep(const float* fmap_nchw, float* out_nhwc, int B, int C, int Hf, int Wf, void* stream);
+int fpm_global_max(const float* fmap, float* out, int B, int C, int HW, int out_stride, int out_offset,
+                   void* stream);
+int fpm_node_features(const float* nodes_nhwc, const float* edges_nhwc, const float* P, const long long* ns,
+                      const long long* ptr, float* X, int B, int nmax, int C1, int H1, int W1, int C2, int H2,
+                      int W2, float ori_w, float ori_h, void* stream);
+int fpm_affinity_coeff(const float* gcat, const float* W, const float* bias, float* coeff, int B, int IN,
+                       int OUT, void* stream);
+
+/* ---- dense contractions ------------------------------------------------------------------------------
+ * C[M,N] = act(A[M,K] * Bt[N,K]^T + bias[N]), act 0 = none, 1 = relu.  fp32 CUDA cores (fpm_gemm_nt_f32)
+ * or tcgen05 tensor cores with fp32-faithful 3xTF32 splitting (fpm_gemm_nt_tc, passes = 3) / plain TF32
+ * (passes = 1).  Used for SplineConv's slab GEMM, the AFA-U projections and feed-forward.
+ */
+int fpm_gemm_nt_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K,
+                    int lda, int ldb, int ldc, int act, void* stream);
+int fpm_gemm_nt_tc(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K,
+                   int lda, int ldb, int ldc, int act, int passes, void* workspace,
+                   long long workspace_bytes, void* stream);
+long long fpm_gemm_nt_tc_workspace_bytes(int M, int N, int K, int passes);
+
+/* ---- (3a) SplineConv -----------------------------------------------------------------------------------
+ * Replaces torch_geometric SplineConv(768,768,dim=2,kernel_size=5,aggr='max') as driven by
+ * src/model/spline_conv.py:28-58.  Y [total_nodes, KS*KS+1, C] = x @ [W_0 .. W_24, root] comes from the GEMM
+ * above; fpm_spline_gather_max blends the 4 active slabs per in-edge, takes the max over in-edges, adds the
+ * root slab + bias, then relu (mode 0) or x + 0.1*out (mode 1).  fpm_csr_by_dst builds the in-edge lists
+ * from edge_index[1] (global node ids of a PyG-style batch; ptr/eptr = node/edge offsets per graph).
+ */
+int fpm_csr_by_dst(const long long* edge_dst, const long long* ptr, const long long* eptr, int* in_ptr,
+                   int* in_eid, int B, int total_nodes, int max_edges_per_graph, void* stream);
+int fpm_spline_gather_max(const float* Y, const float* xin, const long long* edge_src, const float* pseudo,
+                          const int* in_ptr, const int* in_eid, const float* bias, float* out,
+                          int total_nodes, int C, int kernel_size, int mode, void* stream);
+
+/* ---- (2) affinities --------------------------------------------------------------------------------------
+ * Replaces InnerProductWithWeightsAffinity.forward (src/model/affinity_layer.py:11-22) for Kp (node mode:
+ * eidx* = NULL, rows ptrA[b]..ptrA[b+1]) and Ke (edge mode: row r = X[eidx[0][eptr[b]+r]] - X[eidx[1][..]],
+ * src/model/spline_conv.py:73-81), fused with the 0.5 factor of ngm.py:287 (`scale`) and the zero padding of
+ * ngm.py:317-318.  out [B,Rmax,Cmax]; out_t (optional) the transpose [B,Cmax,Rmax] (= emb of ngm.py:321).
+ */
+int fpm_affinity(const float* XA, const float* XB, const float* coeff, const long long* ptrA,
+                 const long long* ptrB, const long long* eptrA, const long long* eptrB, const long long* eidxA,
+                 const long long* eidxB, int EA, int EB, float* out, float* out_t, int B, int Rmax, int Cmax,
+                 int Kdim, float scale, void* stream);
+
+/* ---- (2)/(3b) association-graph GNN -------------------------------------------------------------------------
+ * Replaces construct_sparse_aff_mat + SparseTensor + PYGNNLayer.forward (utils/factorize_graph_matching.py:57-95,
+ * src/model/ngm.py:326-348, src/model/gnn.py:207-218) with the Kronecker structure kept factorised.
+ * edges: [B,2,emax] int32, per pair the (G-node, H-node) of every G/H column, -1 padded.
+ * weights (9 device pointers): lin_l.weight, lin_l.bias, lin_r.weight, n_self_func.0.weight, .0.bias,
+ * n_self_func.2.weight, .2.bias, classifier.weight, classifier.bias.
+ * xprev [B,N,16] (cin = 17) or NULL (cin = 1); mprev_t [B,n2max,n1max]; xout [B,N,16]; score [B,n1max,n2max].
+ * fpm_final_classifier: s[b,i1,i2] = classifier([x1, sinkhorn channel])  (ngm.py:368-369).
+ */
+int fpm_assoc_in_csr(const int* edges, int* in_ptr, int* in_src, int B, int nmax, int emax, void* stream);
+int fpm_gnn_layer(const float* xprev, const float* mprev_t, const int* in_ptr1, const int* in_src1,
+                  const int* in_ptr2, const int* in_src2, const long long* n1, const long long* n2,
+                  const float* const* weights, float* xout, float* score, int B, int n1max, int n2max,
+                  int e1max, int e2max, int cin, void* stream);
+int fpm_final_classifier(const float* x1, const float* sk_t, const float* cw, const float* cb, float* s, int B,
+                         int n1max, int n2max, void* stream);
+
+/* ---- (4) Sinkhorn / soft-top-k ------------------------------------------------------------------------------
+ * fpm_sinkhorn_log replaces Sinkhorn.forward -> pygmtools.sinkhorn(backend='pytorch', batched_operation=False)
+ * (src/model/sinkhorn.py:58-87): s [B,R,C], n1/n2 [B] (NULL = full) -> out [B,R,C] (+ out_t [B,C,R] optional).
+ * fpm_soft_topk replaces soft_topk(..., return_prob=True)[1] (src/model/soft_topk.py:8-53,166-255).
+ * workspace: device scratch of fpm_*_workspace_bytes() bytes, needed only when a pair's matrix does not fit
+ * in shared memory (0 bytes means none).
+ */
+long long fpm_sinkhorn_workspace_bytes(int B, int R, int C, int dummy_row);
+int fpm_sinkhorn_log(const float* s, const long long* n1, const long long* n2, float* out, float* out_t,
+                     void* workspace, int B, int R, int C, int max_iter, float tau, int dummy_row, void* stream);
+long long fpm_soft_topk_workspace_bytes(int B, int R, int C);
+int fpm_soft_topk(const float* scores, const float* ks, const long long* n1, const long long* n2, float* out,
+                  void* workspace, int B, int R, int C, int max_iter, float tau, void* stream);
+
+/* ---- (5) AFA-U ---------------------------------------------------------------------------------------------
+ * fpm_afau_attention replaces CrossSet_MultiHeadAttention.forward (src/model/afau.py:231-300): q [B,nr,256],
+ * k,v [B,nc,256], cost addressed cost[b*cs_b + i*cs_r + j*cs_c] -> out [B,nr,256].
+ * fpm_add_instnorm replaces AddAndInstanceNormalization.forward (afau.py:154-176) (+ optional max over rows,
+ * ngm.py:402-405).  fpm_onehot_proj: projection of the one-hot column embedding of ngm.py:396-399.
+ * fpm_k_head replaces final_row/final_col + sigmoid (ngm.py:406-412); weights (8 pointers): final_row.0.weight,
+ * .0.bias, .2.weight, .2.bias, final_col.0.weight, .0.bias, .2.weight, .2.bias.
+ */
+int fpm_afau_attention(const float* q, const float* k, const float* v, const float* cost, long long cs_b,
+                       long long cs_r, long long cs_c, const float* mix1_w, const float* mix1_b,
+                       const float* mix2_w, const float* mix2_b, float* out, int B, int nr, int nc, void* stream);
+int fpm_add_instnorm(const float* a, const float* other, int other_mode, const float* gamma, const float* beta,
+                     float* out, float* rowmax, int B, int n, int E, float eps, void* stream);
+int fpm_onehot_proj(const float* W, const long long* n, float* out, int B, int nmax, int OUT, int IN,
+                    void* stream);
+int fpm_k_head(const float* g_row, const float* g_col, const float* const* weights, const long long* n1,
+               const long long* n2, float* ks, float* k_scaled, int B, int E, int Hd, int mean_k, void* stream);
+
+/* ---- (6) linear assignment + greedy top-k ------------------------------------------------------------------
+ * fpm_lap_topk replaces utils.hungarian.hungarian (utils/hungarian.py:8-65; scipy linear_sum_assignment,
+ * reproduced exactly including tie-breaks) -> hung_out [B,R,C] (optional), and the argsort + greedy_perm tail
+ * of ngm.py:445-449 -> perm_out [B,R,C] (optional; needs ks [B] = k * min(n1,n2), rounded half-to-even).
+ * status [B] (optional): 1 where the cost matrix was infeasible (scipy would raise).
+ * fpm_greedy_perm replaces src.model.soft_topk.greedy_perm (soft_topk.py:56-77) for caller-supplied orders.
+ */
+int fpm_lap_topk(const float* ds, const long long* n1, const long long* n2, const float* ks, float* hung_out,
+                 float* perm_out, int* status, int B, int R, int C, void* stream);
+int fpm_greedy_perm(float* x, const long long* top_indices, const float* ks, int B, int R, int C, int L,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPMATCH_H_ */
