@@ -31,8 +31,8 @@ SIGNATURES = {
     "fpm_node_features": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "fpm_affinity_coeff": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_gemm_nt_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "fpm_gemm_nt_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _P]),
-    "fpm_gemm_nt_tc_workspace_bytes": (_LL, [_I, _I, _I, _I]),
+    "fpm_tf32_split": (_I, [_P, _P, _P, _LL, _P]),
+    "fpm_gemm_nt_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fpm_csr_by_dst": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_spline_gather_max": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_affinity": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _P]),

@@ -28,11 +28,9 @@ class GraphData:
         return int(self.x.shape[0])
 
     def to(self, device, non_blocking: bool = False):
-        for k in ("x", "edge_index", "edge_attr", "hyperedge_index"):
-            v = getattr(self, k)
-            if isinstance(v, torch.Tensor):
-                setattr(self, k, v.to(device, non_blocking=non_blocking))
-        return self
+        """Returns a NEW graph on ``device`` (the source object is left untouched)."""
+        mv = lambda v: v.to(device, non_blocking=non_blocking) if isinstance(v, torch.Tensor) else v
+        return GraphData(mv(self.x), mv(self.edge_index), mv(self.edge_attr), mv(self.hyperedge_index))
 
 
 class GraphBatch(GraphData):
@@ -77,10 +75,8 @@ class GraphBatch(GraphData):
         return out
 
     def to(self, device, non_blocking: bool = False):
-        super().to(device, non_blocking)
-        self.ptr = self.ptr.to(device, non_blocking=non_blocking)
-        self.eptr = self.eptr.to(device, non_blocking=non_blocking)
-        return self
+        mv = lambda v: v.to(device, non_blocking=non_blocking)
+        return GraphBatch(mv(self.x), mv(self.edge_index), mv(self.edge_attr), mv(self.ptr), mv(self.eptr))
 
 
 def graph_offsets(g, device=None):

@@ -127,8 +127,9 @@ def affinity_coeff(gcat: Tensor, W: Tensor, bias: Tensor) -> Tensor:
 # GEMM
 # ---------------------------------------------------------------------------------------------------
 def gemm_nt(A: Tensor, Bt: Tensor, bias: Optional[Tensor] = None, act: int = 0, out: Optional[Tensor] = None,
-            mode: Optional[str] = None) -> Tensor:
-    """out[M,N] = act(A[M,K] @ Bt[N,K]^T + bias)."""
+            mode: Optional[str] = None, weight_operand: bool = False) -> Tensor:
+    """out[M,N] = act(A[M,K] @ Bt[N,K]^T + bias).  ``weight_operand`` marks Bt as a static weight whose
+    tf32 split may be cached between calls."""
     mode = mode or _GEMM_MODE
     M, K = A.shape
     N = Bt.shape[0]
@@ -138,16 +139,64 @@ def gemm_nt(A: Tensor, Bt: Tensor, bias: Optional[Tensor] = None, act: int = 0, 
     a, b, c = _chk(A, "A"), _chk(Bt, "Bt"), _chk(out, "out")
     bp = _chk(bias, "bias")
     L = _lib.lib()
+    ev = None
     if mode == "fp32":
+        if _GEMM_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)); ev[0].record()
         rc = L.fpm_gemm_nt_f32(a, b, bp, c, M, N, K, K, K, N, act, _stream())
         _lib.check(rc, "fpm_gemm_nt_f32"); _count()
+    elif mode == "tf32":
+        if _GEMM_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)); ev[0].record()
+        rc = L.fpm_gemm_nt_tc(a, None, b, None, bp, c, M, N, K, K, K, N, act, 1, _stream())
+        _lib.check(rc, "fpm_gemm_nt_tc"); _count()
     else:
-        passes = 3 if mode == "3xtf32" else 1
-        wsb = L.fpm_gemm_nt_tc_workspace_bytes(M, N, K, passes)
-        ws = torch.empty((max(int(wsb), 16),), dtype=torch.uint8, device=A.device)
-        rc = L.fpm_gemm_nt_tc(a, b, bp, c, M, N, K, K, K, N, act, passes, ws.data_ptr(), int(wsb), _stream())
-        _lib.check(rc, "fpm_gemm_nt_tc"); _count(3 if passes == 3 else 1)
+        a_hi, a_lo = tf32_split(A)
+        b_hi, b_lo = tf32_split(Bt, cache=weight_operand)
+        if _GEMM_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)); ev[0].record()
+        rc = L.fpm_gemm_nt_tc(a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), bp, c, M, N, K,
+                              K, K, N, act, 3, _stream())
+        _lib.check(rc, "fpm_gemm_nt_tc"); _count()
+    if ev is not None:
+        ev[1].record()
+        _GEMM_EVENTS.append((mode, M, N, K, ev[0], ev[1]))
     return out
+
+
+_GEMM_EVENTS = None
+_SPLIT_CACHE = {}
+
+
+def gemm_profile_start() -> None:
+    """Record a CUDA-event pair around every GEMM kernel launch (bench.py's live roofline measurement)."""
+    global _GEMM_EVENTS
+    _GEMM_EVENTS = []
+
+
+def gemm_profile_stop():
+    global _GEMM_EVENTS
+    ev, _GEMM_EVENTS = _GEMM_EVENTS, None
+    return ev
+
+
+def tf32_split(x: Tensor, cache: bool = False):
+    """x = hi + lo with both parts exactly representable in tf32.  ``cache=True`` memoises the split of a
+    weight matrix (keyed on storage + version), so static weights are split once, not per forward."""
+    key = None
+    if cache:
+        key = (x.data_ptr(), x._version, tuple(x.shape), x.device.index)
+        hit = _SPLIT_CACHE.get(key)
+        if hit is not None:
+            return hit
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    rc = _lib.lib().fpm_tf32_split(_chk(x, "x"), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream())
+    _lib.check(rc, "fpm_tf32_split"); _count()
+    if cache:
+        if len(_SPLIT_CACHE) > 64:
+            _SPLIT_CACHE.clear()
+        _SPLIT_CACHE[key] = (hi, lo)
+    return hi, lo
 
 
 # ---------------------------------------------------------------------------------------------------

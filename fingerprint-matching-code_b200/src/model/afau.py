@@ -65,7 +65,7 @@ class EncoderLayer(nn.Module):
 def _lin(x3, weight, bias=None, act=0):
     B, n, K = x3.shape
     out = ops.gemm_nt(x3.reshape(B * n, K), weight.detach().contiguous(),
-                      None if bias is None else bias.detach().contiguous(), act)
+                      None if bias is None else bias.detach().contiguous(), act, weight_operand=True)
     return out.view(B, n, -1)
 
 

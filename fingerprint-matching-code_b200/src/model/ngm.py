@@ -180,8 +180,11 @@ class Net(CNN):
 
         # ---- node features: normalise + feature_align + concat, then 2x SplineConv  (ngm.py:228-256)
         gcat = torch.empty((B, GLOBAL_STATE_DIM), dtype=torch.float32, device=dev)
+        tables = self._edge_tables(data_dict, dev)
+        e1max, e2max = tables[0].shape[2], tables[1].shape[2]
         feats, offs = [], []
         for gi, ((nodes, edges), P, graph) in enumerate(zip(fmaps, points, graphs)):
+            graph.max_edges_per_graph = tables[gi].shape[2]     # host-known bound: no device sync needed
             nodes = nodes.detach().to(torch.float32).contiguous()
             edges = edges.detach().to(torch.float32).contiguous()
             ops.global_max_into(edges, gcat, gi * GLOBAL_FEATURE_DIM)
@@ -199,8 +202,6 @@ class Net(CNN):
         # ---- affinities (ngm.py:262-287, 317-321)
         coeff_v = self.vertex_affinity.fused_coefficients(gcat)
         Kp, Kp_t = ops.affinity_nodes(feats[0], feats[1], coeff_v, offs[0][0], offs[1][0], n1max, n2max)
-        tables = self._edge_tables(data_dict, dev)
-        e1max, e2max = tables[0].shape[2], tables[1].shape[2]
         Ke = None
         if self.compute_dead_ke:
             coeff_e = self.edge_affinity.fused_coefficients(gcat)

@@ -65,7 +65,7 @@ class SplineConv(torch.nn.Module):
                 eptr = torch.tensor([0, edge_index.shape[1]], dtype=torch.int64, device=x.device)
             max_e = int((eptr[1:] - eptr[:-1]).max())
             csr = ops.csr_by_dst(edge_index.contiguous(), ptr, eptr, total, max_e)
-        Y = ops.gemm_nt(x.detach().contiguous(), self.packed_weight())
+        Y = ops.gemm_nt(x.detach().contiguous(), self.packed_weight(), weight_operand=True)
         bias = self.bias.detach().contiguous()
         mode = 2 if mode is None else mode
         return ops.spline_gather_max(Y, residual, edge_index, pseudo.contiguous(), csr[0], csr[1], bias, mode,
@@ -95,11 +95,13 @@ class SConv(torch.nn.Module):
         edge_index = data.edge_index.to(x.device).contiguous()
         edge_attr = data.edge_attr.to(x.device, torch.float32).contiguous()
         ptr, eptr = graph_offsets(data)
-        csr = getattr(data, "_fpm_csr", None)
-        if csr is None:
+        # in-edge lists: built once per forward and shared by both conv layers.  The per-graph edge bound
+        # comes from the host-side shape when the caller provides it (no device sync), else from eptr.
+        max_e = getattr(data, "max_edges_per_graph", None)
+        if max_e is None:
             max_e = int((eptr[1:] - eptr[:-1]).max()) if eptr.numel() > 1 else 0
-            csr = ops.csr_by_dst(edge_index.contiguous(), ptr.to(x.device), eptr.to(x.device), x.shape[0], max_e)
-            data._fpm_csr = csr
+        csr = ops.csr_by_dst(edge_index, ptr.to(x.device).contiguous(), eptr.to(x.device).contiguous(),
+                             x.shape[0], int(max_e))
         h = self.convs[0](x, edge_index, edge_attr, csr=csr, mode=0)
         if residual_scale_input is not None:
             return self.convs[1](h, edge_index, edge_attr, csr=csr, mode=1, residual=residual_scale_input)

@@ -67,10 +67,10 @@ int fpm_affinity_coeff(const float* gcat, const float* W, const float* bias, flo
  */
 int fpm_gemm_nt_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K,
                     int lda, int ldb, int ldc, int act, void* stream);
-int fpm_gemm_nt_tc(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K,
-                   int lda, int ldb, int ldc, int act, int passes, void* workspace,
-                   long long workspace_bytes, void* stream);
-long long fpm_gemm_nt_tc_workspace_bytes(int M, int N, int K, int passes);
+int fpm_tf32_split(const float* src, float* hi, float* lo, long long n, void* stream); /* src = hi + lo, tf32-exact */
+int fpm_gemm_nt_tc(const float* A_hi, const float* A_lo, const float* Bt_hi, const float* Bt_lo,
+                   const float* bias, float* C, int M, int N, int K, int lda, int ldb, int ldc, int act,
+                   int passes, void* stream);   /* passes = 1: *_hi are the raw operands, *_lo ignored */
 
 /* ---- (3a) SplineConv -----------------------------------------------------------------------------------
  * Replaces torch_geometric SplineConv(768,768,dim=2,kernel_size=5,aggr='max') as driven by

@@ -1,0 +1,143 @@
+"""CPU tests (no GPU): the oracle against the committed golden vectors (which were produced by the
+reference's own modules, see tests/golden/make_golden.py), oracle self-consistency, and host-side logic."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+GOLD = ROOT / "tests" / "golden"
+
+from oracle import ops as oo          # noqa: E402
+from oracle import head, lap           # noqa: E402
+
+
+def test_feature_align_golden():
+    fx = torch.load(GOLD / "feature_align.pt")
+    for tag, c in fx.items():
+        assert torch.equal(oo.feature_align(c["fmap"], c["P"], c["ns"], (320, 240)), c["out"]), tag
+        assert torch.equal(oo.feature_align_loop(c["fmap"], c["P"], c["ns"], (320, 240)), c["out"]), tag
+
+
+def test_feature_align_quirk_known_answer():
+    """with a map that encodes its own (row, col), image corners land on these taps."""
+    Hf, Wf = 15, 20
+    rows = torch.arange(Hf, dtype=torch.float32).view(Hf, 1).expand(Hf, Wf)
+    cols = torch.arange(Wf, dtype=torch.float32).view(1, Wf).expand(Hf, Wf)
+    fmap = torch.stack([rows, cols])[None]
+    P = torch.tensor([[[0.0, 0.0], [160.0, 120.0], [319.0, 239.0], [319.0, 0.0], [0.0, 239.0]]])
+    out = oo.feature_align(fmap, P, torch.tensor([5]), (320, 240))[0]
+    np.testing.assert_allclose(out[1].numpy(), [0.0, 7.0, 14.453125, 14.453125, 0.0], atol=1e-4)
+    np.testing.assert_allclose(out[0].numpy(), [0.0, 9.5, 14.0, 0.0, 14.0], atol=1e-4)
+
+
+def test_hungarian_golden():
+    fx = torch.load(GOLD / "hungarian.pt")
+    assert torch.equal(oo.hungarian(fx["s"], fx["n1"], fx["n2"]), fx["out"])
+
+
+def test_lap_restatement_matches_scipy_bit_exact():
+    """oracle/lap_ref.c (the algorithm the GPU kernel re-states) against the live scipy on tie-heavy input."""
+    import scipy.optimize as opt
+    rng = np.random.RandomState(0)
+    checked = 0
+    for t in range(1500):
+        n1, n2 = rng.randint(1, 30), rng.randint(1, 30)
+        kind = t % 5
+        if kind == 0: m = rng.rand(n1, n2)
+        elif kind == 1: m = rng.randint(0, 3, (n1, n2)).astype(np.float64)
+        elif kind == 2: m = rng.rand(n1, n2) * (rng.rand(n1, n2) < 0.1)
+        elif kind == 3: m = np.zeros((n1, n2))
+        else: m = np.round(rng.rand(n1, n2), 1)
+        cost = -m.astype(np.float32)
+        r, c = opt.linear_sum_assignment(cost)
+        rr, cc = lap.solve(cost)
+        assert np.array_equal(r, rr) and np.array_equal(c, cc), (t, n1, n2)
+        checked += 1
+    assert checked == 1500
+
+
+def test_soft_topk_golden():
+    fx = torch.load(GOLD / "soft_topk.pt")
+    out = oo.soft_topk_prob(fx["scores"], fx["ks"], 10, float(fx["tau"]), fx["nrows"], fx["ncols"])
+    assert torch.equal(out, fx["prob"])
+    assert torch.equal(oo.hungarian(fx["prob"], fx["nrows"], fx["ncols"]), fx["hungarian"])
+    top = torch.argsort(fx["hungarian"].mul(fx["prob"]).reshape(fx["prob"].shape[0], -1), descending=True, dim=-1, stable=True)
+    assert torch.equal(oo.greedy_perm(torch.zeros_like(fx["prob"]), top, fx["ks"]), fx["greedy"])
+    assert torch.equal(oo.greedy_topk_fast(fx["hungarian"], fx["prob"], fx["ks"]), fx["greedy"])
+
+
+def test_soft_topk_k_zero_gives_zero_matrix():
+    s = torch.rand(1, 6, 6)
+    out = oo.soft_topk_prob(s, torch.tensor([0.0]), 10, 0.01, torch.tensor([6]), torch.tensor([6]))
+    assert (out == 0).all()
+
+
+def test_affinity_golden():
+    fx = torch.load(GOLD / "affinity.pt")
+    for X, Y, w, ref in zip(fx["Xs"], fx["Ys"], fx["Ws"], fx["out"]):
+        assert torch.equal(oo.affinity(X, Y, w, fx["A_weight"], fx["A_bias"]), ref)
+
+
+def test_sinkhorn_known_answers():
+    fx = torch.load(GOLD / "sinkhorn_kat.pt")
+    for tag, c in fx["cases"].items():
+        out = oo.sinkhorn(fx["s"], fx["n1"], fx["n2"], dummy_row=c["dummy_row"], max_iter=c["max_iter"], tau=c["tau"])
+        assert (out.double() - c["out"]).abs().max() < 5e-5, tag
+
+
+def test_sinkhorn_doubly_stochastic_property():
+    g = torch.Generator().manual_seed(0)
+    s = torch.randn(3, 8, 8, generator=g)
+    out = oo.sinkhorn(s, None, None, dummy_row=False, max_iter=60, tau=1.0)
+    assert torch.allclose(out.sum(1), torch.ones(3, 8), atol=1e-4)
+    assert torch.allclose(out.sum(2), torch.ones(3, 8), atol=1e-3)
+
+
+def test_afau_golden():
+    fx = torch.load(GOLD / "afau.pt")
+    p = {"encoder_k." + k: v.float() for k, v in fx["state"].items()}
+    r, c = oo.afau_encoder(fx["row"].float(), fx["col"].float(), fx["cost"], p)
+    assert (r - fx["out_row"]).abs().max() < 5e-5 and (c - fx["out_col"]).abs().max() < 5e-5
+
+
+def test_sage_aggregation_equals_factorised_form():
+    """The Kronecker factorisation the CUDA kernel relies on against the explicit index lists."""
+    from fpmatch import synth
+    data = synth.make_batch(3, 9, seed=4, ragged=True, n_min=5, with_kron=True)
+    n1max, n2max = data["Ps"][0].shape[1], data["Ps"][1].shape[1]
+    N = n1max * n2max
+    for b in range(3):
+        idxG, idxH = data["KGHs_sparse"][b]
+        n1b, n2b = int(data["ns"][0][b]), int(data["ns"][1][b])
+        diag = torch.arange(n1b * n2b)
+        row, col = torch.cat((idxG, diag)), torch.cat((idxH, diag))
+        x = torch.randn(N, 3, dtype=torch.float64)
+        ref = oo.sage_mean_aggregate(x, row, col, N)
+        A1, A2 = data["As"][0][b].double(), data["As"][1][b].double()        # A[i, j] = 1 iff edge i -> j
+        X = x.view(n2max, n1max, 3)                                          # [i2, i1, c]
+        agg = torch.einsum("ab,acd,ce->bed", A2, X, A1)                      # sum over in-neighbours
+        cnt = torch.einsum("ab,ce->be", A2, A1).reshape(N).clone()           # indeg2(j2) * indeg1(j1)
+        agg = agg.reshape(N, 3).clone()
+        agg[: n1b * n2b] += x[: n1b * n2b]
+        cnt[: n1b * n2b] += 1
+        fact = agg / cnt.clamp(min=1)[:, None]
+        assert torch.allclose(ref, fact, atol=1e-12)
+
+
+def test_oracle_head_runs_and_is_consistent_between_fp32_and_fp64():
+    from fpmatch import synth
+    from src.model.ngm import Net
+    torch.manual_seed(0)
+    net = Net(regression=True).eval()
+    sd = net.state_dict()
+    data = synth.make_batch(3, 12, seed=1, with_kron=True)
+    o32 = head.forward_head(sd, synth.clone_batch(data), data["fmaps"])
+    o64 = head.forward_head(sd, synth.clone_batch(data), data["fmaps"], dtype=torch.float64)
+    assert (o32["ds_mat"] - o64["ds_mat"].float()).abs().max() < 1e-4
+    assert torch.equal(o32["perm_mat"], o64["perm_mat"])
+    assert o32["perm_mat"].sum((1, 2)).tolist() == [float(k) for k in o32["k_int"]]
+    # loop-structured feature_align (what the CPU baseline times) gives the same result
+    o32b = head.forward_head(sd, synth.clone_batch(data), data["fmaps"], feature_align_loops=True)
+    assert torch.equal(o32["ds_mat"], o32b["ds_mat"])
