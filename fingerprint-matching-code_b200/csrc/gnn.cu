@@ -70,23 +70,31 @@ gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mpre
                  const int64_t* __restrict__ n1, const int64_t* __restrict__ n2, GnnWeights w,
                  float* __restrict__ xout, float* __restrict__ score, int n1max, int n2max, int e1max,
                  int e2max) {
-  extern __shared__ float sm[];
-  float* Rsum = sm;                               // [n1max][CIN] sum over In2(j2) rows
-  float* Wsh = sm + (size_t)n1max * CIN;          // weights
+  // Shared layout: every row is padded to CP floats (a multiple of 4) so that the per-node loops below
+  // read weights and partial sums as 128-bit broadcasts: one LDS.128 per 4 FMAs instead of one LDS per
+  // FMA (the first version of this kernel was LSU-bound: 1256 LDS for 1183 FFMA per node).
+  constexpr int CP = (CIN + 3) / 4 * 4;
+  extern __shared__ __align__(16) float sm[];
+  float* Rsum = sm;                               // [n1max][CP] sum over In2(j2) rows
+  float* Wsh = sm + (size_t)n1max * CP;           // weights
   const int b = blockIdx.y, j2 = blockIdx.x;
   const int N = n1max * n2max;
   const int tid = threadIdx.x;
 
-  float* wl = Wsh;                    // [16][CIN]
-  float* wr = wl + kF * CIN;          // [16][CIN]
-  float* w0 = wr + kF * CIN;          // [16][CIN]
-  float* w2 = w0 + kF * CIN;          // [16][16]
+  float* wl = Wsh;                    // [16][CP]
+  float* wr = wl + kF * CP;           // [16][CP]
+  float* w0 = wr + kF * CP;           // [16][CP]
+  float* w2 = w0 + kF * CP;           // [16][16]
   float* bl = w2 + kF * kF;           // [16]
   float* b0 = bl + kF;
   float* b2 = b0 + kF;
   float* wc = b2 + kF;                // [16] + bias
-  for (int i = tid; i < kF * CIN; i += blockDim.x) {
-    wl[i] = w.lin_l_w[i]; wr[i] = w.lin_r_w[i]; w0[i] = w.self0_w[i];
+  for (int i = tid; i < kF * CP; i += blockDim.x) {
+    const int o = i / CP, c = i - o * CP;
+    const bool in = c < CIN;
+    wl[i] = in ? w.lin_l_w[o * CIN + c] : 0.f;
+    wr[i] = in ? w.lin_r_w[o * CIN + c] : 0.f;
+    w0[i] = in ? w.self0_w[o * CIN + c] : 0.f;
   }
   for (int i = tid; i < kF * kF; i += blockDim.x) w2[i] = w.self2_w[i];
   if (tid < kF) {
@@ -100,13 +108,15 @@ gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mpre
   const int* is2 = in_src2 + (size_t)b * e2max;
   const float* xb = (CIN > 1) ? xprev + (size_t)b * N * kF : nullptr;
   const float* mb = mprev_t + (size_t)b * N;
-  for (int idx = tid; idx < n1max * CIN; idx += blockDim.x) {
-    const int i1 = idx / CIN, c = idx - i1 * CIN;
+  for (int idx = tid; idx < n1max * CP; idx += blockDim.x) {
+    const int i1 = idx / CP, c = idx - i1 * CP;
     float acc = 0.f;
-    for (int q = beg2; q < end2; ++q) {
-      const int i2 = is2[q];
-      const size_t p = (size_t)i2 * n1max + i1;
-      acc += (CIN > 1 && c < kF) ? xb[p * kF + c] : mb[p];
+    if (c < CIN) {
+      for (int q = beg2; q < end2; ++q) {
+        const int i2 = is2[q];
+        const size_t p = (size_t)i2 * n1max + i1;
+        acc += (CIN > 1 && c < kF) ? xb[p * kF + c] : mb[p];
+      }
     }
     Rsum[idx] = acc;
   }
@@ -120,17 +130,26 @@ gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mpre
   const int d2 = end2 - beg2;
   for (int j1 = tid; j1 < n1max; j1 += blockDim.x) {
     const size_t p = (size_t)j2 * n1max + j1;
-    float own[CIN], agg[CIN];
+    float own[CP], agg[CP];
 #pragma unroll
-    for (int c = 0; c < CIN; ++c) {
-      own[c] = (CIN > 1 && c < kF) ? xb[p * kF + c] : mb[p];
-      agg[c] = 0.f;
+    for (int c = 0; c < CP; ++c) { own[c] = 0.f; agg[c] = 0.f; }
+    if (CIN > 1) {
+      const float4* xp = (const float4*)(xb + p * kF);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float4 v = xp[t];
+        own[t * 4] = v.x; own[t * 4 + 1] = v.y; own[t * 4 + 2] = v.z; own[t * 4 + 3] = v.w;
+      }
     }
+    own[CIN - 1] = mb[p];
     const int beg1 = ip1[j1], end1 = ip1[j1 + 1];
     for (int q = beg1; q < end1; ++q) {
-      const float* r = Rsum + (size_t)is1[q] * CIN;
+      const float4* r = (const float4*)(Rsum + (size_t)is1[q] * CP);
 #pragma unroll
-      for (int c = 0; c < CIN; ++c) agg[c] += r[c];
+      for (int t = 0; t < CP / 4; ++t) {
+        const float4 v = r[t];
+        agg[t * 4] += v.x; agg[t * 4 + 1] += v.y; agg[t * 4 + 2] += v.z; agg[t * 4 + 3] += v.w;
+      }
     }
     long long cnt = (long long)d2 * (long long)(end1 - beg1);
     if ((long long)p < ndiag) {
@@ -142,12 +161,17 @@ gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mpre
 #pragma unroll
     for (int c = 0; c < CIN; ++c) agg[c] = agg[c] / inv;
 
+    // padded lanes (c >= CIN) multiply zeros: fmaf(0, 0, a) == a, so the sums keep their c-order value
     float h[kF];
 #pragma unroll
     for (int o = 0; o < kF; ++o) {
       float a = b0[o];
 #pragma unroll
-      for (int c = 0; c < CIN; ++c) a = fmaf(w0[o * CIN + c], own[c], a);
+      for (int t = 0; t < CP / 4; ++t) {
+        const float4 wv = *(const float4*)&w0[o * CP + t * 4];
+        a = fmaf(wv.x, own[t * 4], a); a = fmaf(wv.y, own[t * 4 + 1], a);
+        a = fmaf(wv.z, own[t * 4 + 2], a); a = fmaf(wv.w, own[t * 4 + 3], a);
+      }
       h[o] = fmaxf(a, 0.f);
     }
     float x1[kF];
@@ -155,14 +179,23 @@ gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mpre
 #pragma unroll
     for (int o = 0; o < kF; ++o) {
       float a = bl[o];
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) a = fmaf(wl[o * CIN + c], agg[c], a);
       float r = 0.f;
 #pragma unroll
-      for (int c = 0; c < CIN; ++c) r = fmaf(wr[o * CIN + c], own[c], r);
+      for (int t = 0; t < CP / 4; ++t) {
+        const float4 lv = *(const float4*)&wl[o * CP + t * 4];
+        const float4 rv = *(const float4*)&wr[o * CP + t * 4];
+        a = fmaf(lv.x, agg[t * 4], a); a = fmaf(lv.y, agg[t * 4 + 1], a);
+        a = fmaf(lv.z, agg[t * 4 + 2], a); a = fmaf(lv.w, agg[t * 4 + 3], a);
+        r = fmaf(rv.x, own[t * 4], r); r = fmaf(rv.y, own[t * 4 + 1], r);
+        r = fmaf(rv.z, own[t * 4 + 2], r); r = fmaf(rv.w, own[t * 4 + 3], r);
+      }
       float s2 = b2[o];
 #pragma unroll
-      for (int q = 0; q < kF; ++q) s2 = fmaf(w2[o * kF + q], h[q], s2);
+      for (int t = 0; t < kF / 4; ++t) {
+        const float4 wv = *(const float4*)&w2[o * kF + t * 4];
+        s2 = fmaf(wv.x, h[t * 4], s2); s2 = fmaf(wv.y, h[t * 4 + 1], s2);
+        s2 = fmaf(wv.z, h[t * 4 + 2], s2); s2 = fmaf(wv.w, h[t * 4 + 3], s2);
+      }
       const float v = (a + r) + fmaxf(s2, 0.f);
       x1[o] = v;
       sc = fmaf(wc[o], v, sc);
@@ -228,7 +261,8 @@ extern "C" int fpm_gnn_layer(const float* xprev, const float* mprev_t, const int
   fpm::GnnWeights w{weights[0], weights[1], weights[2], weights[3], weights[4],
                     weights[5], weights[6], weights[7], weights[8]};
   for (int i = 0; i < 9; ++i) FPM_CHECK_ARG(weights[i], "fpm_gnn_layer: null weight");
-  const size_t smem = ((size_t)n1max * cin + 3 * 16 * cin + 16 * 16 + 4 * 16 + 4) * sizeof(float);
+  const int cp = (cin + 3) / 4 * 4;
+  const size_t smem = ((size_t)n1max * cp + 3 * 16 * cp + 16 * 16 + 4 * 16 + 4) * sizeof(float);
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_gnn_layer: n1max too large");
   dim3 grid(n2max, B);
   cudaStream_t st = (cudaStream_t)stream;
