@@ -6,26 +6,33 @@
 // (/root/reference/src/model/afau.py:98-102,124-139,189-199).
 //
 // Design (sm_100a only):
-//   * operands are fp32 in HBM; tiles [128 x 32] (A) and [256 x 32] (B) are brought in by TMA
-//     (cp.async.bulk.tensor, 128-byte swizzle) into a multi-stage shared-memory ring guarded by mbarriers;
-//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=256, K=8) with the
-//     accumulator (128 lanes x 256 fp32 columns) in tensor memory;
-//   * four epilogue warps read the accumulator back with tcgen05.ld, add bias / relu and store fp32.
-//   * passes = 3 ("3xTF32"): A and B are pre-split into tf32-exact hi and lo parts (a = hi + lo) and the
-//     kernel accumulates  lo*hi + hi*lo + hi*hi  into the same TMEM tile, which restores fp32-level
-//     accuracy (dropped term ~2^-22 relative) - needed because the head's outputs are compared to an fp32
-//     reference at 1e-4 after three tau = 0.01 Sinkhorn amplifications.  passes = 1 is plain TF32.
+//   * operand tiles [128 x 128 B] (A) and [256 x 128 B] (B) are brought in by TMA (cp.async.bulk.tensor,
+//     128-byte swizzle) into a multi-stage shared-memory ring guarded by mbarriers;
+//   * one elected thread issues tcgen05.mma.cta_group::1 (M=128, N=256) with the accumulators in tensor
+//     memory; four epilogue warps read them back with tcgen05.ld, apply scales / bias / relu, store fp32;
+//   * CTAs are rasterised in groups of 32 M-tiles so a wave's operands stay L2-resident.
+// Numeric modes (all accumulate in fp32):
+//   kTf32x1  operands are the raw fp32 arrays, read as tf32 (1 MMA per k-step; 2^-11 operand error);
+//   kTf32x3  operands pre-split into tf32-exact hi + lo; per k-step  lo*hi + hi*lo  go to a correction
+//            accumulator (TMEM columns 256..511) and  hi*hi  to the main one: fp32-faithful products.
+//            (One accumulator chain of 288 MMAs measured 3e-5 relative error - the fp32 accumulate of the
+//            tensor core truncates - hence the separate correction tile, added in the epilogue.)
+//   kF16x3   the same error-compensated scheme on fp16 operands: rows are scaled by a power of two into
+//            fp16 range, a*s = hi + 2^-11 lo' with hi, lo' fp16 (11-bit mantissas -> 22 bits, exact products
+//            in the fp32 accumulator); the epilogue computes (main + 2^-11 corr) / (s_a[m] s_b[n]).  Same
+//            accuracy as kTf32x3 at twice the MMA rate and half the operand bytes.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace fpm {
 
-constexpr int TBM = 128, TBN = 256, TBK = 32;          // tile; TBK floats = one 128-byte swizzle row
-constexpr int UMMA_K = 8;                              // tf32
-constexpr uint32_t kABytes = TBM * TBK * 4;            // 16 KB
-constexpr uint32_t kBBytes = TBN * TBK * 4;            // 32 KB
-constexpr int kTmemCols1 = 256, kTmemCols3 = 512;   // 1-pass: one accumulator; 3-pass: main + correction
+constexpr int TBM = 128, TBN = 256;
+constexpr int kRowBytes = 128;                         // one swizzle row = one k-block of a tile
+constexpr uint32_t kABytes = TBM * kRowBytes;          // 16 KB
+constexpr uint32_t kBBytes = TBN * kRowBytes;          // 32 KB
+enum GemmMode { kTf32x1 = 1, kTf32x3 = 3, kF16x3 = 6 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -71,17 +78,28 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
   return d;
 }
-// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 256.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// fp32 accumulate (bits 4-5 = 1), operand format fmt (0 = f16, 2 = tf32) for A (bits 7-9) and B (10-12),
+// both K-major, N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
+template <bool kF16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  if (kF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -100,13 +118,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 
-template <int kPasses, int kStages>
+template <int kMode, int kStages>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const float* __restrict__ inv_a, const float* __restrict__ inv_b,
                const float* __restrict__ bias, float* __restrict__ Cm, int M, int N, int K, int ldc, int act) {
+  constexpr bool kF16 = kMode == kF16x3;
+  constexpr bool kTwoAcc = kMode != kTf32x1;
+  constexpr int kElemBytes = kF16 ? 2 : 4;
+  constexpr int TBK = kRowBytes / kElemBytes;            // 32 tf32 or 64 fp16 elements per k-block
+  constexpr int kUmmaKBytes = 32;                        // K = 8 tf32 / 16 fp16 per instruction
+  constexpr int kTmemCols = kTwoAcc ? 512 : 256;
+  constexpr uint32_t kStageBytes = (kTwoAcc ? 2 : 1) * (kABytes + kBBytes);
   extern __shared__ uint8_t smem_raw[];
-  constexpr uint32_t kStageBytes = (kPasses == 3 ? 2 : 1) * (kABytes + kBBytes);
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
@@ -114,7 +139,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_ptr = (uint32_t*)(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
+  // Grouped rasterisation for L2 reuse: kRasterGroup consecutive M-tiles walk the N-tiles together.  With
+  // the plain (n fastest) order the r1 ncu capture showed 13.0 GB of DRAM reads per launch for 0.28 GB of
+  // operands: every row of M-tiles swept all of B (123 MB ~ the whole L2).
+  constexpr int kRasterGroup = 32;
+  const int tiles_m = (M + TBM - 1) / TBM, tiles_n = (N + TBN - 1) / TBN;
+  const int per_group = kRasterGroup * tiles_n;
+  const int grp = (int)blockIdx.x / per_group, rem = (int)blockIdx.x - grp * per_group;
+  const int gsize = min(kRasterGroup, tiles_m - grp * kRasterGroup);
+  const int m0 = (grp * kRasterGroup + rem % gsize) * TBM, n0 = (rem / gsize) * TBN;
   const int nk = (K + TBK - 1) / TBK;
 
   if (threadIdx.x == 0) {
@@ -125,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                 "n"(kPasses == 3 ? kTmemCols3 : kTmemCols1)
+                 "n"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -146,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int kc = kb * TBK;
         tma_load_2d(&tmA_hi, &full_bar[s], st, kc, m0);
         tma_load_2d(&tmB_hi, &full_bar[s], st + kABytes, kc, n0);
-        if (kPasses == 3) {
+        if (kTwoAcc) {
           tma_load_2d(&tmA_lo, &full_bar[s], st + kABytes + kBBytes, kc, m0);
           tma_load_2d(&tmB_lo, &full_bar[s], st + 2 * kABytes + kBBytes, kc, n0);
         }
@@ -155,7 +188,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TBM, TBN);
+      constexpr uint32_t idesc = make_idesc(TBM, TBN, kF16 ? 0u : 2u);
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
@@ -163,30 +196,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc_fence_after();
         const uint32_t st = smem_u32(smem + (size_t)s * kStageBytes);
         const uint64_t a_hi = make_smem_desc(st), b_hi = make_smem_desc(st + kABytes);
-        if (kPasses == 3) {
+        if (kTwoAcc) {
           const uint64_t a_lo = make_smem_desc(st + kABytes + kBBytes);
           const uint64_t b_lo = make_smem_desc(st + 2 * kABytes + kBBytes);
 #pragma unroll
-          for (int k = 0; k < TBK / UMMA_K; ++k) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-            // The tensor core's fp32 accumulate truncates, so the error grows with the number of MMAs
-            // chained into one accumulator (measured: 288 chained MMAs -> 3e-5 relative).  The correction
-            // terms therefore get their own accumulator (columns 256..511): their truncation error is
-            // 2^-11 smaller, and the main chain shrinks 3x.  The epilogue adds the two in fp32 (RN).
-            umma_tf32(tmem_base + TBN, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-            umma_tf32(tmem_base + TBN, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+          for (int k = 0; k < kRowBytes / kUmmaKBytes; ++k) {
+            const uint64_t adv = (uint64_t)((k * kUmmaKBytes) >> 4);
+            umma<kF16>(tmem_base + TBN, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma<kF16>(tmem_base + TBN, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma<kF16>(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < TBK / UMMA_K; ++k) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-            umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+          for (int k = 0; k < kRowBytes / kUmmaKBytes; ++k) {
+            const uint64_t adv = (uint64_t)((k * kUmmaKBytes) >> 4);
+            umma<kF16>(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
           }
         }
         umma_commit(&empty_bar[s]);           // frees the smem slot once these MMAs have read it
       }
-      umma_commit(tmem_full_bar);             // accumulator complete
+      umma_commit(tmem_full_bar);             // accumulators complete
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
@@ -196,16 +225,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int m = m0 + q * 32 + lane;
     float* crow = Cm + (size_t)m * ldc;
     const bool vec_ok = ((ldc & 3) == 0) && ((((uintptr_t)Cm) & 15) == 0);
+    const float row_scale = (kF16 && m < M) ? inv_a[m] : 1.f;
+    constexpr float kCorrScale = kF16 ? (1.0f / 2048.0f) : 1.0f;
 #pragma unroll 1
     for (int ch = 0; ch < TBN / 32; ++ch) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
-      if (kPasses == 3) {
+      if (kTwoAcc) {
         uint32_t r2[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TBN + ch * 32), r2);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        for (int j = 0; j < 32; ++j)
+          r[j] = __float_as_uint(fmaf(__uint_as_float(r2[j]), kCorrScale, __uint_as_float(r[j])));
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const int nb = n0 + ch * 32;
@@ -217,6 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float x = __uint_as_float(r[g * 4 + j]);
+            if (kF16 && n + j < N) x = x * row_scale * inv_b[n + j];     // exact: powers of two
             if (bias && n + j < N) x += bias[n + j];
             if (act == 1) x = fmaxf(x, 0.f);
             v[j] = x;
@@ -237,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kPasses == 3 ? kTmemCols3 : kTmemCols1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
                  : "memory");
   }
 }
@@ -263,6 +296,41 @@ __global__ void tf32_split_kernel(const float* __restrict__ src, float* __restri
   ((float4*)lo)[i] = l;
 }
 
+// One warp per row: s = 2^-e with amax * s in [0.5, 1);  a*s = hi + 2^-11 * lo,  hi/lo fp16;  inv[row] = 2^e.
+__global__ void __launch_bounds__(256)
+f16_split_rows_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo,
+                      float* __restrict__ inv_scale, int rows, int K) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* s4 = (const float4*)(src + (size_t)row * K);
+  const int n4 = K >> 2;
+  float amax = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = s4[i];
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  amax = warp_max(amax);
+  int e = 0;
+  if (amax > 0.f && amax < INFINITY) frexpf(amax, &e);
+  e = max(-100, min(100, e));
+  const float s = ldexpf(1.f, -e);
+  if (lane == 0) inv_scale[row] = ldexpf(1.f, e);
+  __half2* h2 = (__half2*)(hi + (size_t)row * K);
+  __half2* l2 = (__half2*)(lo + (size_t)row * K);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = s4[i];
+    const float x[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+    __half hh[4], ll[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hh[j] = __float2half_rn(x[j]);
+      ll[j] = __float2half_rn((x[j] - __half2float(hh[j])) * 2048.f);
+    }
+    h2[2 * i] = __halves2half2(hh[0], hh[1]); h2[2 * i + 1] = __halves2half2(hh[2], hh[3]);
+    l2[2 * i] = __halves2half2(ll[0], ll[1]); l2[2 * i + 1] = __halves2half2(ll[2], ll[3]);
+  }
+}
+
 }  // namespace fpm
 
 // ---------------------------------------------------------------------------------------------------
@@ -282,17 +350,41 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
+// 2-d map over a row-major [rows, K] matrix with leading dimension ld (elements); box = [box_rows x 128 bytes].
+static int make_map(CUtensorMap* map, const void* base, int rows, int K, int ld, int box_rows, bool f16) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { fpm_set_error("cuTensorMapEncodeTiled unavailable"); return FPM_ERR_UNSUPPORTED; }
+  const int eb = f16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)fpm::TBK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * eb};
+  cuuint32_t box[2] = {(cuuint32_t)(fpm::kRowBytes / eb), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base,
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { fpm_set_error("cuTensorMapEncodeTiled failed"); return FPM_ERR_ARG; }
+  return FPM_OK;
+}
+
+template <int kMode, int kStages>
+static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, const float* inv_a,
+                     const float* inv_b, const float* bias, float* C, int M, int N, int K, int lda, int ldb,
+                     int ldc, int act, cudaStream_t st) {
+  constexpr bool f16 = kMode == fpm::kF16x3;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  int rc;
+  if ((rc = make_map(&mAh, A_hi, M, K, lda, fpm::TBM, f16)) != FPM_OK) return rc;
+  if ((rc = make_map(&mAl, A_lo, M, K, lda, fpm::TBM, f16)) != FPM_OK) return rc;
+  if ((rc = make_map(&mBh, B_hi, N, K, ldb, fpm::TBN, f16)) != FPM_OK) return rc;
+  if ((rc = make_map(&mBl, B_lo, N, K, ldb, fpm::TBN, f16)) != FPM_OK) return rc;
+  const long long tiles = (long long)fpm_cdiv(N, fpm::TBN) * (long long)fpm_cdiv(M, fpm::TBM);
+  FPM_CHECK_ARG(tiles <= 0x7fffffffLL, "gemm_tc: too many tiles");
+  const size_t smem = (size_t)kStages * (kMode == fpm::kTf32x1 ? 1 : 2) * (fpm::kABytes + fpm::kBBytes) + 1024 + 256;
+  FPM_CUDA(cudaFuncSetAttribute(fpm::gemm_tc_kernel<kMode, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  fpm::gemm_tc_kernel<kMode, kStages><<<(unsigned)tiles, 192, smem, st>>>(mAh, mAl, mBh, mBl, inv_a, inv_b, bias, C,
+                                                                          M, N, K, ldc, act);
+  FPM_LAUNCH_CHECK();
   return FPM_OK;
 }
 
@@ -303,6 +395,18 @@ extern "C" int fpm_tf32_split(const float* src, float* hi, float* lo, long long 
   if (n == 0) return FPM_OK;
   const size_t n4 = (size_t)n / 4;
   fpm::tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, hi, lo, n4);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_f16_split_rows(const float* src, void* hi, void* lo, float* inv_scale, int rows, int K,
+                                  void* stream) {
+  FPM_CHECK_ARG(src && hi && lo && inv_scale, "fpm_f16_split_rows: null tensor");
+  FPM_CHECK_ARG(rows >= 0 && K > 0 && (K & 7) == 0, "fpm_f16_split_rows: K must be a multiple of 8");
+  FPM_CHECK_ARG(((((size_t)src) | ((size_t)hi) | ((size_t)lo)) & 15) == 0, "fpm_f16_split_rows: 16-byte alignment required");
+  if (rows == 0) return FPM_OK;
+  fpm::f16_split_rows_kernel<<<fpm_cdiv((long long)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, (__half*)hi, (__half*)lo, inv_scale, rows, K);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }
@@ -322,26 +426,22 @@ extern "C" int fpm_gemm_nt_tc(const float* A_hi, const float* A_lo, const float*
   FPM_CHECK_ARG(passes == 1 || (((((size_t)A_lo) | ((size_t)Bt_lo)) & 15) == 0), "fpm_gemm_nt_tc: operands must be 16-byte aligned");
   if (M == 0) return FPM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (passes == 1) { A_lo = A_hi; Bt_lo = Bt_hi; }
-  CUtensorMap mAh, mAl, mBh, mBl;
-  int rc;
-  if ((rc = make_map(&mAh, A_hi, M, K, lda, fpm::TBM)) != FPM_OK) return rc;
-  if ((rc = make_map(&mAl, A_lo, M, K, lda, fpm::TBM)) != FPM_OK) return rc;
-  if ((rc = make_map(&mBh, Bt_hi, N, K, ldb, fpm::TBN)) != FPM_OK) return rc;
-  if ((rc = make_map(&mBl, Bt_lo, N, K, ldb, fpm::TBN)) != FPM_OK) return rc;
-  dim3 grid(fpm_cdiv(N, fpm::TBN), fpm_cdiv(M, fpm::TBM));
-  FPM_CHECK_ARG(grid.y <= 65535, "fpm_gemm_nt_tc: M too large");
-  if (passes == 3) {
-    constexpr int kStages = 2;
-    const size_t smem = (size_t)kStages * 2 * (fpm::kABytes + fpm::kBBytes) + 1024 + 256;
-    FPM_CUDA(cudaFuncSetAttribute(fpm::gemm_tc_kernel<3, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fpm::gemm_tc_kernel<3, kStages><<<grid, 192, smem, st>>>(mAh, mAl, mBh, mBl, bias, C, M, N, K, ldc, act);
-  } else {
-    constexpr int kStages = 4;
-    const size_t smem = (size_t)kStages * (fpm::kABytes + fpm::kBBytes) + 1024 + 256;
-    FPM_CUDA(cudaFuncSetAttribute(fpm::gemm_tc_kernel<1, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fpm::gemm_tc_kernel<1, kStages><<<grid, 192, smem, st>>>(mAh, mAl, mBh, mBl, bias, C, M, N, K, ldc, act);
-  }
-  FPM_LAUNCH_CHECK();
-  return FPM_OK;
+  if (passes == 1)
+    return launch_tc<fpm::kTf32x1, 4>(A_hi, A_hi, Bt_hi, Bt_hi, nullptr, nullptr, bias, C, M, N, K, lda, ldb, ldc, act, st);
+  return launch_tc<fpm::kTf32x3, 2>(A_hi, A_lo, Bt_hi, Bt_lo, nullptr, nullptr, bias, C, M, N, K, lda, ldb, ldc, act, st);
+}
+
+// Error-compensated fp16 mode: operands from fpm_f16_split_rows (fp16 hi / lo + per-row inverse scales).
+extern "C" int fpm_gemm_nt_f16x3(const void* A_hi, const void* A_lo, const float* inv_a, const void* Bt_hi,
+                                 const void* Bt_lo, const float* inv_b, const float* bias, float* C, int M, int N,
+                                 int K, int lda, int ldb, int ldc, int act, void* stream) {
+  FPM_CHECK_ARG(A_hi && A_lo && inv_a && Bt_hi && Bt_lo && inv_b && C, "fpm_gemm_nt_f16x3: null tensor");
+  FPM_CHECK_ARG(M >= 0 && N > 0 && K > 0, "fpm_gemm_nt_f16x3: bad sizes");
+  FPM_CHECK_ARG(act == 0 || act == 1, "fpm_gemm_nt_f16x3: unknown activation");
+  FPM_CHECK_ARG((K & 7) == 0 && (lda & 7) == 0 && (ldb & 7) == 0, "fpm_gemm_nt_f16x3: K, lda, ldb must be multiples of 8");
+  FPM_CHECK_ARG(((((size_t)A_hi) | ((size_t)A_lo) | ((size_t)Bt_hi) | ((size_t)Bt_lo)) & 15) == 0,
+                "fpm_gemm_nt_f16x3: operands must be 16-byte aligned");
+  if (M == 0) return FPM_OK;
+  return launch_tc<fpm::kF16x3, 2>(A_hi, A_lo, Bt_hi, Bt_lo, inv_a, inv_b, bias, C, M, N, K, lda, ldb, ldc, act,
+                                   (cudaStream_t)stream);
 }

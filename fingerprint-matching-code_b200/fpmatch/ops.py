@@ -16,14 +16,16 @@ from . import _lib
 
 Tensor = torch.Tensor
 
-# dense-contraction engine: "fp32" (CUDA cores), "3xtf32" (tcgen05, fp32-faithful), "tf32" (tcgen05, 1 pass)
-_GEMM_MODE = os.environ.get("FPMATCH_GEMM", "fp32")
+# dense-contraction engine: "3xtf32" / "3xf16" (tcgen05, error-compensated, fp32-faithful), "tf32" (tcgen05,
+# 1 pass, opt-in), "fp32" (CUDA cores; also the on-device checker for the tensor-core kernels)
+GEMM_MODES = ("fp32", "3xtf32", "3xf16", "tf32")
+_GEMM_MODE = os.environ.get("FPMATCH_GEMM", "3xtf32")
 _LAUNCHES = 0          # kernels launched through this module (bench.py reports it)
 
 
 def set_gemm_mode(mode: str) -> None:
     global _GEMM_MODE
-    if mode not in ("fp32", "3xtf32", "tf32"):
+    if mode not in GEMM_MODES:
         raise ValueError(f"unknown GEMM mode {mode!r}")
     _GEMM_MODE = mode
 
@@ -150,6 +152,14 @@ def gemm_nt(A: Tensor, Bt: Tensor, bias: Optional[Tensor] = None, act: int = 0, 
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)); ev[0].record()
         rc = L.fpm_gemm_nt_tc(a, None, b, None, bp, c, M, N, K, K, K, N, act, 1, _stream())
         _lib.check(rc, "fpm_gemm_nt_tc"); _count()
+    elif mode == "3xf16":
+        a_hi, a_lo, a_inv = f16_split_rows(A)
+        b_hi, b_lo, b_inv = f16_split_rows(Bt, cache=weight_operand)
+        if _GEMM_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)); ev[0].record()
+        rc = L.fpm_gemm_nt_f16x3(a_hi.data_ptr(), a_lo.data_ptr(), a_inv.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(),
+                                 b_inv.data_ptr(), bp, c, M, N, K, K, K, N, act, _stream())
+        _lib.check(rc, "fpm_gemm_nt_f16x3"); _count()
     else:
         a_hi, a_lo = tf32_split(A)
         b_hi, b_lo = tf32_split(Bt, cache=weight_operand)
@@ -178,6 +188,27 @@ def gemm_profile_stop():
     global _GEMM_EVENTS
     ev, _GEMM_EVENTS = _GEMM_EVENTS, None
     return ev
+
+
+def f16_split_rows(x: Tensor, cache: bool = False):
+    """x[r,:] * s_r = hi + 2^-11 lo with hi, lo fp16 and s_r a power of two; returns (hi, lo, 1/s)."""
+    key = None
+    if cache:
+        key = ("f16", x.data_ptr(), x._version, tuple(x.shape), x.device.index)
+        hit = _SPLIT_CACHE.get(key)
+        if hit is not None:
+            return hit
+    rows, K = x.shape
+    hi = torch.empty((rows, K), dtype=torch.float16, device=x.device)
+    lo = torch.empty((rows, K), dtype=torch.float16, device=x.device)
+    inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    rc = _lib.lib().fpm_f16_split_rows(_chk(x, "x"), hi.data_ptr(), lo.data_ptr(), inv.data_ptr(), rows, K, _stream())
+    _lib.check(rc, "fpm_f16_split_rows"); _count()
+    if cache:
+        if len(_SPLIT_CACHE) > 64:
+            _SPLIT_CACHE.clear()
+        _SPLIT_CACHE[key] = (hi, lo, inv)
+    return hi, lo, inv
 
 
 def tf32_split(x: Tensor, cache: bool = False):

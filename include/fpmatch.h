@@ -71,6 +71,13 @@ int fpm_tf32_split(const float* src, float* hi, float* lo, long long n, void* st
 int fpm_gemm_nt_tc(const float* A_hi, const float* A_lo, const float* Bt_hi, const float* Bt_lo,
                    const float* bias, float* C, int M, int N, int K, int lda, int ldb, int ldc, int act,
                    int passes, void* stream);   /* passes = 1: *_hi are the raw operands, *_lo ignored */
+/* Error-compensated fp16 mode (same accuracy as 3xTF32, twice the MMA rate): fpm_f16_split_rows scales each row
+ * by a power of two s and writes a*s = hi + 2^-11 lo (fp16 hi/lo, [rows,K]) and inv_scale[row] = 1/s. */
+int fpm_f16_split_rows(const float* src, void* hi_f16, void* lo_f16, float* inv_scale, int rows, int K,
+                       void* stream);
+int fpm_gemm_nt_f16x3(const void* A_hi, const void* A_lo, const float* inv_a, const void* Bt_hi,
+                      const void* Bt_lo, const float* inv_b, const float* bias, float* C, int M, int N, int K,
+                      int lda, int ldb, int ldc, int act, void* stream);
 
 /* ---- (3a) SplineConv -----------------------------------------------------------------------------------
  * Replaces torch_geometric SplineConv(768,768,dim=2,kernel_size=5,aggr='max') as driven by

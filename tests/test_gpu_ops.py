@@ -281,7 +281,7 @@ def test_gemm_fp32(ops, M, N, K):
 
 # 3xTF32 is held to the fp32 CUDA-core kernel's own error level (7e-6 .. 1e-5 on these shapes, outputs of
 # size ~1.4 * sqrt(2 log) ~ 6): the tensor core's truncating fp32 accumulate is the floor, not the split.
-@pytest.mark.parametrize("mode,tol", [("3xtf32", 2.5e-5), ("tf32", 2e-2)])
+@pytest.mark.parametrize("mode,tol", [("3xtf32", 2.5e-5), ("3xf16", 2.5e-5), ("tf32", 2e-2)])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 32), (300, 520, 768), (1000, 256, 600), (77, 600, 256), (5120, 2048, 768)])
 def test_gemm_tensor_core(ops, mode, tol, M, N, K):
     g = torch.Generator().manual_seed(M + 1)
