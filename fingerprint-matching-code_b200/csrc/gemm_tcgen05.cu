@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace fpm {
 
@@ -64,6 +65,23 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// Same load, delivered to the same shared-memory offset (and mbarrier offset) of every CTA in cta_mask.
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -105,6 +123,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -118,7 +141,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 
-template <int kMode, int kStages>
+// kCluster = 2: two CTAs with adjacent M-tiles and the same N-tile form a cluster; each loads one half of the
+// B tile and multicasts it into both CTAs' shared memory, cutting L2->SM operand traffic per CTA from
+// 96 KB to 64 KB per k-block (the r1 captures show the kernel bound by the ~7 TB/s L2->SM feed, not by MMA).
+template <int kMode, int kStages, int kCluster>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -143,15 +169,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // the plain (n fastest) order the r1 ncu capture showed 13.0 GB of DRAM reads per launch for 0.28 GB of
   // operands: every row of M-tiles swept all of B (123 MB ~ the whole L2).
   constexpr int kRasterGroup = 32;
-  const int tiles_m = (M + TBM - 1) / TBM, tiles_n = (N + TBN - 1) / TBN;
+  const int tiles_m = ((M + TBM - 1) / TBM + kCluster - 1) / kCluster * kCluster;   // padded to the cluster size
+  const int tiles_n = (N + TBN - 1) / TBN;
   const int per_group = kRasterGroup * tiles_n;
   const int grp = (int)blockIdx.x / per_group, rem = (int)blockIdx.x - grp * per_group;
   const int gsize = min(kRasterGroup, tiles_m - grp * kRasterGroup);
   const int m0 = (grp * kRasterGroup + rem % gsize) * TBM, n0 = (rem / gsize) * TBN;
   const int nk = (K + TBK - 1) / TBK;
 
+  const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << kCluster) - 1u);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    // a slot is free again when the MMA warps of ALL CTAs that receive multicast data into it released it
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kCluster); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -164,6 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();      // peers must see initialised barriers before signalling them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -178,10 +209,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_expect_tx(&full_bar[s], kStageBytes);
         const int kc = kb * TBK;
         tma_load_2d(&tmA_hi, &full_bar[s], st, kc, m0);
-        tma_load_2d(&tmB_hi, &full_bar[s], st + kABytes, kc, n0);
-        if (kTwoAcc) {
-          tma_load_2d(&tmA_lo, &full_bar[s], st + kABytes + kBBytes, kc, m0);
-          tma_load_2d(&tmB_lo, &full_bar[s], st + 2 * kABytes + kBBytes, kc, n0);
+        if (kTwoAcc) tma_load_2d(&tmA_lo, &full_bar[s], st + kABytes + kBBytes, kc, m0);
+        if (kCluster == 1) {
+          tma_load_2d(&tmB_hi, &full_bar[s], st + kABytes, kc, n0);
+          if (kTwoAcc) tma_load_2d(&tmB_lo, &full_bar[s], st + 2 * kABytes + kBBytes, kc, n0);
+        } else {
+          // this CTA's share of the B tile (TBN / kCluster rows), delivered to every CTA of the cluster
+          constexpr uint32_t kShare = kBBytes / kCluster;
+          const int nrow = n0 + (int)cta_rank * (TBN / kCluster);
+          tma_load_2d_mc(&tmB_hi, &full_bar[s], st + kABytes + cta_rank * kShare, kc, nrow, kMask);
+          if (kTwoAcc)
+            tma_load_2d_mc(&tmB_lo, &full_bar[s], st + 2 * kABytes + kBBytes + cta_rank * kShare, kc, nrow, kMask);
         }
       }
     }
@@ -213,7 +251,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             umma<kF16>(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
           }
         }
-        umma_commit(&empty_bar[s]);           // frees the smem slot once these MMAs have read it
+        // frees the smem slot (in every CTA that multicasts into it) once these MMAs have read it
+        if (kCluster == 1) umma_commit(&empty_bar[s]); else umma_commit_mc(&empty_bar[s], kMask);
       }
       umma_commit(tmem_full_bar);             // accumulators complete
     }
@@ -268,6 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();      // no CTA may retire while a peer can still write into it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
@@ -366,26 +406,50 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int K, int ld,
   return FPM_OK;
 }
 
-template <int kMode, int kStages>
-static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, const float* inv_a,
-                     const float* inv_b, const float* bias, float* C, int M, int N, int K, int lda, int ldb,
-                     int ldc, int act, cudaStream_t st) {
+static int g_tc_cluster = -1;     // FPMATCH_GEMM_CLUSTER: 1 = no cluster, 2 = B-tile multicast pairs (default)
+
+template <int kMode, int kStages, int kCluster>
+static int launch_tc_impl(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, const float* inv_a,
+                          const float* inv_b, const float* bias, float* C, int M, int N, int K, int lda, int ldb,
+                          int ldc, int act, cudaStream_t st) {
   constexpr bool f16 = kMode == fpm::kF16x3;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_map(&mAh, A_hi, M, K, lda, fpm::TBM, f16)) != FPM_OK) return rc;
   if ((rc = make_map(&mAl, A_lo, M, K, lda, fpm::TBM, f16)) != FPM_OK) return rc;
-  if ((rc = make_map(&mBh, B_hi, N, K, ldb, fpm::TBN, f16)) != FPM_OK) return rc;
-  if ((rc = make_map(&mBl, B_lo, N, K, ldb, fpm::TBN, f16)) != FPM_OK) return rc;
-  const long long tiles = (long long)fpm_cdiv(N, fpm::TBN) * (long long)fpm_cdiv(M, fpm::TBM);
+  if ((rc = make_map(&mBh, B_hi, N, K, ldb, fpm::TBN / kCluster, f16)) != FPM_OK) return rc;
+  if ((rc = make_map(&mBl, B_lo, N, K, ldb, fpm::TBN / kCluster, f16)) != FPM_OK) return rc;
+  const long long tiles_m = (fpm_cdiv(M, fpm::TBM) + kCluster - 1) / kCluster * kCluster;
+  const long long tiles = (long long)fpm_cdiv(N, fpm::TBN) * tiles_m;
   FPM_CHECK_ARG(tiles <= 0x7fffffffLL, "gemm_tc: too many tiles");
   const size_t smem = (size_t)kStages * (kMode == fpm::kTf32x1 ? 1 : 2) * (fpm::kABytes + fpm::kBBytes) + 1024 + 256;
-  FPM_CUDA(cudaFuncSetAttribute(fpm::gemm_tc_kernel<kMode, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-  fpm::gemm_tc_kernel<kMode, kStages><<<(unsigned)tiles, 192, smem, st>>>(mAh, mAl, mBh, mBl, inv_a, inv_b, bias, C,
-                                                                          M, N, K, ldc, act);
-  FPM_LAUNCH_CHECK();
+  auto kern = fpm::gemm_tc_kernel<kMode, kStages, kCluster>;
+  FPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)tiles);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = kCluster > 1 ? 1 : 0;
+  FPM_CUDA(cudaLaunchKernelEx(&cfg, kern, mAh, mAl, mBh, mBl, inv_a, inv_b, bias, C, M, N, K, ldc, act));
   return FPM_OK;
+}
+
+template <int kMode, int kStages>
+static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, const float* inv_a,
+                     const float* inv_b, const float* bias, float* C, int M, int N, int K, int lda, int ldb,
+                     int ldc, int act, cudaStream_t st) {
+  if (g_tc_cluster < 0) {
+    const char* e = getenv("FPMATCH_GEMM_CLUSTER");
+    g_tc_cluster = (e && e[0] == '1') ? 1 : 2;
+  }
+  if (g_tc_cluster == 2)
+    return launch_tc_impl<kMode, kStages, 2>(A_hi, A_lo, B_hi, B_lo, inv_a, inv_b, bias, C, M, N, K, lda, ldb, ldc, act, st);
+  return launch_tc_impl<kMode, kStages, 1>(A_hi, A_lo, B_hi, B_lo, inv_a, inv_b, bias, C, M, N, K, lda, ldb, ldc, act, st);
 }
 
 extern "C" int fpm_tf32_split(const float* src, float* hi, float* lo, long long n, void* stream) {
