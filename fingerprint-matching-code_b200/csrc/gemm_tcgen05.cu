@@ -21,7 +21,7 @@
 //            fp16 range, a*s = hi + 2^-11 lo' with hi, lo' fp16 (11-bit mantissas -> 22 bits, exact products
 //            in the fp32 accumulator); the epilogue computes (main + 2^-11 corr) / (s_a[m] s_b[n]).  Same
 //            accuracy as kTf32x3 at twice the MMA rate and half the operand bytes.
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -145,7 +145,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // B tile and multicasts it into both CTAs' shared memory, cutting L2->SM operand traffic per CTA from
 // 96 KB to 64 KB per k-block (the r1 captures show the kernel bound by the ~7 TB/s L2->SM feed, not by MMA).
 template <int kMode, int kStages, int kCluster>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const float* __restrict__ inv_a, const float* __restrict__ inv_b,
@@ -163,6 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint32_t* tmem_ptr = (uint32_t*)(tmem_full_bar + 1);
+  float* epi_tiles = (float*)(smem + (size_t)kStages * kStageBytes + 256);   // 8 warps x [32][33] floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Grouped rasterisation for L2 reuse: kRasterGroup consecutive M-tiles walk the N-tiles together.  With
@@ -257,19 +258,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       umma_commit(tmem_full_bar);             // accumulators complete
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-    const int q = warp & 3;
+    // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two warps of a quarter split the columns.
+    // Per 32-column chunk: tcgen05.ld (main + correction) -> scales / bias / relu in registers -> transpose
+    // through a padded shared tile -> 128-byte coalesced row stores.  (The first version stored 16 bytes per
+    // thread per row: 32 cache lines per store instruction, and it re-loaded the column scale per element; with
+    // one warp per scheduler nothing hid those latencies and the epilogue cost as much as the main loop.)
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float* tile = epi_tiles + (size_t)(warp - 2) * (32 * 33);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int m = m0 + q * 32 + lane;
-    float* crow = Cm + (size_t)m * ldc;
-    const bool vec_ok = ((ldc & 3) == 0) && ((((uintptr_t)Cm) & 15) == 0);
     const float row_scale = (kF16 && m < M) ? inv_a[m] : 1.f;
     constexpr float kCorrScale = kF16 ? (1.0f / 2048.0f) : 1.0f;
+    constexpr int kChunksPerWarp = TBN / 32 / 2;
 #pragma unroll 1
-    for (int ch = 0; ch < TBN / 32; ++ch) {
+    for (int ch = half * kChunksPerWarp; ch < (half + 1) * kChunksPerWarp; ++ch) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
+      const int nb = n0 + ch * 32;
+      // this lane's column constants, broadcast below with shuffles
+      const int ncol = nb + lane;
+      const float col_scale = (kF16 && ncol < N) ? inv_b[ncol] : 1.f;
+      const float col_bias = (bias && ncol < N) ? bias[ncol] : 0.f;
       if (kTwoAcc) {
         uint32_t r2[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TBN + ch * 32), r2);
@@ -279,29 +289,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           r[j] = __float_as_uint(fmaf(__uint_as_float(r2[j]), kCorrScale, __uint_as_float(r[j])));
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int nb = n0 + ch * 32;
-      if (m < M && nb < N) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int n = nb + g * 4;
-          float v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float x = __uint_as_float(r[g * 4 + j]);
-            if (kF16 && n + j < N) x = x * row_scale * inv_b[n + j];     // exact: powers of two
-            if (bias && n + j < N) x += bias[n + j];
-            if (act == 1) x = fmaxf(x, 0.f);
-            v[j] = x;
-          }
-          if (n + 3 < N && vec_ok) {
-            *(float4*)(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (n + j < N) crow[n + j] = v[j];
-          }
-        }
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]);
+        if (kF16) x = x * row_scale * __shfl_sync(0xffffffffu, col_scale, j);     // exact: powers of two
+        x += __shfl_sync(0xffffffffu, col_bias, j);
+        if (act == 1) x = fmaxf(x, 0.f);
+        tile[lane * 33 + j] = x;                     // row = this thread's accumulator row, conflict-free
       }
+      __syncwarp();
+      if (ncol < N) {
+        const int mrow0 = m0 + q * 32;
+        const int nrows = min(32, M - mrow0);
+        float* cbase = Cm + (size_t)mrow0 * ldc + ncol;
+        for (int rr = 0; rr < nrows; ++rr) cbase[(size_t)rr * ldc] = tile[rr * 33 + lane];
+      }
+      __syncwarp();
     }
   }
 
@@ -422,12 +425,12 @@ static int launch_tc_impl(const void* A_hi, const void* A_lo, const void* B_hi, 
   const long long tiles_m = (fpm_cdiv(M, fpm::TBM) + kCluster - 1) / kCluster * kCluster;
   const long long tiles = (long long)fpm_cdiv(N, fpm::TBN) * tiles_m;
   FPM_CHECK_ARG(tiles <= 0x7fffffffLL, "gemm_tc: too many tiles");
-  const size_t smem = (size_t)kStages * (kMode == fpm::kTf32x1 ? 1 : 2) * (fpm::kABytes + fpm::kBBytes) + 1024 + 256;
+  const size_t smem = (size_t)kStages * (kMode == fpm::kTf32x1 ? 1 : 2) * (fpm::kABytes + fpm::kBBytes) + 1024 + 256 + 8 * 32 * 33 * 4;
   auto kern = fpm::gemm_tc_kernel<kMode, kStages, kCluster>;
   FPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)tiles);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(320);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
