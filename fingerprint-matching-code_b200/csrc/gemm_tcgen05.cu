@@ -101,6 +101,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Optional per-CTA phase trace (fpm_gemm_set_trace): {smid, t_entry, t_setup_done, t_mainloop_done, t_end} in ns.
+__device__ unsigned long long* g_gemm_trace = nullptr;
+__device__ int g_gemm_trace_cap = 0;
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+
 template <bool kF16>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   if (kF16) {
@@ -166,6 +180,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   float* epi_tiles = (float*)(smem + (size_t)kStages * kStageBytes + 256);   // 8 warps x [32][33] floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tracing = g_gemm_trace != nullptr && (int)blockIdx.x < g_gemm_trace_cap && threadIdx.x == 64;
+  unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
+  if (tracing) tr0 = gtime_ns();
   // Grouped rasterisation for L2 reuse: kRasterGroup consecutive M-tiles walk the N-tiles together.  With
   // the plain (n fastest) order the r1 ncu capture showed 13.0 GB of DRAM reads per launch for 0.28 GB of
   // operands: every row of M-tiles swept all of B (123 MB ~ the whole L2).
@@ -265,8 +282,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // one warp per scheduler nothing hid those latencies and the epilogue cost as much as the main loop.)
     const int q = warp & 3, half = (warp - 2) >> 2;
     float* tile = epi_tiles + (size_t)(warp - 2) * (32 * 33);
+    if (tracing) tr1 = gtime_ns();
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (tracing) tr2 = gtime_ns();
     const int m = m0 + q * 32 + lane;
     const float row_scale = (kF16 && m < M) ? inv_a[m] : 1.f;
     constexpr float kCorrScale = kF16 ? (1.0f / 2048.0f) : 1.0f;
@@ -305,6 +324,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int rr = 0; rr < nrows; ++rr) cbase[(size_t)rr * ldc] = tile[rr * 33 + lane];
       }
       __syncwarp();
+    }
+    if (tracing) {
+      unsigned long long* t = g_gemm_trace + (size_t)blockIdx.x * 5;
+      t[0] = smid(); t[1] = tr0; t[2] = tr1; t[3] = tr2; t[4] = gtime_ns();
     }
   }
 
@@ -453,6 +476,15 @@ static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const
   if (g_tc_cluster == 2)
     return launch_tc_impl<kMode, kStages, 2>(A_hi, A_lo, B_hi, B_lo, inv_a, inv_b, bias, C, M, N, K, lda, ldb, ldc, act, st);
   return launch_tc_impl<kMode, kStages, 1>(A_hi, A_lo, B_hi, B_lo, inv_a, inv_b, bias, C, M, N, K, lda, ldb, ldc, act, st);
+}
+
+// Debug aid: point the kernels at a device buffer of 5 * cap uint64 to record per-CTA phase timestamps
+// (NULL switches tracing off).  Used by tools/gemm_phase_trace.py; not part of the product path.
+extern "C" int fpm_gemm_set_trace(void* buf, int cap) {
+  unsigned long long* p = (unsigned long long*)buf;
+  FPM_CUDA(cudaMemcpyToSymbol(fpm::g_gemm_trace, &p, sizeof(p)));
+  FPM_CUDA(cudaMemcpyToSymbol(fpm::g_gemm_trace_cap, &cap, sizeof(cap)));
+  return FPM_OK;
 }
 
 extern "C" int fpm_tf32_split(const float* src, float* hi, float* lo, long long n, void* stream) {

@@ -79,6 +79,9 @@ int fpm_gemm_nt_f16x3(const void* A_hi, const void* A_lo, const float* inv_a, co
                       const void* Bt_lo, const float* inv_b, const float* bias, float* C, int M, int N, int K,
                       int lda, int ldb, int ldc, int act, void* stream);
 
+/* debug aid: record {smid, t_entry, t_setup, t_mainloop_done, t_end} (ns) per CTA into buf[5*cap] (NULL = off) */
+int fpm_gemm_set_trace(void* buf, int cap);
+
 /* ---- (3a) SplineConv -----------------------------------------------------------------------------------
  * Replaces torch_geometric SplineConv(768,768,dim=2,kernel_size=5,aggr='max') as driven by
  * src/model/spline_conv.py:28-58.  Y [total_nodes, KS*KS+1, C] = x @ [W_0 .. W_24, root] comes from the GEMM
