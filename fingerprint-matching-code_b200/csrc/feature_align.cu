@@ -194,6 +194,87 @@ affinity_coeff_kernel(const float* __restrict__ gcat, const float* __restrict__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Backward of the fused gather + normalisation (training, BASELINE.json config 3).  The reference gets these
+// gradients from autograd through `out[:, i] = bilinear_interpolate(...)` (feature_align.py:62) and
+// normalize_over_channels (ngm.py:65-67, 241-243).
+// ------------------------------------------------------------------------------------------
+// dprep[b, pos, c] = sum over the pair's keypoints and their 4 taps of w_tap * dX[ptr[b]+i, coff + c].
+// One CTA per (pair, 64-channel chunk): the chunk's [HW][64] accumulator lives in shared memory, keypoints are
+// walked in index order and every position is owned by one thread group -> deterministic, no atomics.
+__global__ void __launch_bounds__(256)
+node_features_bwd_kernel(const float* __restrict__ dX, const float* __restrict__ P,
+                         const int64_t* __restrict__ ns, const int64_t* __restrict__ ptr,
+                         float* __restrict__ dprep, int nmax, int C, int H, int W, int coff, int ctot,
+                         float ori_w, float ori_h) {
+  extern __shared__ float acc[];                 // [H*W][64]
+  const int b = blockIdx.y, c0 = blockIdx.x * 64;
+  const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;     // 4 groups, position % 4 == grp
+  const int HW = H * W;
+  for (int i = threadIdx.x; i < HW * 64; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int n = (int)ns[b];
+  const float* dx = dX + (size_t)ptr[b] * ctot + coff + c0 + c;
+  for (int i = 0; i < n; ++i) {
+    const Taps t = make_taps(P[((size_t)b * nmax + i) * 2], P[((size_t)b * nmax + i) * 2 + 1], ori_w, ori_h, H, W);
+    const float g = dx[(size_t)i * ctot];
+    const int pa = t.y0 * W + t.x0, pb = t.y1 * W + t.x0, pc = t.y0 * W + t.x1, pd = t.y1 * W + t.x1;
+    if ((pa & 3) == grp) acc[pa * 64 + c] = fmaf(t.wa, g, acc[pa * 64 + c]);
+    if ((pb & 3) == grp) acc[pb * 64 + c] = fmaf(t.wb, g, acc[pb * 64 + c]);
+    if ((pc & 3) == grp) acc[pc * 64 + c] = fmaf(t.wc, g, acc[pc * 64 + c]);
+    if ((pd & 3) == grp) acc[pd * 64 + c] = fmaf(t.wd, g, acc[pd * 64 + c]);
+  }
+  __syncthreads();
+  float* dst = dprep + (size_t)b * HW * C + c0;
+  for (int i = threadIdx.x; i < HW * 64; i += blockDim.x) dst[(size_t)(i >> 6) * C + (i & 63)] = acc[i];
+}
+
+// y = x / ||x||_c  ->  dx = (dy - y * <y, dy>) / ||x||.  x: raw NCHW map, dy: NHWC (gradient of the prepared
+// map), dx: NCHW.  Same tiling as fmap_prep_kernel.
+__global__ void __launch_bounds__(256)
+fmap_prep_bwd_kernel(const float* __restrict__ fmap, const float* __restrict__ dy, float* __restrict__ dxo,
+                     int C, int HW) {
+  extern __shared__ float tile[];              // [C][33]
+  __shared__ float part[8][33];
+  __shared__ float norm[32];
+  const int b = blockIdx.y, p0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = p0 + lane;
+  const float* src = fmap + (size_t)b * C * HW;
+  float ss = 0.f;
+  for (int c = warp; c < C; c += 8) {
+    const float v = (p < HW) ? src[(size_t)c * HW + p] : 0.f;
+    tile[c * 33 + lane] = v;
+    ss = fmaf(v, v, ss);
+  }
+  part[warp][lane] = ss;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    norm[lane] = sqrtf(t);
+  }
+  __syncthreads();
+  const int npos = min(32, HW - p0);
+  for (int q = warp; q < npos; q += 8) {       // warp per position, lanes along channels
+    const float nq = norm[q];
+    const float* g = dy + ((size_t)b * HW + p0 + q) * C;
+    float dot = 0.f;
+    for (int c = lane; c < C; c += 32) dot = fmaf(tile[c * 33 + q] / nq, g[c], dot);
+    dot = warp_sum(dot);
+    for (int c = lane; c < C; c += 32) {
+      const float y = tile[c * 33 + q] / nq;
+      tile[c * 33 + q] = (g[c] - y * dot) / nq;
+    }
+  }
+  __syncthreads();
+  float* dst = dxo + (size_t)b * C * HW;
+  for (int c = warp; c < C; c += 8)
+    if (p < HW) dst[(size_t)c * HW + p] = tile[c * 33 + lane];
+}
+
 }  // namespace fpm
 
 extern "C" int fpm_feature_align(const float* fmap, const float* P, const long long* ns, float* out,
@@ -259,6 +340,42 @@ extern "C" int fpm_affinity_coeff(const float* gcat, const float* W, const float
   if (B == 0) return FPM_OK;
   fpm::affinity_coeff_kernel<<<B, 256, (size_t)IN * sizeof(float), (cudaStream_t)stream>>>(
       gcat, W, bias, coeff, IN, OUT);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_node_features_bwd(const float* dX, const float* P, const long long* ns, const long long* ptr,
+                                     float* dnodes_nhwc, float* dedges_nhwc, int B, int nmax, int C1, int H1,
+                                     int W1, int C2, int H2, int W2, float ori_w, float ori_h, void* stream) {
+  FPM_CHECK_ARG(dX && P && ns && ptr && dnodes_nhwc && dedges_nhwc, "fpm_node_features_bwd: null tensor");
+  FPM_CHECK_ARG(C1 % 64 == 0 && C2 % 64 == 0, "fpm_node_features_bwd: channels must be multiples of 64");
+  if (B == 0) return FPM_OK;
+  FPM_CHECK_ARG(B <= 65535, "fpm_node_features_bwd: batch too large");
+  const size_t s1 = (size_t)H1 * W1 * 64 * sizeof(float), s2 = (size_t)H2 * W2 * 64 * sizeof(float);
+  FPM_CHECK_ARG(s1 <= 200 * 1024 && s2 <= 200 * 1024, "fpm_node_features_bwd: feature map too large");
+  FPM_CUDA(cudaFuncSetAttribute(fpm::node_features_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(s1 > s2 ? s1 : s2)));
+  cudaStream_t st = (cudaStream_t)stream;
+  fpm::node_features_bwd_kernel<<<dim3(C1 / 64, B), 256, s1, st>>>(dX, P, (const int64_t*)ns, (const int64_t*)ptr,
+                                                                  dnodes_nhwc, nmax, C1, H1, W1, 0, C1 + C2, ori_w, ori_h);
+  FPM_LAUNCH_CHECK();
+  fpm::node_features_bwd_kernel<<<dim3(C2 / 64, B), 256, s2, st>>>(dX, P, (const int64_t*)ns, (const int64_t*)ptr,
+                                                                  dedges_nhwc, nmax, C2, H2, W2, C1, C1 + C2, ori_w, ori_h);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_fmap_prep_bwd(const float* fmap_nchw, const float* dy_nhwc, float* dx_nchw, int B, int C,
+                                 int Hf, int Wf, void* stream) {
+  FPM_CHECK_ARG(fmap_nchw && dy_nhwc && dx_nchw, "fpm_fmap_prep_bwd: null tensor");
+  FPM_CHECK_ARG(B >= 0 && C > 0 && Hf > 0 && Wf > 0, "fpm_fmap_prep_bwd: bad sizes");
+  if (B == 0) return FPM_OK;
+  const int HW = Hf * Wf;
+  const size_t smem = (size_t)C * 33 * sizeof(float);
+  FPM_CHECK_ARG(smem <= 200 * 1024 && B <= 65535, "fpm_fmap_prep_bwd: channel count or batch too large");
+  FPM_CUDA(cudaFuncSetAttribute(fpm::fmap_prep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fpm::fmap_prep_bwd_kernel<<<dim3(fpm_cdiv(HW, 32), B), 256, smem, (cudaStream_t)stream>>>(fmap_nchw, dy_nhwc,
+                                                                                           dx_nchw, C, HW);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

@@ -321,7 +321,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int mrow0 = m0 + q * 32;
         const int nrows = min(32, M - mrow0);
         float* cbase = Cm + (size_t)mrow0 * ldc + ncol;
-        for (int rr = 0; rr < nrows; ++rr) cbase[(size_t)rr * ldc] = tile[rr * 33 + lane];
+        if (nrows == 32) {
+#pragma unroll
+          for (int r0 = 0; r0 < 32; r0 += 8) {           // 8 independent LDS in flight, then 8 row stores
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = tile[(r0 + u) * 33 + lane];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cbase[(size_t)(r0 + u) * ldc] = v[u];
+          }
+        } else {
+          for (int rr = 0; rr < nrows; ++rr) cbase[(size_t)rr * ldc] = tile[rr * 33 + lane];
+        }
       }
       __syncwarp();
     }

@@ -254,6 +254,306 @@ __global__ void final_classifier_kernel(const float* __restrict__ x1, const floa
   s[((size_t)b * n1max + i1) * n2max + i2] = acc;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Backward of gnn_layer_kernel (training).  The reference differentiates SAGEConv's mean aggregation,
+// lin_l / lin_r, n_self_func and the classifier with autograd (src/model/gnn.py:207-218).  Here, per
+// (pair, j2) CTA, the forward is recomputed from the layer inputs (nothing is saved but the inputs), then
+// every node produces
+//   * its direct input gradient  d_own = Wr^T dx1 + W0^T dh0 (+ d_agg / cnt on the self loop),
+//   * gagg[p, :] = Wl^T dx1 / cnt  - to be pushed to the in-neighbours by assoc_aggregate_add_kernel,
+//   * its outer-product contributions to the 9 weight gradients, reduced over the CTA's nodes in shared
+//     memory and added to `grads` with one atomic per weight entry per CTA.
+// grads layout (floats): Wl[16*CIN] bl[16] Wr[16*CIN] W0[16*CIN] b0[16] W2[256] b2[16] wc[16] cb[1].
+// dxout: gradient wrt xout [B,N,16]; dscore: gradient wrt score [B,n1max,n2max].
+// dxprev [B,N,16] (CIN == 17) and dm [B,n1max,n2max] receive d_own (overwritten, not accumulated).
+// ------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(128, 2)
+gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ mprev_t,
+                     const int* __restrict__ in_ptr1, const int* __restrict__ in_src1,
+                     const int* __restrict__ in_ptr2, const int* __restrict__ in_src2,
+                     const int64_t* __restrict__ n1, const int64_t* __restrict__ n2, GnnWeights w,
+                     const float* __restrict__ dxout, const float* __restrict__ dscore,
+                     float* __restrict__ dxprev, float* __restrict__ dm, float* __restrict__ gagg,
+                     float* __restrict__ grads, int n1max, int n2max, int e1max, int e2max) {
+  constexpr int CP = (CIN + 3) / 4 * 4;
+  constexpr int LV = 49;                       // dx1[16] ds2[16] dh0[16] dsc
+  constexpr int RV = 2 * CP + 33;              // agg[CP] own[CP] h0[16] x1[16] one
+  constexpr int VS = LV + RV;
+  constexpr int NQ = 3 * kF * CIN + kF * kF + 4 * kF + 1;
+  constexpr int QPT = (NQ + 127) / 128;
+  extern __shared__ __align__(16) float sm[];
+  float* Rsum = sm;                               // [n1max][CP]
+  float* Wsh = sm + (size_t)n1max * CP;
+  const int b = blockIdx.y, j2 = blockIdx.x;
+  const int N = n1max * n2max;
+  const int tid = threadIdx.x;
+
+  float* wl = Wsh;                    // [16][CP]
+  float* wr = wl + kF * CP;
+  float* w0 = wr + kF * CP;
+  float* w2 = w0 + kF * CP;           // [16][16]
+  float* bl = w2 + kF * kF;
+  float* b0 = bl + kF;
+  float* b2 = b0 + kF;
+  float* wc = b2 + kF;                // [16] + bias (+3 pad)
+  float* V = wc + kF + 4;             // [128][VS]
+  short* qlo = (short*)(V + 128 * VS);   // [NQ]
+  short* qro = qlo + NQ;
+  for (int i = tid; i < kF * CP; i += blockDim.x) {
+    const int o = i / CP, c = i - o * CP;
+    const bool in = c < CIN;
+    wl[i] = in ? w.lin_l_w[o * CIN + c] : 0.f;
+    wr[i] = in ? w.lin_r_w[o * CIN + c] : 0.f;
+    w0[i] = in ? w.self0_w[o * CIN + c] : 0.f;
+  }
+  for (int i = tid; i < kF * kF; i += blockDim.x) w2[i] = w.self2_w[i];
+  if (tid < kF) {
+    bl[tid] = w.lin_l_b[tid]; b0[tid] = w.self0_b[tid]; b2[tid] = w.self2_b[tid]; wc[tid] = w.cls_w[tid];
+  }
+  if (tid == 0) wc[kF] = w.cls_b[0];
+  // weight-gradient task table: entry q = <left vector component, right vector component>
+  for (int q = tid; q < NQ; q += blockDim.x) {
+    int lo, ro, r = q;
+    constexpr int ONE = 2 * CP + 32;
+    if (r < kF * CIN) { lo = r / CIN; ro = r % CIN; }                                   // Wl: dx1 x agg
+    else if ((r -= kF * CIN) < kF) { lo = r; ro = ONE; }                                // bl
+    else if ((r -= kF) < kF * CIN) { lo = r / CIN; ro = CP + r % CIN; }                 // Wr: dx1 x own
+    else if ((r -= kF * CIN) < kF * CIN) { lo = 32 + r / CIN; ro = CP + r % CIN; }      // W0: dh0 x own
+    else if ((r -= kF * CIN) < kF) { lo = 32 + r; ro = ONE; }                           // b0
+    else if ((r -= kF) < kF * kF) { lo = 16 + r / kF; ro = 2 * CP + r % kF; }           // W2: ds2 x h0
+    else if ((r -= kF * kF) < kF) { lo = 16 + r; ro = ONE; }                            // b2
+    else if ((r -= kF) < kF) { lo = 48; ro = 2 * CP + 16 + r; }                         // wc: dsc x x1
+    else { lo = 48; ro = ONE; }                                                         // cb
+    qlo[q] = (short)lo; qro[q] = (short)(LV + ro);
+  }
+
+  // ---- stage 1 (as the forward): Rsum[i1, c] = sum_{i2 in In2(j2)} feat[(i2, i1), c]
+  const int* ip2 = in_ptr2 + (size_t)b * (n2max + 1);
+  const int beg2 = ip2[j2], end2 = ip2[j2 + 1];
+  const int* is2 = in_src2 + (size_t)b * e2max;
+  const float* xb = (CIN > 1) ? xprev + (size_t)b * N * kF : nullptr;
+  const float* mb = mprev_t + (size_t)b * N;
+  if (CIN > 1) {
+    const int nvec = n1max * (kF / 4);
+    for (int f = tid; f < nvec; f += blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = beg2; q < end2; ++q) {
+        const float4 v = ((const float4*)(xb + (size_t)is2[q] * n1max * kF))[f];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *(float4*)&Rsum[(size_t)(f >> 2) * CP + (f & 3) * 4] = acc;
+    }
+  }
+  for (int i1 = tid; i1 < n1max; i1 += blockDim.x) {
+    float a = 0.f;
+    for (int q = beg2; q < end2; ++q) a += mb[(size_t)is2[q] * n1max + i1];
+    Rsum[(size_t)i1 * CP + (CIN - 1)] = a;
+#pragma unroll
+    for (int c = CIN; c < CP; ++c) Rsum[(size_t)i1 * CP + c] = 0.f;
+  }
+  __syncthreads();
+
+  const int n1b = (int)n1[b], n2b = (int)n2[b];
+  const long long ndiag = (long long)n1b * (long long)n2b;
+  const int* ip1 = in_ptr1 + (size_t)b * (n1max + 1);
+  const int* is1 = in_src1 + (size_t)b * e1max;
+  const int d2 = end2 - beg2;
+  float wacc[QPT];
+#pragma unroll
+  for (int u = 0; u < QPT; ++u) wacc[u] = 0.f;
+
+  for (int j0 = 0; j0 < n1max; j0 += blockDim.x) {
+    const int j1 = j0 + tid;
+    float* v = V + (size_t)tid * VS;
+    if (j1 < n1max) {
+      const size_t p = (size_t)j2 * n1max + j1;
+      float own[CP], agg[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) { own[c] = 0.f; agg[c] = 0.f; }
+      if (CIN > 1) {
+        const float4* xp = (const float4*)(xb + p * kF);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 q4 = xp[t];
+          own[t * 4] = q4.x; own[t * 4 + 1] = q4.y; own[t * 4 + 2] = q4.z; own[t * 4 + 3] = q4.w;
+        }
+      }
+      own[CIN - 1] = mb[p];
+      const int beg1 = ip1[j1], end1 = ip1[j1 + 1];
+      for (int q = beg1; q < end1; ++q) {
+        const float4* r = (const float4*)(Rsum + (size_t)is1[q] * CP);
+#pragma unroll
+        for (int t = 0; t < CP / 4; ++t) {
+          const float4 q4 = r[t];
+          agg[t * 4] += q4.x; agg[t * 4 + 1] += q4.y; agg[t * 4 + 2] += q4.z; agg[t * 4 + 3] += q4.w;
+        }
+      }
+      long long cnt = (long long)d2 * (long long)(end1 - beg1);
+      const bool self = (long long)p < ndiag;
+      if (self) {
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) agg[c] += own[c];
+        cnt += 1;
+      }
+      const float inv = cnt > 0 ? (float)cnt : 1.f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) agg[c] = agg[c] / inv;
+
+      // forward recompute: h0 = relu(W0 own + b0), s2 = W2 h0 + b2, x1 = Wl agg + bl + Wr own + relu(s2)
+      float h0[kF], s2[kF], x1[kF];
+#pragma unroll
+      for (int o = 0; o < kF; ++o) {
+        float a = b0[o];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) a = fmaf(w0[o * CP + c], own[c], a);
+        h0[o] = fmaxf(a, 0.f);
+      }
+#pragma unroll
+      for (int o = 0; o < kF; ++o) {
+        float a = bl[o], r = 0.f, q2 = b2[o];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) { a = fmaf(wl[o * CP + c], agg[c], a); r = fmaf(wr[o * CP + c], own[c], r); }
+#pragma unroll
+        for (int c = 0; c < kF; ++c) q2 = fmaf(w2[o * kF + c], h0[c], q2);
+        s2[o] = q2;
+        x1[o] = (a + r) + fmaxf(q2, 0.f);
+      }
+      // incoming gradients
+      const float dsc = dscore[((size_t)b * n1max + j1) * n2max + j2];
+      float dx1[kF];
+      {
+        const float4* gp = (const float4*)(dxout + ((size_t)b * N + p) * kF);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 q4 = gp[t];
+          dx1[t * 4] = q4.x; dx1[t * 4 + 1] = q4.y; dx1[t * 4 + 2] = q4.z; dx1[t * 4 + 3] = q4.w;
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < kF; ++o) dx1[o] = fmaf(dsc, wc[o], dx1[o]);
+      float ds2[kF], dh0[kF];
+#pragma unroll
+      for (int o = 0; o < kF; ++o) ds2[o] = s2[o] > 0.f ? dx1[o] : 0.f;
+#pragma unroll
+      for (int c = 0; c < kF; ++c) {
+        float a = 0.f;
+#pragma unroll
+        for (int o = 0; o < kF; ++o) a = fmaf(w2[o * kF + c], ds2[o], a);
+        dh0[c] = h0[c] > 0.f ? a : 0.f;
+      }
+      float down[CP], dagg[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        float a = 0.f, g = 0.f;
+#pragma unroll
+        for (int o = 0; o < kF; ++o) {
+          a = fmaf(wr[o * CP + c], dx1[o], a);
+          a = fmaf(w0[o * CP + c], dh0[o], a);
+          g = fmaf(wl[o * CP + c], dx1[o], g);
+        }
+        g = g / inv;
+        dagg[c] = g;
+        down[c] = self ? a + g : a;
+      }
+      // outputs
+      float4* gd = (float4*)(gagg + ((size_t)b * N + p) * CP);
+#pragma unroll
+      for (int t = 0; t < CP / 4; ++t) gd[t] = make_float4(dagg[t * 4], dagg[t * 4 + 1], dagg[t * 4 + 2], dagg[t * 4 + 3]);
+      if (CIN > 1) {
+        float4* dd = (float4*)(dxprev + ((size_t)b * N + p) * kF);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dd[t] = make_float4(down[t * 4], down[t * 4 + 1], down[t * 4 + 2], down[t * 4 + 3]);
+      }
+      dm[((size_t)b * n1max + j1) * n2max + j2] = down[CIN - 1];
+      // per-node vectors for the weight-gradient reduction
+#pragma unroll
+      for (int o = 0; o < kF; ++o) { v[o] = dx1[o]; v[16 + o] = ds2[o]; v[32 + o] = dh0[o]; }
+      v[48] = dsc;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) { v[LV + c] = agg[c]; v[LV + CP + c] = own[c]; }
+#pragma unroll
+      for (int o = 0; o < kF; ++o) { v[LV + 2 * CP + o] = h0[o]; v[LV + 2 * CP + 16 + o] = x1[o]; }
+      v[LV + 2 * CP + 32] = 1.f;
+    }
+    __syncthreads();
+    const int nn = min((int)blockDim.x, n1max - j0);
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+      const int q = tid + u * 128;
+      if (q < NQ) {
+        const int lo = qlo[q], ro = qro[q];
+        float a = 0.f;
+        for (int nd = 0; nd < nn; ++nd) a = fmaf(V[(size_t)nd * VS + lo], V[(size_t)nd * VS + ro], a);
+        wacc[u] += a;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < QPT; ++u) {
+    const int q = tid + u * 128;
+    if (q < NQ && wacc[u] != 0.f) atomicAdd(grads + q, wacc[u]);
+  }
+}
+
+// Pushes gagg (the mean-aggregation gradient of every destination node, already divided by its count) back to
+// the sources:  d_feat[(i2,i1), c] += sum_{j2 in Out2(i2)} sum_{j1 in Out1(i1)} gagg[(j2,j1), c]  - the same
+// factorised two-stage sum as the forward, over the OUT-neighbour lists.  Channels 0..15 go to dxprev
+// (CIN == 17), channel CIN-1 to dm [B,n1max,n2max].
+template <int CIN>
+__global__ void __launch_bounds__(128, 4)
+assoc_aggregate_add_kernel(const float* __restrict__ gagg, const int* __restrict__ out_ptr1,
+                           const int* __restrict__ out_dst1, const int* __restrict__ out_ptr2,
+                           const int* __restrict__ out_dst2, float* __restrict__ dxprev,
+                           float* __restrict__ dm, int n1max, int n2max, int e1max, int e2max) {
+  constexpr int CP = (CIN + 3) / 4 * 4;
+  extern __shared__ __align__(16) float Rs[];       // [n1max][CP]
+  const int b = blockIdx.y, i2 = blockIdx.x, tid = threadIdx.x;
+  const int N = n1max * n2max;
+  const int* op2 = out_ptr2 + (size_t)b * (n2max + 1);
+  const int beg2 = op2[i2], end2 = op2[i2 + 1];
+  const int* od2 = out_dst2 + (size_t)b * e2max;
+  const float* gb = gagg + (size_t)b * N * CP;
+  const int nvec = n1max * (CP / 4);
+  for (int f = tid; f < nvec; f += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = beg2; q < end2; ++q) {
+      const float4 v = ((const float4*)(gb + (size_t)od2[q] * n1max * CP))[f];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    ((float4*)Rs)[f] = acc;
+  }
+  __syncthreads();
+  const int* op1 = out_ptr1 + (size_t)b * (n1max + 1);
+  const int* od1 = out_dst1 + (size_t)b * e1max;
+  for (int i1 = tid; i1 < n1max; i1 += blockDim.x) {
+    float acc[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) acc[c] = 0.f;
+    for (int q = op1[i1]; q < op1[i1 + 1]; ++q) {
+      const float4* r = (const float4*)(Rs + (size_t)od1[q] * CP);
+#pragma unroll
+      for (int t = 0; t < CP / 4; ++t) {
+        const float4 v = r[t];
+        acc[t * 4] += v.x; acc[t * 4 + 1] += v.y; acc[t * 4 + 2] += v.z; acc[t * 4 + 3] += v.w;
+      }
+    }
+    const size_t p = (size_t)i2 * n1max + i1;
+    if (CIN > 1) {
+      float4* dd = (float4*)(dxprev + ((size_t)b * N + p) * kF);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float4 v = dd[t];
+        v.x += acc[t * 4]; v.y += acc[t * 4 + 1]; v.z += acc[t * 4 + 2]; v.w += acc[t * 4 + 3];
+        dd[t] = v;
+      }
+    }
+    dm[((size_t)b * n1max + i1) * n2max + i2] += acc[CIN - 1];
+  }
+}
+
 }  // namespace fpm
 
 extern "C" int fpm_assoc_in_csr(const int* edges, int* in_ptr, int* in_src, int B, int nmax, int emax,
@@ -312,6 +612,56 @@ extern "C" int fpm_final_classifier(const float* x1, const float* sk_t, const fl
   FPM_CHECK_ARG(B <= 65535, "fpm_final_classifier: batch too large");
   dim3 grid(fpm_cdiv((long long)n1max * n2max, 256), B);
   fpm::final_classifier_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x1, sk_t, cw, cb, s, n1max, n2max);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+// Backward of fpm_gnn_layer.  out_ptr*/out_dst*: OUT-neighbour lists (fpm_assoc_in_csr on the edge tables with
+// the two rows swapped).  gagg: scratch [B, N, CP] floats (CP = 4 for cin 1, 20 for cin 17).  grads: see the
+// kernel comment; the caller zeroes it.  dxprev may be NULL for cin = 1.
+extern "C" int fpm_gnn_layer_bwd(const float* xprev, const float* mprev_t, const int* in_ptr1, const int* in_src1,
+                                 const int* in_ptr2, const int* in_src2, const int* out_ptr1, const int* out_dst1,
+                                 const int* out_ptr2, const int* out_dst2, const long long* n1, const long long* n2,
+                                 const float* const* weights, const float* dxout, const float* dscore,
+                                 float* dxprev, float* dm, float* gagg, float* grads, int B, int n1max, int n2max,
+                                 int e1max, int e2max, int cin, void* stream) {
+  FPM_CHECK_ARG(mprev_t && in_ptr1 && in_src1 && in_ptr2 && in_src2 && out_ptr1 && out_dst1 && out_ptr2 && out_dst2 &&
+                n1 && n2 && weights && dxout && dscore && dm && gagg && grads, "fpm_gnn_layer_bwd: null tensor");
+  FPM_CHECK_ARG(cin == 1 || (cin == 17 && xprev && dxprev), "fpm_gnn_layer_bwd: cin must be 1 or 17 (with xprev, dxprev)");
+  FPM_CHECK_ARG(B >= 0 && n1max > 0 && n2max > 0, "fpm_gnn_layer_bwd: bad sizes");
+  if (B == 0) return FPM_OK;
+  FPM_CHECK_ARG(B <= 65535, "fpm_gnn_layer_bwd: batch too large");
+  fpm::GnnWeights w{weights[0], weights[1], weights[2], weights[3], weights[4],
+                    weights[5], weights[6], weights[7], weights[8]};
+  for (int i = 0; i < 9; ++i) FPM_CHECK_ARG(weights[i], "fpm_gnn_layer_bwd: null weight");
+  const int cp = (cin + 3) / 4 * 4;
+  const int nq = 3 * 16 * cin + 16 * 16 + 4 * 16 + 1;
+  const int vs = 49 + 2 * cp + 33;
+  const size_t smem = ((size_t)n1max * cp + 3 * 16 * cp + 16 * 16 + 4 * 16 + 4 + (size_t)128 * vs) * sizeof(float) +
+                      (size_t)2 * nq * sizeof(short) + 16;
+  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_gnn_layer_bwd: n1max too large");
+  dim3 grid(n2max, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem2 = (size_t)n1max * cp * sizeof(float);
+  if (cin == 1) {
+    FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fpm::gnn_layer_bwd_kernel<1><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
+                                                          (const int64_t*)n1, (const int64_t*)n2, w, dxout, dscore,
+                                                          dxprev, dm, gagg, grads, n1max, n2max, e1max, e2max);
+    FPM_LAUNCH_CHECK();
+    FPM_CUDA(cudaFuncSetAttribute(fpm::assoc_aggregate_add_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    fpm::assoc_aggregate_add_kernel<1><<<grid, 128, smem2, st>>>(gagg, out_ptr1, out_dst1, out_ptr2, out_dst2, dxprev, dm,
+                                                                n1max, n2max, e1max, e2max);
+  } else {
+    FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_bwd_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fpm::gnn_layer_bwd_kernel<17><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
+                                                           (const int64_t*)n1, (const int64_t*)n2, w, dxout, dscore,
+                                                           dxprev, dm, gagg, grads, n1max, n2max, e1max, e2max);
+    FPM_LAUNCH_CHECK();
+    FPM_CUDA(cudaFuncSetAttribute(fpm::assoc_aggregate_add_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    fpm::assoc_aggregate_add_kernel<17><<<grid, 128, smem2, st>>>(gagg, out_ptr1, out_dst1, out_ptr2, out_dst2, dxprev, dm,
+                                                                 n1max, n2max, e1max, e2max);
+  }
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

@@ -238,6 +238,376 @@ soft_topk_kernel(const float* __restrict__ scores, const float* __restrict__ ks,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Backward of sinkhorn_log_kernel (training).  The reference differentiates pygmtools' unrolled iterations with
+// autograd; here one CTA per pair re-runs the forward in shared memory keeping only the log-sum-exp vector of
+// every iteration ([max_iter][D] floats), then walks the iterations backwards:
+//     x_{t+1} = x_t - lse_t   =>   g_t = g_{t+1} - exp(x_{t+1}) * sum_dim(g_{t+1}),   x_t = x_{t+1} + lse_t
+// (exp(x_{t+1}) is the softmax of x_t along the normalised dimension).  gs = g_0 / tau on the valid block.
+// ------------------------------------------------------------------------------------------
+template <bool kGlobal>
+__global__ void __launch_bounds__(512)
+sinkhorn_log_bwd_kernel(const float* __restrict__ s, const int64_t* __restrict__ n1,
+                        const int64_t* __restrict__ n2, const float* __restrict__ gout,
+                        float* __restrict__ gs, float* __restrict__ workspace, int R, int C, int max_iter,
+                        float tau, int dummy_row) {
+  extern __shared__ float smem[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const int D = R > C ? R : C;
+
+  int n1b = n1 ? (int)n1[b] : R;
+  int n2b = n2 ? (int)n2[b] : C;
+  n1b = min(max(n1b, 0), R);
+  n2b = min(max(n2b, 0), C);
+  const bool frameT = C < R;
+  const bool opT = frameT ? (n1b >= n2b) : (n1b > n2b);
+  const int nr = opT ? n2b : n1b;
+  const int nc = opT ? n1b : n2b;
+  const int rows = dummy_row ? nc : nr;
+
+  float* M = kGlobal ? workspace + (size_t)b * 2 * D * D : smem;
+  float* G = M + (size_t)D * D;
+  float* part = kGlobal ? smem : smem + (size_t)2 * D * D;      // [3 * nwarps][D]
+  float* LSE = part + (size_t)3 * nwarps * D;                   // [max_iter][D]
+  const float* sb = s + (size_t)b * R * C;
+  const int ld = nc;
+
+  for (int idx = tid; idx < rows * nc; idx += nthreads) {
+    const int i = idx / nc, j = idx - i * nc;
+    float v = -100.0f;
+    if (i < nr) v = (opT ? sb[(size_t)j * C + i] : sb[(size_t)i * C + j]) / tau;
+    M[idx] = v;
+  }
+  __syncthreads();
+
+  const int chunks = (nc + 31) >> 5;
+  const int wpc = max(1, nwarps / max(chunks, 1));
+  const int groups = nwarps / wpc;
+  const int slot = warp / wpc, sub = warp % wpc;
+
+  // ---- forward replay (identical arithmetic to sinkhorn_log_kernel), keeping lse_t
+  for (int it = 0; it < max_iter; ++it) {
+    float* lse_t = LSE + (size_t)it * D;
+    if ((it & 1) == 0) {
+      for (int r = warp; r < rows; r += nwarps) {
+        float* row = M + (size_t)r * ld;
+        float mx = kNegInf;
+        for (int j = lane; j < nc; j += 32) mx = fmaxf(mx, row[j]);
+        mx = warp_max(mx);
+        const float sh = (mx == kNegInf) ? 0.f : mx;
+        float sum = 0.f;
+        for (int j = lane; j < nc; j += 32) sum += expf(row[j] - sh);
+        sum = warp_sum(sum);
+        const float lse = logf(sum) + sh;
+        for (int j = lane; j < nc; j += 32) row[j] = row[j] - lse;
+        if (lane == 0) lse_t[r] = lse;
+      }
+      __syncthreads();
+    } else {
+      if (slot < groups) {
+        for (int ch = slot; ch < chunks; ch += groups) {
+          const int j = (ch << 5) + lane;
+          float mx = kNegInf;
+          if (j < nc)
+            for (int r = sub; r < rows; r += wpc) mx = fmaxf(mx, M[(size_t)r * ld + j]);
+          if (j < nc) part[sub * D + j] = mx;
+        }
+      }
+      __syncthreads();
+      if (slot < groups) {
+        for (int ch = slot; ch < chunks; ch += groups) {
+          const int j = (ch << 5) + lane;
+          if (j < nc) {
+            float mx = kNegInf;
+            for (int w = 0; w < wpc; ++w) mx = fmaxf(mx, part[w * D + j]);
+            const float sh = (mx == kNegInf) ? 0.f : mx;
+            float sum = 0.f;
+            for (int r = sub; r < rows; r += wpc) sum += expf(M[(size_t)r * ld + j] - sh);
+            part[(wpc + sub) * D + j] = sum;
+            if (sub == 0) part[2 * wpc * D + j] = sh;
+          }
+        }
+      }
+      __syncthreads();
+      if (slot < groups) {
+        for (int ch = slot; ch < chunks; ch += groups) {
+          const int j = (ch << 5) + lane;
+          if (j < nc) {
+            float sum = 0.f;
+            for (int w = 0; w < wpc; ++w) sum += part[(wpc + w) * D + j];
+            const float lse = logf(sum) + part[2 * wpc * D + j];
+            for (int r = sub; r < rows; r += wpc) M[(size_t)r * ld + j] -= lse;
+            if (sub == 0) lse_t[j] = lse;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- gradient of the cropped exp: G = gout * exp(x_T) on the real rows, 0 on dummy rows
+  const float* gb = gout + (size_t)b * R * C;
+  for (int idx = tid; idx < rows * nc; idx += nthreads) {
+    const int i = idx / nc, j = idx - i * nc;
+    float g = 0.f;
+    if (i < nr) {
+      const int a = opT ? j : i, c = opT ? i : j;
+      g = gb[(size_t)a * C + c] * expf(M[idx]);
+    }
+    G[idx] = g;
+  }
+  __syncthreads();
+
+  // ---- reverse iterations
+  for (int it = max_iter - 1; it >= 0; --it) {
+    const float* lse_t = LSE + (size_t)it * D;
+    if ((it & 1) == 0) {
+      for (int r = warp; r < rows; r += nwarps) {
+        float* row = M + (size_t)r * ld;
+        float* grow = G + (size_t)r * ld;
+        float rs = 0.f;
+        for (int j = lane; j < nc; j += 32) rs += grow[j];
+        rs = warp_sum(rs);
+        const float lse = lse_t[r];
+        for (int j = lane; j < nc; j += 32) {
+          const float x = row[j];
+          grow[j] = fmaf(-expf(x), rs, grow[j]);
+          row[j] = x + lse;
+        }
+      }
+      __syncthreads();
+    } else {
+      if (slot < groups) {
+        for (int ch = slot; ch < chunks; ch += groups) {
+          const int j = (ch << 5) + lane;
+          if (j < nc) {
+            float cs = 0.f;
+            for (int r = sub; r < rows; r += wpc) cs += G[(size_t)r * ld + j];
+            part[sub * D + j] = cs;
+          }
+        }
+      }
+      __syncthreads();
+      if (slot < groups) {
+        for (int ch = slot; ch < chunks; ch += groups) {
+          const int j = (ch << 5) + lane;
+          if (j < nc) {
+            float cs = 0.f;
+            for (int w = 0; w < wpc; ++w) cs += part[w * D + j];
+            const float lse = lse_t[j];
+            for (int r = sub; r < rows; r += wpc) {
+              const float x = M[(size_t)r * ld + j];
+              G[(size_t)r * ld + j] = fmaf(-expf(x), cs, G[(size_t)r * ld + j]);
+              M[(size_t)r * ld + j] = x + lse;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  float* ob = gs + (size_t)b * R * C;
+  for (int idx = tid; idx < R * C; idx += nthreads) {
+    const int a = idx / C, c = idx - a * C;
+    float v = 0.f;
+    if (a < n1b && c < n2b) {
+      const int fi = opT ? c : a, fj = opT ? a : c;
+      v = G[(size_t)fi * ld + fj] / tau;
+    }
+    ob[idx] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward of soft_topk_kernel.  The plan's iterations carry NaN clean-ups and a data-dependent extra step, so
+// instead of inverting them the kernel replays: for t = T-1 .. 0 it recomputes the input of step t from the
+// scores (t forward steps on chip; T <= 12, N*2 values) and applies that step's vector-Jacobian product.
+// Anchors are constants (soft_topk.py:27 detaches them); d|x|/dx = sign(x) with sign(0) = 0 as in torch.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stk_forward_step(float* L0, float* L1, int N, int it, float lc0, float lc1,
+                                                 float* red) {
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  if ((it & 1) == 0) {
+    for (int p = tid; p < N; p += nthreads) {
+      const float a = L0[p], c = L1[p];
+      const float m = fmaxf(a, c);
+      const float sh = (m == kNegInf || m == INFINITY) ? 0.f : m;
+      const float lse = logf(expf(a - sh) + expf(c - sh)) + sh;
+      float na = a - lse + 0.0f, nc_ = c - lse + 0.0f;
+      L0[p] = isnan(na) ? kNegInf : na;
+      L1[p] = isnan(nc_) ? kNegInf : nc_;
+    }
+    __syncthreads();
+  } else {
+    float m0 = kNegInf, m1 = kNegInf;
+    for (int p = tid; p < N; p += nthreads) {
+      m0 = fmaxf(m0, L0[p]);
+      m1 = fmaxf(m1, L1[p]);
+    }
+    m0 = block_max(m0, red);
+    m1 = block_max(m1, red + 32);
+    const float sh0 = (m0 == kNegInf || m0 == INFINITY) ? 0.f : m0;
+    const float sh1 = (m1 == kNegInf || m1 == INFINITY) ? 0.f : m1;
+    float s0 = 0.f, s1 = 0.f;
+    for (int p = tid; p < N; p += nthreads) {
+      s0 += expf(L0[p] - sh0);
+      s1 += expf(L1[p] - sh1);
+    }
+    s0 = block_sum(s0, red);
+    s1 = block_sum(s1, red + 32);
+    const float lse0 = logf(s0) + sh0, lse1 = logf(s1) + sh1;
+    for (int p = tid; p < N; p += nthreads) {
+      float na = L0[p] - lse0 + lc0, nc_ = L1[p] - lse1 + lc1;
+      L0[p] = isnan(na) ? kNegInf : na;
+      L1[p] = isnan(nc_) ? kNegInf : nc_;
+    }
+    __syncthreads();
+  }
+}
+
+template <bool kGlobal>
+__global__ void __launch_bounds__(512)
+soft_topk_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ ks,
+                     const int64_t* __restrict__ n1, const int64_t* __restrict__ n2,
+                     const float* __restrict__ gout, float* __restrict__ gscores,
+                     float* __restrict__ workspace, int R, int C, int max_iter, float tau) {
+  extern __shared__ float smem[];
+  __shared__ float red[64];
+  const int b = blockIdx.x, tid = threadIdx.x, nthreads = blockDim.x;
+  int n1b = n1 ? (int)n1[b] : R;
+  int n2b = n2 ? (int)n2[b] : C;
+  n1b = min(max(n1b, 0), R);
+  n2b = min(max(n2b, 0), C);
+  const int N = n1b * n2b;
+  float* L0 = kGlobal ? workspace + (size_t)b * 4 * R * C : smem;
+  float* L1 = L0 + (size_t)R * C;
+  float* G0 = L1 + (size_t)R * C;
+  float* G1 = G0 + (size_t)R * C;
+  const float* sb = scores + (size_t)b * R * C;
+
+  float mn = INFINITY, mx = kNegInf;
+  for (int p = tid; p < N; p += nthreads) {
+    const int i = p / n2b, j = p - i * n2b;
+    const float v = sb[(size_t)i * C + j];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  mn = block_min(mn, red);
+  mx = block_max(mx, red + 32);
+  const float k = ks[b];
+  const float lc0 = logf((float)((long long)n1b * (long long)n2b) - k);
+  const float lc1 = logf(k);
+
+  auto init = [&]() {
+    for (int p = tid; p < N; p += nthreads) {
+      const int i = p / n2b, j = p - i * n2b;
+      const float v = sb[(size_t)i * C + j];
+      L0[p] = (-fabsf(v - mn)) / tau;
+      L1[p] = (-fabsf(v - mx)) / tau;
+    }
+    __syncthreads();
+  };
+
+  // ---- full forward: number of steps actually taken, final plan
+  init();
+  int T = 0;
+  while (true) {
+    if (T >= max_iter) {
+      int pos = 0;
+      for (int p = tid; p < N; p += nthreads) pos |= (L0[p] > 0.f) | (L1[p] > 0.f);
+      if (!__syncthreads_or(pos)) break;
+    }
+    stk_forward_step(L0, L1, N, T, lc0, lc1, red);
+    ++T;
+    if (T > max_iter + 64) break;
+  }
+  const float* gb = gout + (size_t)b * R * C;
+  for (int p = tid; p < N; p += nthreads) {
+    const int i = p / n2b, j = p - i * n2b;
+    const float e = expf(L1[p]);
+    G0[p] = 0.f;
+    G1[p] = e > 0.f ? gb[(size_t)i * C + j] * e : 0.f;
+  }
+  __syncthreads();
+
+  // ---- reverse sweep with recomputation
+  for (int t = T - 1; t >= 0; --t) {
+    init();
+    for (int u = 0; u < t; ++u) stk_forward_step(L0, L1, N, u, lc0, lc1, red);
+    if ((t & 1) == 0) {
+      for (int p = tid; p < N; p += nthreads) {
+        const float a = L0[p], c = L1[p];
+        const float m = fmaxf(a, c);
+        const float sh = (m == kNegInf || m == INFINITY) ? 0.f : m;
+        const float lse = logf(expf(a - sh) + expf(c - sh)) + sh;
+        const float na = a - lse, nc_ = c - lse;
+        const float ga = isnan(na) ? 0.f : G0[p], gc = isnan(nc_) ? 0.f : G1[p];
+        const float sum = ga + gc;
+        float sa = expf(na), sc = expf(nc_);
+        if (isnan(sa)) sa = 0.f;
+        if (isnan(sc)) sc = 0.f;
+        G0[p] = ga - sa * sum;
+        G1[p] = gc - sc * sum;
+      }
+      __syncthreads();
+    } else {
+      float m0 = kNegInf, m1 = kNegInf;
+      for (int p = tid; p < N; p += nthreads) {
+        m0 = fmaxf(m0, L0[p]);
+        m1 = fmaxf(m1, L1[p]);
+      }
+      m0 = block_max(m0, red);
+      m1 = block_max(m1, red + 32);
+      const float sh0 = (m0 == kNegInf || m0 == INFINITY) ? 0.f : m0;
+      const float sh1 = (m1 == kNegInf || m1 == INFINITY) ? 0.f : m1;
+      float s0 = 0.f, s1 = 0.f;
+      for (int p = tid; p < N; p += nthreads) {
+        s0 += expf(L0[p] - sh0);
+        s1 += expf(L1[p] - sh1);
+      }
+      s0 = block_sum(s0, red);
+      s1 = block_sum(s1, red + 32);
+      const float lse0 = logf(s0) + sh0, lse1 = logf(s1) + sh1;
+      float S0 = 0.f, S1 = 0.f;
+      for (int p = tid; p < N; p += nthreads) {
+        const float na = L0[p] - lse0 + lc0, nc_ = L1[p] - lse1 + lc1;
+        const float g0 = isnan(na) ? 0.f : G0[p], g1 = isnan(nc_) ? 0.f : G1[p];
+        G0[p] = g0; G1[p] = g1;
+        S0 += g0; S1 += g1;
+      }
+      S0 = block_sum(S0, red);
+      S1 = block_sum(S1, red + 32);
+      for (int p = tid; p < N; p += nthreads) {
+        float p0 = expf(L0[p] - lse0), p1 = expf(L1[p] - lse1);
+        if (isnan(p0)) p0 = 0.f;
+        if (isnan(p1)) p1 = 0.f;
+        G0[p] = G0[p] - p0 * S0;
+        G1[p] = G1[p] - p1 * S1;
+      }
+      __syncthreads();
+    }
+  }
+
+  float* ob = gscores + (size_t)b * R * C;
+  for (int idx = tid; idx < R * C; idx += nthreads) {
+    const int i = idx / C, j = idx - i * C;
+    float g = 0.f;
+    if (i < n1b && j < n2b) {
+      const int p = i * n2b + j;
+      const float v = sb[idx];
+      const float d0 = v - mn, d1 = v - mx;
+      const float s0 = d0 > 0.f ? 1.f : (d0 < 0.f ? -1.f : 0.f);
+      const float s1 = d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f);
+      g = (-(G0[p] * s0) - (G1[p] * s1)) / tau;
+    }
+    ob[idx] = g;
+  }
+}
+
 }  // namespace fpm
 
 // ------------------------------------------------------------------------------------------
@@ -307,6 +677,72 @@ extern "C" int fpm_soft_topk(const float* scores, const float* ks, const long lo
     FPM_CHECK_ARG(workspace, "fpm_soft_topk: matrix exceeds shared memory, workspace required");
     fpm::soft_topk_kernel<true><<<B, threads, 0, st>>>(
         scores, ks, (const int64_t*)n1, (const int64_t*)n2, out, (float*)workspace, R, C, max_iter, tau);
+  }
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" long long fpm_sinkhorn_bwd_workspace_bytes(int B, int R, int C, int max_iter) {
+  const int D = R > C ? R : C;
+  const int threads = 512;
+  const size_t need = ((size_t)2 * D * D + (size_t)(3 * (threads / 32)) * D + (size_t)max_iter * D) * sizeof(float);
+  return need <= kSmemLimit ? 0 : (long long)B * 2 * D * D * (long long)sizeof(float);
+}
+
+extern "C" int fpm_sinkhorn_log_bwd(const float* s, const long long* n1, const long long* n2, const float* gout,
+                                    float* gs, void* workspace, int B, int R, int C, int max_iter, float tau,
+                                    int dummy_row, void* stream) {
+  FPM_CHECK_ARG(s && gout && gs, "fpm_sinkhorn_log_bwd: null tensor");
+  FPM_CHECK_ARG(B >= 0 && R > 0 && C > 0 && max_iter >= 0, "fpm_sinkhorn_log_bwd: bad sizes");
+  FPM_CHECK_ARG(tau != 0.f, "fpm_sinkhorn_log_bwd: tau must be non-zero");
+  if (B == 0) return FPM_OK;
+  const int D = R > C ? R : C;
+  const int threads = D <= 48 ? 128 : (D <= 96 ? 256 : 512);
+  const int nwarps = threads / 32;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t aux = ((size_t)(3 * nwarps) * D + (size_t)max_iter * D) * sizeof(float);
+  const size_t full = (size_t)2 * D * D * sizeof(float) + aux;
+  if (full <= kSmemLimit) {
+    FPM_CUDA(cudaFuncSetAttribute(fpm::sinkhorn_log_bwd_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full));
+    fpm::sinkhorn_log_bwd_kernel<false><<<B, threads, full, st>>>(
+        s, (const int64_t*)n1, (const int64_t*)n2, gout, gs, nullptr, R, C, max_iter, tau, dummy_row);
+  } else {
+    FPM_CHECK_ARG(workspace, "fpm_sinkhorn_log_bwd: matrix exceeds shared memory, workspace required");
+    FPM_CHECK_ARG(aux <= kSmemLimit, "fpm_sinkhorn_log_bwd: problem too large");
+    FPM_CUDA(cudaFuncSetAttribute(fpm::sinkhorn_log_bwd_kernel<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aux));
+    fpm::sinkhorn_log_bwd_kernel<true><<<B, threads, aux, st>>>(
+        s, (const int64_t*)n1, (const int64_t*)n2, gout, gs, (float*)workspace, R, C, max_iter, tau, dummy_row);
+  }
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" long long fpm_soft_topk_bwd_workspace_bytes(int B, int R, int C) {
+  const size_t need = (size_t)4 * R * C * sizeof(float);
+  return need <= kSmemLimit - 1024 ? 0 : (long long)B * 4 * R * C * (long long)sizeof(float);
+}
+
+extern "C" int fpm_soft_topk_bwd(const float* scores, const float* ks, const long long* n1, const long long* n2,
+                                 const float* gout, float* gscores, void* workspace, int B, int R, int C,
+                                 int max_iter, float tau, void* stream) {
+  FPM_CHECK_ARG(scores && ks && gout && gscores, "fpm_soft_topk_bwd: null tensor");
+  FPM_CHECK_ARG(B >= 0 && R > 0 && C > 0 && max_iter >= 0, "fpm_soft_topk_bwd: bad sizes");
+  FPM_CHECK_ARG(tau != 0.f, "fpm_soft_topk_bwd: tau must be non-zero");
+  if (B == 0) return FPM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = (R * C) <= 4096 ? 256 : 512;
+  const size_t need = (size_t)4 * R * C * sizeof(float);
+  if (need <= kSmemLimit - 1024) {
+    FPM_CUDA(cudaFuncSetAttribute(fpm::soft_topk_bwd_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    fpm::soft_topk_bwd_kernel<false><<<B, threads, need, st>>>(
+        scores, ks, (const int64_t*)n1, (const int64_t*)n2, gout, gscores, nullptr, R, C, max_iter, tau);
+  } else {
+    FPM_CHECK_ARG(workspace, "fpm_soft_topk_bwd: matrix exceeds shared memory, workspace required");
+    fpm::soft_topk_bwd_kernel<true><<<B, threads, 0, st>>>(
+        scores, ks, (const int64_t*)n1, (const int64_t*)n2, gout, gscores, (float*)workspace, R, C, max_iter, tau);
   }
   FPM_LAUNCH_CHECK();
   return FPM_OK;

@@ -85,17 +85,20 @@ __device__ __forceinline__ void spline_basis4(float u0, float u1, int KS, float*
 
 // One CTA (192 threads x float4 = 768 channels) per destination node.
 // Y: [total_nodes, NS, C] with NS = KS*KS + 1 slabs.  mode 0: out = relu(conv); mode 1: out = x + 0.1*conv.
+// argmax (training only): [total_nodes, C] int32, the edge id that won the max per channel (-1: no in-edge).
 __global__ void __launch_bounds__(192)
 spline_gather_max_kernel(const float* __restrict__ Y, const float* __restrict__ xin,
                          const int64_t* __restrict__ edge_src, const float* __restrict__ pseudo,
                          const int* __restrict__ in_ptr, const int* __restrict__ in_eid,
-                         const float* __restrict__ bias, float* __restrict__ out, int C, int KS, int mode) {
+                         const float* __restrict__ bias, float* __restrict__ out, int* __restrict__ argmax,
+                         int C, int KS, int mode) {
   const int i = blockIdx.x;
   const int NS = KS * KS + 1;
   const int e_beg = in_ptr[i], e_end = in_ptr[i + 1];
   const int c4 = threadIdx.x;                 // float4 index along channels
   if (c4 * 4 >= C) return;
   float4 best = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+  int4 arg = make_int4(-1, -1, -1, -1);
   for (int q = e_beg; q < e_end; ++q) {
     const int e = in_eid[q];
     const int j = (int)edge_src[e];
@@ -109,9 +112,16 @@ spline_gather_max_kernel(const float* __restrict__ Y, const float* __restrict__ 
       m.x = fmaf(bas[s], y.x, m.x); m.y = fmaf(bas[s], y.y, m.y);
       m.z = fmaf(bas[s], y.z, m.z); m.w = fmaf(bas[s], y.w, m.w);
     }
+    if (argmax) {                              // first maximum wins (ascending edge order)
+      if (m.x > best.x) arg.x = e;
+      if (m.y > best.y) arg.y = e;
+      if (m.z > best.z) arg.z = e;
+      if (m.w > best.w) arg.w = e;
+    }
     best.x = fmaxf(best.x, m.x); best.y = fmaxf(best.y, m.y);
     best.z = fmaxf(best.z, m.z); best.w = fmaxf(best.w, m.w);
   }
+  if (argmax) *(int4*)(argmax + (size_t)i * C + c4 * 4) = arg;
   if (e_beg == e_end) best = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 r = *(const float4*)(Y + ((size_t)i * NS + (NS - 1)) * C + c4 * 4);
   const float4 bi = *(const float4*)(bias + c4 * 4);
@@ -125,6 +135,50 @@ spline_gather_max_kernel(const float* __restrict__ Y, const float* __restrict__ 
     v.x = x0.x + 0.1f * v.x; v.y = x0.y + 0.1f * v.y; v.z = x0.z + 0.1f * v.z; v.w = x0.w + 0.1f * v.w;
   }
   *(float4*)(out + (size_t)i * C + c4 * 4) = v;
+}
+
+// Backward of the gather/max: dY[j, k, :] = sum over out-edges e = (j -> i) whose message won the max at
+// (i, c) of basis_s(e) * G[i, c] for the 4 slabs k = wi_s(e), plus the root slab dY[j, KS*KS, :] = G[j, :].
+// G is the gradient of the conv output before relu / residual scaling.  One CTA per SOURCE node; its
+// [NS][C] block of dY is accumulated in shared memory over the out-edge list (ascending edge order ->
+// deterministic) and written once, zeros included, so dY needs no memset.
+__global__ void __launch_bounds__(192)
+spline_scatter_bwd_kernel(const float* __restrict__ G, const int* __restrict__ argmax,
+                          const int64_t* __restrict__ edge_dst, const float* __restrict__ pseudo,
+                          const int* __restrict__ out_ptr, const int* __restrict__ out_eid,
+                          float* __restrict__ dY, int C, int KS) {
+  extern __shared__ __align__(16) float blk[];       // [NS][C]
+  const int j = blockIdx.x;
+  const int NS = KS * KS + 1;
+  const int c4 = threadIdx.x;
+  if (c4 * 4 >= C) return;                           // threads own disjoint channel quads: no syncs needed
+  for (int k = 0; k < NS - 1; ++k) *(float4*)(blk + (size_t)k * C + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  *(float4*)(blk + (size_t)(NS - 1) * C + c4 * 4) = *(const float4*)(G + (size_t)j * C + c4 * 4);
+  const int e_beg = out_ptr[j], e_end = out_ptr[j + 1];
+  for (int q = e_beg; q < e_end; ++q) {
+    const int e = out_eid[q];
+    const int i = (int)edge_dst[e];
+    const int4 a = *(const int4*)(argmax + (size_t)i * C + c4 * 4);
+    if (a.x != e && a.y != e && a.z != e && a.w != e) continue;
+    float4 g = *(const float4*)(G + (size_t)i * C + c4 * 4);
+    if (a.x != e) g.x = 0.f;
+    if (a.y != e) g.y = 0.f;
+    if (a.z != e) g.z = 0.f;
+    if (a.w != e) g.w = 0.f;
+    float bas[4]; int wi[4];
+    spline_basis4(pseudo[(size_t)e * 2], pseudo[(size_t)e * 2 + 1], KS, bas, wi);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      float4* d = (float4*)(blk + (size_t)wi[s] * C + c4 * 4);
+      float4 v = *d;
+      v.x = fmaf(bas[s], g.x, v.x); v.y = fmaf(bas[s], g.y, v.y);
+      v.z = fmaf(bas[s], g.z, v.z); v.w = fmaf(bas[s], g.w, v.w);
+      *d = v;
+    }
+  }
+  float* dst = dY + (size_t)j * NS * C;
+  for (int k = 0; k < NS; ++k)
+    *(float4*)(dst + (size_t)k * C + c4 * 4) = *(const float4*)(blk + (size_t)k * C + c4 * 4);
 }
 
 }  // namespace fpm
@@ -146,14 +200,29 @@ extern "C" int fpm_csr_by_dst(const long long* edge_dst, const long long* ptr, c
 
 extern "C" int fpm_spline_gather_max(const float* Y, const float* xin, const long long* edge_src,
                                      const float* pseudo, const int* in_ptr, const int* in_eid,
-                                     const float* bias, float* out, int total_nodes, int C,
+                                     const float* bias, float* out, int* argmax, int total_nodes, int C,
                                      int kernel_size, int mode, void* stream) {
   FPM_CHECK_ARG(Y && edge_src && pseudo && in_ptr && in_eid && bias && out, "fpm_spline_gather_max: null tensor");
   FPM_CHECK_ARG(mode == 0 || mode == 2 || (mode == 1 && xin), "fpm_spline_gather_max: bad mode / residual mode needs xin");
   FPM_CHECK_ARG(C % 4 == 0 && C <= 768, "fpm_spline_gather_max: C must be a multiple of 4, at most 768");
   if (total_nodes == 0) return FPM_OK;
   fpm::spline_gather_max_kernel<<<total_nodes, 192, 0, (cudaStream_t)stream>>>(
-      Y, xin, (const int64_t*)edge_src, pseudo, in_ptr, in_eid, bias, out, C, kernel_size, mode);
+      Y, xin, (const int64_t*)edge_src, pseudo, in_ptr, in_eid, bias, out, argmax, C, kernel_size, mode);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_spline_scatter_bwd(const float* G, const int* argmax, const long long* edge_dst,
+                                      const float* pseudo, const int* out_ptr, const int* out_eid, float* dY,
+                                      int total_nodes, int C, int kernel_size, void* stream) {
+  FPM_CHECK_ARG(G && argmax && edge_dst && pseudo && out_ptr && out_eid && dY, "fpm_spline_scatter_bwd: null tensor");
+  FPM_CHECK_ARG(C % 4 == 0 && C <= 768, "fpm_spline_scatter_bwd: C must be a multiple of 4, at most 768");
+  if (total_nodes == 0) return FPM_OK;
+  const size_t smem = (size_t)(kernel_size * kernel_size + 1) * C * sizeof(float);
+  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_spline_scatter_bwd: kernel_size too large");
+  FPM_CUDA(cudaFuncSetAttribute(fpm::spline_scatter_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fpm::spline_scatter_bwd_kernel<<<total_nodes, 192, smem, (cudaStream_t)stream>>>(
+      G, argmax, (const int64_t*)edge_dst, pseudo, out_ptr, out_eid, dY, C, kernel_size);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

@@ -37,8 +37,9 @@ SIGNATURES = {
     "fpm_f16_split_rows": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "fpm_gemm_nt_f16x3": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fpm_csr_by_dst": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
-    "fpm_spline_gather_max": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "fpm_affinity": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "fpm_spline_gather_max": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fpm_affinity": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "fpm_affinity_edges_factored": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _F, _P]),
     "fpm_assoc_in_csr": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "fpm_gnn_layer": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "fpm_final_classifier": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
@@ -52,6 +53,18 @@ SIGNATURES = {
     "fpm_k_head": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_lap_topk": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_greedy_perm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    # training (backward) entry points
+    "fpm_node_features_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
+    "fpm_fmap_prep_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "fpm_spline_scatter_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_transpose_f32": (_I, [_P, _P, _I, _I, _I, _P]),
+    "fpm_bmm_ragged": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "fpm_segment_rowdot": (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    "fpm_gnn_layer_bwd": (_I, [_P] * 19 + [_I] * 6 + [_P]),
+    "fpm_sinkhorn_bwd_workspace_bytes": (_LL, [_I, _I, _I, _I]),
+    "fpm_sinkhorn_log_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "fpm_soft_topk_bwd_workspace_bytes": (_LL, [_I, _I, _I]),
+    "fpm_soft_topk_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
 }
 
 

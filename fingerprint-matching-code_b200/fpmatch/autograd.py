@@ -1,0 +1,216 @@
+"""torch.autograd.Function wrappers: the differentiable ops of the matching head for TRAINING
+(BASELINE.json config 3: stage-1 step, ``/root/reference/train.py`` + ``src/train/training_loop.py:33-64``).
+
+The reference lets torch autograd differentiate its python forward.  Here every stage of the head is one
+Function whose forward launches the inference kernels (``fpmatch.ops``) and whose backward launches the
+hand-written vector-Jacobian kernels declared under "training" in ``include/fpmatch.h``.  PyTorch only routes
+tensors between them and differentiates the handful of ``[B, 1024]``-sized expressions left in python.
+
+Nothing here has a CPU path: the ops raise for CPU tensors.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+class NodeFeaturesFn(Function):
+    """normalize_over_channels + feature_align + concat (ngm.py:241-248): raw NCHW maps -> X [sum n, C1+C2]."""
+
+    @staticmethod
+    def forward(ctx, nodes: Tensor, edges: Tensor, P: Tensor, ns: Tensor, ptr: Tensor, total: int, ori_size):
+        nodes = nodes.contiguous(); edges = edges.contiguous()
+        ncl, ecl = ops.fmap_prep(nodes), ops.fmap_prep(edges)
+        X = ops.node_features(ncl, ecl, nodes.shape[2:], edges.shape[2:], P, ns, ptr, total, ori_size)
+        ctx.save_for_backward(nodes, edges, P, ns, ptr)
+        ctx.ori_size = ori_size
+        return X
+
+    @staticmethod
+    def backward(ctx, dX: Tensor):
+        nodes, edges, P, ns, ptr = ctx.saved_tensors
+        d1, d2 = ops.node_features_bwd(dX.contiguous(), P, ns, ptr, tuple(nodes.shape[1:]), tuple(edges.shape[1:]),
+                                       ctx.ori_size)
+        return ops.fmap_prep_bwd(nodes, d1), ops.fmap_prep_bwd(edges, d2), None, None, None, None, None
+
+
+class GraphCtx:
+    """Per-graph-batch structure shared by both SplineConv layers: edge lists grouped by destination (forward
+    gather) and by source (backward scatter)."""
+
+    def __init__(self, edge_index: Tensor, pseudo: Tensor, ptr: Tensor, eptr: Tensor, total: int, max_edges: int):
+        self.edge_index = edge_index.contiguous()
+        self.pseudo = pseudo.contiguous()
+        self.in_csr = ops.csr_by_dst(self.edge_index, ptr, eptr, total, max_edges)
+        swapped = torch.stack((self.edge_index[1], self.edge_index[0]), 0).contiguous()
+        self.out_csr = ops.csr_by_dst(swapped, ptr, eptr, total, max_edges)
+
+
+class SplineConvFn(Function):
+    """SplineConv(768,768,dim=2,kernel_size=5,aggr='max') + relu (mode 0) / xin + 0.1*out (mode 1) / nothing (2)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, root: Tensor, bias: Tensor, xin: Optional[Tensor], packed: Tensor,
+                g: GraphCtx, mode: int, kernel_size: int):
+        x = x.contiguous()
+        Y = ops.gemm_nt(x, packed, weight_operand=True)
+        out, arg = ops.spline_gather_max(Y, xin, g.edge_index, g.pseudo, g.in_csr[0], g.in_csr[1],
+                                         bias.detach().contiguous(), mode, kernel_size, want_argmax=True)
+        del Y
+        ctx.save_for_backward(x, packed, out if mode == 0 else None, arg)
+        ctx.g, ctx.mode, ctx.ks = g, mode, kernel_size
+        ctx.wshape = tuple(weight.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        x, packed, out, arg = ctx.saved_tensors
+        g, mode = ctx.g, ctx.mode
+        K, cin, cout = ctx.wshape
+        gout = gout.contiguous()
+        dxin = None
+        if mode == 0:
+            G = gout * (out > 0).to(gout.dtype)
+        elif mode == 1:
+            G = gout * 0.1
+            dxin = gout
+        else:
+            G = gout
+        dbias = G.sum(0)
+        dY = ops.spline_scatter_bwd(G, arg, g.edge_index, g.pseudo, g.out_csr[0], g.out_csr[1], ctx.ks)
+        # dX = dY W : [total, (K+1)*out] x [(K+1)*out, in]
+        dx = ops.gemm_nt(dY, ops.transpose_pad(packed))
+        # dW = dY^T X : both operands K-major along the node dimension
+        dW = ops.gemm_nt(ops.transpose_pad(dY), ops.transpose_pad(x))          # [(K+1)*out, in]
+        del dY
+        dW = dW.view(K + 1, cout, cin)
+        dweight = dW[:K].permute(0, 2, 1)
+        droot = dW[K].t()
+        return dx, dweight, droot, dbias, dxin, None, None, None, None
+
+
+class AffinityFn(Function):
+    """Kp = softplus((X1 (.) c) X2^T) - 0.5, padded, with its transpose (affinity_layer.py:11-19, ngm.py:317-321)."""
+
+    @staticmethod
+    def forward(ctx, X1: Tensor, X2: Tensor, coeff: Tensor, ptr1: Tensor, ptr2: Tensor, n1max: int, n2max: int):
+        X1 = X1.contiguous(); X2 = X2.contiguous(); coeff = coeff.contiguous()
+        Kp, Kp_t = ops.affinity_nodes(X1, X2, coeff, ptr1, ptr2, n1max, n2max)
+        ctx.save_for_backward(X1, X2, coeff, ptr1, ptr2, Kp)
+        return Kp, Kp_t
+
+    @staticmethod
+    def backward(ctx, dKp: Optional[Tensor], dKp_t: Optional[Tensor]):
+        X1, X2, coeff, ptr1, ptr2, Kp = ctx.saved_tensors
+        dK = None
+        if dKp is not None:
+            dK = dKp
+        if dKp_t is not None:
+            dK = dKp_t.transpose(1, 2) if dK is None else dK + dKp_t.transpose(1, 2)
+        # softplus'(p) = sigmoid(p) = 1 - exp(-softplus(p)),  softplus(p) = Kp + 0.5
+        dP = (dK * (1.0 - torch.exp(-(Kp + 0.5)))).contiguous()
+        T = ops.bmm_ragged(dP, False, X2, ptr2, ptr1, X1.shape[0])             # dP X2
+        dcoeff = ops.segment_rowdot(X1, T, ptr1)
+        n1 = ptr1[1:] - ptr1[:-1]
+        bidx = torch.repeat_interleave(torch.arange(n1.numel(), device=X1.device), n1, output_size=X1.shape[0])
+        dX1 = T * coeff[bidx]
+        dX2 = ops.bmm_ragged(dP, True, X1, ptr1, ptr2, X2.shape[0], coeff_in=coeff)   # dP^T (c (.) X1)
+        return dX1, dX2, dcoeff, None, None, None, None
+
+
+class SinkhornFn(Function):
+    @staticmethod
+    def forward(ctx, s: Tensor, n1: Tensor, n2: Tensor, max_iter: int, tau: float, dummy_row: bool):
+        s = s.contiguous()
+        out = ops.sinkhorn_log(s, n1, n2, max_iter, tau, dummy_row)
+        ctx.save_for_backward(s, n1, n2)
+        ctx.cfg = (max_iter, tau, dummy_row)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        s, n1, n2 = ctx.saved_tensors
+        return ops.sinkhorn_log_bwd(s, n1, n2, gout.contiguous(), *ctx.cfg), None, None, None, None, None
+
+
+class SoftTopkFn(Function):
+    @staticmethod
+    def forward(ctx, ss: Tensor, ks: Tensor, n1: Tensor, n2: Tensor, max_iter: int, tau: float):
+        ss = ss.contiguous()
+        out = ops.soft_topk(ss, ks, n1, n2, max_iter, tau)
+        ctx.save_for_backward(ss, ks, n1, n2)
+        ctx.cfg = (max_iter, tau)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        ss, ks, n1, n2 = ctx.saved_tensors
+        return ops.soft_topk_bwd(ss, ks, n1, n2, gout.contiguous(), *ctx.cfg), None, None, None, None, None
+
+
+class NgmSolverFn(Function):
+    """The three PYGNNLayers (factorised SAGE aggregation + linears + classifier + Sinkhorn) and the final
+    classifier (ngm.py:326-369): Kp^T -> s.  ``params`` = 9 tensors per layer in ``PYGNNLayer.kernel_weights``
+    order, then classifier.weight, classifier.bias."""
+
+    @staticmethod
+    def forward(ctx, Kp_t: Tensor, meta: dict, *params: Tensor):
+        csr1, csr2, n1, n2 = meta["csr1"], meta["csr2"], meta["n1"], meta["n2"]
+        n1max, n2max, e1max, e2max = meta["n1max"], meta["n2max"], meta["e1max"], meta["e2max"]
+        nl = meta["layers"]
+        det = lambda t: t.detach().contiguous()
+        lw = [[det(params[9 * i + j]).reshape(-1) if j == 7 else det(params[9 * i + j]) for j in range(9)]
+              for i in range(nl)]
+        cw, cb = det(params[9 * nl]).reshape(-1), det(params[9 * nl + 1])
+        xprev, m_t = None, Kp_t.contiguous()
+        saved = []
+        for i in range(nl):
+            x1, score = ops.gnn_layer(xprev, m_t, csr1, csr2, n1, n2, lw[i], n1max, n2max, e1max, e2max)
+            _, sk_t = ops.sinkhorn_log(score, n1, n2, meta["sk_iter"], meta["sk_tau"], True, want_t=True)
+            saved.append((xprev, m_t, score))
+            xprev, m_t = x1, sk_t
+        s = ops.final_classifier(xprev, m_t, cw, cb, n1max, n2max)
+        ctx.meta, ctx.lw, ctx.cw = meta, lw, cw
+        ctx.saved = saved + [(xprev, m_t, None)]
+        ctx.pshapes = [tuple(p.shape) for p in params]
+        return s
+
+    @staticmethod
+    def backward(ctx, ds: Tensor):
+        meta = ctx.meta
+        csr1, csr2, ocsr1, ocsr2 = meta["csr1"], meta["csr2"], meta["ocsr1"], meta["ocsr2"]
+        n1, n2 = meta["n1"], meta["n2"]
+        n1max, n2max, e1max, e2max = meta["n1max"], meta["n2max"], meta["e1max"], meta["e2max"]
+        nl = meta["layers"]
+        B = ds.shape[0]
+        N = n1max * n2max
+        x_last, skt_last, _ = ctx.saved[nl]
+        ds = ds.contiguous()
+        ds_t = ds.transpose(1, 2).reshape(B, N)                      # association-node order p = i2*n1max + i1
+        cw = ctx.cw
+        dcw = torch.empty_like(cw)
+        dcw[:16] = torch.einsum("bp,bpc->c", ds_t, x_last)
+        dcw[16] = (ds_t * skt_last.reshape(B, N)).sum()
+        dcb = ds.sum().reshape(1)
+        dx1 = (ds_t.unsqueeze(-1) * cw[:16]).contiguous()
+        dsk = (ds * cw[16]).contiguous()
+        grads: List[Optional[Tensor]] = [None] * len(ctx.pshapes)
+        for i in range(nl - 1, -1, -1):
+            xprev, m_t, score = ctx.saved[i]
+            dscore = ops.sinkhorn_log_bwd(score, n1, n2, dsk, meta["sk_iter"], meta["sk_tau"], True)
+            dxprev, dm, wg = ops.gnn_layer_bwd(xprev, m_t, csr1, csr2, ocsr1, ocsr2, n1, n2, ctx.lw[i], dx1, dscore,
+                                               n1max, n2max, e1max, e2max)
+            for j in range(9):
+                grads[9 * i + j] = wg[j].reshape(ctx.pshapes[9 * i + j])
+            dx1, dsk = dxprev, dm
+        grads[9 * nl] = dcw.reshape(ctx.pshapes[9 * nl])
+        grads[9 * nl + 1] = dcb.reshape(ctx.pshapes[9 * nl + 1])
+        dKp_t = dsk.transpose(1, 2).contiguous()
+        ctx.saved = None
+        return (dKp_t, None, *grads)

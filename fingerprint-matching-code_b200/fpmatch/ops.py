@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -19,7 +20,7 @@ Tensor = torch.Tensor
 # dense-contraction engine: "3xtf32" / "3xf16" (tcgen05, error-compensated, fp32-faithful), "tf32" (tcgen05,
 # 1 pass, opt-in), "fp32" (CUDA cores; also the on-device checker for the tensor-core kernels)
 GEMM_MODES = ("fp32", "3xtf32", "3xf16", "tf32")
-_GEMM_MODE = os.environ.get("FPMATCH_GEMM", "3xtf32")
+_GEMM_MODE = os.environ.get("FPMATCH_GEMM", "3xf16")
 _LAUNCHES = 0          # kernels launched through this module (bench.py reports it)
 
 
@@ -178,6 +179,24 @@ _GEMM_EVENTS = None
 _SPLIT_CACHE = {}
 
 
+def _cache_get(kind: str, x: Tensor):
+    """Split of a static weight, valid only while the SAME tensor object is alive and unmodified.  (Keying on
+    data_ptr alone served a freed tensor's split to a new tensor allocated at the same address.)"""
+    ent = _SPLIT_CACHE.get((kind, id(x)))
+    if ent is not None and ent[0]() is x and ent[1] == x._version and ent[2] == x.data_ptr():
+        return ent[3]
+    return None
+
+
+def _cache_put(kind: str, x: Tensor, value) -> None:
+    dead = [k for k, e in _SPLIT_CACHE.items() if e[0]() is None]
+    for k in dead:
+        del _SPLIT_CACHE[k]
+    if len(_SPLIT_CACHE) > 64:
+        _SPLIT_CACHE.clear()
+    _SPLIT_CACHE[(kind, id(x))] = (weakref.ref(x), x._version, x.data_ptr(), value)
+
+
 def gemm_profile_start() -> None:
     """Record a CUDA-event pair around every GEMM kernel launch (bench.py's live roofline measurement)."""
     global _GEMM_EVENTS
@@ -192,10 +211,8 @@ def gemm_profile_stop():
 
 def f16_split_rows(x: Tensor, cache: bool = False):
     """x[r,:] * s_r = hi + 2^-11 lo with hi, lo fp16 and s_r a power of two; returns (hi, lo, 1/s)."""
-    key = None
     if cache:
-        key = ("f16", x.data_ptr(), x._version, tuple(x.shape), x.device.index)
-        hit = _SPLIT_CACHE.get(key)
+        hit = _cache_get("f16", x)
         if hit is not None:
             return hit
     rows, K = x.shape
@@ -205,28 +222,22 @@ def f16_split_rows(x: Tensor, cache: bool = False):
     rc = _lib.lib().fpm_f16_split_rows(_chk(x, "x"), hi.data_ptr(), lo.data_ptr(), inv.data_ptr(), rows, K, _stream())
     _lib.check(rc, "fpm_f16_split_rows"); _count()
     if cache:
-        if len(_SPLIT_CACHE) > 64:
-            _SPLIT_CACHE.clear()
-        _SPLIT_CACHE[key] = (hi, lo, inv)
+        _cache_put("f16", x, (hi, lo, inv))
     return hi, lo, inv
 
 
 def tf32_split(x: Tensor, cache: bool = False):
     """x = hi + lo with both parts exactly representable in tf32.  ``cache=True`` memoises the split of a
     weight matrix (keyed on storage + version), so static weights are split once, not per forward."""
-    key = None
     if cache:
-        key = (x.data_ptr(), x._version, tuple(x.shape), x.device.index)
-        hit = _SPLIT_CACHE.get(key)
+        hit = _cache_get("tf32", x)
         if hit is not None:
             return hit
     hi, lo = torch.empty_like(x), torch.empty_like(x)
     rc = _lib.lib().fpm_tf32_split(_chk(x, "x"), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream())
     _lib.check(rc, "fpm_tf32_split"); _count()
     if cache:
-        if len(_SPLIT_CACHE) > 64:
-            _SPLIT_CACHE.clear()
-        _SPLIT_CACHE[key] = (hi, lo)
+        _cache_put("tf32", x, (hi, lo))
     return hi, lo
 
 
@@ -247,29 +258,32 @@ def csr_by_dst(edge_index: Tensor, ptr: Tensor, eptr: Tensor, total_nodes: int, 
 
 
 def spline_gather_max(Y: Tensor, xin: Optional[Tensor], edge_index: Tensor, pseudo: Tensor, in_ptr: Tensor,
-                      in_eid: Tensor, bias: Tensor, mode: int, kernel_size: int = 5) -> Tensor:
+                      in_eid: Tensor, bias: Tensor, mode: int, kernel_size: int = 5, want_argmax: bool = False):
     total, Cc = Y.shape[0], bias.shape[0]
     out = torch.empty((total, Cc), dtype=torch.float32, device=Y.device)
+    arg = torch.empty((total, Cc), dtype=torch.int32, device=Y.device) if want_argmax else None
     rc = _lib.lib().fpm_spline_gather_max(_chk(Y, "Y"), _chk(xin, "xin"), _chk(edge_index[0], "edge_index[0]", torch.int64),
                                           _chk(pseudo, "pseudo"), _chk(in_ptr, "in_ptr", torch.int32),
                                           _chk(in_eid, "in_eid", torch.int32), _chk(bias, "bias"), out.data_ptr(),
-                                          total, Cc, kernel_size, mode, _stream())
+                                          arg.data_ptr() if want_argmax else None, total, Cc, kernel_size, mode,
+                                          _stream())
     _lib.check(rc, "fpm_spline_gather_max"); _count()
-    return out
+    return (out, arg) if want_argmax else out
 
 
 # ---------------------------------------------------------------------------------------------------
 # affinities
 # ---------------------------------------------------------------------------------------------------
 def affinity_nodes(XA: Tensor, XB: Tensor, coeff: Tensor, ptrA: Tensor, ptrB: Tensor, Rmax: int, Cmax: int,
-                   scale: float = 1.0, want_t: bool = True):
+                   scale: float = 1.0, want_t: bool = True, raw: bool = False):
     B = coeff.shape[0]
     out = torch.empty((B, Rmax, Cmax), dtype=torch.float32, device=XA.device)
     out_t = torch.empty((B, Cmax, Rmax), dtype=torch.float32, device=XA.device) if want_t else None
     rc = _lib.lib().fpm_affinity(_chk(XA, "XA"), _chk(XB, "XB"), _chk(coeff, "coeff"),
                                  _chk(ptrA, "ptrA", torch.int64), _chk(ptrB, "ptrB", torch.int64),
                                  None, None, None, None, 0, 0, out.data_ptr(),
-                                 out_t.data_ptr() if want_t else None, B, Rmax, Cmax, XA.shape[1], scale, _stream())
+                                 out_t.data_ptr() if want_t else None, B, Rmax, Cmax, XA.shape[1], scale, int(raw),
+                                 _stream())
     _lib.check(rc, "fpm_affinity"); _count()
     return out, out_t
 
@@ -282,8 +296,25 @@ def affinity_edges(XA: Tensor, XB: Tensor, coeff: Tensor, eptrA: Tensor, eptrB: 
                                  _chk(eptrA, "eptrA", torch.int64), _chk(eptrB, "eptrB", torch.int64),
                                  _chk(eidxA, "edge_index A", torch.int64), _chk(eidxB, "edge_index B", torch.int64),
                                  eidxA.shape[1], eidxB.shape[1], out.data_ptr(), None, B, Rmax, Cmax, XA.shape[1],
-                                 scale, _stream())
+                                 scale, 0, _stream())
     _lib.check(rc, "fpm_affinity"); _count()
+    return out
+
+
+def affinity_edges_factored(XA: Tensor, XB: Tensor, coeff: Tensor, ptrA: Tensor, ptrB: Tensor, eptrA: Tensor,
+                            eptrB: Tensor, eidxA: Tensor, eidxB: Tensor, n1max: int, n2max: int, e1max: int,
+                            e2max: int, scale: float = 0.5) -> Tensor:
+    """Ke from the [n1, n2] node products by linearity (edge feature = x[src] - x[dst]); see gemm_simt.cu."""
+    B = coeff.shape[0]
+    P, _ = affinity_nodes(XA, XB, coeff, ptrA, ptrB, n1max, n2max, want_t=False, raw=True)
+    out = torch.empty((B, e1max, e2max), dtype=torch.float32, device=XA.device)
+    rc = _lib.lib().fpm_affinity_edges_factored(P.data_ptr(), _chk(eidxA, "edge_index A", torch.int64),
+                                                _chk(eptrA, "eptrA", torch.int64), _chk(ptrA, "ptrA", torch.int64),
+                                                _chk(eidxB, "edge_index B", torch.int64),
+                                                _chk(eptrB, "eptrB", torch.int64), _chk(ptrB, "ptrB", torch.int64),
+                                                eidxA.shape[1], eidxB.shape[1], out.data_ptr(), B, n1max, n2max,
+                                                e1max, e2max, scale, _stream())
+    _lib.check(rc, "fpm_affinity_edges_factored"); _count()
     return out
 
 
@@ -455,3 +486,136 @@ def greedy_perm(x: Tensor, top_indices: Tensor, ks: Tensor) -> Tensor:
                                     B, R, Cc, top_indices.shape[1], _stream())
     _lib.check(rc, "fpm_greedy_perm"); _count()
     return x
+
+
+# ---------------------------------------------------------------------------------------------------
+# training: vector-Jacobian products (wired into autograd by fpmatch/autograd.py)
+# ---------------------------------------------------------------------------------------------------
+def node_features_bwd(dX: Tensor, P: Tensor, ns: Tensor, ptr: Tensor, shape1, shape2, ori_size):
+    """dX [total, C1+C2] -> gradients of the prepared channels-last maps [B,H1*W1,C1], [B,H2*W2,C2]."""
+    B, nmax = P.shape[0], P.shape[1]
+    (C1, H1, W1), (C2, H2, W2) = shape1, shape2
+    d1 = torch.empty((B, H1 * W1, C1), dtype=torch.float32, device=dX.device)
+    d2 = torch.empty((B, H2 * W2, C2), dtype=torch.float32, device=dX.device)
+    rc = _lib.lib().fpm_node_features_bwd(_chk(dX, "dX"), _chk(P, "P"), _chk(ns, "ns", torch.int64),
+                                          _chk(ptr, "ptr", torch.int64), d1.data_ptr(), d2.data_ptr(), B, nmax,
+                                          C1, H1, W1, C2, H2, W2, float(ori_size[0]), float(ori_size[1]), _stream())
+    _lib.check(rc, "fpm_node_features_bwd"); _count(2)
+    return d1, d2
+
+
+def fmap_prep_bwd(fmap: Tensor, dy_nhwc: Tensor) -> Tensor:
+    B, Cc, Hf, Wf = fmap.shape
+    dx = torch.empty_like(fmap)
+    rc = _lib.lib().fpm_fmap_prep_bwd(_chk(fmap, "fmap"), _chk(dy_nhwc, "dy"), dx.data_ptr(), B, Cc, Hf, Wf, _stream())
+    _lib.check(rc, "fpm_fmap_prep_bwd"); _count()
+    return dx
+
+
+def spline_scatter_bwd(G: Tensor, argmax: Tensor, edge_index: Tensor, pseudo: Tensor, out_ptr: Tensor,
+                       out_eid: Tensor, kernel_size: int = 5) -> Tensor:
+    total, Cc = G.shape
+    NS = kernel_size * kernel_size + 1
+    dY = torch.empty((total, NS * Cc), dtype=torch.float32, device=G.device)
+    rc = _lib.lib().fpm_spline_scatter_bwd(_chk(G, "G"), _chk(argmax, "argmax", torch.int32),
+                                           _chk(edge_index[1], "edge_index[1]", torch.int64), _chk(pseudo, "pseudo"),
+                                           _chk(out_ptr, "out_ptr", torch.int32), _chk(out_eid, "out_eid", torch.int32),
+                                           dY.data_ptr(), total, Cc, kernel_size, _stream())
+    _lib.check(rc, "fpm_spline_scatter_bwd"); _count()
+    return dY
+
+
+def transpose_pad(x: Tensor, multiple: int = 8) -> Tensor:
+    """[R, C] -> [C, ldo] with ldo = R rounded up to `multiple`, zero padded (K-major GEMM operand)."""
+    R, Cc = x.shape
+    ldo = (R + multiple - 1) // multiple * multiple
+    out = torch.empty((Cc, ldo), dtype=torch.float32, device=x.device)
+    rc = _lib.lib().fpm_transpose_f32(_chk(x, "x"), out.data_ptr(), R, Cc, ldo, _stream())
+    _lib.check(rc, "fpm_transpose_f32"); _count()
+    return out
+
+
+def bmm_ragged(Mat: Tensor, trans: bool, X: Tensor, ptrX: Tensor, ptrO: Tensor, total_out: int,
+               coeff_in: Optional[Tensor] = None, coeff_out: Optional[Tensor] = None) -> Tensor:
+    B, Rmax, Cmax = Mat.shape
+    D = X.shape[1]
+    out = torch.empty((total_out, D), dtype=torch.float32, device=X.device)
+    rc = _lib.lib().fpm_bmm_ragged(_chk(Mat, "Mat"), B, Rmax, Cmax, int(trans), _chk(X, "X"),
+                                   _chk(ptrX, "ptrX", torch.int64), _chk(ptrO, "ptrO", torch.int64),
+                                   _chk(coeff_in, "coeff_in"), _chk(coeff_out, "coeff_out"), out.data_ptr(), D,
+                                   _stream())
+    _lib.check(rc, "fpm_bmm_ragged"); _count()
+    return out
+
+
+def segment_rowdot(X: Tensor, Y: Tensor, ptr: Tensor) -> Tensor:
+    B, D = ptr.numel() - 1, X.shape[1]
+    out = torch.empty((B, D), dtype=torch.float32, device=X.device)
+    rc = _lib.lib().fpm_segment_rowdot(_chk(X, "X"), _chk(Y, "Y"), _chk(ptr, "ptr", torch.int64), out.data_ptr(),
+                                       B, D, _stream())
+    _lib.check(rc, "fpm_segment_rowdot"); _count()
+    return out
+
+
+GNN_GRAD_SIZES = lambda cin: [16 * cin, 16, 16 * cin, 16 * cin, 16, 256, 16, 16, 1]
+
+
+def gnn_layer_bwd(xprev: Optional[Tensor], mprev_t: Tensor, csr1, csr2, ocsr1, ocsr2, n1: Tensor, n2: Tensor,
+                  weights, dxout: Tensor, dscore: Tensor, n1max: int, n2max: int, e1max: int, e2max: int):
+    """Returns (dxprev [B,N,16] or None, dm [B,n1max,n2max], list of the 9 weight gradients)."""
+    B = mprev_t.shape[0]
+    N = n1max * n2max
+    dev = mprev_t.device
+    cin = 1 if xprev is None else 17
+    cp = (cin + 3) // 4 * 4
+    dxprev = torch.empty((B, N, 16), dtype=torch.float32, device=dev) if cin > 1 else None
+    dm = torch.empty((B, n1max, n2max), dtype=torch.float32, device=dev)
+    gagg = torch.empty((B, N, cp), dtype=torch.float32, device=dev)
+    sizes = GNN_GRAD_SIZES(cin)
+    grads = torch.zeros((sum(sizes),), dtype=torch.float32, device=dev)
+    for i, w in enumerate(weights):
+        _chk(w, f"gnn weight {i}")
+    rc = _lib.lib().fpm_gnn_layer_bwd(
+        _chk(xprev, "xprev"), _chk(mprev_t, "mprev_t"),
+        _chk(csr1[0], "in_ptr1", torch.int32), _chk(csr1[1], "in_src1", torch.int32),
+        _chk(csr2[0], "in_ptr2", torch.int32), _chk(csr2[1], "in_src2", torch.int32),
+        _chk(ocsr1[0], "out_ptr1", torch.int32), _chk(ocsr1[1], "out_dst1", torch.int32),
+        _chk(ocsr2[0], "out_ptr2", torch.int32), _chk(ocsr2[1], "out_dst2", torch.int32),
+        _chk(n1, "n1", torch.int64), _chk(n2, "n2", torch.int64), _ptr_array(weights),
+        _chk(dxout, "dxout"), _chk(dscore, "dscore"), dxprev.data_ptr() if cin > 1 else None, dm.data_ptr(),
+        gagg.data_ptr(), grads.data_ptr(), B, n1max, n2max, e1max, e2max, cin, _stream())
+    _lib.check(rc, "fpm_gnn_layer_bwd"); _count(2)
+    return dxprev, dm, list(torch.split(grads, sizes))
+
+
+def sinkhorn_log_bwd(s: Tensor, n1: Optional[Tensor], n2: Optional[Tensor], gout: Tensor, max_iter: int,
+                     tau: float, dummy_row: bool) -> Tensor:
+    B, R, Cc = s.shape
+    L = _lib.lib()
+    gs = torch.empty_like(s)
+    wsb = int(L.fpm_sinkhorn_bwd_workspace_bytes(B, R, Cc, int(max_iter)))
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=s.device) if wsb else None
+    n1 = _i64(n1) if n1 is not None else None
+    n2 = _i64(n2) if n2 is not None else None
+    rc = L.fpm_sinkhorn_log_bwd(_chk(s, "s"), _chk(n1, "nrows", torch.int64), _chk(n2, "ncols", torch.int64),
+                                _chk(gout, "gout"), gs.data_ptr(), ws.data_ptr() if ws is not None else None,
+                                B, R, Cc, int(max_iter), float(tau), int(bool(dummy_row)), _stream())
+    _lib.check(rc, "fpm_sinkhorn_log_bwd"); _count()
+    return gs
+
+
+def soft_topk_bwd(scores: Tensor, ks: Tensor, n1: Optional[Tensor], n2: Optional[Tensor], gout: Tensor,
+                  max_iter: int, tau: float) -> Tensor:
+    B, R, Cc = scores.shape
+    L = _lib.lib()
+    gs = torch.empty_like(scores)
+    wsb = int(L.fpm_soft_topk_bwd_workspace_bytes(B, R, Cc))
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=scores.device) if wsb else None
+    n1 = _i64(n1) if n1 is not None else None
+    n2 = _i64(n2) if n2 is not None else None
+    ks = ks.to(torch.float32).contiguous()
+    rc = L.fpm_soft_topk_bwd(_chk(scores, "scores"), _chk(ks, "ks"), _chk(n1, "nrows", torch.int64),
+                             _chk(n2, "ncols", torch.int64), _chk(gout, "gout"), gs.data_ptr(),
+                             ws.data_ptr() if ws is not None else None, B, R, Cc, int(max_iter), float(tau), _stream())
+    _lib.check(rc, "fpm_soft_topk_bwd"); _count()
+    return gs

@@ -135,6 +135,7 @@ class Net(CNN):
         # The reference computes the edge affinity Ke although SAGEConv drops its values
         # (SURVEY.md section 0.4); keep paying for it by default so throughput comparisons are honest.
         self.compute_dead_ke = True
+        self.ke_mode = "factored"
 
     # ------------------------------------------------------------------------------------------
     def forward(self, data_dict, regression=True):
@@ -148,6 +149,8 @@ class Net(CNN):
                 nodes = self.node_layers(image)
                 edges = self.edge_layers(nodes)
                 fmaps.append((nodes, edges))
+        if self.training and torch.is_grad_enabled():
+            return self.matching_head_train(data_dict, fmaps)
         return self.matching_head(data_dict, fmaps)
 
     @staticmethod
@@ -163,6 +166,95 @@ class Net(CNN):
             dst = torch.where(valid, H.argmax(dim=1), torch.full_like(valid, -1, dtype=torch.long))
             tables.append(torch.stack([src, dst], 1).to(torch.int32).contiguous())
         return tables
+
+    def matching_head_train(self, data_dict, fmaps):
+        """Differentiable head for ``model.train()`` (stage-1..6 steps of train.py): the same kernels as
+        ``matching_head`` wrapped in ``fpmatch.autograd`` Functions whose backward is hand-written CUDA.  The
+        AFA-U k-branch reads ``ss.detach()`` (ngm.py:400), soft-top-k uses the ground-truth k (ngm.py:418-428)."""
+        from fpmatch import autograd as fa
+        points, n_points, graphs = data_dict['Ps'], data_dict['ns'], data_dict['pyg_graphs']
+        dev = fmaps[0][0].device
+        if dev.type != 'cuda':
+            raise RuntimeError("fpmatch: the matching head runs on CUDA (sm_100a) only; there is no CPU path")
+        B = data_dict['gt_perm_mat'].shape[0]
+        n1 = n_points[0].to(dev, torch.int64).contiguous()
+        n2 = n_points[1].to(dev, torch.int64).contiguous()
+        ns = [n1, n2]
+        n1max, n2max = points[0].shape[1], points[1].shape[1]
+        tables = self._edge_tables(data_dict, dev)
+        e1max, e2max = tables[0].shape[2], tables[1].shape[2]
+
+        feats, offs, globals_ = [], [], []
+        for gi, ((nodes, edges), P, graph) in enumerate(zip(fmaps, points, graphs)):
+            nodes = nodes.to(torch.float32); edges = edges.to(torch.float32)
+            globals_.append(edges.amax(dim=(2, 3)))                     # final_layers = AdaptiveMaxPool2d(1,1)
+            ptr, eptr = graph_offsets(graph)
+            ptr, eptr = ptr.to(dev).contiguous(), eptr.to(dev).contiguous()
+            total = graph.x.shape[0]
+            x0 = fa.NodeFeaturesFn.apply(nodes, edges, P.to(dev, torch.float32).contiguous(), ns[gi], ptr, total,
+                                         self.rescale)
+            gctx = fa.GraphCtx(graph.edge_index.to(dev), graph.edge_attr.to(dev, torch.float32), ptr, eptr, total,
+                               tables[gi].shape[2])
+            convs = self.message_pass_node_features.mp_network.convs
+            h = fa.SplineConvFn.apply(x0, convs[0].weight, convs[0].root, convs[0].bias, None,
+                                      convs[0].packed_weight(), gctx, 0, convs[0].kernel_size)
+            x = fa.SplineConvFn.apply(h, convs[1].weight, convs[1].root, convs[1].bias, x0,
+                                      convs[1].packed_weight(), gctx, 1, convs[1].kernel_size)
+            graph.x = x
+            feats.append(x)
+            offs.append((ptr, eptr))
+
+        gcat = torch.cat(globals_, dim=-1)
+        gn = gcat / torch.norm(gcat, dim=1, keepdim=True)                # normalize_over_channels, ngm.py:268
+        A = self.vertex_affinity.A
+        coeff_v = torch.tanh(torch.nn.functional.linear(gn, A.weight, A.bias))
+        Kp, Kp_t = fa.AffinityFn.apply(feats[0], feats[1], coeff_v, offs[0][0], offs[1][0], n1max, n2max)
+        Ke = None
+        if self.compute_dead_ke:                                         # values never reach an output (SURVEY 0.4)
+            with torch.no_grad():
+                coeff_e = self.edge_affinity.fused_coefficients(gcat)
+                Ke = ops.affinity_edges_factored(feats[0].detach(), feats[1].detach(), coeff_e, offs[0][0], offs[1][0],
+                                                 offs[0][1], offs[1][1], graphs[0].edge_index.to(dev).contiguous(),
+                                                 graphs[1].edge_index.to(dev).contiguous(), n1max, n2max, e1max,
+                                                 e2max, scale=0.5)
+
+        swap = lambda t: torch.stack((t[:, 1], t[:, 0]), 1).contiguous()
+        meta = {"csr1": ops.assoc_in_csr(tables[0], n1max), "csr2": ops.assoc_in_csr(tables[1], n2max),
+                "ocsr1": ops.assoc_in_csr(swap(tables[0]), n1max), "ocsr2": ops.assoc_in_csr(swap(tables[1]), n2max),
+                "n1": n1, "n2": n2, "n1max": n1max, "n2max": n2max, "e1max": e1max, "e2max": e2max,
+                "layers": self.gnn_layer, "sk_iter": self.gnn_layer_0.sk.max_iter, "sk_tau": self.gnn_layer_0.sk.tau}
+        params = []
+        for i in range(self.gnn_layer):
+            L = getattr(self, 'gnn_layer_{}'.format(i))
+            params += [L.conv2.lin_l.weight, L.conv2.lin_l.bias, L.conv2.lin_r.weight, L.n_self_func[0].weight,
+                       L.n_self_func[0].bias, L.n_self_func[2].weight, L.n_self_func[2].bias, L.classifier.weight,
+                       L.classifier.bias]
+        params += [self.classifier.weight, self.classifier.bias]
+        s = fa.NgmSolverFn.apply(Kp_t, meta, *params)
+        ss = fa.SinkhornFn.apply(s, n1, n2, self.sinkhorn.max_iter, self.sinkhorn.tau, True)
+
+        min_point_tensor = torch.minimum(n1, n2).to(torch.float32)
+        gt_perm = data_dict['gt_perm_mat'].to(dev)
+        gt_ks = gt_perm.sum(dim=(1, 2)).to(torch.float32)
+        if self.regression:
+            raise NotImplementedError("training the AFA-U k-branch (stages 2-5) is not implemented yet; "
+                                      "stage 1 / Net(regression=False) is")
+        ks = gt_ks / min_point_tensor
+        k_scaled = ks * min_point_tensor
+        ss_out = fa.SoftTopkFn.apply(ss, gt_ks, n1, n2, SK_ITER_NUM, self.tau)
+        with torch.no_grad():
+            _, x = ops.lap_topk(ss_out.detach(), n1, n2, ks=k_scaled, want_hungarian=False, want_perm=True)
+        matched_sim = s * x
+        cls_logits = self.match_cls(matched_sim)
+        cls_prob = torch.sigmoid(cls_logits)
+        cls_loss = torch.tensor(0.0, device=dev)
+        if 'label' in data_dict:
+            label_tensor = data_dict['label'].to(dev).view(-1).float()
+            cls_loss = torch.nn.functional.binary_cross_entropy_with_logits(cls_logits, label_tensor)
+        data_dict.update({'ds_mat': ss_out, 'perm_mat': x, 'ks_loss': 0.0, 'ks_error': 0.0, 'cls_loss': cls_loss,
+                          'cls_prob': cls_prob, 'k_prob': ks})
+        data_dict['_fpm_inter'] = {'node_feat': feats, 'Kp': Kp, 'Ke': Ke, 's': s, 'ss': ss, 'k_scaled': k_scaled}
+        return data_dict
 
     @torch.no_grad()
     def matching_head(self, data_dict, fmaps):
@@ -205,9 +297,14 @@ class Net(CNN):
         Ke = None
         if self.compute_dead_ke:
             coeff_e = self.edge_affinity.fused_coefficients(gcat)
-            Ke = ops.affinity_edges(feats[0], feats[1], coeff_e, offs[0][1], offs[1][1],
-                                    graphs[0].edge_index.to(dev).contiguous(),
-                                    graphs[1].edge_index.to(dev).contiguous(), e1max, e2max, scale=0.5)
+            ei1 = graphs[0].edge_index.to(dev).contiguous()
+            ei2 = graphs[1].edge_index.to(dev).contiguous()
+            if self.ke_mode == "factored":      # same values through linearity, 33x fewer FLOPs
+                Ke = ops.affinity_edges_factored(feats[0], feats[1], coeff_e, offs[0][0], offs[1][0], offs[0][1],
+                                                 offs[1][1], ei1, ei2, n1max, n2max, e1max, e2max, scale=0.5)
+            else:                               # "direct": the reference's e1 x 768 x e2 product
+                Ke = ops.affinity_edges(feats[0], feats[1], coeff_e, offs[0][1], offs[1][1], ei1, ei2,
+                                        e1max, e2max, scale=0.5)
 
         # ---- NGM layers on the factorised association graph (ngm.py:326-362)
         csr1 = ops.assoc_in_csr(tables[0], n1max)

@@ -92,8 +92,9 @@ int fpm_gemm_set_trace(void* buf, int cap);
 int fpm_csr_by_dst(const long long* edge_dst, const long long* ptr, const long long* eptr, int* in_ptr,
                    int* in_eid, int B, int total_nodes, int max_edges_per_graph, void* stream);
 int fpm_spline_gather_max(const float* Y, const float* xin, const long long* edge_src, const float* pseudo,
-                          const int* in_ptr, const int* in_eid, const float* bias, float* out,
+                          const int* in_ptr, const int* in_eid, const float* bias, float* out, int* argmax,
                           int total_nodes, int C, int kernel_size, int mode, void* stream);
+                          /* argmax (optional, training): [total_nodes,C] int32 winning edge id per channel */
 
 /* ---- (2) affinities --------------------------------------------------------------------------------------
  * Replaces InnerProductWithWeightsAffinity.forward (src/model/affinity_layer.py:11-22) for Kp (node mode:
@@ -104,7 +105,14 @@ int fpm_spline_gather_max(const float* Y, const float* xin, const long long* edg
 int fpm_affinity(const float* XA, const float* XB, const float* coeff, const long long* ptrA,
                  const long long* ptrB, const long long* eptrA, const long long* eptrB, const long long* eidxA,
                  const long long* eidxB, int EA, int EB, float* out, float* out_t, int B, int Rmax, int Cmax,
-                 int Kdim, float scale, void* stream);
+                 int Kdim, float scale, int raw, void* stream);   /* raw = 1: plain dot products, no softplus */
+/* Ke through linearity: with P = raw node products (X1 (.) c_edge) X2^T [B,Rn,Cn] (fpm_affinity, raw = 1),
+ * out[b,k1,k2] = scale * (softplus(P[s1,s2] - P[s1,d2] - P[d1,s2] + P[d1,d2]) - 0.5); 33x fewer FLOPs than
+ * the reference's e1 x 768 x e2 product (ngm.py:282-287). */
+int fpm_affinity_edges_factored(const float* P, const long long* eidxA, const long long* eptrA,
+                                const long long* ptrA, const long long* eidxB, const long long* eptrB,
+                                const long long* ptrB, int EA, int EB, float* out, int B, int Rn, int Cn,
+                                int e1max, int e2max, float scale, void* stream);
 
 /* ---- (2)/(3b) association-graph GNN -------------------------------------------------------------------------
  * Replaces construct_sparse_aff_mat + SparseTensor + PYGNNLayer.forward (utils/factorize_graph_matching.py:57-95,
@@ -166,6 +174,55 @@ int fpm_lap_topk(const float* ds, const long long* n1, const long long* n2, cons
                  float* perm_out, int* status, int B, int R, int C, void* stream);
 int fpm_greedy_perm(float* x, const long long* top_indices, const float* ks, int B, int R, int C, int L,
                     void* stream);
+
+/* ---- training: hand-written backward of the differentiable ops -----------------------------------------------
+ * The reference differentiates its forward with torch autograd (train.py / src/train/training_loop.py:33-64 call
+ * loss.backward() on PermutationLoss(ds_mat)); these entry points are the vector-Jacobian products of the kernels
+ * above, wired into torch.autograd.Function objects by fpmatch/autograd.py.  Row of SURVEY.md section 8(a) in brackets.
+ *
+ * [A1] fpm_node_features_bwd: dX [total,C1+C2] -> gradients of the two PREPARED (channels-last, normalised) maps;
+ *      fpm_fmap_prep_bwd: through the channel L2 normalisation back to the raw NCHW map (ngm.py:65-67,241-251).
+ * [A2] fpm_spline_scatter_bwd: G [total,C] (gradient of the conv output before relu / residual scaling) + the
+ *      argmax edge ids -> dY [total, KS*KS+1, C]; out_ptr/out_eid = edge lists grouped by SOURCE node
+ *      (fpm_csr_by_dst on edge_index[0]).  dX = dY W and dW = dY^T X are the dense GEMMs above; fpm_transpose_f32
+ *      makes their K-major operands ([R,C] -> [C,ldo], zero padded).
+ * [A4] fpm_bmm_ragged: Out[ptrO[b]+i,:] = coeff_out[b,:] (.) sum_j M[b,i,j] (X[ptrX[b]+j,:] (.) coeff_in[b,:]) (trans = 1:
+ *      M[b,j,i]); fpm_segment_rowdot: out[b,:] = sum_{rows of pair b} X (.) Y.  Together: dX1, dX2, d coeff of
+ *      InnerProductWithWeightsAffinity (affinity_layer.py:11-19).
+ * [A7] fpm_gnn_layer_bwd: backward of fpm_gnn_layer (forward recomputed from its inputs); grads = flat fp32 buffer
+ *      lin_l.weight[16*cin] lin_l.bias[16] lin_r.weight[16*cin] n_self_func.0.weight[16*cin] .0.bias[16]
+ *      n_self_func.2.weight[256] .2.bias[16] classifier.weight[16] classifier.bias[1], accumulated (caller zeroes);
+ *      out_ptr/out_dst: out-neighbour lists (fpm_assoc_in_csr on the edge table with its two rows swapped);
+ *      gagg: scratch [B,N,4] (cin 1) / [B,N,20] (cin 17); dxprev [B,N,16], dm [B,n1max,n2max] are overwritten.
+ * [A8] fpm_sinkhorn_log_bwd: gout [B,R,C] -> gs [B,R,C] through the unrolled iterations (forward replayed on chip).
+ * [A10] fpm_soft_topk_bwd: gout [B,R,C] -> gscores [B,R,C]; anchors and k carry no gradient (soft_topk.py:27).
+ */
+int fpm_node_features_bwd(const float* dX, const float* P, const long long* ns, const long long* ptr,
+                          float* dnodes_nhwc, float* dedges_nhwc, int B, int nmax, int C1, int H1, int W1, int C2,
+                          int H2, int W2, float ori_w, float ori_h, void* stream);
+int fpm_fmap_prep_bwd(const float* fmap_nchw, const float* dy_nhwc, float* dx_nchw, int B, int C, int Hf, int Wf,
+                      void* stream);
+int fpm_spline_scatter_bwd(const float* G, const int* argmax, const long long* edge_dst, const float* pseudo,
+                           const int* out_ptr, const int* out_eid, float* dY, int total_nodes, int C,
+                           int kernel_size, void* stream);
+int fpm_transpose_f32(const float* src, float* dst, int R, int C, int ldo, void* stream);
+int fpm_bmm_ragged(const float* Mat, int B, int Rmax, int Cmax, int trans, const float* X, const long long* ptrX,
+                   const long long* ptrO, const float* coeff_in, const float* coeff_out, float* Out, int D,
+                   void* stream);
+int fpm_segment_rowdot(const float* X, const float* Y, const long long* ptr, float* out, int B, int D, void* stream);
+int fpm_gnn_layer_bwd(const float* xprev, const float* mprev_t, const int* in_ptr1, const int* in_src1,
+                      const int* in_ptr2, const int* in_src2, const int* out_ptr1, const int* out_dst1,
+                      const int* out_ptr2, const int* out_dst2, const long long* n1, const long long* n2,
+                      const float* const* weights, const float* dxout, const float* dscore, float* dxprev,
+                      float* dm, float* gagg, float* grads, int B, int n1max, int n2max, int e1max, int e2max,
+                      int cin, void* stream);
+long long fpm_sinkhorn_bwd_workspace_bytes(int B, int R, int C, int max_iter);
+int fpm_sinkhorn_log_bwd(const float* s, const long long* n1, const long long* n2, const float* gout, float* gs,
+                         void* workspace, int B, int R, int C, int max_iter, float tau, int dummy_row, void* stream);
+long long fpm_soft_topk_bwd_workspace_bytes(int B, int R, int C);
+int fpm_soft_topk_bwd(const float* scores, const float* ks, const long long* n1, const long long* n2,
+                      const float* gout, float* gscores, void* workspace, int B, int R, int C, int max_iter,
+                      float tau, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,8 +39,11 @@ def _pad_stack(ts: List[Tensor]) -> Tensor:
 def forward_head(p: Dict[str, Tensor], data: dict, fmaps, regression: bool = True,
                  training: bool = False, feature_align_loops: bool = False,
                  compute_ke: bool = True, stable_sort: bool = True,
-                 dtype: torch.dtype = torch.float32) -> dict:
-    p = {k: (v.detach().to(dtype) if v.is_floating_point() else v.detach()) for k, v in p.items()}
+                 dtype: torch.dtype = torch.float32, keep_graph: bool = False) -> dict:
+    """``keep_graph=True`` leaves the parameters attached so that torch autograd differentiates this restatement
+    exactly as it differentiates the reference's forward (used by oracle/train.py)."""
+    if not keep_graph:
+        p = {k: (v.detach().to(dtype) if v.is_floating_point() else v.detach()) for k, v in p.items()}
     points, n_points, graphs = data["Ps"], data["ns"], data["pyg_graphs"]
     B = data["gt_perm_mat"].shape[0]
     fa = ops.feature_align_loop if feature_align_loops else ops.feature_align
@@ -130,12 +133,12 @@ def forward_head(p: Dict[str, Tensor], data: dict, fmaps, regression: bool = Tru
     k_for_topk = gt_ks.view(-1) if training else ks.view(-1) * min_pts                    # :418-439
     ss_out = ops.soft_topk_prob(ss, k_for_topk, SK_ITER_NUM, SK_TAU, n_points[0], n_points[1])
     x = ops.hungarian(ss_out.to(torch.float32), n_points[0], n_points[1])                 # :444
-    top_indices = torch.argsort(x.mul(ss_out.to(torch.float32)).reshape(B, -1), descending=True,
+    top_indices = torch.argsort(x.mul(ss_out.detach().to(torch.float32)).reshape(B, -1), descending=True,
                                 dim=-1, stable=stable_sort)                               # :445-447
     k_greedy = ks.view(-1) * min_pts
     perm = ops.greedy_perm(torch.zeros(ss_out.shape), top_indices, k_greedy)              # :448-449
     matched_sim = s * perm.to(dtype)                                                      # :451
-    cls_logits = ops.match_classifier(matched_sim, p)
+    cls_logits = ops.match_classifier(matched_sim, p, training=training and keep_graph)
     cls_prob = torch.sigmoid(cls_logits)
     out = {
         "ds_mat": ss_out, "perm_mat": perm, "k_prob": ks, "cls_prob": cls_prob,

@@ -477,7 +477,7 @@ def match_classifier(m: Tensor, p: dict, training: bool = False, prefix: str = "
         x = F.relu(x)
         x = F.batch_norm(x, p[f"{prefix}.conv.{bn_i}.running_mean"], p[f"{prefix}.conv.{bn_i}.running_var"],
                          p[f"{prefix}.conv.{bn_i}.weight"], p[f"{prefix}.conv.{bn_i}.bias"],
-                         training=False, eps=1e-5)
+                         training=training, eps=1e-5)
         x = F.max_pool2d(x, 2)
     x = F.adaptive_avg_pool2d(x, 1).view(x.size(0), -1)
     return F.linear(x, p[f"{prefix}.fc.weight"], p[f"{prefix}.fc.bias"]).squeeze(-1)

@@ -371,6 +371,14 @@ def test_affinity_golden_and_edges(ops, oo):
         assert (Ke[b, ref.shape[0]:].cpu() == 0).all() and (Ke[b, :, ref.shape[1]:].cpu() == 0).all()
     report("affinity_edges", max_abs=worst)
     assert worst < 1e-5
+    # the linearity form (4-term gather over the [n1, n2] node products) gives the same values
+    n1max = int((g1.ptr[1:] - g1.ptr[:-1]).max()); n2max = int((g2.ptr[1:] - g2.ptr[:-1]).max())
+    Kf = ops.affinity_edges_factored(X1.to(DEV), X2.to(DEV), coeff, g1.ptr.to(DEV), g2.ptr.to(DEV), g1.eptr.to(DEV),
+                                     g2.eptr.to(DEV), g1.edge_index.to(DEV), g2.edge_index.to(DEV), n1max, n2max,
+                                     emax1, emax2, scale=0.5)
+    err = (Kf - Ke).abs().max().item()
+    report("affinity_edges_factored_vs_direct", max_abs=err)
+    assert err < 1e-5
 
 
 # ------------------------------------------------------------------------------------------------- GNN

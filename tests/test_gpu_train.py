@@ -1,0 +1,332 @@
+"""GPU parity of the TRAINING path (BASELINE.json config 3): every hand-written backward kernel against torch
+autograd through the CPU oracle on the same inputs, the full stage-1 loss gradient, and the 100-step loss
+trajectory (north-star bar: 1e-3 relative after 100 steps)."""
+import json
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+DEV = "cuda"
+
+
+def report(name, **kv):
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    with open(out / "parity_report.jsonl", "a") as f:
+        f.write(json.dumps({"test": name, **kv}) + "\n")
+
+
+def rel_err(a, b, floor=1e-30):
+    """max |a - b| / max(max |b|, floor) (b = oracle).  ``floor`` guards gradients that are zero in exact arithmetic
+    (e.g. the per-layer classifier bias: Sinkhorn is invariant to a constant shift, so autograd returns rounding
+    noise of ~1e-8 there) from a meaningless relative comparison."""
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp(min=floor)).item()
+
+
+# ------------------------------------------------------------------------------------------------- Sinkhorn
+@pytest.mark.parametrize("B,R,C,iters,ragged", [(3, 12, 12, 10, False), (4, 20, 24, 20, True), (2, 33, 33, 20, True),
+                                                (2, 100, 100, 20, False)])
+def test_sinkhorn_backward(B, R, C, iters, ragged):
+    from fpmatch import ops
+    from oracle import ops as oo
+    g = torch.Generator().manual_seed(B * 100 + R)
+    s = torch.randn(B, R, C, generator=g) * 0.3
+    n1 = torch.full((B,), R); n2 = torch.full((B,), C)
+    if ragged:
+        n1 = torch.randint(R // 2, R + 1, (B,), generator=g); n2 = torch.randint(C // 2, C + 1, (B,), generator=g)
+        n1[0], n2[0] = R, C
+    gout = torch.randn(B, R, C, generator=g)
+    sr = s.clone().requires_grad_(True)
+    out = oo.sinkhorn(sr, n1, n2, dummy_row=True, max_iter=iters, tau=0.05)
+    (out * gout).sum().backward()
+    gs = ops.sinkhorn_log_bwd(s.to(DEV), n1.to(DEV), n2.to(DEV), gout.to(DEV), iters, 0.05, True)
+    err = rel_err(gs, sr.grad)
+    report("sinkhorn_bwd", B=B, R=R, C=C, iters=iters, rel=err)
+    assert err < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------- soft-top-k
+@pytest.mark.parametrize("B,n,ks", [(3, 10, [4.0, 10.0, 2.5]), (2, 30, [30.0, 11.0]), (2, 100, [100.0, 57.0])])
+def test_soft_topk_backward(B, n, ks):
+    from fpmatch import ops
+    from oracle import ops as oo
+    g = torch.Generator().manual_seed(n)
+    n1 = torch.full((B,), n); n2 = torch.full((B,), n)
+    if n == 30:
+        n1[1], n2[1] = 22, 27
+    ss = oo.sinkhorn(torch.randn(B, n, n, generator=g), n1, n2, dummy_row=True, max_iter=10, tau=0.05)
+    ks = torch.tensor(ks)
+    gout = torch.randn(B, n, n, generator=g)
+    sr = ss.clone().requires_grad_(True)
+    out = oo.soft_topk_prob(sr, ks, 10, 0.01, n1, n2)
+    (out * gout).sum().backward()
+    gs = ops.soft_topk_bwd(ss.to(DEV), ks.to(DEV), n1.to(DEV), n2.to(DEV), gout.to(DEV), 10, 0.01)
+    err = rel_err(gs, sr.grad)
+    report("soft_topk_bwd", B=B, n=n, rel=err)
+    assert err < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------- stages
+def _setup(B=4, n=20, seed=3, ragged=False):
+    from fpmatch import synth
+    from src.model.ngm import Net
+    torch.manual_seed(0)
+    net = Net(regression=False)
+    data = synth.make_batch(B, n, seed=seed, imposter_every=0, ragged=ragged, with_kron=True)
+    data.pop("label")            # config 3: genuine pairs from get_pair(), which carries no label -> cls_loss = 0
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    return net, sd, data
+
+
+def test_node_features_backward():
+    from fpmatch import autograd as fa, synth
+    from oracle import ops as oo
+    net, sd, data = _setup(ragged=True)
+    nodes, edges = data["fmaps"][0]
+    P, ns, graph = data["Ps"][0], data["ns"][0], data["pyg_graphs"][0]
+    a = nodes.clone().requires_grad_(True); b = edges.clone().requires_grad_(True)
+    U = oo.concat_features(oo.feature_align(oo.normalize_over_channels(a), P, ns, (320, 240)), ns)
+    Fe = oo.concat_features(oo.feature_align(oo.normalize_over_channels(b), P, ns, (320, 240)), ns)
+    x0 = torch.cat((U, Fe), 1)
+    g = torch.randn(x0.shape, generator=torch.Generator().manual_seed(1))
+    (x0 * g).sum().backward()
+    ag = nodes.to(DEV).requires_grad_(True); bg = edges.to(DEV).requires_grad_(True)
+    X = fa.NodeFeaturesFn.apply(ag, bg, P.to(DEV), ns.to(DEV), graph.ptr.to(DEV), x0.shape[0], (320, 240))
+    assert (X.detach().cpu() - x0.detach()).abs().max() < 1e-6
+    (X * g.to(DEV)).sum().backward()
+    e1, e2 = rel_err(ag.grad, a.grad), rel_err(bg.grad, b.grad)
+    report("node_features_bwd", nodes=e1, edges=e2)
+    assert e1 < 1e-5 and e2 < 1e-5
+
+
+def test_spline_conv_backward():
+    from fpmatch import autograd as fa
+    from oracle import ops as oo
+    net, sd, data = _setup(B=3, n=16, ragged=True)
+    graph = data["pyg_graphs"][0]
+    total = graph.x.shape[0]
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(total, 768, generator=gen) * 0.05
+    conv = net.message_pass_node_features.mp_network.convs[0]
+    with torch.no_grad():
+        conv.bias.copy_(torch.randn(768, generator=gen) * 0.01)
+    g = torch.randn(total, 768, generator=gen)
+    for mode in (0, 1):
+        w = conv.weight.detach().clone().requires_grad_(True); r = conv.root.detach().clone().requires_grad_(True)
+        bb = conv.bias.detach().clone().requires_grad_(True); xr = x.clone().requires_grad_(True)
+        o = oo.spline_conv(xr, graph.edge_index, graph.edge_attr, w, r, bb)
+        o = torch.relu(o) if mode == 0 else xr + 0.1 * o
+        (o * g).sum().backward()
+        convg = conv.to(DEV)
+        for q in convg.parameters():
+            q.grad = None
+        gctx = fa.GraphCtx(graph.edge_index.to(DEV), graph.edge_attr.to(DEV), graph.ptr.to(DEV), graph.eptr.to(DEV),
+                           total, int((graph.eptr[1:] - graph.eptr[:-1]).max()))
+        xg = x.to(DEV).requires_grad_(True)
+        og = fa.SplineConvFn.apply(xg, convg.weight, convg.root, convg.bias, xg if mode == 1 else None,
+                                   convg.packed_weight(), gctx, mode, 5)
+        fwd = (og.detach().cpu() - o.detach()).abs().max().item()
+        (og * g.to(DEV)).sum().backward()
+        errs = {"x": rel_err(xg.grad, xr.grad), "weight": rel_err(convg.weight.grad, w.grad),
+                "root": rel_err(convg.root.grad, r.grad), "bias": rel_err(convg.bias.grad, bb.grad)}
+        report("spline_conv_bwd", mode=mode, fwd=fwd, **errs)
+        assert fwd < 1e-5 and max(errs.values()) < 1e-4, errs
+        conv = conv.cpu()
+
+
+def test_affinity_backward():
+    from fpmatch import autograd as fa
+    from oracle import ops as oo
+    gen = torch.Generator().manual_seed(5)
+    n1 = [7, 12, 9]; n2 = [10, 12, 5]
+    X1 = torch.randn(sum(n1), 768, generator=gen) * 0.1; X2 = torch.randn(sum(n2), 768, generator=gen) * 0.1
+    coeff = torch.tanh(torch.randn(3, 768, generator=gen))
+    ptr1 = torch.tensor([0, 7, 19, 28]); ptr2 = torch.tensor([0, 10, 22, 27])
+    g = torch.randn(3, 12, 12, generator=gen)
+    a = X1.clone().requires_grad_(True); b = X2.clone().requires_grad_(True); c = coeff.clone().requires_grad_(True)
+    tot = 0
+    for i in range(3):
+        Kb = torch.nn.functional.softplus((a[ptr1[i]:ptr1[i + 1]] * c[i]) @ b[ptr2[i]:ptr2[i + 1]].t()) - 0.5
+        tot = tot + (Kb * g[i, :n1[i], :n2[i]]).sum()
+    tot.backward()
+    ag = X1.to(DEV).requires_grad_(True); bg = X2.to(DEV).requires_grad_(True); cg = coeff.to(DEV).requires_grad_(True)
+    Kp, Kp_t = fa.AffinityFn.apply(ag, bg, cg, ptr1.to(DEV), ptr2.to(DEV), 12, 12)
+    # split the upstream gradient between the two outputs to exercise both routes
+    ((Kp * (0.25 * g).to(DEV)).sum() + (Kp_t * (0.75 * g).transpose(1, 2).to(DEV)).sum()).backward()
+    errs = {"X1": rel_err(ag.grad, a.grad), "X2": rel_err(bg.grad, b.grad), "coeff": rel_err(cg.grad, c.grad)}
+    report("affinity_bwd", **errs)
+    assert max(errs.values()) < 1e-5, errs
+
+
+def test_ngm_solver_backward():
+    """Three PYGNNLayers + final classifier against autograd through the oracle's explicit index lists."""
+    from fpmatch import autograd as fa, ops
+    from oracle import ops as oo
+    import torch.nn.functional as F
+    net, sd, data = _setup(B=3, n=12, ragged=True)
+    n1, n2 = data["ns"]
+    n1max, n2max = data["Ps"][0].shape[1], data["Ps"][1].shape[1]
+    gen = torch.Generator().manual_seed(7)
+    B = 3
+    Kp = torch.zeros(B, n1max, n2max)
+    for b in range(B):
+        Kp[b, :n1[b], :n2[b]] = torch.randn(int(n1[b]), int(n2[b]), generator=gen) * 0.3
+    gs = torch.randn(B, n1max, n2max, generator=gen)
+    # oracle
+    names = [k for k in sd if k.startswith("gnn_layer_") and ".conv." not in k] + ["classifier.weight", "classifier.bias"]
+    p = {k: v.clone() for k, v in sd.items()}
+    for k in names:
+        p[k].requires_grad_(True)
+    Kr = Kp.clone().requires_grad_(True)
+    emb = Kr.transpose(1, 2).contiguous().view(B, -1, 1)
+    outs = []
+    for b in range(B):
+        idxG, idxH = data["KGHs_sparse"][b]
+        n1b, n2b = int(n1[b]), int(n2[b])
+        diag = torch.arange(n1b * n2b)
+        row = torch.cat((idxG.long(), diag)); col = torch.cat((idxH.long(), diag))
+        t = emb[b]
+        for i in range(3):
+            t = oo.pygnn_layer(t, row, col, n1b, n2b, n1max, n2max, p, f"gnn_layer_{i}", sk_iter=20, sk_tau=0.01)
+        outs.append(t)
+    v = F.linear(torch.stack(outs, 0), p["classifier.weight"], p["classifier.bias"])
+    s_ref = v.view(B, n2max, -1).transpose(1, 2)
+    (s_ref * gs).sum().backward()
+    # GPU
+    net = net.to(DEV)
+    tables = net._edge_tables(data | {"Gs": [t.to(DEV) for t in data["Gs"]], "Hs": [t.to(DEV) for t in data["Hs"]]}, DEV) \
+        if "edge_lists" not in data else [t.to(DEV, torch.int32).contiguous() for t in data["edge_lists"]]
+    swap = lambda t: torch.stack((t[:, 1], t[:, 0]), 1).contiguous()
+    meta = {"csr1": ops.assoc_in_csr(tables[0], n1max), "csr2": ops.assoc_in_csr(tables[1], n2max),
+            "ocsr1": ops.assoc_in_csr(swap(tables[0]), n1max), "ocsr2": ops.assoc_in_csr(swap(tables[1]), n2max),
+            "n1": n1.to(DEV), "n2": n2.to(DEV), "n1max": n1max, "n2max": n2max, "e1max": tables[0].shape[2],
+            "e2max": tables[1].shape[2], "layers": 3, "sk_iter": 20, "sk_tau": 0.01}
+    params, pnames = [], []
+    for i in range(3):
+        L = getattr(net, f"gnn_layer_{i}")
+        params += [L.conv2.lin_l.weight, L.conv2.lin_l.bias, L.conv2.lin_r.weight, L.n_self_func[0].weight,
+                   L.n_self_func[0].bias, L.n_self_func[2].weight, L.n_self_func[2].bias, L.classifier.weight,
+                   L.classifier.bias]
+        pre = f"gnn_layer_{i}."
+        pnames += [pre + "conv2.lin_l.weight", pre + "conv2.lin_l.bias", pre + "conv2.lin_r.weight",
+                   pre + "n_self_func.0.weight", pre + "n_self_func.0.bias", pre + "n_self_func.2.weight",
+                   pre + "n_self_func.2.bias", pre + "classifier.weight", pre + "classifier.bias"]
+    params += [net.classifier.weight, net.classifier.bias]; pnames += ["classifier.weight", "classifier.bias"]
+    Kg = Kp.to(DEV).requires_grad_(True)
+    s = fa.NgmSolverFn.apply(Kg.transpose(1, 2).contiguous(), meta, *params)
+    fwd = (s.detach().cpu() - s_ref.detach()).abs().max().item()
+    (s * gs.to(DEV)).sum().backward()
+    errs = {"Kp": rel_err(Kg.grad, Kr.grad)}
+    scale = max(p[nm].grad.abs().max().item() for nm in pnames)
+    for nm, q in zip(pnames, params):
+        errs[nm] = rel_err(q.grad, p[nm].grad, floor=1e-3 * scale)
+    report("ngm_solver_bwd", fwd=fwd, worst=max(errs.values()), **{k: v for k, v in errs.items() if v > 1e-4})
+    assert fwd < 1e-4
+    bad = {k: v for k, v in errs.items() if v > 1e-3}
+    assert not bad, bad
+
+
+# ------------------------------------------------------------------------------------------------- whole step
+@pytest.mark.parametrize("with_label", [False, True])
+def test_stage1_loss_gradients_match_oracle(with_label):
+    """d(loss)/d(every trainable parameter and both feature maps) of one stage-1 step.  The bar per tensor is
+    max(1e-4 x max|g|, 4 x the fp32 oracle's own distance to an fp64 evaluation of the same formulae): with
+    tau = 0.01 Sinkhorn layers the fp32 autograd of the reference is itself only good to ~3e-4 on the GNN
+    weights, and every GNN bias gradient is exactly zero in exact arithmetic (the loss only sees s through
+    shift-invariant Sinkhorn layers), so fp32 returns pure rounding noise there."""
+    from fpmatch import synth
+    from oracle import train as otrain
+    net, sd, data = _setup(B=3, n=14, seed=3)
+    if with_label:       # classify-task batches: cls_loss joins the objective and reaches s through s * perm_mat
+        data["label"] = torch.ones(3)
+    loss_ref, g32, f32, _ = otrain.loss_and_grads(sd, synth.clone_batch(data), data["fmaps"], fmap_grads=True)
+    loss64, g64, f64, _ = otrain.loss_and_grads(sd, synth.clone_batch(data), data["fmaps"], fmap_grads=True,
+                                                dtype=torch.float64)
+    net = net.to(DEV).train()
+    d = synth.batch_to(synth.clone_batch(data), DEV)
+    fm = [(a.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)) for a, b in data["fmaps"]]
+    d["fmaps"] = fm
+    out = net(d)
+    loss = gpu_permutation_loss(out["ds_mat"], d["gt_perm_mat"], d["ns"][0], d["ns"][1])
+    (loss + out["cls_loss"]).backward()
+    named = dict(net.named_parameters())
+    got = {k: named[k].grad for k in g64}
+    for k in g64:
+        assert got[k] is not None, f"no gradient for {k}"
+    for gi in range(2):
+        for j, nm in enumerate(("nodes", "edges")):
+            key = f"fmap{gi}.{nm}"
+            got[key] = fm[gi][j].grad; g32[key] = f32[gi][j]; g64[key] = f64[gi][j]
+    # gradient scale of the group a tensor belongs to (a zero-in-exact-arithmetic bias is judged on its layer's scale)
+    group = lambda k: k.split(".")[0]
+    gscale = {}
+    for k, g in g64.items():
+        gscale[group(k)] = max(gscale.get(group(k), 0.0), g.abs().max().item())
+    rows, bad = {}, {}
+    for k, t in g64.items():
+        e_gpu = (got[k].detach().double().cpu() - t).abs().max().item()
+        e_o32 = (g32[k].double() - t).abs().max().item()
+        tol = max(1e-4 * gscale[group(k)], 4.0 * e_o32)
+        rows[k] = (e_gpu, e_o32, tol)
+        if e_gpu > tol:
+            bad[k] = rows[k]
+    lerr = abs(loss.item() - loss64.item()) / abs(loss64.item())
+    worst = max(rows.items(), key=lambda kv: kv[1][0] / kv[1][2])
+    report("stage1_grads", with_label=with_label, loss_rel_vs_fp64=lerr,
+           oracle32_loss_rel_vs_fp64=abs(loss_ref.item() - loss64.item()) / abs(loss64.item()),
+           worst=worst[0], worst_gpu_err=worst[1][0], worst_oracle32_err=worst[1][1], worst_tol=worst[1][2],
+           max_ratio_gpu_over_oracle32=max(r[0] / max(r[1], 1e-30) for r in rows.values()))
+    assert lerr < 1e-5
+    extra = [k for k, q in named.items() if q.grad is not None and k not in g64 and q.grad.abs().max() > 0]
+    assert not extra, f"gradients the reference does not produce: {extra}"
+    assert not bad, bad
+
+
+def gpu_permutation_loss(ds, gt, n1, n2):
+    """PermutationLoss (loss_func.py:26-59) with torch ops on the device (the reference's own criterion)."""
+    B, R, C = ds.shape
+    mask = (torch.arange(R, device=ds.device)[None, :, None] < n1.view(B, 1, 1)) & \
+           (torch.arange(C, device=ds.device)[None, None, :] < n2.view(B, 1, 1))
+    bce = torch.nn.functional.binary_cross_entropy(ds, gt, reduction="none")
+    return (bce * mask).sum() / n1.sum().to(torch.float32)
+
+
+def test_stage1_loss_trajectory_100_steps():
+    """AdamW(lr 1e-3, wd 1e-4), clip 5.0, 100 steps on a fixed cycle of 2 genuine batches: the loss after 100
+    steps must be within 1e-3 relative of the oracle's (north star)."""
+    from fpmatch import synth
+    from oracle import train as otrain
+    from src.model.ngm import Net
+    torch.manual_seed(0)
+    net = Net(regression=False)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    batches = [synth.make_batch(2, 12, seed=11 + i, imposter_every=0, with_kron=True) for i in range(2)]
+    for b in batches:
+        b.pop("label")
+    steps = 100
+    ref = otrain.train_trajectory(sd, batches, steps)
+    net = net.to(DEV).train()
+    names = set(otrain.trainable_names(sd))
+    params = [q for k, q in net.named_parameters() if k in names]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4)
+    dev_batches = [synth.batch_to(synth.clone_batch(b), DEV) for b in batches]
+    got = []
+    for it in range(steps):
+        d = dict(dev_batches[it % len(dev_batches)])
+        d["pyg_graphs"] = [g.to(DEV) for g in d["pyg_graphs"]]
+        opt.zero_grad()
+        out = net(d)
+        loss = gpu_permutation_loss(out["ds_mat"], d["gt_perm_mat"], d["ns"][0], d["ns"][1])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([q for q in params if q.grad is not None], max_norm=5.0)
+        opt.step()
+        got.append(loss.item())
+    rel = [abs(a - b) / abs(b) for a, b in zip(got, ref)]
+    report("stage1_trajectory", steps=steps, first=got[0], last=got[-1], ref_last=ref[-1], rel_last=rel[-1],
+           rel_max=max(rel), rel_at=[rel[i] for i in (0, 9, 24, 49, 74, 99)])
+    assert rel[0] < 1e-4
+    assert rel[-1] < 1e-3

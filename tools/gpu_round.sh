@@ -1,0 +1,22 @@
+#!/bin/bash
+# One GPU-box visit: GPU tests (as the driver runs them), smoke, bench lines, ncu launch list and full captures.
+# Usage (under gpurun): bash tools/gpu_round.sh <tag>
+TAG=${1:-rX}
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+O=gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${TAG}_smi.txt 2>&1
+timeout 1500 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/${TAG}_pytest_gpu.log
+tail -3 $O/${TAG}_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/${TAG}_smoke.log
+timeout 600 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench rc=$?"; tail -1 $O/${TAG}_bench.json
+timeout 300 python bench.py --gemm 3xtf32 --steps 5 --no-cpu-baseline > $O/${TAG}_bench_3xtf32.json 2> $O/${TAG}_bench_3xtf32.err; tail -1 $O/${TAG}_bench_3xtf32.json
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err; tail -1 $O/${TAG}_bench_reference.json
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+$CMD > $O/${TAG}_plain.log 2>&1 &&
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_launch.log 2>&1
+echo "ncu launches rc=$?"
+$CMD > $O/${TAG}_plain2.log 2>&1 &&
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel|gnn_layer_kernel|lap_topk|ke_factored|spline_gather|afau_attention|sinkhorn_log" -s 46 -c 23 -o $O/${TAG}_prof $CMD > $O/${TAG}_ncu_full.log 2>&1
+echo "ncu full rc=$?"
+ls -la $O | tail -20
