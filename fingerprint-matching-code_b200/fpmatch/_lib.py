@@ -53,6 +53,12 @@ SIGNATURES = {
     "fpm_k_head": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_lap_topk": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_greedy_perm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    # batched CSR / CSC containers + dense FGM affinity
+    "fpm_csr_dot_diag": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_csr_dot_csc_dense": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_dense_dot_csc_dense": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fpm_bilinear_diag": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_fgm_rebuild": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     # training (backward) entry points
     "fpm_node_features_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "fpm_fmap_prep_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

@@ -619,3 +619,61 @@ def soft_topk_bwd(scores: Tensor, ks: Tensor, n1: Optional[Tensor], n2: Optional
                              ws.data_ptr() if ws is not None else None, B, R, Cc, int(max_iter), float(tau), _stream())
     _lib.check(rc, "fpm_soft_topk_bwd"); _count()
     return gs
+
+
+# ---------------------------------------------------------------------------------------------------
+# batched CSR / CSC products and the dense FGM affinity (src.sparse_torch, src.sparse, RebuildFGM)
+# ---------------------------------------------------------------------------------------------------
+def _csx(m, name):
+    return (_chk(m.indices, name + ".indices", torch.int64), _chk(m.indptr, name + ".indptr", torch.int64),
+            _chk(m.data, name + ".data"))
+
+
+def csr_dot_diag(indices: Tensor, indptr: Tensor, data: Tensor, diag: Tensor, shape) -> Tensor:
+    B, h, w = shape
+    out = torch.empty_like(data)
+    rc = _lib.lib().fpm_csr_dot_diag(_chk(indices, "indices", torch.int64), _chk(indptr, "indptr", torch.int64),
+                                     _chk(data, "data"), _chk(diag.contiguous(), "diag"), out.data_ptr(), B, h, w,
+                                     _stream())
+    _lib.check(rc, "fpm_csr_dot_diag"); _count()
+    return out
+
+
+def csr_dot_csc_dense(t1, t2) -> Tensor:
+    B, h, _ = t1.shape
+    w = t2.shape[2]
+    out = torch.empty((B, h, w), dtype=torch.float32, device=t1.device)
+    rc = _lib.lib().fpm_csr_dot_csc_dense(*_csx(t1, "t1"), *_csx(t2, "t2"), out.data_ptr(), B, h, w, _stream())
+    _lib.check(rc, "fpm_csr_dot_csc_dense"); _count()
+    return out
+
+
+def dense_dot_csc_dense(d: Tensor, t2) -> Tensor:
+    B, h, k = d.shape
+    w = t2.shape[2]
+    out = torch.empty((B, h, w), dtype=torch.float32, device=d.device)
+    rc = _lib.lib().fpm_dense_dot_csc_dense(_chk(d.contiguous(), "dense"), *_csx(t2, "t2"), out.data_ptr(), B, h, k, w,
+                                            _stream())
+    _lib.check(rc, "fpm_dense_dot_csc_dense"); _count()
+    return out
+
+
+def bilinear_diag(t1, d: Tensor, t3) -> Tensor:
+    B, x, f = t1.shape
+    out = torch.empty((B, x), dtype=torch.float32, device=d.device)
+    i1, p1, d1 = _csx(t1, "t1")
+    i3, p3, d3 = _csx(t3, "t3")
+    rc = _lib.lib().fpm_bilinear_diag(i1, p1, d1, _chk(d.contiguous(), "t2"), i3, p3, d3, out.data_ptr(), B, x, f,
+                                      _stream())
+    _lib.check(rc, "fpm_bilinear_diag"); _count()
+    return out
+
+
+def fgm_rebuild(KroGt, KroHt, ke_vec: Tensor, kp_vec: Tensor) -> Tensor:
+    """K [B,N,N] from the transposed Kronecker factors (CSR [B,E,N], CSC [B,N,E]) and vec(Ke), vec(Kp)."""
+    B, E, N = KroGt.shape
+    K = torch.empty((B, N, N), dtype=torch.float32, device=ke_vec.device)
+    rc = _lib.lib().fpm_fgm_rebuild(*_csx(KroGt, "KroGt"), *_csx(KroHt, "KroHt"), _chk(ke_vec, "vec(Ke)"),
+                                    _chk(kp_vec, "vec(Kp)"), K.data_ptr(), B, E, N, _stream())
+    _lib.check(rc, "fpm_fgm_rebuild"); _count(2)
+    return K

@@ -80,11 +80,14 @@ def _pad_stack(arrs, dtype=torch.float32):
 def make_batch(batch_size: int, n: int, seed: int = 1234, imposter_every: int = 2,
                ragged: bool = False, n_min: Optional[int] = None, with_kron: bool = False,
                with_dense_gh: bool = True, with_fmaps: bool = True, jitter: float = 1.5,
-               fmap_seed: Optional[int] = None) -> dict:
+               fmap_seed: Optional[int] = None, fmap_noise: Optional[float] = None) -> dict:
     """Build one batch.
 
     ``imposter_every = k`` makes every k-th pair (b % k == k-1) an imposter; 0 = all genuine.
     ``ragged`` draws n1_b, n2_b uniformly from [n_min, n] (imposters get independent sizes).
+    ``fmap_noise = s`` makes the second image's feature maps a noisy copy of the first's (maps2 = maps1 + s*N(0,1)),
+    so that matching keypoints of a genuine pair have related features and training has something to learn;
+    the default draws the two images' maps independently.
     """
     rng = np.random.RandomState(seed)
     n_min = n_min if n_min is not None else max(4, n // 2)
@@ -165,6 +168,9 @@ def make_batch(batch_size: int, n: int, seed: int = 1234, imposter_every: int = 
              torch.randn(batch_size, 512, 8, 10, generator=g))
             for _ in range(2)
         ]
+        if fmap_noise is not None:
+            a, b = data["fmaps"][0]
+            data["fmaps"][1] = (a + fmap_noise * data["fmaps"][1][0], b + fmap_noise * data["fmaps"][1][1])
     return data
 
 

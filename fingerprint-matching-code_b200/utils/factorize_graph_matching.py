@@ -4,7 +4,7 @@
 index lists; ``Net.forward`` does not call it - the association graph stays factorised on the GPU
 (``csrc/gnn.cu``).  ``kronecker_torch`` / ``kronecker_sparse`` (:98-137) are host/data-pipeline helpers.
 The dense ``construct_aff_mat`` / ``RebuildFGM`` path (:10-54,140-186) is dormant in the reference
-(``ngm.py:294-315`` is commented out) and is listed as a "next" row in DESIGN.md.
+(``ngm.py:294-315`` is commented out); it is rebuilt here as a scatter / gather pair over the Kronecker columns.
 """
 import numpy as np
 import scipy.sparse as ssp
@@ -43,6 +43,41 @@ def kronecker_sparse(arr1: np.ndarray, arr2: np.ndarray):
     return ssp.kron(ssp.coo_matrix(arr1), ssp.coo_matrix(arr2))
 
 
-def construct_aff_mat(Ke, Kp, KroG, KroH, KroGt=None, KroHt=None):
-    raise NotImplementedError(
-        "the dense NGM-v1 affinity path is dormant in the reference (ngm.py:294-315) and not yet built here")
+def construct_aff_mat(Ke: Tensor, Kp: Tensor, KroG, KroH, KroGt=None, KroHt=None) -> Tensor:
+    r"""
+    Dense affinity matrix :math:`K = diag(vec(K_p)) + (G_2 \otimes G_1) diag(vec(K_e)) (H_2 \otimes H_1)^\top`
+    (factorize_graph_matching.py:10-54).  ``KroG``: ``CSRMatrix3d`` [b, n1n2, ne1ne2]; ``KroH``: ``CSCMatrix3d``
+    [b, ne1ne2, n1n2] (the transposed Kronecker factor, as the reference's collate function builds it);
+    ``KroGt`` / ``KroHt``: their ``transpose(keep_type=True)`` (computed when omitted).  Differentiable in Ke, Kp.
+    """
+    return RebuildFGM.apply(Ke, Kp, KroG, KroH, KroGt, KroHt)
+
+
+class RebuildFGM(torch.autograd.Function):
+    """factorize_graph_matching.py:140-186.  Forward: one scatter launch over the Kronecker columns instead of the
+    reference's CSR.diag + CSR.CSC merge-join over all (n1n2)^2 outputs; backward: the matching gather for dKe and
+    the diagonal for dKp (``csrc/sparse.cu``)."""
+
+    @staticmethod
+    def forward(ctx, Ke, Kp, Kro1, Kro2, Kro1T=None, Kro2T=None):
+        from fpmatch import ops
+        if Kro1T is None or Kro2T is None:
+            Kro1T, Kro2T = Kro1.transpose(keep_type=True), Kro2.transpose(keep_type=True)
+        ctx.K = (Kro1T, Kro2T)
+        ctx.shapes = (tuple(Ke.shape), tuple(Kp.shape))
+        B = Ke.shape[0]
+        ke_vec = Ke.detach().transpose(1, 2).contiguous().view(B, -1).to(torch.float32)
+        kp_vec = Kp.detach().transpose(1, 2).contiguous().view(B, -1).to(torch.float32)
+        return ops.fgm_rebuild(Kro1T, Kro2T, ke_vec, kp_vec)
+
+    @staticmethod
+    def backward(ctx, dK):
+        from src.sparse import bilinear_diag_torch
+        Kro1T, Kro2T = ctx.K
+        (B, e1, e2), (_, n1, n2) = ctx.shapes
+        dKe = dKp = None
+        if ctx.needs_input_grad[0]:
+            dKe = bilinear_diag_torch(Kro1T, dK.contiguous(), Kro2T).view(B, e2, e1).transpose(1, 2)
+        if ctx.needs_input_grad[1]:
+            dKp = torch.diagonal(dK, dim1=-2, dim2=-1).reshape(B, n2, n1).transpose(1, 2)
+        return dKe, dKp, None, None, None, None

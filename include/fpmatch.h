@@ -175,6 +175,33 @@ int fpm_lap_topk(const float* ds, const long long* n1, const long long* n2, cons
 int fpm_greedy_perm(float* x, const long long* top_indices, const float* ks, int B, int R, int C, int L,
                     void* stream);
 
+/* ---- (A14) batched CSR / CSC products, dense factorised-graph-matching affinity ------------------------------------
+ * Replace the reference's JIT extension (src/extension/sparse_dot/sparse_dot.cpp:191-331, bilinear_diag.cpp:303-326)
+ * behind src.sparse_torch.CSRMatrix3d.dot / dotdiag, src.sparse.bilinear_diag_torch and RebuildFGM
+ * (utils/factorize_graph_matching.py:140-186).  Container layout as src/sparse_torch/csx_matrix.py:20-93: indices
+ * int64 [nnz] (local, ascending per row / column), indptr int64 [B*h+1] (CSR) / [B*w+1] (CSC) with global offsets.
+ *   fpm_csr_dot_diag        out_data[p] = data[p] * diag[b, indices[p]]                 (csr_dot_diag_to_csr)
+ *   fpm_csr_dot_csc_dense   out [B,h,w] = CSR [B,h,k] . CSC [B,k,w]                      (csr_dot_csc_to_dense)
+ *   fpm_dense_dot_csc_dense out [B,h,w] = dense [B,h,k] . CSC [B,k,w]                    (dense_dot_csc_to_dense)
+ *   fpm_bilinear_diag       out [B,x] = diag(CSR [B,x,f] . T [B,f,f] . CSC [B,f,x])      (bilinear_diag)
+ *   fpm_fgm_rebuild         K [B,N,N] = sum_t G[:,t] ke_vec[b,t] H[:,t]^T + diag(kp_vec), from GT = CSR [B,E,N] and
+ *                           HT = CSC [B,N,E] (the transposed Kronecker factors): one scatter over the E columns.
+ * The reference's sparse x sparse -> sparse product exists on the CPU only (sparse_dot.cpp:50-144, raises for CUDA
+ * at :204) and is not rebuilt.
+ */
+int fpm_csr_dot_diag(const long long* indices, const long long* indptr, const float* data, const float* diag,
+                     float* out_data, int B, int h, int w, void* stream);
+int fpm_csr_dot_csc_dense(const long long* ind1, const long long* ptr1, const float* dat1, const long long* ind2,
+                          const long long* ptr2, const float* dat2, float* out, int B, int h, int w, void* stream);
+int fpm_dense_dot_csc_dense(const float* dense, const long long* ind2, const long long* ptr2, const float* dat2,
+                            float* out, int B, int h, int k, int w, void* stream);
+int fpm_bilinear_diag(const long long* ind1, const long long* ptr1, const float* dat1, const float* T,
+                      const long long* ind3, const long long* ptr3, const float* dat3, float* out, int B, int x,
+                      int f, void* stream);
+int fpm_fgm_rebuild(const long long* indg, const long long* ptrg, const float* datg, const long long* indh,
+                    const long long* ptrh, const float* dath, const float* ke_vec, const float* kp_vec, float* K,
+                    int B, int E, int N, void* stream);
+
 /* ---- training: hand-written backward of the differentiable ops -----------------------------------------------
  * The reference differentiates its forward with torch autograd (train.py / src/train/training_loop.py:33-64 call
  * loss.backward() on PermutationLoss(ds_mat)); these entry points are the vector-Jacobian products of the kernels

@@ -1,0 +1,70 @@
+"""Generates tests/golden/train_trajectory.json: the CPU oracle's stage-1 loss trajectory (BASELINE.json config 3 at
+a size the CPU finishes in minutes).  Run from the repo root:  python tests/golden/make_train_golden.py [--fp64]
+
+Set-up (mirrored by tests/test_gpu_train.py::test_stage1_loss_trajectory_100_steps):
+  Net(regression=False), torch.manual_seed(0) default initialisation, train mode;
+  step t uses a FRESH batch  synth.make_batch(B, n, seed=1000+t, imposter_every=0, fmap_noise=0.5)  without labels
+  (genuine pairs from get_pair(): no cls_loss) - a model cannot memorise a stream of new pairs, so the loss falls
+  smoothly instead of collapsing to 1e-40 within 30 steps as it does on a repeated batch;
+  AdamW(lr 1e-3, weight_decay 1e-4) on the stage-1 parameter group, clip_grad_norm_ 5.0  (train.py:157-181,
+  training_loop.py:59-61).
+"""
+import json
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path[:0] = [str(ROOT / "fingerprint-matching-code_b200"), str(ROOT)]
+import torch  # noqa: E402
+
+from fpmatch import synth  # noqa: E402
+from oracle import head, train as otrain  # noqa: E402
+from src.model.ngm import Net  # noqa: E402
+
+B, N_KPTS, STEPS = 3, 14, 100
+
+
+def batch(t):
+    d = synth.make_batch(B, N_KPTS, seed=1000 + t, imposter_every=0, with_kron=True, fmap_noise=0.5)
+    d.pop("label")
+    return d
+
+
+def run(dtype):
+    torch.manual_seed(0)
+    net = Net(regression=False)
+    p = {k: (v.detach().clone().to(dtype) if v.is_floating_point() else v.detach().clone())
+         for k, v in net.state_dict().items()}
+    names = otrain.trainable_names(p)
+    params = [p[k].requires_grad_(True) for k in names]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4)
+    losses = []
+    for t in range(STEPS):
+        d = batch(t)
+        opt.zero_grad()
+        fm = [(a.to(dtype), b.to(dtype)) for a, b in d["fmaps"]]
+        out = head.forward_head(p, d, fm, regression=False, training=True, keep_graph=True, dtype=dtype)
+        loss = otrain.permutation_loss(out["ds_mat"], d["gt_perm_mat"], d["ns"][0], d["ns"][1], dtype)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([q for q in params if q.grad is not None], max_norm=5.0)
+        opt.step()
+        losses.append(float(loss.detach()))
+        if t % 10 == 0:
+            print(t, losses[-1], flush=True)
+    return losses
+
+
+if __name__ == "__main__":
+    out = ROOT / "tests" / "golden" / "train_trajectory.json"
+    rec = json.loads(out.read_text()) if out.exists() else {}
+    rec.update({"B": B, "n": N_KPTS, "steps": STEPS, "seed_base": 1000, "fmap_noise": 0.5, "lr": 1e-3,
+                "weight_decay": 1e-4, "clip": 5.0, "torch": torch.__version__})
+    t0 = time.time()
+    if "--fp64" in sys.argv:
+        rec["loss_fp64"] = run(torch.float64)
+    else:
+        rec["loss_fp32"] = run(torch.float32)
+    rec["seconds_" + ("fp64" if "--fp64" in sys.argv else "fp32")] = time.time() - t0
+    out.write_text(json.dumps(rec))
+    print("wrote", out)
