@@ -352,6 +352,260 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Persistent CTA-pair variant (the default for the error-compensated modes).
+//
+// Why: the r1b captures show the one-tile-per-CTA kernel above keeps the tensor pipe busy 48.6 % of the
+// time - its main loop runs at ~86 % (shared-memory bandwidth: the three products of a k-step re-read their
+// operands), but the epilogue (32 % of a CTA's life) and the CTA turn-over (7 %) are serial, because the two
+// accumulators of a 128x256 tile fill all 512 TMEM columns and nothing can be computed while they drain.
+// Here two CTAs of a cluster issue tcgen05.mma.cta_group::2 on a 256 x 128 tile: each CTA holds 128 rows x 128
+// columns (main + correction = 256 TMEM columns), so TMEM has room for TWO tiles and the epilogue of tile i
+// overlaps the main loop of tile i+1.  Each CTA loads its own A rows and one half of the B tile (the pair's
+// tensor cores share both halves), every TMA load signals the LEADER's full barrier, the leader alone issues
+// the MMAs, and tcgen05.commit multicasts slot-release / accumulator-ready to both CTAs.  The kernel is
+// persistent: one cluster per SM pair walks the tile list with the same L2-friendly rasterisation as above.
+// ---------------------------------------------------------------------------------------------------
+constexpr int P_TBM = 128;                    // rows per CTA (256 per pair)
+constexpr int P_TBN = 128;                    // columns per pair tile
+constexpr uint32_t kPABytes = P_TBM * kRowBytes;              // 16 KB
+constexpr uint32_t kPBHalfBytes = (P_TBN / 2) * kRowBytes;    //  8 KB: this CTA's half of the B tile
+constexpr uint32_t kPStageBytes = 2 * (kPABytes + kPBHalfBytes);   // hi + lo: 48 KB
+constexpr int kPStages = 4;
+constexpr int kEpiWarps = 8;
+
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t saddr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA-pair kernel: data lands in THIS CTA's shared memory, the bytes are counted on the mbarrier at
+// `bar_cluster_addr` (the leader CTA's barrier, a shared::cluster address).
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <bool kF16>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  if (kF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const float* __restrict__ inv_a, const float* __restrict__ inv_b,
+                    const float* __restrict__ bias, float* __restrict__ Cm, int M, int N, int K, int ldc, int act) {
+  static_assert(kMode == kTf32x3 || kMode == kF16x3, "the pair kernel serves the two-accumulator modes");
+  constexpr bool kF16 = kMode == kF16x3;
+  constexpr int kElemBytes = kF16 ? 2 : 4;
+  constexpr int TBK = kRowBytes / kElemBytes;
+  constexpr int kUmmaKBytes = 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)kPStages * kPStageBytes);
+  uint64_t* empty_bar = full_bar + kPStages;
+  uint64_t* tmem_full_bar = empty_bar + kPStages;       // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2] (the leader's copy is the one in use)
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty_bar + 2);
+  float* epi_tiles = (float*)(smem + (size_t)kPStages * kPStageBytes + 256);   // kEpiWarps x [32][33] floats
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int cluster_id = (int)blockIdx.x >> 1, num_clusters = (int)gridDim.x >> 1;
+
+  constexpr int kRasterGroup = 16;                       // 16 pair tiles = 4096 rows walk the N tiles together
+  const int tiles_m = (M + 2 * P_TBM - 1) / (2 * P_TBM);
+  const int tiles_n = (N + P_TBN - 1) / P_TBN;
+  const long long total_tiles = (long long)tiles_m * tiles_n;
+  const int per_group = kRasterGroup * tiles_n;
+  const int nk = (K + TBK - 1) / TBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  auto tile_origin = [&](long long tile, int& m0, int& n0) {
+    const int grp = (int)(tile / per_group), rem = (int)(tile - (long long)grp * per_group);
+    const int gsize = min(kRasterGroup, tiles_m - grp * kRasterGroup);
+    m0 = (grp * kRasterGroup + rem % gsize) * (2 * P_TBM);
+    n0 = (rem / gsize) * P_TBN;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A rows + own half of the B tile, counted on the leader's barrier =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        int m0, n0;
+        tile_origin(tile, m0, n0);
+        const int am = m0 + (int)cta_rank * P_TBM, bn = n0 + (int)cta_rank * (P_TBN / 2);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % kPStages;
+          const uint32_t ph = (it / kPStages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * kPStageBytes);
+          const uint32_t bar = mapa_rank0(smem_u32(&full_bar[s]));
+          uint8_t* st = smem + (size_t)s * kPStageBytes;
+          const int kc = kb * TBK;
+          tma_load_2d_pair(&tmA_hi, bar, st, kc, am);
+          tma_load_2d_pair(&tmA_lo, bar, st + kPABytes, kc, am);
+          tma_load_2d_pair(&tmB_hi, bar, st + 2 * kPABytes, kc, bn);
+          tma_load_2d_pair(&tmB_lo, bar, st + 2 * kPABytes + kPBHalfBytes, kc, bn);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (cta_rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * P_TBM, P_TBN, kF16 ? 0u : 2u);
+      uint32_t it = 0, t = 0;
+      for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters, ++t) {
+        const uint32_t buf = t & 1u, bph = (t >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[buf], bph ^ 1u);        // both CTAs' epilogues have drained this buffer
+        tc_fence_after();
+        const uint32_t acc_main = tmem_base + buf * (2 * P_TBN), acc_corr = acc_main + P_TBN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % kPStages;
+          const uint32_t ph = (it / kPStages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + (size_t)s * kPStageBytes);
+          const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + kPABytes);
+          const uint64_t b_hi = make_smem_desc(st + 2 * kPABytes);
+          const uint64_t b_lo = make_smem_desc(st + 2 * kPABytes + kPBHalfBytes);
+#pragma unroll
+          for (int k = 0; k < kRowBytes / kUmmaKBytes; ++k) {
+            const uint64_t adv = (uint64_t)((k * kUmmaKBytes) >> 4);
+            umma_pair<kF16>(acc_corr, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_pair<kF16>(acc_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_pair<kF16>(acc_main, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+          }
+          umma_commit_pair(&empty_bar[s]);                // frees slot s in both CTAs
+        }
+        umma_commit_pair(&tmem_full_bar[buf]);            // accumulators of this tile complete, in both CTAs
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): warps 2..9, TMEM lane quarter = warp % 4, two warps per quarter split the columns
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float* tile_s = epi_tiles + (size_t)(warp - 2) * (32 * 33);
+    const uint32_t empty_addr0 = mapa_rank0(smem_u32(&tmem_empty_bar[0]));
+    const uint32_t empty_addr1 = mapa_rank0(smem_u32(&tmem_empty_bar[1]));
+    constexpr float kCorrScale = kF16 ? (1.0f / 2048.0f) : 1.0f;
+    constexpr int kChunksPerWarp = P_TBN / 32 / 2;          // 2
+    uint32_t t = 0;
+    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters, ++t) {
+      int m0, n0;
+      tile_origin(tile, m0, n0);
+      m0 += (int)cta_rank * P_TBM;
+      const uint32_t buf = t & 1u, bph = (t >> 1) & 1u;
+      mbar_wait(&tmem_full_bar[buf], bph);
+      tc_fence_after();
+      const uint32_t acc_main = tmem_base + buf * (2 * P_TBN) + ((uint32_t)(q * 32) << 16);
+      // all of this warp's accumulator columns -> registers, then hand the TMEM buffer back before storing
+      uint32_t r[kChunksPerWarp][32];
+#pragma unroll
+      for (int c = 0; c < kChunksPerWarp; ++c) {
+        const int ch = half * kChunksPerWarp + c;
+        uint32_t r2[32];
+        tmem_ld32(acc_main + (uint32_t)(ch * 32), r[c]);
+        tmem_ld32(acc_main + (uint32_t)(P_TBN + ch * 32), r2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          r[c][j] = __float_as_uint(fmaf(__uint_as_float(r2[j]), kCorrScale, __uint_as_float(r[c][j])));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0);
+
+      const int m = m0 + q * 32 + lane;
+      const float row_scale = (kF16 && m < M) ? inv_a[m] : 1.f;
+#pragma unroll
+      for (int c = 0; c < kChunksPerWarp; ++c) {
+        const int ch = half * kChunksPerWarp + c;
+        const int ncol = n0 + ch * 32 + lane;
+        const float col_scale = (kF16 && ncol < N) ? inv_b[ncol] : 1.f;
+        const float col_bias = (bias && ncol < N) ? bias[ncol] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[c][j]);
+          if (kF16) x = x * row_scale * __shfl_sync(0xffffffffu, col_scale, j);
+          x += __shfl_sync(0xffffffffu, col_bias, j);
+          if (act == 1) x = fmaxf(x, 0.f);
+          tile_s[lane * 33 + j] = x;
+        }
+        __syncwarp();
+        if (ncol < N) {
+          const int mrow0 = m0 + q * 32;
+          const int nrows = min(32, M - mrow0);
+          float* cbase = Cm + (size_t)mrow0 * ldc + ncol;
+          if (nrows == 32) {
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              float v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] = tile_s[(r0 + u) * 33 + lane];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) cbase[(size_t)(r0 + u) * ldc] = v[u];
+            }
+          } else {
+            for (int rr = 0; rr < nrows; ++rr) cbase[(size_t)rr * ldc] = tile_s[rr * 33 + lane];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
 // a = hi + lo with hi, lo exactly representable in tf32 (round-to-nearest split).
 __global__ void tf32_split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
                                   size_t n4) {
@@ -476,10 +730,65 @@ static int launch_tc_impl(const void* A_hi, const void* A_lo, const void* B_hi, 
   return FPM_OK;
 }
 
+static int g_tc_pair = -1;        // FPMATCH_GEMM_PAIR / fpm_gemm_set_pair: 1 = persistent CTA-pair kernel (default), 0 = off
+static int g_pair_clusters[2] = {0, 0};   // co-resident clusters of the pair kernel per mode (occupancy query, cached)
+
+template <int kMode>
+static int launch_tc_pair(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, const float* inv_a,
+                          const float* inv_b, const float* bias, float* C, int M, int N, int K, int lda, int ldb,
+                          int ldc, int act, cudaStream_t st) {
+  constexpr bool f16 = kMode == fpm::kF16x3;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  int rc;
+  if ((rc = make_map(&mAh, A_hi, M, K, lda, fpm::P_TBM, f16)) != FPM_OK) return rc;
+  if ((rc = make_map(&mAl, A_lo, M, K, lda, fpm::P_TBM, f16)) != FPM_OK) return rc;
+  if ((rc = make_map(&mBh, B_hi, N, K, ldb, fpm::P_TBN / 2, f16)) != FPM_OK) return rc;
+  if ((rc = make_map(&mBl, B_lo, N, K, ldb, fpm::P_TBN / 2, f16)) != FPM_OK) return rc;
+  const size_t smem = (size_t)fpm::kPStages * fpm::kPStageBytes + 1024 + 256 + (size_t)fpm::kEpiWarps * 32 * 33 * 4;
+  auto kern = fpm::gemm_tc_pair_kernel<kMode>;
+  FPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(64 + 32 * fpm::kEpiWarps);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int& ncl = g_pair_clusters[f16 ? 1 : 0];
+  if (ncl == 0) {
+    // a persistent kernel must not launch more clusters than can be resident at once: a late cluster would run
+    // its whole tile list after the others have finished
+    int dev = 0, sms = 0, maxc = 0;
+    FPM_CUDA(cudaGetDevice(&dev));
+    FPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cfg.gridDim = dim3((unsigned)(sms / 2 * 2));
+    if (cudaOccupancyMaxActiveClusters(&maxc, kern, &cfg) != cudaSuccess || maxc <= 0) {
+      (void)cudaGetLastError();
+      maxc = sms / 2;
+    }
+    ncl = maxc < sms / 2 ? maxc : sms / 2;
+  }
+  const long long tiles = (long long)fpm_cdiv(M, 2 * fpm::P_TBM) * fpm_cdiv(N, fpm::P_TBN);
+  const long long clusters = tiles < ncl ? tiles : ncl;
+  cfg.gridDim = dim3((unsigned)(2 * clusters));
+  FPM_CUDA(cudaLaunchKernelEx(&cfg, kern, mAh, mAl, mBh, mBl, inv_a, inv_b, bias, C, M, N, K, ldc, act));
+  return FPM_OK;
+}
+
 template <int kMode, int kStages>
 static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, const float* inv_a,
                      const float* inv_b, const float* bias, float* C, int M, int N, int K, int lda, int ldb,
                      int ldc, int act, cudaStream_t st) {
+  if (g_tc_pair < 0) {
+    const char* e = getenv("FPMATCH_GEMM_PAIR");
+    g_tc_pair = (e && e[0] == '0') ? 0 : 1;
+  }
+  if constexpr (kMode != fpm::kTf32x1) {
+    if (g_tc_pair == 1)
+      return launch_tc_pair<kMode>(A_hi, A_lo, B_hi, B_lo, inv_a, inv_b, bias, C, M, N, K, lda, ldb, ldc, act, st);
+  }
   if (g_tc_cluster < 0) {
     const char* e = getenv("FPMATCH_GEMM_CLUSTER");
     g_tc_cluster = (e && e[0] == '1') ? 1 : 2;
@@ -495,6 +804,12 @@ extern "C" int fpm_gemm_set_trace(void* buf, int cap) {
   unsigned long long* p = (unsigned long long*)buf;
   FPM_CUDA(cudaMemcpyToSymbol(fpm::g_gemm_trace, &p, sizeof(p)));
   FPM_CUDA(cudaMemcpyToSymbol(fpm::g_gemm_trace_cap, &cap, sizeof(cap)));
+  return FPM_OK;
+}
+
+// 1: the error-compensated modes run the persistent CTA-pair kernel (default); 0: the one-tile-per-CTA kernel.
+extern "C" int fpm_gemm_set_pair(int on) {
+  g_tc_pair = on ? 1 : 0;
   return FPM_OK;
 }
 

@@ -1,7 +1,10 @@
 """Data-parallel plumbing: fingerprint pairs are independent, so a batch shards across ranks by contiguous
 slices of the pair dimension with NO collective on the data path.  The only exchange
 is the gather of per-pair results for metrics (what evaluate_binary_classifier.py accumulates at
-``evaluate_binary_classifier.py:98-103``) - NCCL on GPUs, gloo in the CPU tests.
+``evaluate_binary_classifier.py:98-103``) - NCCL on GPUs, gloo in the CPU tests.  Training adds the gradient
+all-reduce: ``wrap_ddp`` puts the model under ``torch.nn.parallel.DistributedDataParallel`` (bucketed NCCL
+all-reduce overlapped with the hand-written backward kernels), replacing the reference's disabled single-process
+``nn.DataParallel`` subclass (``/root/reference/src/parallel/data_parallel.py:6-17``, ``train.py:148``).
 """
 from __future__ import annotations
 
@@ -56,3 +59,13 @@ def gather_pairs(local: Dict[str, torch.Tensor], batch_size: int) -> Dict[str, t
         dist.all_gather(bufs, pad)
         out[k] = torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], 0)
     return out
+
+
+def wrap_ddp(net: torch.nn.Module, device: torch.device) -> torch.nn.Module:
+    """One process per GPU: gradients are averaged over ranks by NCCL all-reduce during ``backward``.
+
+    ``find_unused_parameters`` is on because the reference model carries parameters its forward never touches (the
+    GCNConv of every PYGNNLayer, gnn.py:198; the k-branch in stage 1; edge_affinity, whose output SAGEConv drops)."""
+    from torch.nn.parallel import DistributedDataParallel
+    return DistributedDataParallel(net, device_ids=[device.index] if device.type == "cuda" else None,
+                                   find_unused_parameters=True, broadcast_buffers=False)

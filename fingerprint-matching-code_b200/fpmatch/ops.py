@@ -35,6 +35,11 @@ def gemm_mode() -> str:
     return _GEMM_MODE
 
 
+def set_gemm_pair(on: bool) -> None:
+    """True (default): the error-compensated modes use the persistent CTA-pair kernel; False: one tile per CTA."""
+    _lib.check(_lib.lib().fpm_gemm_set_pair(int(bool(on))), "fpm_gemm_set_pair")
+
+
 def launch_count() -> int:
     return _LAUNCHES
 

@@ -79,6 +79,11 @@ int fpm_gemm_nt_f16x3(const void* A_hi, const void* A_lo, const float* inv_a, co
                       const void* Bt_lo, const float* inv_b, const float* bias, float* C, int M, int N, int K,
                       int lda, int ldb, int ldc, int act, void* stream);
 
+/* Kernel choice for the error-compensated modes: 1 (default) = persistent CTA-pair kernel (tcgen05.mma.cta_group::2 on
+ * 256x128 tiles, TMEM double-buffered so the epilogue of one tile overlaps the main loop of the next), 0 = one 128x256
+ * tile per CTA.  Also settable with the environment variable FPMATCH_GEMM_PAIR=0/1 before the first call. */
+int fpm_gemm_set_pair(int on);
+
 /* debug aid: record {smid, t_entry, t_setup, t_mainloop_done, t_end} (ns) per CTA into buf[5*cap] (NULL = off) */
 int fpm_gemm_set_trace(void* buf, int cap);
 

@@ -3,9 +3,12 @@ a size the CPU finishes in minutes).  Run from the repo root:  python tests/gold
 
 Set-up (mirrored by tests/test_gpu_train.py::test_stage1_loss_trajectory_100_steps):
   Net(regression=False), torch.manual_seed(0) default initialisation, train mode;
-  step t uses a FRESH batch  synth.make_batch(B, n, seed=1000+t, imposter_every=0, fmap_noise=0.5)  without labels
-  (genuine pairs from get_pair(): no cls_loss) - a model cannot memorise a stream of new pairs, so the loss falls
-  smoothly instead of collapsing to 1e-40 within 30 steps as it does on a repeated batch;
+  step t uses a FRESH batch  synth.make_batch(B, n, seed=1000+t, imposter_every=0)  without labels (genuine pairs
+  from get_pair(): no cls_loss) whose two images carry INDEPENDENT random feature maps.  On any learnable synthetic
+  task (a repeated batch, or image-2 maps = image-1 maps + noise) AdamW at the reference's lr = 1e-3 drives the
+  loss to < 1e-25 within 15-35 steps (measured), after which a relative comparison is meaningless; on a stream of
+  unrelated pairs the loss stays O(1) for all 100 steps while every update still moves every parameter, so the
+  loss at step t is a well-conditioned function of the whole update history;
   AdamW(lr 1e-3, weight_decay 1e-4) on the stage-1 parameter group, clip_grad_norm_ 5.0  (train.py:157-181,
   training_loop.py:59-61).
 """
@@ -26,7 +29,7 @@ B, N_KPTS, STEPS = 3, 14, 100
 
 
 def batch(t):
-    d = synth.make_batch(B, N_KPTS, seed=1000 + t, imposter_every=0, with_kron=True, fmap_noise=0.5)
+    d = synth.make_batch(B, N_KPTS, seed=1000 + t, imposter_every=0, with_kron=True)
     d.pop("label")
     return d
 
@@ -58,7 +61,7 @@ def run(dtype):
 if __name__ == "__main__":
     out = ROOT / "tests" / "golden" / "train_trajectory.json"
     rec = json.loads(out.read_text()) if out.exists() else {}
-    rec.update({"B": B, "n": N_KPTS, "steps": STEPS, "seed_base": 1000, "fmap_noise": 0.5, "lr": 1e-3,
+    rec.update({"B": B, "n": N_KPTS, "steps": STEPS, "seed_base": 1000, "fmap_noise": None, "lr": 1e-3,
                 "weight_decay": 1e-4, "clip": 5.0, "torch": torch.__version__})
     t0 = time.time()
     if "--fp64" in sys.argv:

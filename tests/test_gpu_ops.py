@@ -281,17 +281,29 @@ def test_gemm_fp32(ops, M, N, K):
 
 # 3xTF32 is held to the fp32 CUDA-core kernel's own error level (7e-6 .. 1e-5 on these shapes, outputs of
 # size ~1.4 * sqrt(2 log) ~ 6): the tensor core's truncating fp32 accumulate is the floor, not the split.
+# kernel = "pair": persistent CTA-pair kernel (tcgen05.mma.cta_group::2, double-buffered TMEM; the default);
+# kernel = "single": one 128x256 tile per CTA.  Shapes include partial tiles in M, N and K and M < one CTA's rows.
+@pytest.mark.parametrize("kernel", ["pair", "single"])
 @pytest.mark.parametrize("mode,tol", [("3xtf32", 2.5e-5), ("3xf16", 2.5e-5), ("tf32", 2e-2)])
-@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (300, 520, 768), (1000, 256, 600), (77, 600, 256), (5120, 2048, 768)])
-def test_gemm_tensor_core(ops, mode, tol, M, N, K):
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (300, 520, 768), (1000, 256, 600), (77, 600, 256), (5120, 2048, 768),
+                                   (131, 19968, 768), (6000, 1000, 1000)])
+def test_gemm_tensor_core(ops, kernel, mode, tol, M, N, K):
+    if mode == "tf32" and kernel == "pair":
+        pytest.skip("plain TF32 has a single accumulator and keeps the one-tile-per-CTA kernel")
     g = torch.Generator().manual_seed(M + 1)
     A = torch.randn(M, K, generator=g); Bt = torch.randn(N, K, generator=g) * 0.05; bias = torch.randn(N, generator=g)
     ref = (A.double() @ Bt.double().t() + bias.double())
-    out = ops.gemm_nt(A.to(DEV), Bt.to(DEV), bias.to(DEV), act=0, mode=mode)
-    torch.cuda.synchronize()
+    ops.set_gemm_pair(kernel == "pair")
+    try:
+        out = ops.gemm_nt(A.to(DEV), Bt.to(DEV), bias.to(DEV), act=0, mode=mode)
+        torch.cuda.synchronize()
+        out2 = ops.gemm_nt(A.to(DEV), Bt.to(DEV), bias.to(DEV), act=1, mode=mode)
+    finally:
+        ops.set_gemm_pair(True)
     err = (out.cpu().double() - ref).abs().max().item()
-    report("gemm_tc", mode=mode, M=M, N=N, K=K, max_abs=err)
+    report("gemm_tc", kernel=kernel, mode=mode, M=M, N=N, K=K, max_abs=err)
     assert err < tol
+    assert (out2.cpu().double() - ref.clamp(min=0)).abs().max().item() < tol
 
 
 # ---------------------------------------------------------------------------------------------- spline
