@@ -54,6 +54,10 @@ SIGNATURES = {
     "fpm_k_head": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_lap_topk": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_greedy_perm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    # loss / metrics
+    "fpm_permutation_loss": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_permutation_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_matching_stats": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     # batched CSR / CSC containers + dense FGM affinity
     "fpm_csr_dot_diag": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_csr_dot_csc_dense": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),

@@ -682,3 +682,36 @@ def fgm_rebuild(KroGt, KroHt, ke_vec: Tensor, kp_vec: Tensor) -> Tensor:
                                     _chk(kp_vec, "vec(Kp)"), K.data_ptr(), B, E, N, _stream())
     _lib.check(rc, "fpm_fgm_rebuild"); _count(2)
     return K
+
+
+# ---------------------------------------------------------------------------------------------------
+# loss / metrics (src.loss_func.PermutationLoss, src.evaluation_metric.matching_recall)
+# ---------------------------------------------------------------------------------------------------
+def permutation_loss_pairs(pred: Tensor, gt: Tensor, n1: Tensor, n2: Tensor) -> Tensor:
+    """Per-pair summed BCE over the valid block, [B]."""
+    B, R, Cc = pred.shape
+    out = torch.empty((B,), dtype=torch.float32, device=pred.device)
+    rc = _lib.lib().fpm_permutation_loss(_chk(pred, "pred"), _chk(gt, "gt"), _chk(n1, "n1", torch.int64),
+                                         _chk(n2, "n2", torch.int64), out.data_ptr(), B, R, Cc, _stream())
+    _lib.check(rc, "fpm_permutation_loss"); _count()
+    return out
+
+
+def permutation_loss_bwd(pred: Tensor, gt: Tensor, n1: Tensor, n2: Tensor, gscale: Tensor) -> Tensor:
+    B, R, Cc = pred.shape
+    grad = torch.empty_like(pred)
+    rc = _lib.lib().fpm_permutation_loss_bwd(_chk(pred, "pred"), _chk(gt, "gt"), _chk(n1, "n1", torch.int64),
+                                             _chk(n2, "n2", torch.int64), _chk(gscale, "gscale"), grad.data_ptr(),
+                                             B, R, Cc, _stream())
+    _lib.check(rc, "fpm_permutation_loss_bwd"); _count()
+    return grad
+
+
+def matching_stats(pred: Tensor, gt: Tensor, ns: Tensor) -> Tensor:
+    """[B, 3]: sum(pred * gt), sum(gt), sum(pred) over rows < ns[b]."""
+    B, R, Cc = pred.shape
+    out = torch.empty((B, 3), dtype=torch.float32, device=pred.device)
+    rc = _lib.lib().fpm_matching_stats(_chk(pred, "pred"), _chk(gt, "gt"), _chk(ns, "ns", torch.int64), out.data_ptr(),
+                                       B, R, Cc, _stream())
+    _lib.check(rc, "fpm_matching_stats"); _count()
+    return out

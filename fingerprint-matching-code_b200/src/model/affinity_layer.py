@@ -17,10 +17,16 @@ class InnerProductWithWeightsAffinity(nn.Module):
         self.A = torch.nn.Linear(input_dim, output_dim)
 
     def fused_coefficients(self, global_cat: torch.Tensor) -> torch.Tensor:
-        """tanh(A (g / ||g||) + a) for UN-normalised ``global_cat [B, input_dim]`` in one launch
-        (normalize_over_channels of ngm.py:268 + affinity_layer.py:13)."""
-        return ops.affinity_coeff(global_cat.detach().contiguous(), self.A.weight.detach().contiguous(),
-                                  self.A.bias.detach().contiguous())
+        """tanh(A (g / ||g||) + a) for UN-normalised ``global_cat [B, input_dim]`` (normalize_over_channels of
+        ngm.py:268 + affinity_layer.py:13).  Batches of 32 pairs or more go through the tensor-core GEMM (the
+        per-pair mat-vec kernel re-reads the 3 MB weight once per pair: 0.19 ms at 256 pairs against ~0.02 ms)."""
+        g = global_cat.detach().contiguous()
+        if g.shape[0] >= 32:
+            gn = (g / torch.norm(g, dim=1, keepdim=True)).contiguous()
+            lin = ops.gemm_nt(gn, self.A.weight.detach().contiguous(), self.A.bias.detach().contiguous(),
+                              weight_operand=True)
+            return torch.tanh(lin)
+        return ops.affinity_coeff(g, self.A.weight.detach().contiguous(), self.A.bias.detach().contiguous())
 
     def _forward(self, X, Y, weights, use_global):
         return self.forward([X], [Y], weights.unsqueeze(0), use_global)[0]

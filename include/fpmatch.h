@@ -180,6 +180,21 @@ int fpm_lap_topk(const float* ds, const long long* n1, const long long* n2, cons
 int fpm_greedy_perm(float* x, const long long* top_indices, const float* ks, int B, int R, int C, int L,
                     void* stream);
 
+/* ---- (N2) loss and metrics --------------------------------------------------------------------------------------
+ * fpm_permutation_loss replaces the per-pair loop of PermutationLoss.forward (src/loss_func.py:26-59):
+ *   pair_sum[b] = sum over the valid n1_b x n2_b block of BCE(pred, gt) (logs clamped at -100 as torch does);
+ *   the loss is sum_b pair_sum[b] / sum_b n1_b.  fpm_permutation_loss_bwd: grad = gscale[0] * (p - y) / max(p(1-p), 1e-12)
+ *   inside the valid blocks, 0 outside (gscale = upstream gradient / sum n1, a device scalar).
+ * fpm_matching_stats replaces the loops of matching_recall / matching_precision (src/evaluation_metric.py:58-131):
+ *   stats[b] = {sum(pred*gt), sum(gt), sum(pred)} over rows < ns[b].
+ */
+int fpm_permutation_loss(const float* pred, const float* gt, const long long* n1, const long long* n2,
+                         float* pair_sum, int B, int R, int C, void* stream);
+int fpm_permutation_loss_bwd(const float* pred, const float* gt, const long long* n1, const long long* n2,
+                             const float* gscale, float* grad, int B, int R, int C, void* stream);
+int fpm_matching_stats(const float* pred, const float* gt, const long long* ns, float* stats, int B, int R, int C,
+                       void* stream);
+
 /* ---- (A14) batched CSR / CSC products, dense factorised-graph-matching affinity ------------------------------------
  * Replace the reference's JIT extension (src/extension/sparse_dot/sparse_dot.cpp:191-331, bilinear_diag.cpp:303-326)
  * behind src.sparse_torch.CSRMatrix3d.dot / dotdiag, src.sparse.bilinear_diag_torch and RebuildFGM

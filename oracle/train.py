@@ -67,9 +67,17 @@ def loss_and_grads(state: Dict[str, Tensor], data: dict, fmaps, fmap_grads: bool
     return loss.detach(), grads, fg, out
 
 
+def warmup_lr(t: int, base_lr: float = 1e-3, warmup_epochs: int = 10, steps_per_epoch: int = 75) -> float:
+    """Learning rate of training step t under the reference's WarmupScheduler (utils/scheduler.py:11-13, stepped once
+    per epoch, train.py:246-252,297) with 3 x num_iterations = 75 steps per epoch (training_loop.py:21-22)."""
+    epoch = t // steps_per_epoch
+    return base_lr * float(epoch + 1) / warmup_epochs if epoch < warmup_epochs else base_lr
+
+
 def train_trajectory(state: Dict[str, Tensor], batches: List[dict], steps: int, lr: float = 1e-3,
-                     weight_decay: float = 1e-4, clip: float = 5.0) -> List[float]:
-    """`steps` AdamW steps over a fixed cycle of batches; returns the per-step PermutationLoss values."""
+                     weight_decay: float = 1e-4, clip: float = 5.0, lr_schedule=None) -> List[float]:
+    """`steps` AdamW steps over a fixed cycle of batches; returns the per-step PermutationLoss values.
+    ``lr_schedule``: optional callable step -> learning rate (e.g. ``warmup_lr``)."""
     p = {k: v.clone() for k, v in state.items()}
     names = trainable_names(p)
     params = [p[k].requires_grad_(True) for k in names]
@@ -77,6 +85,9 @@ def train_trajectory(state: Dict[str, Tensor], batches: List[dict], steps: int, 
     losses = []
     for it in range(steps):
         data = batches[it % len(batches)]
+        if lr_schedule is not None:
+            for gp in opt.param_groups:
+                gp["lr"] = lr_schedule(it)
         opt.zero_grad()
         from fpmatch import synth          # only for clone_batch (pure python container copy)
         out = head.forward_head(p, synth.clone_batch(data), data["fmaps"], regression=False, training=True,
@@ -86,5 +97,5 @@ def train_trajectory(state: Dict[str, Tensor], batches: List[dict], steps: int, 
         total.backward()
         torch.nn.utils.clip_grad_norm_([q for q in params if q.grad is not None], max_norm=clip)
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     return losses

@@ -9,8 +9,12 @@ Set-up (mirrored by tests/test_gpu_train.py::test_stage1_loss_trajectory_100_ste
   loss to < 1e-25 within 15-35 steps (measured), after which a relative comparison is meaningless; on a stream of
   unrelated pairs the loss stays O(1) for all 100 steps while every update still moves every parameter, so the
   loss at step t is a well-conditioned function of the whole update history;
-  AdamW(lr 1e-3, weight_decay 1e-4) on the stage-1 parameter group, clip_grad_norm_ 5.0  (train.py:157-181,
-  training_loop.py:59-61).
+  AdamW(weight_decay 1e-4) on the stage-1 parameter group, clip_grad_norm_ 5.0 (train.py:157-181,
+  training_loop.py:59-61), with the reference's learning-rate warm-up: LR = 1e-3 (stage1.yml) is scaled by
+  (epoch + 1) / 10 during the first 10 epochs (train.py:246-252,297; utils/scheduler.py:11-13) and an epoch is
+  3 x num_iterations = 75 steps (training_loop.py:21-22, stage1.yml), so steps 0-74 run at 1e-4 and 75-99 at 2e-4.
+  (A first version of this file used a constant 1e-3: the loss then collapses chaotically between steps 60 and 95
+  and even the fp32 oracle is 46 % away from its own fp64 evaluation at step 69.)
 """
 import json
 import sys
@@ -26,6 +30,11 @@ from oracle import head, train as otrain  # noqa: E402
 from src.model.ngm import Net  # noqa: E402
 
 B, N_KPTS, STEPS = 3, 14, 100
+BASE_LR, WARMUP_EPOCHS, STEPS_PER_EPOCH = 1e-3, 10, 75
+
+
+def lr_at(t):
+    return BASE_LR * float(t // STEPS_PER_EPOCH + 1) / WARMUP_EPOCHS
 
 
 def batch(t):
@@ -41,10 +50,12 @@ def run(dtype):
          for k, v in net.state_dict().items()}
     names = otrain.trainable_names(p)
     params = [p[k].requires_grad_(True) for k in names]
-    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4)
+    opt = torch.optim.AdamW(params, lr=lr_at(0), weight_decay=1e-4)
     losses = []
     for t in range(STEPS):
         d = batch(t)
+        for gp in opt.param_groups:
+            gp["lr"] = lr_at(t)
         opt.zero_grad()
         fm = [(a.to(dtype), b.to(dtype)) for a, b in d["fmaps"]]
         out = head.forward_head(p, d, fm, regression=False, training=True, keep_graph=True, dtype=dtype)
@@ -61,7 +72,8 @@ def run(dtype):
 if __name__ == "__main__":
     out = ROOT / "tests" / "golden" / "train_trajectory.json"
     rec = json.loads(out.read_text()) if out.exists() else {}
-    rec.update({"B": B, "n": N_KPTS, "steps": STEPS, "seed_base": 1000, "fmap_noise": None, "lr": 1e-3,
+    rec.update({"B": B, "n": N_KPTS, "steps": STEPS, "seed_base": 1000, "fmap_noise": None, "lr": BASE_LR,
+                "warmup_epochs": WARMUP_EPOCHS, "steps_per_epoch": STEPS_PER_EPOCH,
                 "weight_decay": 1e-4, "clip": 5.0, "torch": torch.__version__})
     t0 = time.time()
     if "--fp64" in sys.argv:

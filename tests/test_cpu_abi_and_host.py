@@ -181,3 +181,29 @@ def test_data_parallel_sharding_and_gather_gloo_world2(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_data_to_cuda_walks_every_container_type():
+    """Host logic of the utils.data_to_cuda drop-in (reference: utils/data_to_cuda.py:5-33) with a CPU mover."""
+    import numpy as np
+    import scipy.sparse as ssp
+    from fpmatch import synth
+    from src.sparse_torch import CSRMatrix3d
+    from utils.data_to_cuda import data_to_cuda
+    d = synth.make_batch(2, 6, seed=1)
+    d["KGHs"] = (CSRMatrix3d([ssp.identity(3, dtype=np.float32, format="csr")] * 2), "tag", 3, 0.5)
+    seen = []
+
+    def mover(t):
+        seen.append(t.shape)
+        return t.clone()
+
+    src_ps = d["Ps"][0]
+    out = data_to_cuda(d, device="cpu", mover=mover)
+    assert out is d                                           # dicts / lists are updated in place
+    assert isinstance(out["fmaps"][0], list)                  # tuples come back as lists
+    assert out["Ps"][0] is not src_ps and torch.equal(out["Ps"][0], src_ps)
+    assert type(out["pyg_graphs"][0]).__name__ == "GraphBatch" and out["KGHs"][1:] == ["tag", 3, 0.5]
+    assert out["KGHs"][0].shape == (2, 3, 3) and len(seen) > 20
+    with pytest.raises(TypeError):
+        data_to_cuda({"bad": object()}, device="cpu")

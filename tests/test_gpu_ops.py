@@ -370,6 +370,13 @@ def test_affinity_golden_and_edges(ops, oo):
     coeff = aff.fused_coefficients(gcat.to(DEV))
     ref_c = torch.tanh(torch.nn.functional.linear(w, aff.A.weight.detach().cpu(), aff.A.bias.detach().cpu()))
     assert (coeff.cpu() - ref_c).abs().max() < 2e-6
+    # batches of >= 32 pairs take the tensor-core GEMM route: same values
+    gbig = torch.randn(70, 1024, generator=torch.Generator().manual_seed(6))
+    cbig = aff.fused_coefficients(gbig.to(DEV))
+    ref_big = torch.tanh(torch.nn.functional.linear(oo.normalize_over_channels(gbig), aff.A.weight.detach().cpu(),
+                                                    aff.A.bias.detach().cpu()))
+    report("affinity_coeff_gemm_route", max_abs=(cbig.cpu() - ref_big).abs().max().item())
+    assert (cbig.cpu() - ref_big).abs().max() < 2e-6
     emax1 = int((g1.eptr[1:] - g1.eptr[:-1]).max()); emax2 = int((g2.eptr[1:] - g2.eptr[:-1]).max())
     Ke = ops.affinity_edges(X1.to(DEV), X2.to(DEV), coeff, g1.eptr.to(DEV), g2.eptr.to(DEV), g1.edge_index.to(DEV),
                             g2.edge_index.to(DEV), emax1, emax2, scale=0.5)
@@ -456,3 +463,26 @@ def test_afau_encoder_golden_and_structured(ops, oo):
     ec = (g_col.cpu() - fx["out_col_struct"].max(1).values).abs().max().item()
     report("afau_structured_fast", row_err=er, col_err=ec)
     assert er < 3e-4 and ec < 3e-4
+
+
+# ---------------------------------------------------------------------------------------------- loss / metrics
+def test_permutation_loss_and_matching_metrics_golden():
+    """PermutationLoss (value + gradient) and matching_recall / precision / accuracy against vectors produced by the
+    reference's own src/loss_func.py and src/evaluation_metric.py (tests/golden/make_loss_golden.py)."""
+    from src.evaluation_metric import matching_accuracy, matching_precision, matching_recall
+    from src.loss_func import PermutationLoss
+    fx = torch.load(GOLD / "loss_metric.pt")
+    p = fx["pred"].to(DEV).requires_grad_(True)
+    loss = PermutationLoss()(p, fx["gt"].to(DEV), fx["n1"].to(DEV), fx["n2"].to(DEV))
+    loss.backward()
+    e_loss = abs(loss.item() - fx["loss"].item()) / abs(fx["loss"].item())
+    e_grad = ((p.grad.cpu() - fx["grad"]).abs().max() / fx["grad"].abs().max()).item()
+    rec = matching_recall(fx["hard"].to(DEV), fx["gt"].to(DEV), fx["n1"].to(DEV))
+    prec = matching_precision(fx["hard"].to(DEV), fx["gt"], fx["n1"].to(DEV))
+    acc = matching_accuracy(fx["hard"].to(DEV), fx["gt"].to(DEV), [fx["n1"].to(DEV), fx["n2"].to(DEV)], 0)
+    report("loss_metrics", loss_rel=e_loss, grad_rel=e_grad)
+    assert e_loss < 1e-6 and e_grad < 1e-6
+    assert torch.equal(rec.cpu(), fx["recall"]) and torch.equal(prec.cpu(), fx["precision"])
+    assert torch.equal(acc.cpu(), fx["accuracy"])
+    with pytest.raises(AssertionError):
+        PermutationLoss()(fx["pred"].to(DEV) * 1.5, fx["gt"].to(DEV), fx["n1"].to(DEV), fx["n2"].to(DEV))

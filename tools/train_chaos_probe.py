@@ -31,9 +31,13 @@ def run(mode, steps):
     names = set(otrain.trainable_names(sd))
     net = net.to(DEV).train()
     params = [q for k, q in net.named_parameters() if k in names]
-    opt = torch.optim.AdamW(params, lr=gold["lr"], weight_decay=gold["weight_decay"])
+    lr_at = lambda t: otrain.warmup_lr(t, gold["lr"], gold.get("warmup_epochs", 1), gold.get("steps_per_epoch", 10 ** 9)) \
+        if "warmup_epochs" in gold else gold["lr"]
+    opt = torch.optim.AdamW(params, lr=lr_at(0), weight_decay=gold["weight_decay"])
     out_l = []
     for t in range(steps):
+        for gp in opt.param_groups:
+            gp["lr"] = lr_at(t)
         d = synth.make_batch(gold["B"], gold["n"], seed=gold["seed_base"] + t, imposter_every=0, with_kron=False,
                              fmap_noise=gold["fmap_noise"])
         d.pop("label")
