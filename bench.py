@@ -252,6 +252,9 @@ def main():
     else:
         peak = tf32_peak
         peak_note = f"TF32 dense = {peak_kind} sustained bf16 cuBLAS peak / 2 (no TF32 figure is measured)"
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape, from the committed
+    # `ncu --set full` capture profiles/r1c_ncu_full_gemm_pair.md (algorithmic bytes: 2.185e9)
+    traffic = 2.644e9 if (mode == "3xf16" and (big[1], big[2], big[3]) == (25600, 19968, 768)) else None
     achieved = flops / (gemm_ms / 1e3) / 1e12
     gemm_share = gemm_ms * len(same) / args.steps / ms_step
 
@@ -299,7 +302,7 @@ def main():
                        "l2": "inputs + intermediates per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "dead_ke_computed": True, "parallelism": f"dp{world} (independent pairs, no data-path collective)"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": f"gemm_nt[{mode}] M={big[1]} N={big[2]} K={big[3]}",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": f"gemm_nt[{mode}] M={big[1]} N={big[2]} K={big[3]}",
                          "launch_ms": gemm_ms, "share_of_step": gemm_share, "peak_source": peak_note},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

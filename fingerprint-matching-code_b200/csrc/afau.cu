@@ -170,6 +170,202 @@ k_head_kernel(const float* __restrict__ g_row, const float* __restrict__ g_col,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Backward of afau_attention_kernel (training of the AFA-U k-branch, stages 2-5 of train.py; the reference
+// differentiates afau.py:253-297 with autograd through its [B,n,16,n,16] intermediates).
+// Same decomposition as the forward: CTA per (row tile, head, pair), thread per query row, scores recomputed.
+//   w_ij = softmax_j(s_ij),  out_i = sum_j w_ij v_j
+//   ds_ij = w_ij (dout_i . v_j - dout_i . out_i);  dv_j += w_ij dout_i
+//   s = sum_m relu(dot w1a_m + c w1b_m + b1_m) w2_m + b2  ->  gradients of the 65 per-head mixing parameters
+//   (thread-local sums, block reduction, one atomic per parameter per CTA) and d dot -> dq_i, dk_j.
+// dk / dv are accumulated with shared-memory atomics per CTA and added to global memory (zero-filled by the caller).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+afau_attention_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                          const float* __restrict__ cost, long long cs_b, long long cs_r, long long cs_c,
+                          const float* __restrict__ mix1_w, const float* __restrict__ mix1_b,
+                          const float* __restrict__ mix2_w, const float* __restrict__ mix2_b,
+                          const float* __restrict__ out, const float* __restrict__ dout, float* __restrict__ dq,
+                          float* __restrict__ dk, float* __restrict__ dv, float* __restrict__ dmix, int nr, int nc) {
+  extern __shared__ float sm[];
+  float* ks = sm;                                  // [nc][16]
+  float* vs = ks + (size_t)nc * kQkv;
+  float* dks = vs + (size_t)nc * kQkv;             // [nc][16] accumulators
+  float* dvs = dks + (size_t)nc * kQkv;
+  __shared__ float w1a[kMs], w1b[kMs], b1[kMs], w2[kMs];
+  __shared__ float b2s;
+  __shared__ float pred[4][4 * kMs + 1];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int E = kHeads * kQkv;
+  for (int idx = threadIdx.x; idx < nc * kQkv; idx += blockDim.x) {
+    const int j = idx / kQkv, d = idx - j * kQkv;
+    const size_t g = ((size_t)b * nc + j) * E + h * kQkv + d;
+    ks[idx] = k[g];
+    vs[idx] = v[g];
+    dks[idx] = 0.f;
+    dvs[idx] = 0.f;
+  }
+  if (threadIdx.x < kMs) {
+    w1a[threadIdx.x] = mix1_w[(h * 2 + 0) * kMs + threadIdx.x];
+    w1b[threadIdx.x] = mix1_w[(h * 2 + 1) * kMs + threadIdx.x];
+    b1[threadIdx.x] = mix1_b[h * kMs + threadIdx.x];
+    w2[threadIdx.x] = mix2_w[h * kMs + threadIdx.x];
+  }
+  if (threadIdx.x == 0) b2s = mix2_b[h];
+  __syncthreads();
+
+  // per-thread sums of the mixing-parameter gradients: w1a[16] w1b[16] b1[16] w2[16] b2
+  float gw1a[kMs], gw1b[kMs], gb1[kMs], gw2[kMs], gb2 = 0.f;
+#pragma unroll
+  for (int m = 0; m < kMs; ++m) { gw1a[m] = 0.f; gw1b[m] = 0.f; gb1[m] = 0.f; gw2[m] = 0.f; }
+
+  if (i < nr) {
+    float qv[kQkv], go[kQkv], dqv[kQkv];
+    float go_dot_out = 0.f;
+    {
+      const size_t base = ((size_t)b * nr + i) * E + h * kQkv;
+#pragma unroll
+      for (int d = 0; d < kQkv; ++d) {
+        qv[d] = q[base + d]; go[d] = dout[base + d]; dqv[d] = 0.f;
+        go_dot_out = fmaf(go[d], out[base + d], go_dot_out);
+      }
+    }
+    const float* crow = cost + (size_t)b * cs_b + (size_t)i * cs_r;
+    auto score = [&](int j, float& dot, float& c) -> float {
+      dot = 0.f;
+#pragma unroll
+      for (int d = 0; d < kQkv; ++d) dot = fmaf(qv[d], ks[j * kQkv + d], dot);
+      dot = dot / 4.0f;
+      c = crow[(size_t)j * cs_c];
+      float s = 0.f;
+#pragma unroll
+      for (int m = 0; m < kMs; ++m) {
+        const float h1 = fmaxf(fmaf(c, w1b[m], dot * w1a[m]) + b1[m], 0.f);
+        s = fmaf(h1, w2[m], s);
+      }
+      return s + b2s;
+    };
+    float mx = kNegInf, dot, c;
+    for (int j = 0; j < nc; ++j) mx = fmaxf(mx, score(j, dot, c));
+    float den = 0.f;
+    for (int j = 0; j < nc; ++j) den += expf(score(j, dot, c) - mx);
+    for (int j = 0; j < nc; ++j) {
+      const float w = expf(score(j, dot, c) - mx) / den;
+      float gv = 0.f;
+#pragma unroll
+      for (int d = 0; d < kQkv; ++d) gv = fmaf(go[d], vs[j * kQkv + d], gv);
+      const float ds = w * (gv - go_dot_out);
+#pragma unroll
+      for (int d = 0; d < kQkv; ++d) atomicAdd(&dvs[j * kQkv + d], w * go[d]);
+      float ddot = 0.f;
+      gb2 += ds;
+#pragma unroll
+      for (int m = 0; m < kMs; ++m) {
+        const float pre = fmaf(c, w1b[m], dot * w1a[m]) + b1[m];
+        const float h1 = fmaxf(pre, 0.f);
+        gw2[m] = fmaf(ds, h1, gw2[m]);
+        const float dh = pre > 0.f ? ds * w2[m] : 0.f;
+        gw1a[m] = fmaf(dh, dot, gw1a[m]);
+        gw1b[m] = fmaf(dh, c, gw1b[m]);
+        gb1[m] += dh;
+        ddot = fmaf(dh, w1a[m], ddot);
+      }
+      ddot = ddot / 4.0f;
+      if (ddot != 0.f) {
+#pragma unroll
+        for (int d = 0; d < kQkv; ++d) {
+          dqv[d] = fmaf(ddot, ks[j * kQkv + d], dqv[d]);
+          atomicAdd(&dks[j * kQkv + d], ddot * qv[d]);
+        }
+      }
+    }
+    const size_t base = ((size_t)b * nr + i) * E + h * kQkv;
+#pragma unroll
+    for (int d = 0; d < kQkv; ++d) dq[base + d] = dqv[d];
+  }
+  // block reduction of the 65 mixing-parameter sums, then one atomic each
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int m = 0; m < kMs; ++m) {
+    const float a0 = warp_sum(gw1a[m]), a1 = warp_sum(gw1b[m]), a2 = warp_sum(gb1[m]), a3 = warp_sum(gw2[m]);
+    if (lane == 0) { pred[warp][m] = a0; pred[warp][kMs + m] = a1; pred[warp][2 * kMs + m] = a2; pred[warp][3 * kMs + m] = a3; }
+  }
+  {
+    const float a4 = warp_sum(gb2);
+    if (lane == 0) pred[warp][4 * kMs] = a4;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 * kMs + 1) {
+    const float t = pred[0][threadIdx.x] + pred[1][threadIdx.x] + pred[2][threadIdx.x] + pred[3][threadIdx.x];
+    if (t != 0.f) atomicAdd(dmix + (size_t)h * (4 * kMs + 1) + threadIdx.x, t);
+  }
+  for (int idx = threadIdx.x; idx < nc * kQkv; idx += blockDim.x) {
+    const int j = idx / kQkv, d = idx - j * kQkv;
+    const size_t g = ((size_t)b * nc + j) * E + h * kQkv + d;
+    if (dks[idx] != 0.f) atomicAdd(dk + g, dks[idx]);
+    if (dvs[idx] != 0.f) atomicAdd(dv + g, dvs[idx]);
+  }
+}
+
+// Backward of add_instnorm_kernel.  dy [B,n,E] and/or drowmax [B,E] (gradient of the row maximum, routed to the
+// first arg-max row) -> dx [B,n,E] (= gradient of `a` and of a tensor `other`); dgamma/dbeta [E] and, for a
+// row-vector `other` (mode 2), dvec [E] are accumulated with atomics (zero-filled by the caller).
+__global__ void __launch_bounds__(128)
+add_instnorm_bwd_kernel(const float* __restrict__ a, const float* __restrict__ other, int other_mode,
+                        const float* __restrict__ gamma, const float* __restrict__ dy,
+                        const float* __restrict__ drowmax, float* __restrict__ dx, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, float* __restrict__ dvec, int n, int E, float eps) {
+  const int b = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const float* ab = a + (size_t)b * n * E + e;
+  const float* ob = other_mode == 1 ? other + (size_t)b * n * E + e : nullptr;
+  const float ov = other_mode == 2 ? other[e] : 0.f;
+  const float* dyb = dy ? dy + (size_t)b * n * E + e : nullptr;
+  float sum = 0.f;
+  for (int r = 0; r < n; ++r) sum += ab[(size_t)r * E] + (ob ? ob[(size_t)r * E] : ov);
+  const float mean = sum / (float)n;
+  float vs = 0.f;
+  for (int r = 0; r < n; ++r) {
+    const float d = ab[(size_t)r * E] + (ob ? ob[(size_t)r * E] : ov) - mean;
+    vs = fmaf(d, d, vs);
+  }
+  const float inv = 1.0f / sqrtf(vs / (float)n + eps);
+  const float g = gamma[e];
+  int arg = -1;
+  float gmax = 0.f;
+  if (drowmax) {
+    gmax = drowmax[(size_t)b * E + e];
+    float mxv = kNegInf;
+    for (int r = 0; r < n; ++r) {
+      const float x = ab[(size_t)r * E] + (ob ? ob[(size_t)r * E] : ov);
+      const float y = (x - mean) * inv * g;            // + beta: constant, does not move the arg-max
+      if (y > mxv) { mxv = y; arg = r; }
+    }
+  }
+  float s1 = 0.f, s2 = 0.f;                            // sum dy, sum dy * xhat
+  for (int r = 0; r < n; ++r) {
+    const float xh = (ab[(size_t)r * E] + (ob ? ob[(size_t)r * E] : ov) - mean) * inv;
+    const float d = (dyb ? dyb[(size_t)r * E] : 0.f) + (r == arg ? gmax : 0.f);
+    s1 += d;
+    s2 = fmaf(d, xh, s2);
+  }
+  atomicAdd(dgamma + e, s2);
+  atomicAdd(dbeta + e, s1);
+  const float scale = g * inv / (float)n;
+  float* dxb = dx + (size_t)b * n * E + e;
+  float tot = 0.f;
+  for (int r = 0; r < n; ++r) {
+    const float xh = (ab[(size_t)r * E] + (ob ? ob[(size_t)r * E] : ov) - mean) * inv;
+    const float d = (dyb ? dyb[(size_t)r * E] : 0.f) + (r == arg ? gmax : 0.f);
+    const float v = scale * ((float)n * d - s1 - xh * s2);
+    dxb[(size_t)r * E] = v;
+    tot += v;
+  }
+  if (other_mode == 2 && dvec) atomicAdd(dvec + e, tot);
+}
+
 }  // namespace fpm
 
 extern "C" int fpm_afau_attention(const float* q, const float* k, const float* v, const float* cost,
@@ -229,6 +425,43 @@ extern "C" int fpm_k_head(const float* g_row, const float* g_col, const float* c
   fpm::k_head_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(
       g_row, g_col, weights[0], weights[1], weights[2], weights[3], weights[4], weights[5], weights[6],
       weights[7], (const int64_t*)n1, (const int64_t*)n2, ks, k_scaled, E, Hd, mean_k);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+// dq [B,nr,256] is overwritten; dk, dv [B,nc,256] and dmix [16 heads x 65] (mix1_w[0][16] mix1_w[1][16] mix1_b[16]
+// mix2_w[16] mix2_b per head) are ACCUMULATED: the caller zero-fills them.
+extern "C" int fpm_afau_attention_bwd(const float* q, const float* k, const float* v, const float* cost, long long cs_b,
+                                      long long cs_r, long long cs_c, const float* mix1_w, const float* mix1_b,
+                                      const float* mix2_w, const float* mix2_b, const float* out, const float* dout,
+                                      float* dq, float* dk, float* dv, float* dmix, int B, int nr, int nc,
+                                      void* stream) {
+  FPM_CHECK_ARG(q && k && v && cost && mix1_w && mix1_b && mix2_w && mix2_b && out && dout && dq && dk && dv && dmix,
+                "fpm_afau_attention_bwd: null tensor");
+  FPM_CHECK_ARG(B >= 0 && nr > 0 && nc > 0, "fpm_afau_attention_bwd: bad sizes");
+  if (B == 0) return FPM_OK;
+  FPM_CHECK_ARG(B <= 65535, "fpm_afau_attention_bwd: batch too large");
+  const size_t smem = (size_t)4 * nc * fpm::kQkv * sizeof(float);
+  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_afau_attention_bwd: too many columns");
+  FPM_CUDA(cudaFuncSetAttribute(fpm::afau_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(fpm_cdiv(nr, 128), fpm::kHeads, B);
+  fpm::afau_attention_bwd_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(
+      q, k, v, cost, cs_b, cs_r, cs_c, mix1_w, mix1_b, mix2_w, mix2_b, out, dout, dq, dk, dv, dmix, nr, nc);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_add_instnorm_bwd(const float* a, const float* other, int other_mode, const float* gamma,
+                                    const float* dy, const float* drowmax, float* dx, float* dgamma, float* dbeta,
+                                    float* dvec, int B, int n, int E, float eps, void* stream) {
+  FPM_CHECK_ARG(a && gamma && dx && dgamma && dbeta && (dy || drowmax), "fpm_add_instnorm_bwd: null tensor");
+  FPM_CHECK_ARG(other_mode == 0 || other, "fpm_add_instnorm_bwd: other tensor missing");
+  FPM_CHECK_ARG(other_mode >= 0 && other_mode <= 2, "fpm_add_instnorm_bwd: bad mode");
+  if (B == 0) return FPM_OK;
+  FPM_CHECK_ARG(B <= 65535, "fpm_add_instnorm_bwd: batch too large");
+  dim3 grid(fpm_cdiv(E, 128), B);
+  fpm::add_instnorm_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, other, other_mode, gamma, dy, drowmax, dx,
+                                                                        dgamma, dbeta, dvec, n, E, eps);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

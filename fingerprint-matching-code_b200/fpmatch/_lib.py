@@ -72,6 +72,8 @@ SIGNATURES = {
     "fpm_bmm_ragged": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
     "fpm_segment_rowdot": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "fpm_gnn_layer_bwd": (_I, [_P] * 19 + [_I] * 6 + [_P]),
+    "fpm_afau_attention_bwd": (_I, [_P, _P, _P, _P, _LL, _LL, _LL] + [_P] * 10 + [_I, _I, _I, _P]),
+    "fpm_add_instnorm_bwd": (_I, [_P, _P, _I] + [_P] * 7 + [_I, _I, _I, _F, _P]),
     "fpm_sinkhorn_bwd_workspace_bytes": (_LL, [_I, _I, _I, _I]),
     "fpm_sinkhorn_log_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "fpm_soft_topk_bwd_workspace_bytes": (_LL, [_I, _I, _I]),

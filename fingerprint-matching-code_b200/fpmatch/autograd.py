@@ -214,3 +214,108 @@ class NgmSolverFn(Function):
         dKp_t = dsk.transpose(1, 2).contiguous()
         ctx.saved = None
         return (dKp_t, None, *grads)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# AFA-U k-branch (afau.py:22-300, ngm.py:386-412): trained in stages 2-5 of train.py
+# ---------------------------------------------------------------------------------------------------------------------
+class LinearFn(Function):
+    """act(x W^T + b) on the tensor-core GEMM; x [..., K], W [N, K].  act: 0 none, 1 relu.
+
+    Runs in the 3xTF32 mode: the fp16 split keeps 22 bits of each ROW's maximum, the tf32 split 21 bits of each
+    ELEMENT.  The k-branch feeds these outputs to an InstanceNorm over nearly identical rows (the row embedding is
+    all zeros), which amplifies absolute errors of small elements by ~1e5; with the fp16 split the FFN gradients
+    were 7x further from an fp64 evaluation than the fp32 oracle is, with tf32 they are on par.  The GEMMs are
+    small (K = 256 / 600), so the halved MMA rate is invisible."""
+    MODE = "3xtf32"
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], act: int):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).contiguous()
+        w = weight.detach().contiguous()
+        out = ops.gemm_nt(x2, w, None if bias is None else bias.detach().contiguous(), act, mode=LinearFn.MODE)
+        ctx.save_for_backward(x2, w, out if act == 1 else None)
+        ctx.meta = (shape, act, bias is not None)
+        return out.view(*shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        x2, w, out = ctx.saved_tensors
+        shape, act, has_bias = ctx.meta
+        g2 = g.reshape(-1, w.shape[0]).contiguous()
+        if act == 1:
+            g2 = g2 * (out > 0).to(g2.dtype)
+        dx = ops.gemm_nt(g2, ops.transpose_pad(w), mode=LinearFn.MODE)                         # g2 [M, N] . W [N, K]
+        dw = ops.gemm_nt(ops.transpose_pad(g2), ops.transpose_pad(x2), mode=LinearFn.MODE)     # g2^T . x
+        return dx.view(shape), dw, (g2.sum(0) if has_bias else None), None
+
+
+class OnehotProjFn(Function):
+    """Projection of the one-hot column embedding: out[b, j, :] = W[:, j] for j < n[b], else 0 (ngm.py:396-399)."""
+
+    @staticmethod
+    def forward(ctx, W: Tensor, n: Tensor, nmax: int):
+        ctx.save_for_backward(n)
+        ctx.meta = (tuple(W.shape), nmax)
+        return ops.onehot_proj(W.detach().contiguous(), n, nmax)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (n,) = ctx.saved_tensors
+        (OUT, IN), nmax = ctx.meta
+        mask = (torch.arange(nmax, device=g.device)[None, :] < n[:, None]).to(g.dtype)       # [B, nmax]
+        dW = torch.zeros((OUT, IN), dtype=g.dtype, device=g.device)
+        m = min(nmax, IN)
+        dW[:, :m] = (g * mask[:, :, None]).sum(0).t()[:, :m]
+        return dW, None, None
+
+
+class AfauAttentionFn(Function):
+    """CrossSet_MultiHeadAttention.forward (afau.py:231-300) with the heads concatenated: q [B,nr,256], k/v [B,nc,256]."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, cost, transposed_cost, mix1_w, mix1_b, mix2_w, mix2_b):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        cost = cost.detach().contiguous()
+        d = lambda t: t.detach().contiguous()
+        out = ops.afau_attention(q, k, v, cost, transposed_cost, d(mix1_w), d(mix1_b), d(mix2_w), d(mix2_b))
+        ctx.save_for_backward(q, k, v, cost, d(mix1_w), d(mix1_b), d(mix2_w), d(mix2_b), out)
+        ctx.transposed_cost = transposed_cost
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k, v, cost, m1w, m1b, m2w, m2b, out = ctx.saved_tensors
+        dq, dk, dv, dm1w, dm1b, dm2w, dm2b = ops.afau_attention_bwd(q, k, v, cost, ctx.transposed_cost, m1w, m1b, m2w,
+                                                                    m2b, out, g.contiguous())
+        return dq, dk, dv, None, None, dm1w, dm1b, dm2w, dm2b
+
+
+class AddInstNormFn(Function):
+    """AddAndInstanceNormalization.forward (afau.py:154-176): InstanceNorm1d(affine) over the rows of a + other;
+    ``want_rowmax`` additionally returns the per-channel maximum over rows (the padded MaxPool1d of ngm.py:402-405)."""
+
+    @staticmethod
+    def forward(ctx, a, other, gamma, beta, eps, want_rowmax):
+        a = a.contiguous()
+        other_c = None if other is None else other.detach().contiguous()
+        g, b = gamma.detach().contiguous(), beta.detach().contiguous()
+        res = ops.add_instnorm(a, other_c, g, b, want_rowmax=want_rowmax, eps=eps)
+        ctx.save_for_backward(a, other_c, g)
+        ctx.meta = (eps, want_rowmax, other is not None and other.dim() == 1)
+        if want_rowmax:
+            return res[0], res[1]
+        return res
+
+    @staticmethod
+    def backward(ctx, dy, drowmax=None):
+        a, other, g = ctx.saved_tensors
+        eps, want_rowmax, vec = ctx.meta
+        dy_c = None if dy is None else dy.contiguous()
+        dr_c = None if (drowmax is None or not want_rowmax) else drowmax.contiguous()
+        if dy_c is None and dr_c is None:
+            return None, None, None, None, None, None
+        dx, dgamma, dbeta, dvec = ops.add_instnorm_bwd(a, other, g, dy_c, dr_c, eps)
+        dother = None if other is None else (dvec if vec else dx)
+        return dx, dother, dgamma, dbeta, None, None

@@ -715,3 +715,51 @@ def matching_stats(pred: Tensor, gt: Tensor, ns: Tensor) -> Tensor:
                                        B, R, Cc, _stream())
     _lib.check(rc, "fpm_matching_stats"); _count()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# AFA-U backward (k-branch training, stages 2-5)
+# ---------------------------------------------------------------------------------------------------
+def _cost_strides(cost: Tensor, nr: int, nc: int, transposed_cost: bool):
+    R, Cc = cost.shape[1], cost.shape[2]
+    if transposed_cost:
+        assert (nr, nc) == (Cc, R)
+        return R * Cc, 1, Cc
+    assert (nr, nc) == (R, Cc)
+    return R * Cc, Cc, 1
+
+
+def afau_attention_bwd(q: Tensor, k: Tensor, v: Tensor, cost: Tensor, transposed_cost: bool, mix1_w: Tensor,
+                       mix1_b: Tensor, mix2_w: Tensor, mix2_b: Tensor, out: Tensor, dout: Tensor):
+    """Returns (dq, dk, dv, dmix1_w [16,2,16], dmix1_b [16,16], dmix2_w [16,16,1], dmix2_b [16,1])."""
+    B, nr, E = q.shape
+    nc = k.shape[1]
+    dq = torch.empty_like(q)
+    dk = torch.zeros_like(k); dv = torch.zeros_like(v)
+    dmix = torch.zeros((16, 65), dtype=torch.float32, device=q.device)
+    cs_b, cs_r, cs_c = _cost_strides(cost, nr, nc, transposed_cost)
+    rc = _lib.lib().fpm_afau_attention_bwd(_chk(q, "q"), _chk(k, "k"), _chk(v, "v"), _chk(cost, "cost"), cs_b, cs_r, cs_c,
+                                           _chk(mix1_w, "mix1_weight"), _chk(mix1_b, "mix1_bias"),
+                                           _chk(mix2_w, "mix2_weight"), _chk(mix2_b, "mix2_bias"), _chk(out, "out"),
+                                           _chk(dout, "dout"), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                           dmix.data_ptr(), B, nr, nc, _stream())
+    _lib.check(rc, "fpm_afau_attention_bwd"); _count()
+    dm1w = torch.stack((dmix[:, 0:16], dmix[:, 16:32]), dim=1)
+    return dq, dk, dv, dm1w, dmix[:, 32:48].clone(), dmix[:, 48:64].reshape(16, 16, 1).clone(), dmix[:, 64:65].clone()
+
+
+def add_instnorm_bwd(a: Tensor, other: Optional[Tensor], gamma: Tensor, dy: Optional[Tensor],
+                     drowmax: Optional[Tensor], eps: float = 1e-5):
+    """Returns (dx [B,n,E], dgamma [E], dbeta [E], dvec [E] or None)."""
+    B, n, E = a.shape
+    mode = 0 if other is None else (2 if other.dim() == 1 else 1)
+    dx = torch.empty_like(a)
+    dgamma = torch.zeros((E,), dtype=torch.float32, device=a.device)
+    dbeta = torch.zeros((E,), dtype=torch.float32, device=a.device)
+    dvec = torch.zeros((E,), dtype=torch.float32, device=a.device) if mode == 2 else None
+    rc = _lib.lib().fpm_add_instnorm_bwd(_chk(a, "a"), _chk(other, "other"), mode, _chk(gamma, "norm.weight"),
+                                         _chk(dy, "dy"), _chk(drowmax, "drowmax"), dx.data_ptr(), dgamma.data_ptr(),
+                                         dbeta.data_ptr(), dvec.data_ptr() if dvec is not None else None, B, n, E,
+                                         float(eps), _stream())
+    _lib.check(rc, "fpm_add_instnorm_bwd"); _count()
+    return dx, dgamma, dbeta, dvec

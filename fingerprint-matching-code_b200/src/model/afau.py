@@ -50,6 +50,24 @@ class Encoder(nn.Module):
         return g_row, g_col
 
 
+    def forward_k_inputs_train(self, cost_mat, n2, n1max, n2max):
+        """Differentiable twin of ``forward_k_inputs`` (stages 2-5 of train.py train this branch): the same kernels
+        behind ``fpmatch.autograd`` Functions.  Returns (g_row, g_col, zero) where ``zero`` is an exact 0 that is
+        connected to the parameters whose gradient is identically zero in the reference's graph (projections of the
+        all-zero row embedding, the column block's attention): autograd then hands the optimiser zero tensors rather
+        than ``None`` for them, exactly as it does in the reference (AdamW still applies weight decay to those)."""
+        assert len(self.layers) == 1
+        layer = self.layers[0]
+        g_row = layer.row_encoding_block.forward_zero_rows_train(cost_mat, n2, n1max, n2max)
+        g_col = layer.col_encoding_block.forward_onehot_rows_zero_cols_train(n2, n2max)
+        rb, cb = layer.row_encoding_block, layer.col_encoding_block
+        dead = [rb.Wq.weight, cb.Wq.weight, cb.Wk.weight, cb.Wv.weight, cb.multi_head_combine.weight,
+                cb.mixed_score_MHA.mix1_weight, cb.mixed_score_MHA.mix1_bias, cb.mixed_score_MHA.mix2_weight,
+                cb.mixed_score_MHA.mix2_bias]
+        zero = sum((p.sum() * 0.0 for p in dead))
+        return g_row, g_col, zero
+
+
 class EncoderLayer(nn.Module):
     def __init__(self, **model_params):
         super().__init__()
@@ -64,8 +82,11 @@ class EncoderLayer(nn.Module):
 
 def _lin(x3, weight, bias=None, act=0):
     B, n, K = x3.shape
-    out = ops.gemm_nt(x3.reshape(B * n, K), weight.detach().contiguous(),
-                      None if bias is None else bias.detach().contiguous(), act, weight_operand=True)
+    # the Parameter object itself is handed down: the operand-split cache is keyed on the live tensor object, and
+    # .detach() would mint a new one per call
+    w = weight if weight.is_contiguous() else weight.detach().contiguous()
+    out = ops.gemm_nt(x3.reshape(B * n, K), w, None if bias is None else bias.detach().contiguous(), act,
+                      weight_operand=True)
     return out.view(B, n, -1)
 
 
@@ -137,6 +158,34 @@ class EncodingBlock(nn.Module):
         out2 = self.feed_forward(out1)
         _, rowmax = self.add_n_normalization_2(out1, out2, want_rowmax=True)
         return rowmax
+
+
+    # ---- the same two forms, differentiable ---------------------------------------------------------------------
+    def _tail_train(self, first, second):
+        from fpmatch import autograd as fa
+        n1, n2 = self.add_n_normalization_1.norm, self.add_n_normalization_2.norm
+        out1 = fa.AddInstNormFn.apply(first, second, n1.weight, n1.bias, n1.eps, False)
+        ff = self.feed_forward
+        hid = fa.LinearFn.apply(out1, ff.W1.weight, ff.W1.bias, 1)
+        out2 = fa.LinearFn.apply(hid, ff.W2.weight, ff.W2.bias, 0)
+        _, rowmax = fa.AddInstNormFn.apply(out1, out2, n2.weight, n2.bias, n2.eps, True)
+        return rowmax
+
+    def forward_zero_rows_train(self, cost_mat, n2, n1max, n2max):
+        from fpmatch import autograd as fa
+        B, dev = cost_mat.shape[0], cost_mat.device
+        q = torch.zeros((B, n1max, self.Wq.out_features), dtype=torch.float32, device=dev)
+        k = fa.OnehotProjFn.apply(self.Wk.weight, n2, n2max)
+        v = fa.OnehotProjFn.apply(self.Wv.weight, n2, n2max)
+        m = self.mixed_score_MHA
+        att = fa.AfauAttentionFn.apply(q, k, v, cost_mat, False, m.mix1_weight, m.mix1_bias, m.mix2_weight, m.mix2_bias)
+        mh = fa.LinearFn.apply(att, self.multi_head_combine.weight, self.multi_head_combine.bias, 0)
+        return self._tail_train(mh, None)
+
+    def forward_onehot_rows_zero_cols_train(self, n2, n2max):
+        dev = n2.device
+        onehot = ops.onehot_proj(torch.eye(self.Wq.in_features, dtype=torch.float32, device=dev), n2, n2max)
+        return self._tail_train(onehot, self.multi_head_combine.bias)
 
 
 class AddAndInstanceNormalization(nn.Module):

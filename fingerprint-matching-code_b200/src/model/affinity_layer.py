@@ -23,8 +23,7 @@ class InnerProductWithWeightsAffinity(nn.Module):
         g = global_cat.detach().contiguous()
         if g.shape[0] >= 32:
             gn = (g / torch.norm(g, dim=1, keepdim=True)).contiguous()
-            lin = ops.gemm_nt(gn, self.A.weight.detach().contiguous(), self.A.bias.detach().contiguous(),
-                              weight_operand=True)
+            lin = ops.gemm_nt(gn, self.A.weight, self.A.bias.detach().contiguous(), weight_operand=True)
             return torch.tanh(lin)
         return ops.affinity_coeff(g, self.A.weight.detach().contiguous(), self.A.bias.detach().contiguous())
 

@@ -236,11 +236,20 @@ class Net(CNN):
         min_point_tensor = torch.minimum(n1, n2).to(torch.float32)
         gt_perm = data_dict['gt_perm_mat'].to(dev)
         gt_ks = gt_perm.sum(dim=(1, 2)).to(torch.float32)
-        if self.regression:
-            raise NotImplementedError("training the AFA-U k-branch (stages 2-5) is not implemented yet; "
-                                      "stage 1 / Net(regression=False) is")
-        ks = gt_ks / min_point_tensor
-        k_scaled = ks * min_point_tensor
+        supervised_ks = gt_ks / min_point_tensor
+        if self.regression:                                              # AFA-U reads ss.detach() (ngm.py:400)
+            assert self.univ_size - n1max >= 0 and self.univ_size - n2max >= 0
+            g_row, g_col, zero = self.encoder_k.forward_k_inputs_train(ss.detach(), n2, n1max, n2max)
+            k_row_logit = self.final_row(g_row).squeeze(-1)
+            k_col_logit = self.final_col(g_col).squeeze(-1)
+            k_logits = (k_row_logit + k_col_logit) / 2 if self.mean_k else k_row_logit
+            ks = torch.sigmoid(k_logits) + zero
+            ks_loss = torch.nn.functional.mse_loss(ks, supervised_ks) * self.k_factor
+            ks_error = torch.nn.functional.l1_loss(ks * min_point_tensor, gt_ks)
+        else:
+            ks = supervised_ks
+            ks_loss, ks_error = 0.0, 0.0
+        k_scaled = ks.detach() * min_point_tensor
         ss_out = fa.SoftTopkFn.apply(ss, gt_ks, n1, n2, SK_ITER_NUM, self.tau)
         with torch.no_grad():
             _, x = ops.lap_topk(ss_out.detach(), n1, n2, ks=k_scaled, want_hungarian=False, want_perm=True)
@@ -251,8 +260,8 @@ class Net(CNN):
         if 'label' in data_dict:
             label_tensor = data_dict['label'].to(dev).view(-1).float()
             cls_loss = torch.nn.functional.binary_cross_entropy_with_logits(cls_logits, label_tensor)
-        data_dict.update({'ds_mat': ss_out, 'perm_mat': x, 'ks_loss': 0.0, 'ks_error': 0.0, 'cls_loss': cls_loss,
-                          'cls_prob': cls_prob, 'k_prob': ks})
+        data_dict.update({'ds_mat': ss_out, 'perm_mat': x, 'ks_loss': ks_loss, 'ks_error': ks_error,
+                          'cls_loss': cls_loss, 'cls_prob': cls_prob, 'k_prob': ks})
         data_dict['_fpm_inter'] = {'node_feat': feats, 'Kp': Kp, 'Ke': Ke, 's': s, 'ss': ss, 'k_scaled': k_scaled}
         return data_dict
 

@@ -263,6 +263,17 @@ int fpm_gnn_layer_bwd(const float* xprev, const float* mprev_t, const int* in_pt
                       const float* const* weights, const float* dxout, const float* dscore, float* dxprev,
                       float* dm, float* gagg, float* grads, int B, int n1max, int n2max, int e1max, int e2max,
                       int cin, void* stream);
+/* [A9] fpm_afau_attention_bwd: backward of fpm_afau_attention (out = its forward output); dq is overwritten, dk / dv and
+ *      dmix [16 heads x 65: mix1_weight[h,0,:], mix1_weight[h,1,:], mix1_bias[h,:], mix2_weight[h,:], mix2_bias[h]] are
+ *      accumulated (caller zero-fills).  fpm_add_instnorm_bwd: dy [B,n,E] and / or drowmax [B,E] -> dx [B,n,E] (gradient of
+ *      `a` and of a tensor `other`); dgamma, dbeta, dvec (row-vector `other`, mode 2) [E] are accumulated. */
+int fpm_afau_attention_bwd(const float* q, const float* k, const float* v, const float* cost, long long cs_b,
+                           long long cs_r, long long cs_c, const float* mix1_w, const float* mix1_b,
+                           const float* mix2_w, const float* mix2_b, const float* out, const float* dout, float* dq,
+                           float* dk, float* dv, float* dmix, int B, int nr, int nc, void* stream);
+int fpm_add_instnorm_bwd(const float* a, const float* other, int other_mode, const float* gamma, const float* dy,
+                         const float* drowmax, float* dx, float* dgamma, float* dbeta, float* dvec, int B, int n, int E,
+                         float eps, void* stream);
 long long fpm_sinkhorn_bwd_workspace_bytes(int B, int R, int C, int max_iter);
 int fpm_sinkhorn_log_bwd(const float* s, const long long* n1, const long long* n2, const float* gout, float* gs,
                          void* workspace, int B, int R, int C, int max_iter, float tau, int dummy_row, void* stream);

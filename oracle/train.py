@@ -39,28 +39,30 @@ K_PREFIXES = ("encoder_k.", "final_row.", "final_col.")
 FROZEN_PREFIXES = K_PREFIXES + ("match_cls.", "node_layers.", "edge_layers.")
 
 
-def trainable_names(state: Dict[str, Tensor], with_cls: bool = False) -> List[str]:
+def trainable_names(state: Dict[str, Tensor], with_cls: bool = False, with_k: bool = False) -> List[str]:
     """Names the stage-1 optimizer updates (train.py:157-181), restricted to float parameters (not BN buffers).
-    ``with_cls`` adds the match_cls parameters (train.py:239 gives them their own AdamW)."""
-    frozen = tuple(q for q in FROZEN_PREFIXES if not (with_cls and q == "match_cls."))
+    ``with_cls`` adds the match_cls parameters (train.py:239 gives them their own AdamW); ``with_k`` the AFA-U
+    k-branch (encoder_k, final_row, final_col: trained from stage 2 on, train.py:183-215)."""
+    frozen = tuple(q for q in FROZEN_PREFIXES if not (with_cls and q == "match_cls.") and not (with_k and q in K_PREFIXES))
     return [k for k, v in state.items() if v.is_floating_point() and not k.startswith(frozen)
             and "running_" not in k and "num_batches" not in k]
 
 
 def loss_and_grads(state: Dict[str, Tensor], data: dict, fmaps, fmap_grads: bool = False,
-                   dtype: torch.dtype = torch.float32):
+                   dtype: torch.dtype = torch.float32, regression: bool = False):
     """One forward/backward of the stage-1 objective (PermutationLoss, + cls_loss when the batch carries labels);
     returns (loss, {name: grad}, [fmap grads], forward outputs).  ``dtype=torch.float64`` evaluates the same
     formulae in double precision: the tests use it to bound the fp32 oracle's own rounding noise."""
     p = {k: (v.clone().to(dtype) if v.is_floating_point() else v.clone()) for k, v in state.items()}
-    names = trainable_names(p, with_cls="label" in data)
+    names = trainable_names(p, with_cls="label" in data, with_k=regression)
     for k in names:
         p[k].requires_grad_(True)
     fm = [(a.clone().to(dtype).requires_grad_(fmap_grads), b.clone().to(dtype).requires_grad_(fmap_grads))
           for a, b in fmaps]
-    out = head.forward_head(p, data, fm, regression=False, training=True, keep_graph=True, dtype=dtype)
+    out = head.forward_head(p, data, fm, regression=regression, training=True, keep_graph=True, dtype=dtype)
     loss = permutation_loss(out["ds_mat"], data["gt_perm_mat"], data["ns"][0], data["ns"][1], dtype)
-    total = loss + (out["cls_loss"] if "cls_loss" in out else 0.0)
+    # stage objective of training_loop.py:48-50: primary loss + ks_loss + cls_loss
+    total = loss + (out["cls_loss"] if "cls_loss" in out else 0.0) + (out["ks_loss"] if regression else 0.0)
     total.backward()
     grads = {k: p[k].grad for k in names if p[k].grad is not None}
     fg = [(a.grad, b.grad) for a, b in fm] if fmap_grads else None

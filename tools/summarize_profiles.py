@@ -80,9 +80,10 @@ def full():
         for m in cols:
             out.append(f"| {m} | {d[idx[m]]} | {units[idx[m]]} |")
         try:
-            rd = float(d[idx["dram__bytes_read.sum"]].replace(",", "")); wr = float(d[idx["dram__bytes_write.sum"]].replace(",", ""))
-            un = units[idx["dram__bytes_read.sum"]]
-            out.append(f"| dram traffic (read + write) | {rd + wr:.4g} | {un} |")
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd = float(d[idx["dram__bytes_read.sum"]].replace(",", "")) * mult[units[idx["dram__bytes_read.sum"]]]
+            wr = float(d[idx["dram__bytes_write.sum"]].replace(",", "")) * mult[units[idx["dram__bytes_write.sum"]]]
+            out.append(f"| dram traffic (read + write) | {(rd + wr) / 1e6:.1f} | Mbyte |")
         except Exception:
             pass
         out.append("")
