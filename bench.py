@@ -12,7 +12,9 @@ classifier) over one batch of 256 synthetic fingerprint pairs with 100 keypoints
 `value`   device-timed pairs/s with inputs resident in HBM (CUDA events, max over ranks).
 `e2e`     the same metric through the public API with pinned HOST inputs: fpmatch.prefetch.CudaPrefetcher (the
           drop-in for the reference's data_to_cuda call, copying step i+1 on a side stream while step i runs) ->
-          Net.forward(data_dict) -> outputs read back to the host; every step's copies are inside the timed region.
+          Net.forward(data_dict) -> fpmatch.prefetch.HostResultRing (outputs copied to pinned host buffers on a side
+          stream, handed to the caller one step later); every step's copies are inside the timed region and the
+          region ends only when the last step's results are on the host.
 `roofline` for the dominant kernel (the SplineConv slab GEMM): algorithmic FLOPs / live CUDA-event time.
 `cpu_baseline` the oracle port of the reference's PyTorch+scipy CPU path on a bounded sample.
 --impl reference times that CPU path alone (rank 0 only).
@@ -261,16 +263,22 @@ def main():
     # ---- end to end through the public API with pinned host inputs: CudaPrefetcher (the host->device copy of step
     # i+1 runs on a side stream while step i is matched) -> Net.forward -> outputs copied to the host.  Every step's
     # H2D and D2H happen inside the timed region; wall clock, max over ranks.
-    from fpmatch.prefetch import CudaPrefetcher
+    from fpmatch.prefetch import CudaPrefetcher, HostResultRing
     e2e_steps = max(3, min(args.steps, 10))
 
+    ring = HostResultRing(device=dev)                        # pinned result buffers and device staging buffers
+    feeder = CudaPrefetcher([], device=dev)                  # are allocated once and reused across steps
+
     def e2e_run(nsteps):
-        res = None
-        for d in CudaPrefetcher([host] * nsteps, device=dev):
+        got = 0
+        feeder.batches = [host] * nsteps
+        for d in feeder:
             with torch.no_grad():
                 o = net(d)
-            res = [o[k].to("cpu", non_blocking=True) for k in out_keys]
-            torch.cuda.current_stream().synchronize()        # this step's result is on the host
+            done = ring.push([o[k] for k in out_keys])       # returns the previous step's results, on the host
+            got += done is not None
+        res = ring.flush()                                   # the last step's results are on the host here
+        assert res is not None and got == nsteps - 1
         return res
 
     e2e_run(2)

@@ -84,3 +84,45 @@ class CudaPrefetcher:
             done = torch.cuda.Event()                          # everything the consumer enqueued on this batch
             done.record(main)
             self.released[cur] = done
+
+
+class HostResultRing:
+    """Device -> host side of the pipeline: per-step result tensors are copied into pinned host buffers on a side
+    stream; ``push`` returns the PREVIOUS step's results (now complete on the host), so the CPU never stalls on the
+    step it has just enqueued.  ``flush`` returns the last step's results.  (The reference reads results with
+    blocking ``.cpu()`` / ``.item()`` calls right after the forward, e.g. evaluate_binary_classifier.py:93-103.)"""
+
+    def __init__(self, device="cuda", slots: int = 2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [dict(bufs=None, done=None) for _ in range(slots)]
+        self.i = 0
+        self.pending = None
+
+    def push(self, tensors):
+        slot = self.slots[self.i % len(self.slots)]
+        self.i += 1
+        if slot["bufs"] is None or any(b.shape != t.shape or b.dtype != t.dtype for b, t in zip(slot["bufs"], tensors)):
+            slot["bufs"] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+        main = torch.cuda.current_stream(self.device)
+        produced = torch.cuda.Event()
+        produced.record(main)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(produced)
+            for b, t in zip(slot["bufs"], tensors):
+                b.copy_(t, non_blocking=True)
+                t.record_stream(self.stream)
+            slot["done"] = torch.cuda.Event()
+            slot["done"].record(self.stream)
+        prev, self.pending = self.pending, slot
+        if prev is not None:
+            prev["done"].synchronize()
+            return prev["bufs"]
+        return None
+
+    def flush(self):
+        if self.pending is None:
+            return None
+        self.pending["done"].synchronize()
+        out, self.pending = self.pending["bufs"], None
+        return out
