@@ -147,15 +147,28 @@ def test_sinkhorn_module_api():
     assert (out.cpu() - ref).abs().max() < 1e-6
 
 
-def test_sinkhorn_large_uses_workspace(ops, oo):
-    g = torch.Generator().manual_seed(5)
-    s = torch.randn(2, 300, 300, generator=g)
-    n1 = torch.tensor([300, 250]); n2 = torch.tensor([300, 280])
-    ref = oo.sinkhorn(s, n1, n2, dummy_row=True, max_iter=10, tau=0.05)
-    out = ops.sinkhorn_log(s.to(DEV), n1.to(DEV), n2.to(DEV), 10, 0.05, True)
+@pytest.mark.parametrize("R,C,n1,n2,it,tau", [(300, 300, [300, 250], [300, 280], 10, 0.05),      # cluster of 8 CTAs
+                                              (400, 400, [400, 333, 17], [400, 390, 400], 20, 0.01),
+                                              (260, 410, [260, 100], [410, 300], 10, 0.05),
+                                              (410, 260, [410, 300], [260, 100], 10, 0.05),
+                                              (700, 700, [700, 512], [700, 600], 4, 0.05)])      # global workspace
+def test_sinkhorn_beyond_one_cta(ops, oo, R, C, n1, n2, it, tau):
+    """Matrices larger than one CTA's shared memory: thread-block cluster with distributed shared memory up to
+    n ~ 660, global workspace beyond."""
+    g = torch.Generator().manual_seed(R + C)
+    B = len(n1)
+    s = torch.randn(B, R, C, generator=g)
+    n1 = torch.tensor(n1); n2 = torch.tensor(n2)
+    ref = oo.sinkhorn(s, n1, n2, dummy_row=True, max_iter=it, tau=tau)
+    out, out_t = ops.sinkhorn_log(s.to(DEV), n1.to(DEV), n2.to(DEV), it, tau, True, want_t=True)
     err = (out.cpu() - ref).abs().max().item()
-    report("sinkhorn_large", max_abs=err)
+    report("sinkhorn_large", R=R, C=C, iters=it, max_abs=err)
     assert err < 2e-4
+    assert torch.equal(out_t.cpu(), out.cpu().transpose(1, 2))
+    pad = torch.ones_like(ref, dtype=torch.bool)
+    for b in range(B):
+        pad[b, :n1[b], :n2[b]] = False
+    assert (out.cpu()[pad] == 0).all()
 
 
 # ------------------------------------------------------------------------------------------ soft top-k

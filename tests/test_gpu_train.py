@@ -29,7 +29,8 @@ def rel_err(a, b, floor=1e-30):
 
 # ------------------------------------------------------------------------------------------------- Sinkhorn
 @pytest.mark.parametrize("B,R,C,iters,ragged", [(3, 12, 12, 10, False), (4, 20, 24, 20, True), (2, 33, 33, 20, True),
-                                                (2, 100, 100, 20, False)])
+                                                (2, 100, 100, 20, False), (2, 24, 17, 10, True),
+                                                (2, 200, 200, 10, True)])      # last: global-workspace path
 def test_sinkhorn_backward(B, R, C, iters, ragged):
     from fpmatch import ops
     from oracle import ops as oo
@@ -50,7 +51,8 @@ def test_sinkhorn_backward(B, R, C, iters, ragged):
 
 
 # ------------------------------------------------------------------------------------------------- soft-top-k
-@pytest.mark.parametrize("B,n,ks", [(3, 10, [4.0, 10.0, 2.5]), (2, 30, [30.0, 11.0]), (2, 100, [100.0, 57.0])])
+@pytest.mark.parametrize("B,n,ks", [(3, 10, [4.0, 10.0, 2.5]), (2, 30, [30.0, 11.0]), (2, 100, [100.0, 57.0]),
+                                    (2, 150, [150.0, 31.0])])                  # last: global-workspace path
 def test_soft_topk_backward(B, n, ks):
     from fpmatch import ops
     from oracle import ops as oo
