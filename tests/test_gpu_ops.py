@@ -235,7 +235,9 @@ def test_hungarian_golden_bit_exact():
     assert torch.equal(out.cpu(), fx["out"])
 
 
-@pytest.mark.parametrize("nmax,count,seed", [(12, 400, 1), (40, 300, 2), (100, 120, 3), (160, 24, 4), (256, 10, 5)])
+# nmax >= 160: the cost matrix leaves shared memory -> the 8-warp block kernel (lap_topk_block_kernel)
+@pytest.mark.parametrize("nmax,count,seed", [(12, 400, 1), (40, 300, 2), (100, 120, 3), (160, 24, 4), (256, 10, 5),
+                                             (400, 6, 6)])
 def test_hungarian_matches_scipy_exactly(oo, nmax, count, seed):
     from utils.hungarian import hungarian
     s, n1, n2 = _pack(_tie_heavy(np.random.RandomState(seed), count, nmax))
@@ -255,9 +257,9 @@ def test_hungarian_api_shapes():
         hungarian(torch.rand(2, 2, 2, 2, device=DEV))
 
 
-def test_greedy_topk_matches_reference_loop(ops, oo):
+@pytest.mark.parametrize("B,R,C", [(12, 30, 34), (4, 170, 180)])        # second: block kernel (cost beyond smem)
+def test_greedy_topk_matches_reference_loop(ops, oo, B, R, C):
     g = torch.Generator().manual_seed(7)
-    B, R, C = 12, 30, 34
     n1 = torch.randint(10, R + 1, (B,), generator=g); n2 = torch.randint(10, C + 1, (B,), generator=g)
     ss = oo.sinkhorn(torch.randn(B, R, C, generator=g), n1, n2, dummy_row=True, max_iter=10, tau=0.05)
     ks = torch.rand(B, generator=g) * torch.minimum(n1, n2).float()
