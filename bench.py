@@ -239,11 +239,25 @@ def main():
     ms_step = t.item() / args.steps
     value = B * world / (ms_step / 1e3)
 
-    # dominant kernel = the SplineConv slab GEMM (largest M*N*K in the step)
-    big = max(gemm_events, key=lambda e: e[1] * e[2] * e[3])
-    same = [e for e in gemm_events if (e[1], e[2], e[3]) == (big[1], big[2], big[3])]
+    # dominant kernel = the SplineConv slab GEMM (largest FLOP count in the step).  With the slab planner the launch
+    # computes only the tiles listed in its device-side table: FLOPs = executed tiles x 256 x 128 x K x 2.
+    def flops_of(e):
+        if e[0] == "3xf16-slabs":
+            return 2.0 * e[1].tiles_used() * 256 * 128 * e[3]
+        return 2.0 * e[1] * e[2] * e[3]
+    big = max(gemm_events, key=flops_of)
+    if big[0] == "3xf16-slabs":
+        same = [e for e in gemm_events if e[0] == big[0] and e[1].T == big[1].T and e[2] == big[2]]
+        flops = sum(flops_of(e) for e in same) / len(same)
+        kernel_label = (f"spline slab GEMM [3xf16, tile table]: {big[1].tiles_used()} tiles of 256x128x{big[3]} "
+                        f"(the dense product would be M={big[1].T} N={big[2]} K={big[3]} = "
+                        f"{(big[1].T_pad // 256) * (big[2] // 128)} tiles)")
+        big = ("3xf16", big[1].T, big[2], big[3], big[4], big[5])
+    else:
+        same = [e for e in gemm_events if (e[0], e[1], e[2], e[3]) == big[:4]]
+        flops = 2.0 * big[1] * big[2] * big[3]
+        kernel_label = None
     gemm_ms = sum(e[4].elapsed_time(e[5]) for e in same) / len(same)
-    flops = 2.0 * big[1] * big[2] * big[3]
     peaks, peak_kind = measured_peaks()
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
     mode = big[0]
@@ -256,7 +270,7 @@ def main():
         peak_note = f"TF32 dense = {peak_kind} sustained bf16 cuBLAS peak / 2 (no TF32 figure is measured)"
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape, from the committed
     # `ncu --set full` capture profiles/r1c_ncu_full_gemm_pair.md (algorithmic bytes: 2.185e9)
-    traffic = 2.644e9 if (mode == "3xf16" and (big[1], big[2], big[3]) == (25600, 19968, 768)) else None
+    traffic = 2.644e9 if (kernel_label is None and mode == "3xf16" and (big[1], big[2], big[3]) == (25600, 19968, 768)) else None
     achieved = flops / (gemm_ms / 1e3) / 1e12
     gemm_share = gemm_ms * len(same) / args.steps / ms_step
 
@@ -310,7 +324,7 @@ def main():
                        "l2": "inputs + intermediates per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "dead_ke_computed": True, "parallelism": f"dp{world} (independent pairs, no data-path collective)"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel": f"gemm_nt[{mode}] M={big[1]} N={big[2]} K={big[3]}",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": kernel_label or f"gemm_nt[{mode}] M={big[1]} N={big[2]} K={big[3]}",
                          "launch_ms": gemm_ms, "share_of_step": gemm_share, "peak_source": peak_note},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

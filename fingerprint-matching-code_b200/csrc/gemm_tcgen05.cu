@@ -415,12 +415,20 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                : "memory");
 }
 
+// Optional tile table (device memory, built without a host round trip by the SplineConv planner in spline.cu):
+// entry t = {first A row of the 256-row pair tile, first B row of the 128-row tile, first C column, rowmap offset};
+// rowmap offset < 0: C rows = A rows; otherwise C row of A row a0 + r is rowmap[offset + r] (-1 = padding, skipped).
+// *tab_count entries are valid.  Lets one launch compute only the (row block, weight slab) products that are used.
+struct PairTile { int a_row0, b_row0, c_col0, rowmap_off; };
+
 template <int kMode>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const float* __restrict__ inv_a, const float* __restrict__ inv_b,
-                    const float* __restrict__ bias, float* __restrict__ Cm, int M, int N, int K, int ldc, int act) {
+                    const float* __restrict__ bias, float* __restrict__ Cm, int M, int N, int K, int ldc, int act,
+                    const PairTile* __restrict__ tab, const int* __restrict__ tab_count,
+                    const int* __restrict__ rowmap, int m_ident) {
   static_assert(kMode == kTf32x3 || kMode == kF16x3, "the pair kernel serves the two-accumulator modes");
   constexpr bool kF16 = kMode == kF16x3;
   constexpr int kElemBytes = kF16 ? 2 : 4;
@@ -442,7 +450,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   constexpr int kRasterGroup = 16;                       // 16 pair tiles = 4096 rows walk the N tiles together
   const int tiles_m = (M + 2 * P_TBM - 1) / (2 * P_TBM);
   const int tiles_n = (N + P_TBN - 1) / P_TBN;
-  const long long total_tiles = (long long)tiles_m * tiles_n;
+  const long long total_tiles = tab ? (long long)*tab_count : (long long)tiles_m * tiles_n;
   const int per_group = kRasterGroup * tiles_n;
   const int nk = (K + TBK - 1) / TBK;
 
@@ -463,11 +471,18 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  auto tile_origin = [&](long long tile, int& m0, int& n0) {
+  // m0: first A row, n0: first B row, c0: first C column, rm: rowmap offset (-1 = identity rows)
+  auto tile_origin = [&](long long tile, int& m0, int& n0, int& c0, int& rm) {
+    if (tab) {
+      const PairTile t = tab[tile];
+      m0 = t.a_row0; n0 = t.b_row0; c0 = t.c_col0; rm = t.rowmap_off;
+      return;
+    }
     const int grp = (int)(tile / per_group), rem = (int)(tile - (long long)grp * per_group);
     const int gsize = min(kRasterGroup, tiles_m - grp * kRasterGroup);
     m0 = (grp * kRasterGroup + rem % gsize) * (2 * P_TBM);
     n0 = (rem / gsize) * P_TBN;
+    c0 = n0; rm = -1;
   };
 
   if (warp == 0) {
@@ -475,8 +490,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     if (lane == 0) {
       uint32_t it = 0;
       for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        int m0, n0;
-        tile_origin(tile, m0, n0);
+        int m0, n0, c0, rm;
+        tile_origin(tile, m0, n0, c0, rm);
         const int am = m0 + (int)cta_rank * P_TBM, bn = n0 + (int)cta_rank * (P_TBN / 2);
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % kPStages;
@@ -534,9 +549,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     constexpr int kChunksPerWarp = P_TBN / 32 / 2;          // 2
     uint32_t t = 0;
     for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters, ++t) {
-      int m0, n0;
-      tile_origin(tile, m0, n0);
+      int m0, n0, c0, rm;
+      tile_origin(tile, m0, n0, c0, rm);
       m0 += (int)cta_rank * P_TBM;
+      if (rm >= 0) rm += (int)cta_rank * P_TBM;
       const uint32_t buf = t & 1u, bph = (t >> 1) & 1u;
       mbar_wait(&tmem_full_bar[buf], bph);
       tc_fence_after();
@@ -560,12 +576,16 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
       const int m = m0 + q * 32 + lane;
       const float row_scale = (kF16 && m < M) ? inv_a[m] : 1.f;
+      // destination row of this lane's accumulator row (identity, or through the planner's row map)
+      // (m_ident: rows of C that identity tiles may write - the A buffer of a planned launch is longer than C)
+      const int crow_lane = rm < 0 ? (m < m_ident ? m : -1) : (m < M ? rowmap[rm + q * 32 + lane] : -1);
 #pragma unroll
       for (int c = 0; c < kChunksPerWarp; ++c) {
         const int ch = half * kChunksPerWarp + c;
-        const int ncol = n0 + ch * 32 + lane;
-        const float col_scale = (kF16 && ncol < N) ? inv_b[ncol] : 1.f;
-        const float col_bias = (bias && ncol < N) ? bias[ncol] : 0.f;
+        const int brow = n0 + ch * 32 + lane;                 // row of Bt = output feature
+        const int ncol = c0 + ch * 32 + lane;                 // column of C
+        const float col_scale = (kF16 && brow < N) ? inv_b[brow] : 1.f;
+        const float col_bias = (bias && brow < N) ? bias[brow] : 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(r[c][j]);
@@ -575,9 +595,15 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           tile_s[lane * 33 + j] = x;
         }
         __syncwarp();
-        if (ncol < N) {
+        if (rm >= 0) {
+          // mapped rows (gathered A): every row has its own destination
+          for (int rr = 0; rr < 32; ++rr) {
+            const int crow = __shfl_sync(0xffffffffu, crow_lane, rr);
+            if (crow >= 0 && brow < N) Cm[(size_t)crow * ldc + ncol] = tile_s[rr * 33 + lane];
+          }
+        } else if (brow < N) {
           const int mrow0 = m0 + q * 32;
-          const int nrows = min(32, M - mrow0);
+          const int nrows = min(32, m_ident - mrow0);
           float* cbase = Cm + (size_t)mrow0 * ldc + ncol;
           if (nrows == 32) {
 #pragma unroll
@@ -736,7 +762,9 @@ static int g_pair_clusters[2] = {0, 0};   // co-resident clusters of the pair ke
 template <int kMode>
 static int launch_tc_pair(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, const float* inv_a,
                           const float* inv_b, const float* bias, float* C, int M, int N, int K, int lda, int ldb,
-                          int ldc, int act, cudaStream_t st) {
+                          int ldc, int act, cudaStream_t st, const fpm::PairTile* tab = nullptr,
+                          const int* tab_count = nullptr, const int* rowmap = nullptr, long long max_tiles = 0,
+                          int m_ident = -1) {
   constexpr bool f16 = kMode == fpm::kF16x3;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
@@ -770,10 +798,11 @@ static int launch_tc_pair(const void* A_hi, const void* A_lo, const void* B_hi, 
     }
     ncl = maxc < sms / 2 ? maxc : sms / 2;
   }
-  const long long tiles = (long long)fpm_cdiv(M, 2 * fpm::P_TBM) * fpm_cdiv(N, fpm::P_TBN);
-  const long long clusters = tiles < ncl ? tiles : ncl;
+  const long long tiles = tab ? max_tiles : (long long)fpm_cdiv(M, 2 * fpm::P_TBM) * fpm_cdiv(N, fpm::P_TBN);
+  const long long clusters = tiles < ncl ? (tiles > 0 ? tiles : 1) : ncl;
   cfg.gridDim = dim3((unsigned)(2 * clusters));
-  FPM_CUDA(cudaLaunchKernelEx(&cfg, kern, mAh, mAl, mBh, mBl, inv_a, inv_b, bias, C, M, N, K, ldc, act));
+  FPM_CUDA(cudaLaunchKernelEx(&cfg, kern, mAh, mAl, mBh, mBl, inv_a, inv_b, bias, C, M, N, K, ldc, act, tab, tab_count,
+                              rowmap, m_ident < 0 ? M : m_ident));
   return FPM_OK;
 }
 
@@ -869,4 +898,25 @@ extern "C" int fpm_gemm_nt_f16x3(const void* A_hi, const void* A_lo, const float
   if (M == 0) return FPM_OK;
   return launch_tc<fpm::kF16x3, 2>(A_hi, A_lo, Bt_hi, Bt_lo, inv_a, inv_b, bias, C, M, N, K, lda, ldb, ldc, act,
                                    (cudaStream_t)stream);
+}
+
+// Tile-table form of fpm_gemm_nt_f16x3 (persistent CTA-pair kernel only): computes C blocks for the *tab_count tiles
+// listed in `tab` (device memory, 4 ints per tile: first A row of a 256-row block, first Bt row of a 128-row block,
+// first C column, rowmap offset or -1); see PairTile above.  max_tiles bounds the grid (host-side upper bound of
+// *tab_count); M = rows of the A buffer, m_ident = rows of C that identity-mapped tiles may write.  Used by the SplineConv forward to skip the (node block, weight slab) products no edge refers to.
+extern "C" int fpm_gemm_nt_f16x3_tiles(const void* A_hi, const void* A_lo, const float* inv_a, const void* Bt_hi,
+                                       const void* Bt_lo, const float* inv_b, float* C, int M, int N, int K, int lda,
+                                       int ldb, int ldc, const int* tab, const int* tab_count, const int* rowmap,
+                                       long long max_tiles, int m_ident, void* stream) {
+  FPM_CHECK_ARG(A_hi && A_lo && inv_a && Bt_hi && Bt_lo && inv_b && C && tab && tab_count,
+                "fpm_gemm_nt_f16x3_tiles: null tensor");
+  FPM_CHECK_ARG(M >= 0 && N > 0 && K > 0 && max_tiles >= 0 && m_ident >= 0 && m_ident <= M,
+                "fpm_gemm_nt_f16x3_tiles: bad sizes");
+  FPM_CHECK_ARG((K & 7) == 0 && (lda & 7) == 0 && (ldb & 7) == 0, "fpm_gemm_nt_f16x3_tiles: K, lda, ldb must be multiples of 8");
+  FPM_CHECK_ARG(((((size_t)A_hi) | ((size_t)A_lo) | ((size_t)Bt_hi) | ((size_t)Bt_lo) | ((size_t)tab)) & 15) == 0,
+                "fpm_gemm_nt_f16x3_tiles: operands must be 16-byte aligned");
+  if (M == 0 || max_tiles == 0) return FPM_OK;
+  return launch_tc_pair<fpm::kF16x3>(A_hi, A_lo, Bt_hi, Bt_lo, inv_a, inv_b, nullptr, C, M, N, K, lda, ldb, ldc, 0,
+                                     (cudaStream_t)stream, (const fpm::PairTile*)tab, tab_count, rowmap, max_tiles,
+                                     m_ident);
 }

@@ -181,6 +181,125 @@ spline_scatter_bwd_kernel(const float* __restrict__ G, const int* __restrict__ a
     *(float4*)(dst + (size_t)k * C + c4 * 4) = *(const float4*)(blk + (size_t)k * C + c4 * 4);
 }
 
+// ------------------------------------------------------------------------------------------
+// Slab planner: which (node, weight slab) products does the gather actually read?
+//
+// An edge src -> dst touches the 4 slabs wi_s(pseudo) of its SOURCE node, and the pseudo-coordinates of a keypoint
+// graph are 0.5 + (P_src - P_dst) / 640: Delaunay neighbours are close, so almost every edge lands in the 3 x 3
+// centre of the 5 x 5 kernel (measured on the synthetic pairs: 8.6 of 25 slabs per node).  Computing all 26 slab
+// products for all nodes - the first design - spends 63 % of the tensor-core work on blocks nobody reads.
+// The planner (device side, no host round trip) marks the slabs every node needs, then emits a tile table for the
+// persistent GEMM (gemm_tcgen05.cu, PairTile):
+//   * a slab needed by >= 1/4 of the nodes is "dense": it is computed for ALL nodes straight from X (no gather);
+//   * the other slabs are "sparse": their nodes are compacted into 256-row groups behind X in the A buffer and the
+//     GEMM scatters the result rows back to Y[node, slab, :] through the row map.
+// The products that are computed are the same numbers as before; the ones skipped are never read.
+// ------------------------------------------------------------------------------------------
+constexpr int kPlanThreads = 1024;
+constexpr int kTileM = 256, kTileN = 128;             // PairTile geometry of gemm_tc_pair_kernel
+
+__global__ void slab_mask_kernel(const int64_t* __restrict__ edge_src, const float* __restrict__ pseudo,
+                                 unsigned* __restrict__ mask, int E, int KS) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  float bas[4]; int wi[4];
+  spline_basis4(pseudo[(size_t)e * 2], pseudo[(size_t)e * 2 + 1], KS, bas, wi);
+  const unsigned m = (1u << wi[0]) | (1u << wi[1]) | (1u << wi[2]) | (1u << wi[3]);
+  atomicOr(mask + (int)edge_src[e], m);
+}
+
+// meta (ints): [0] tile count, [1] sparse rows in use, [2 .. 2+NS) dense flag per slab, [2+NS .. 2+2NS] sparse row
+// offset per slab (+ total), [2+2NS+1 .. ) cursors.  One CTA.
+__global__ void __launch_bounds__(kPlanThreads)
+slab_plan_kernel(const unsigned* __restrict__ mask, int T, int KS, int C, int* __restrict__ meta,
+                 int4* __restrict__ tab, int max_tiles) {
+  const int NS = KS * KS + 1;
+  __shared__ int cnt[32], dense[32], off[33], dlist[32];
+  __shared__ int nd, total_sparse;
+  const int tid = threadIdx.x;
+  if (tid < 32) cnt[tid] = 0;
+  __syncthreads();
+  for (int j = tid; j < T; j += kPlanThreads) {
+    unsigned m = mask[j];
+    while (m) { const int k = __ffs(m) - 1; m &= m - 1; atomicAdd(&cnt[k], 1); }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    cnt[NS - 1] = T;                                  // the root slab serves every node
+    int n = 0, run = 0;
+    for (int k = 0; k < NS; ++k) {
+      dense[k] = (k == NS - 1) || (4LL * cnt[k] >= (long long)T && cnt[k] > 0);
+      if (dense[k]) dlist[n++] = k;
+      off[k] = run;
+      if (!dense[k]) run += (cnt[k] + kTileM - 1) / kTileM * kTileM;
+    }
+    off[NS] = run;
+    nd = n; total_sparse = run;
+  }
+  __syncthreads();
+  const int ntn = C / kTileN;                         // N tiles per slab
+  const int tiles_m = (T + kTileM - 1) / kTileM, T_pad = tiles_m * kTileM;
+  const int grp_rows = 16;
+  const int per_group = grp_rows * nd * ntn;
+  const int total_dense = tiles_m * nd * ntn;
+  for (int t = tid; t < total_dense && t < max_tiles; t += kPlanThreads) {
+    const int grp = t / per_group, rem = t - grp * per_group;
+    const int gsize = min(grp_rows, tiles_m - grp * grp_rows);
+    const int mi = grp * grp_rows + rem % gsize, sn = rem / gsize;
+    const int k = dlist[sn / ntn], nt = sn % ntn;
+    tab[t] = make_int4(mi * kTileM, k * C + nt * kTileN, k * C + nt * kTileN, -1);
+  }
+  if (tid == 0) {
+    int t = total_dense;
+    for (int k = 0; k < NS; ++k) {
+      if (dense[k] || cnt[k] == 0) continue;
+      const int mt = (cnt[k] + kTileM - 1) / kTileM;
+      for (int nt = 0; nt < ntn; ++nt)
+        for (int m = 0; m < mt && t < max_tiles; ++m, ++t)
+          tab[t] = make_int4(T_pad + off[k] + m * kTileM, k * C + nt * kTileN, k * C + nt * kTileN, off[k] + m * kTileM);
+    }
+    meta[0] = t;
+    meta[1] = total_sparse;
+  }
+  if (tid < NS) { meta[2 + tid] = dense[tid]; meta[2 + 2 * NS + 1 + tid] = 0; }
+  if (tid <= NS) meta[2 + NS + tid] = off[tid];
+}
+
+// rowmap[off[k] + pos] = node for every sparse slab k the node needs (rowmap pre-filled with -1).
+__global__ void slab_compact_kernel(const unsigned* __restrict__ mask, int T, int KS, int* __restrict__ meta,
+                                    int* __restrict__ rowmap, int rowmap_cap) {
+  const int NS = KS * KS + 1;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= T) return;
+  unsigned m = mask[j];
+  while (m) {
+    const int k = __ffs(m) - 1;
+    m &= m - 1;
+    if (meta[2 + k]) continue;                        // dense slab: computed for everybody
+    const int pos = meta[2 + NS + k] + atomicAdd(&meta[2 + 2 * NS + 1 + k], 1);
+    if (pos < rowmap_cap) rowmap[pos] = j;
+  }
+}
+
+// Copies the fp16 hi / lo halves and the row scale of every mapped node behind the dense rows of the A buffer.
+// One warp per compact row; the row count is read from meta[1] (device), the grid is sized for the worst case.
+__global__ void __launch_bounds__(256)
+slab_gather_rows_kernel(const int* __restrict__ meta, const int* __restrict__ rowmap, uint4* __restrict__ hi,
+                        uint4* __restrict__ lo, float* __restrict__ inv, int T_pad, int K) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int total = meta[1];
+  const int vec = K / 8;                              // uint4 = 8 halves
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < total; r += nwarps) {
+    const int node = rowmap[r];
+    if (node < 0) continue;
+    const uint4* sh = hi + (size_t)node * vec; const uint4* sl = lo + (size_t)node * vec;
+    uint4* dh = hi + (size_t)(T_pad + r) * vec; uint4* dl = lo + (size_t)(T_pad + r) * vec;
+    for (int i = lane; i < vec; i += 32) { dh[i] = sh[i]; dl[i] = sl[i]; }
+    if (lane == 0) inv[T_pad + r] = inv[node];
+  }
+}
+
 }  // namespace fpm
 
 extern "C" int fpm_csr_by_dst(const long long* edge_dst, const long long* ptr, const long long* eptr,
@@ -223,6 +342,38 @@ extern "C" int fpm_spline_scatter_bwd(const float* G, const int* argmax, const l
   FPM_CUDA(cudaFuncSetAttribute(fpm::spline_scatter_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fpm::spline_scatter_bwd_kernel<<<total_nodes, 192, smem, (cudaStream_t)stream>>>(
       G, argmax, (const int64_t*)edge_dst, pseudo, out_ptr, out_eid, dY, C, kernel_size);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+// Builds the slab plan of one graph batch (see the planner comment above).  mask [T] uint32 and rowmap [rowmap_cap]
+// int32 are scratch the caller zero- / -1-fills; meta needs 2 + 3*(KS*KS+1) + 2 ints; tab holds max_tiles int4.
+extern "C" int fpm_spline_plan(const long long* edge_src, const float* pseudo, unsigned* mask, int* meta, int* tab,
+                               int* rowmap, int T, int E, int C, int kernel_size, int max_tiles, int rowmap_cap,
+                               void* stream) {
+  FPM_CHECK_ARG(edge_src && pseudo && mask && meta && tab && rowmap, "fpm_spline_plan: null tensor");
+  FPM_CHECK_ARG(T > 0 && E >= 0 && kernel_size * kernel_size + 1 <= 32 && C % 128 == 0 && max_tiles > 0,
+                "fpm_spline_plan: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (E > 0) {
+    fpm::slab_mask_kernel<<<fpm_cdiv(E, 256), 256, 0, st>>>((const int64_t*)edge_src, pseudo, mask, E, kernel_size);
+    FPM_LAUNCH_CHECK();
+  }
+  fpm::slab_plan_kernel<<<1, fpm::kPlanThreads, 0, st>>>(mask, T, kernel_size, C, meta, (int4*)tab, max_tiles);
+  FPM_LAUNCH_CHECK();
+  fpm::slab_compact_kernel<<<fpm_cdiv(T, 256), 256, 0, st>>>(mask, T, kernel_size, meta, rowmap, rowmap_cap);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_spline_gather_rows(const int* meta, const int* rowmap, void* a_hi, void* a_lo, float* inv_a,
+                                      int T_pad, int K, int rowmap_cap, void* stream) {
+  FPM_CHECK_ARG(meta && rowmap && a_hi && a_lo && inv_a, "fpm_spline_gather_rows: null tensor");
+  FPM_CHECK_ARG(K % 8 == 0, "fpm_spline_gather_rows: K must be a multiple of 8");
+  if (rowmap_cap == 0) return FPM_OK;
+  const int blocks = fpm_cdiv(rowmap_cap < 148 * 64 ? rowmap_cap : 148 * 64, 8);
+  fpm::slab_gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(meta, rowmap, (uint4*)a_hi, (uint4*)a_lo, inv_a,
+                                                                        T_pad, K);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

@@ -37,6 +37,9 @@ SIGNATURES = {
     "fpm_gemm_set_pair": (_I, [_I]),
     "fpm_f16_split_rows": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "fpm_gemm_nt_f16x3": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fpm_gemm_nt_f16x3_tiles": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _LL, _I, _P]),
+    "fpm_spline_plan": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "fpm_spline_gather_rows": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_csr_by_dst": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_spline_gather_max": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_affinity": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P]),

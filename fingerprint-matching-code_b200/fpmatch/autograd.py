@@ -50,6 +50,18 @@ class GraphCtx:
         self.in_csr = ops.csr_by_dst(self.edge_index, ptr, eptr, total, max_edges)
         swapped = torch.stack((self.edge_index[1], self.edge_index[0]), 0).contiguous()
         self.out_csr = ops.csr_by_dst(swapped, ptr, eptr, total, max_edges)
+        self.total = total
+        self._plans = {}
+
+    def plan(self, channels: int, kernel_size: int):
+        """Slab plan of this graph (built once, shared by both conv layers) or None when the dense product is used."""
+        from src.model.spline_conv import slab_plan_enabled
+        if not slab_plan_enabled() or channels % 128:
+            return None
+        key = (channels, kernel_size)
+        if key not in self._plans:
+            self._plans[key] = ops.SlabPlan(self.edge_index, self.pseudo, self.total, channels, kernel_size)
+        return self._plans[key]
 
 
 class SplineConvFn(Function):
@@ -59,7 +71,8 @@ class SplineConvFn(Function):
     def forward(ctx, x: Tensor, weight: Tensor, root: Tensor, bias: Tensor, xin: Optional[Tensor], packed: Tensor,
                 g: GraphCtx, mode: int, kernel_size: int):
         x = x.contiguous()
-        Y = ops.gemm_nt(x, packed, weight_operand=True)
+        plan = g.plan(weight.shape[2], kernel_size)
+        Y = ops.spline_slab_gemm(x, packed, plan) if plan is not None else ops.gemm_nt(x, packed, weight_operand=True)
         out, arg = ops.spline_gather_max(Y, xin, g.edge_index, g.pseudo, g.in_csr[0], g.in_csr[1],
                                          bias.detach().contiguous(), mode, kernel_size, want_argmax=True)
         del Y

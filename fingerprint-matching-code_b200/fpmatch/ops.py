@@ -35,9 +35,30 @@ def gemm_mode() -> str:
     return _GEMM_MODE
 
 
+_GEMM_PAIR = os.environ.get("FPMATCH_GEMM_PAIR", "1") != "0"
+_SLAB_PLAN = os.environ.get("FPMATCH_SLAB_PLAN", "1") != "0"
+
+
 def set_gemm_pair(on: bool) -> None:
     """True (default): the error-compensated modes use the persistent CTA-pair kernel; False: one tile per CTA."""
+    global _GEMM_PAIR
     _lib.check(_lib.lib().fpm_gemm_set_pair(int(bool(on))), "fpm_gemm_set_pair")
+    _GEMM_PAIR = bool(on)
+
+
+def gemm_pair_enabled() -> bool:
+    return _GEMM_PAIR
+
+
+def set_slab_plan(on: bool) -> None:
+    """True (default): SplineConv computes only the (node, weight slab) products its edges read (tile-table GEMM);
+    False: the dense 26-slab product."""
+    global _SLAB_PLAN
+    _SLAB_PLAN = bool(on)
+
+
+def slab_plan_enabled() -> bool:
+    return _SLAB_PLAN
 
 
 def launch_count() -> int:
@@ -214,16 +235,20 @@ def gemm_profile_stop():
     return ev
 
 
-def f16_split_rows(x: Tensor, cache: bool = False):
-    """x[r,:] * s_r = hi + 2^-11 lo with hi, lo fp16 and s_r a power of two; returns (hi, lo, 1/s)."""
+def f16_split_rows(x: Tensor, cache: bool = False, out=None):
+    """x[r,:] * s_r = hi + 2^-11 lo with hi, lo fp16 and s_r a power of two; returns (hi, lo, 1/s).
+    ``out`` = (hi, lo, inv) buffers with at least x.shape[0] rows to write into (rows beyond are left untouched)."""
     if cache:
         hit = _cache_get("f16", x)
         if hit is not None:
             return hit
     rows, K = x.shape
-    hi = torch.empty((rows, K), dtype=torch.float16, device=x.device)
-    lo = torch.empty((rows, K), dtype=torch.float16, device=x.device)
-    inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    if out is not None:
+        hi, lo, inv = out
+    else:
+        hi = torch.empty((rows, K), dtype=torch.float16, device=x.device)
+        lo = torch.empty((rows, K), dtype=torch.float16, device=x.device)
+        inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
     rc = _lib.lib().fpm_f16_split_rows(_chk(x, "x"), hi.data_ptr(), lo.data_ptr(), inv.data_ptr(), rows, K, _stream())
     _lib.check(rc, "fpm_f16_split_rows"); _count()
     if cache:
@@ -260,6 +285,75 @@ def csr_by_dst(edge_index: Tensor, ptr: Tensor, eptr: Tensor, total_nodes: int, 
                                    ptr.numel() - 1, total_nodes, max_edges, _stream())
     _lib.check(rc, "fpm_csr_by_dst"); _count()
     return in_ptr, in_eid
+
+
+class SlabPlan:
+    """Device-side plan of one graph batch for the slab-sparse SplineConv GEMM (csrc/spline.cu, planner): which
+    (node block, weight slab) tiles to compute.  Depends on the graph only, so both conv layers share it."""
+
+    def __init__(self, edge_index: Tensor, pseudo: Tensor, total: int, channels: int, kernel_size: int = 5):
+        dev = edge_index.device
+        NS = kernel_size * kernel_size + 1
+        self.T, self.C, self.NS = total, channels, NS
+        self.T_pad = (total + 255) // 256 * 256
+        tiles_m, ntn = self.T_pad // 256, channels // 128
+        # sparse slabs hold < T/4 nodes each (padded to 256-row groups)
+        self.rowmap_cap = (NS - 1) * ((total // 4 + 255) // 256 * 256 + 256)
+        self.max_tiles = tiles_m * NS * ntn + (self.rowmap_cap // 256) * ntn
+        self.mask = torch.zeros((total,), dtype=torch.int32, device=dev)
+        self.meta = torch.zeros((2 + 3 * NS + 2,), dtype=torch.int32, device=dev)
+        self.tab = torch.empty((self.max_tiles, 4), dtype=torch.int32, device=dev)
+        self.rowmap = torch.full((self.rowmap_cap,), -1, dtype=torch.int32, device=dev)
+        src = edge_index[0]
+        rc = _lib.lib().fpm_spline_plan(_chk(src, "edge_index[0]", torch.int64), _chk(pseudo, "pseudo"),
+                                        self.mask.data_ptr(), self.meta.data_ptr(), self.tab.data_ptr(),
+                                        self.rowmap.data_ptr(), total, edge_index.shape[1], channels, kernel_size,
+                                        self.max_tiles, self.rowmap_cap, _stream())
+        _lib.check(rc, "fpm_spline_plan"); _count(3)
+
+    def tiles_used(self) -> int:
+        """Number of 256 x 128 tiles the GEMM computes (forces a device sync; for reporting only)."""
+        return int(self.meta[0].item())
+
+
+class _PlanInfo:
+    def __init__(self, plan: SlabPlan):
+        self.T, self.T_pad, self.meta = plan.T, plan.T_pad, plan.meta
+
+    def tiles_used(self) -> int:
+        return int(self.meta[0].item())
+
+
+def spline_slab_gemm(x: Tensor, packed: Tensor, plan: SlabPlan) -> Tensor:
+    """Y [total, NS*C] = x @ packed^T restricted to the (node, slab) blocks of ``plan`` (other blocks are left
+    uninitialised: no edge reads them).  Error-compensated fp16 on the persistent CTA-pair kernel."""
+    T, K = x.shape
+    assert T == plan.T and packed.shape[0] == plan.NS * plan.C
+    dev = x.device
+    rows = plan.T_pad + plan.rowmap_cap
+    a_hi = torch.empty((rows, K), dtype=torch.float16, device=dev)
+    a_lo = torch.empty((rows, K), dtype=torch.float16, device=dev)
+    a_inv = torch.empty((rows,), dtype=torch.float32, device=dev)
+    f16_split_rows(x, out=(a_hi, a_lo, a_inv))
+    L = _lib.lib()
+    rc = L.fpm_spline_gather_rows(plan.meta.data_ptr(), plan.rowmap.data_ptr(), a_hi.data_ptr(), a_lo.data_ptr(),
+                                  a_inv.data_ptr(), plan.T_pad, K, plan.rowmap_cap, _stream())
+    _lib.check(rc, "fpm_spline_gather_rows"); _count()
+    b_hi, b_lo, b_inv = f16_split_rows(packed, cache=True)
+    Y = torch.empty((T, plan.NS * plan.C), dtype=torch.float32, device=dev)
+    ev = None
+    if _GEMM_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)); ev[0].record()
+    rc = L.fpm_gemm_nt_f16x3_tiles(a_hi.data_ptr(), a_lo.data_ptr(), a_inv.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(),
+                                   b_inv.data_ptr(), Y.data_ptr(), rows, packed.shape[0], K, K, K, Y.shape[1],
+                                   plan.tab.data_ptr(), plan.meta.data_ptr(), plan.rowmap.data_ptr(), plan.max_tiles,
+                                   T, _stream())
+    _lib.check(rc, "fpm_gemm_nt_f16x3_tiles"); _count()
+    if ev is not None:
+        ev[1].record()
+        # keep only the 88-int meta tensor alive (holding the whole plan would pin its buffers in the allocator)
+        _GEMM_EVENTS.append(("3xf16-slabs", _PlanInfo(plan), packed.shape[0], K, ev[0], ev[1]))
+    return Y
 
 
 def spline_gather_max(Y: Tensor, xin: Optional[Tensor], edge_index: Tensor, pseudo: Tensor, in_ptr: Tensor,

@@ -16,6 +16,11 @@ from fpmatch import ops
 from fpmatch.graph import GraphData, graph_offsets
 
 
+def slab_plan_enabled() -> bool:
+    """The slab-sparse GEMM runs on the persistent fp16x3 kernel; other GEMM modes keep the dense slab product."""
+    return ops.gemm_mode() == "3xf16" and ops.gemm_pair_enabled() and ops.slab_plan_enabled()
+
+
 class SplineConv(torch.nn.Module):
     """SplineConv(in, out, dim=2, kernel_size=5, is_open_spline=True, degree=1, aggr='max',
     root_weight=True, bias=True): the configuration of ``spline_conv.py:17``; others are rejected."""
@@ -55,9 +60,10 @@ class SplineConv(torch.nn.Module):
             self._packed = (key, w.permute(0, 2, 1).reshape(-1, self.in_channels).contiguous())
         return self._packed[1]
 
-    def forward(self, x, edge_index, pseudo, csr=None, ptr=None, eptr=None, mode=None, residual=None):
+    def forward(self, x, edge_index, pseudo, csr=None, ptr=None, eptr=None, mode=None, residual=None, plan=None):
         """``csr`` = in-edge lists from ``ops.csr_by_dst``; built on the fly when missing.  ``mode``:
-        None / 2 = plain conv output, 0 = relu(out), 1 = residual + 0.1 * out."""
+        None / 2 = plain conv output, 0 = relu(out), 1 = residual + 0.1 * out.  ``plan`` = ``ops.SlabPlan`` of the
+        graph (shared by the layers of an SConv): only the (node, slab) products some edge reads are computed."""
         total = x.shape[0]
         if csr is None:
             if ptr is None:
@@ -65,7 +71,12 @@ class SplineConv(torch.nn.Module):
                 eptr = torch.tensor([0, edge_index.shape[1]], dtype=torch.int64, device=x.device)
             max_e = int((eptr[1:] - eptr[:-1]).max())
             csr = ops.csr_by_dst(edge_index.contiguous(), ptr, eptr, total, max_e)
-        Y = ops.gemm_nt(x.detach().contiguous(), self.packed_weight(), weight_operand=True)
+        if plan is None and slab_plan_enabled() and self.out_channels % 128 == 0 and self.in_channels % 8 == 0:
+            plan = ops.SlabPlan(edge_index.contiguous(), pseudo.contiguous(), total, self.out_channels, self.kernel_size)
+        if plan is not None:
+            Y = ops.spline_slab_gemm(x.detach().contiguous(), self.packed_weight(), plan)
+        else:
+            Y = ops.gemm_nt(x.detach().contiguous(), self.packed_weight(), weight_operand=True)
         bias = self.bias.detach().contiguous()
         mode = 2 if mode is None else mode
         return ops.spline_gather_max(Y, residual, edge_index, pseudo.contiguous(), csr[0], csr[1], bias, mode,
@@ -102,10 +113,14 @@ class SConv(torch.nn.Module):
             max_e = int((eptr[1:] - eptr[:-1]).max()) if eptr.numel() > 1 else 0
         csr = ops.csr_by_dst(edge_index, ptr.to(x.device).contiguous(), eptr.to(x.device).contiguous(),
                              x.shape[0], int(max_e))
-        h = self.convs[0](x, edge_index, edge_attr, csr=csr, mode=0)
+        plan = None
+        c0 = self.convs[0]
+        if slab_plan_enabled() and c0.out_channels % 128 == 0 and c0.in_channels % 8 == 0:
+            plan = ops.SlabPlan(edge_index, edge_attr, x.shape[0], c0.out_channels, c0.kernel_size)
+        h = self.convs[0](x, edge_index, edge_attr, csr=csr, mode=0, plan=plan)
         if residual_scale_input is not None:
-            return self.convs[1](h, edge_index, edge_attr, csr=csr, mode=1, residual=residual_scale_input)
-        return self.convs[1](h, edge_index, edge_attr, csr=csr, mode=2)
+            return self.convs[1](h, edge_index, edge_attr, csr=csr, mode=1, residual=residual_scale_input, plan=plan)
+        return self.convs[1](h, edge_index, edge_attr, csr=csr, mode=2, plan=plan)
 
 
 class SiameseSConvOnNodes(torch.nn.Module):

@@ -84,6 +84,15 @@ int fpm_gemm_nt_f16x3(const void* A_hi, const void* A_lo, const float* inv_a, co
  * tile per CTA.  Also settable with the environment variable FPMATCH_GEMM_PAIR=0/1 before the first call. */
 int fpm_gemm_set_pair(int on);
 
+/* Tile-table form of fpm_gemm_nt_f16x3 (persistent CTA-pair kernel): computes only the *tab_count C blocks listed in
+ * tab (device, 4 ints per tile: first A row of a 256-row block, first Bt row of a 128-row block, first C column, row-map
+ * offset or -1 for C row = A row); rowmap[off + r] = C row of A row (a0 + r), -1 = padding.  M = rows of the A buffer,
+ * m_ident = rows of C that identity tiles may write, max_tiles = host-side bound of *tab_count (sizes the grid). */
+int fpm_gemm_nt_f16x3_tiles(const void* A_hi, const void* A_lo, const float* inv_a, const void* Bt_hi,
+                            const void* Bt_lo, const float* inv_b, float* C, int M, int N, int K, int lda, int ldb,
+                            int ldc, const int* tab, const int* tab_count, const int* rowmap, long long max_tiles,
+                            int m_ident, void* stream);
+
 /* debug aid: record {smid, t_entry, t_setup, t_mainloop_done, t_end} (ns) per CTA into buf[5*cap] (NULL = off) */
 int fpm_gemm_set_trace(void* buf, int cap);
 
@@ -94,6 +103,15 @@ int fpm_gemm_set_trace(void* buf, int cap);
  * root slab + bias, then relu (mode 0) or x + 0.1*out (mode 1).  fpm_csr_by_dst builds the in-edge lists
  * from edge_index[1] (global node ids of a PyG-style batch; ptr/eptr = node/edge offsets per graph).
  */
+/* Slab planner (device side, no host round trip): marks the (node, weight slab) products the gather will read and emits
+ * the tile table for fpm_gemm_nt_f16x3_tiles - slabs needed by >= 1/4 of the nodes are computed for all nodes, the
+ * others only for their nodes, compacted behind the dense rows of the A buffer (fpm_spline_gather_rows copies the
+ * fp16 halves there).  mask [T] u32 zero-filled, rowmap [rowmap_cap] i32 filled with -1, meta [2 + 3*(KS*KS+1) + 2] i32
+ * (meta[0] = tile count, meta[1] = compact rows in use), tab [max_tiles] int4. */
+int fpm_spline_plan(const long long* edge_src, const float* pseudo, unsigned* mask, int* meta, int* tab, int* rowmap,
+                    int T, int E, int C, int kernel_size, int max_tiles, int rowmap_cap, void* stream);
+int fpm_spline_gather_rows(const int* meta, const int* rowmap, void* a_hi, void* a_lo, float* inv_a, int T_pad, int K,
+                           int rowmap_cap, void* stream);
 int fpm_csr_by_dst(const long long* edge_dst, const long long* ptr, const long long* eptr, int* in_ptr,
                    int* in_eid, int B, int total_nodes, int max_edges_per_graph, void* stream);
 int fpm_spline_gather_max(const float* Y, const float* xin, const long long* edge_src, const float* pseudo,
