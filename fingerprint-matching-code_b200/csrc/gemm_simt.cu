@@ -219,39 +219,50 @@ affinity_kernel(const float* __restrict__ XA, const float* __restrict__ XB, cons
 //     (E1 (.) c) E2^T [k1, k2] = P[s1,s2] - P[s1,d2] - P[d1,s2] + P[d1,d2],   edge k = (s -> d)
 // which replaces the reference's [e1 x 768] x [768 x e2] product per pair (0.50 GFLOP at n = 100) by a
 // [n1 x 768] x [768 x n2] product (15 MFLOP) plus a 4-term gather: the kernel is bound by writing Ke.
-// One CTA per (128 columns of k2, k1, pair); the two needed rows of P sit in shared memory.
+// One CTA per (128 columns of k2, block of kKeRows rows k1, pair): the 2 * kKeRows rows of P the block needs
+// (source and target node of each of its edges) are staged in shared memory; every thread keeps its column's
+// (s2, d2) and walks the k1 rows.  (The first version used one CTA per single k1 row: 742 k tiny CTAs at B = 256,
+// launch-bound at 0.57 ms.)
+constexpr int kKeRows = 16;
 __global__ void __launch_bounds__(128)
 ke_factored_kernel(const float* __restrict__ P, const int64_t* __restrict__ eidxA,
                    const int64_t* __restrict__ eptrA, const int64_t* __restrict__ ptrA,
                    const int64_t* __restrict__ eidxB, const int64_t* __restrict__ eptrB,
                    const int64_t* __restrict__ ptrB, int EA, int EB, float* __restrict__ out, int Rn, int Cn,
                    int e1max, int e2max, float scale) {
-  extern __shared__ float rows[];               // [2][Cn]
-  const int b = blockIdx.z, k1 = blockIdx.y;
+  extern __shared__ float rows[];               // [2 * kKeRows][Cn]
+  const int b = blockIdx.z, k1_0 = blockIdx.y * kKeRows;
   const int k2 = blockIdx.x * blockDim.x + threadIdx.x;
   const int e1 = (int)(eptrA[b + 1] - eptrA[b]), e2 = (int)(eptrB[b + 1] - eptrB[b]);
-  float* o = out + ((size_t)b * e1max + k1) * e2max;
-  if (k1 >= e1) {                               // padding row
-    if (k2 < e2max) o[k2] = 0.f;
-    return;
-  }
-  const int64_t ea = eptrA[b] + k1;
-  const int s1 = (int)(eidxA[ea] - ptrA[b]), d1 = (int)(eidxA[(size_t)EA + ea] - ptrA[b]);
   const float* Pb = P + (size_t)b * Rn * Cn;
-  for (int j = threadIdx.x; j < Cn; j += blockDim.x) {
-    rows[j] = Pb[(size_t)s1 * Cn + j];
-    rows[Cn + j] = Pb[(size_t)d1 * Cn + j];
+  const int64_t pa = ptrA[b], ea0 = eptrA[b];
+  const int nrow = min(kKeRows, e1 - k1_0);     // valid edge rows of this block (<= 0: padding only)
+  for (int r = 0; r < nrow; ++r) {
+    const int s1 = (int)(eidxA[ea0 + k1_0 + r] - pa), d1 = (int)(eidxA[(size_t)EA + ea0 + k1_0 + r] - pa);
+    for (int j = threadIdx.x; j < Cn; j += blockDim.x) {
+      rows[(2 * r) * Cn + j] = Pb[(size_t)s1 * Cn + j];
+      rows[(2 * r + 1) * Cn + j] = Pb[(size_t)d1 * Cn + j];
+    }
   }
   __syncthreads();
   if (k2 >= e2max) return;
-  float v = 0.f;
-  if (k2 < e2) {
+  int s2 = 0, d2 = 0;
+  const bool col_ok = k2 < e2;
+  if (col_ok) {
     const int64_t eb = eptrB[b] + k2;
-    const int s2 = (int)(eidxB[eb] - ptrB[b]), d2 = (int)(eidxB[(size_t)EB + eb] - ptrB[b]);
-    const float dot = (rows[s2] - rows[d2]) - (rows[Cn + s2] - rows[Cn + d2]);
-    v = scale * (softplus_torch(dot) - 0.5f);
+    s2 = (int)(eidxB[eb] - ptrB[b]); d2 = (int)(eidxB[(size_t)EB + eb] - ptrB[b]);
   }
-  o[k2] = v;
+  for (int r = 0; r < kKeRows; ++r) {
+    const int k1 = k1_0 + r;
+    if (k1 >= e1max) break;
+    float v = 0.f;
+    if (r < nrow && col_ok) {
+      const float* ps = rows + (2 * r) * Cn; const float* pd = ps + Cn;
+      const float dot = (ps[s2] - ps[d2]) - (pd[s2] - pd[d2]);
+      v = scale * (softplus_torch(dot) - 0.5f);
+    }
+    out[((size_t)b * e1max + k1) * e2max + k2] = v;
+  }
 }
 
 }  // namespace fpm
@@ -301,8 +312,11 @@ extern "C" int fpm_affinity_edges_factored(const float* P, const long long* eidx
   FPM_CHECK_ARG(B >= 0 && Rn > 0 && Cn > 0 && e1max > 0 && e2max > 0, "fpm_affinity_edges_factored: bad sizes");
   if (B == 0) return FPM_OK;
   FPM_CHECK_ARG(B <= 65535 && e1max <= 65535, "fpm_affinity_edges_factored: batch or edge count too large");
-  dim3 grid(fpm_cdiv(e2max, 128), e1max, B);
-  fpm::ke_factored_kernel<<<grid, 128, (size_t)2 * Cn * sizeof(float), (cudaStream_t)stream>>>(
+  const size_t smem = (size_t)2 * fpm::kKeRows * Cn * sizeof(float);
+  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_affinity_edges_factored: too many columns for shared memory");
+  FPM_CUDA(cudaFuncSetAttribute(fpm::ke_factored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(fpm_cdiv(e2max, 128), fpm_cdiv(e1max, fpm::kKeRows), B);
+  fpm::ke_factored_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(
       P, (const int64_t*)eidxA, (const int64_t*)eptrA, (const int64_t*)ptrA, (const int64_t*)eidxB,
       (const int64_t*)eptrB, (const int64_t*)ptrB, EA, EB, out, Rn, Cn, e1max, e2max, scale);
   FPM_LAUNCH_CHECK();
