@@ -270,7 +270,11 @@ def main():
         peak_note = f"TF32 dense = {peak_kind} sustained bf16 cuBLAS peak / 2 (no TF32 figure is measured)"
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape, from the committed
     # `ncu --set full` capture profiles/r1c_ncu_full_gemm_pair.md (algorithmic bytes: 2.185e9)
-    traffic = 2.644e9 if (kernel_label is None and mode == "3xf16" and (big[1], big[2], big[3]) == (25600, 19968, 768)) else None
+    # (dense product: profiles/r1c_ncu_full_gemm_pair.md, 2.644e9 for 2.185e9 algorithmic; tile-table launch at
+    # 6084 tiles: profiles/r1d_ncu_full.md, 1.047e9 for 0.90e9 algorithmic)
+    traffic = None
+    if mode == "3xf16" and (big[1], big[2], big[3]) == (25600, 19968, 768):
+        traffic = 2.644e9 if kernel_label is None else 1.047e9
     achieved = flops / (gemm_ms / 1e3) / 1e12
     gemm_share = gemm_ms * len(same) / args.steps / ms_step
 
@@ -307,6 +311,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = B * world / t.item()
     d2h = sum(r.numel() * r.element_size() for r in res)
+    # the e2e step moves 262 MB host->device: report what this box's link gives for a plain pinned copy of that size,
+    # so a link-bound e2e figure can be told from a compute-bound one
+    probe = host["fmaps"][0][0]
+    dst = torch.empty_like(probe, device=dev)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(4):
+        dst.copy_(probe, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * probe.numel() * probe.element_size() / (c0.elapsed_time(c1) / 1e3) / 1e9
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -327,7 +343,8 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "kernel": kernel_label or f"gemm_nt[{mode}] M={big[1]} N={big[2]} K={big[3]}",
                          "launch_ms": gemm_ms, "share_of_step": gemm_share, "peak_source": peak_note},
             "cpu_baseline": cpu_base,
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "h2d_link_gbs_measured": h2d_gbs, "h2d_ms_per_step_at_that_rate": h2d / h2d_gbs / 1e6},
             "gpu_launches": launches,
             "clocks": clk.summary(),
         }

@@ -115,44 +115,25 @@ lap_topk_kernel(const float* __restrict__ ds, const int64_t* __restrict__ n1,
         double best = INFINITY;
         int upos = -1;          // last position at `best` whose column is unassigned
         int fpos = INT_MAX;     // first position at `best`
-        // four candidates per trip: their load chains (remaining -> cost -> v, spc, row4col) are independent and
-        // overlap; the best / first / last-unassigned bookkeeping then runs in ascending position order as before.
-        // (One candidate per trip left ~5 dependent shared-memory loads on the critical path of every step.)
-        for (int it0 = lane; it0 < num_remaining; it0 += 128) {
-          double curv[4];
-          bool unas[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int it = it0 + 32 * u;
-            curv[u] = INFINITY; unas[u] = false;
-            if (it < num_remaining) {
-              const int j = sm.remaining[it];
-              const float sc = kCostSmem ? sm.cost[(size_t)i * nc + j]
-                                         : (tr ? dsb[(size_t)j * C + i] : dsb[(size_t)i * C + j]);
-              const double c = -(double)sc;
-              double r = minVal + c;
-              r = r - ui;
-              r = r - sm.v[j];
-              double cur = sm.spc[j];
-              if (r < cur) {
-                sm.path[j] = i;
-                sm.spc[j] = r;
-                cur = r;
-              }
-              curv[u] = cur;
-              unas[u] = sm.row4col[j] == -1;
-            }
+        for (int it = lane; it < num_remaining; it += 32) {
+          const int j = sm.remaining[it];
+          const float sc = kCostSmem ? sm.cost[(size_t)i * nc + j]
+                                     : (tr ? dsb[(size_t)j * C + i] : dsb[(size_t)i * C + j]);
+          const double c = -(double)sc;
+          double r = minVal + c;
+          r = r - ui;
+          r = r - sm.v[j];
+          double cur = sm.spc[j];
+          if (r < cur) {
+            sm.path[j] = i;
+            sm.spc[j] = r;
+            cur = r;
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int it = it0 + 32 * u;
-            if (it < num_remaining) {
-              if (curv[u] < best) {
-                best = curv[u]; fpos = it; upos = unas[u] ? it : -1;
-              } else if (curv[u] == best) {
-                if (unas[u]) upos = it;
-              }
-            }
+          const bool unassigned = sm.row4col[j] == -1;
+          if (cur < best) {
+            best = cur; fpos = it; upos = unassigned ? it : -1;
+          } else if (cur == best) {
+            if (unassigned) upos = it;
           }
         }
         // warp-wide: global minimum value, then last-unassigned / first position at that value
