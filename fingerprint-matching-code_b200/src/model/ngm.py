@@ -256,7 +256,7 @@ class Net(CNN):
         matched_sim = s * x
         cls_logits = self.match_cls(matched_sim)
         cls_prob = torch.sigmoid(cls_logits)
-        cls_loss = torch.tensor(0.0, device=dev)
+        cls_loss = torch.zeros((), device=dev)          # a fill kernel: torch.tensor(0.0, device=...) is a blocking host copy
         if 'label' in data_dict:
             label_tensor = data_dict['label'].to(dev).view(-1).float()
             cls_loss = torch.nn.functional.binary_cross_entropy_with_logits(cls_logits, label_tensor)
@@ -351,7 +351,7 @@ class Net(CNN):
         matched_sim = s * x
         cls_logits = self.match_cls(matched_sim)
         cls_prob = torch.sigmoid(cls_logits)
-        cls_loss = torch.tensor(0.0, device=dev)
+        cls_loss = torch.zeros((), device=dev)          # a fill kernel: torch.tensor(0.0, device=...) is a blocking host copy
         if 'label' in data_dict:
             label_tensor = data_dict['label'].to(dev).view(-1).float()
             cls_loss = torch.nn.functional.binary_cross_entropy_with_logits(cls_logits, label_tensor)
