@@ -32,7 +32,7 @@ def trainable(net):
 
 def run(net, batches, dev, steps):
     params = trainable(net.module if hasattr(net, "module") else net)
-    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4)
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4)      # stage-1 warm-up LR (train.py:246-252,297)
     losses = []
     for t in range(steps):
         d = synth.batch_to(synth.clone_batch(batches[t % len(batches)]), dev)
