@@ -58,6 +58,43 @@ struct GnnWeights {
 
 constexpr int kF = 16;   // GNN_FEAT, ngm.py:47
 
+// The layer's weights live in CONSTANT memory during the forward: every thread of a warp multiplies by the same
+// weight, so the FMAs take it as a constant-bank operand and stage 2 issues no load at all for it.  (With the
+// weights in shared memory the kernel spent 27 % of its warp samples waiting on LDS and 18 % on the dependent
+// FMAs behind them, at 12 warps per SM - r1c ncu source view.)  Layout for row padding CP (4 or 20):
+//   wl[16][CP] wr[16][CP] w0[16][CP] w2[16][16] bl[16] b0[16] b2[16] wc[16] cb
+// gnn_pack_weights_kernel writes that layout into a device staging buffer and one cudaMemcpyToSymbolAsync
+// (device to device, stream ordered) publishes it before the layer kernel; calls on one stream are ordered,
+// concurrent forwards on different streams of one process are not supported.
+constexpr int kGnnConstFloats = 3 * 16 * 20 + 16 * 16 + 4 * 16 + 4;
+__constant__ float c_gnn[kGnnConstFloats];
+
+template <int CP>
+struct GnnOff {
+  static constexpr int wl = 0, wr = 16 * CP, w0 = 32 * CP, w2 = 48 * CP, bl = w2 + 256, b0 = bl + 16, b2 = b0 + 16,
+                       wc = b2 + 16, cb = wc + 16, total = cb + 1;
+};
+
+template <int CIN>
+__global__ void gnn_pack_weights_kernel(GnnWeights w, float* __restrict__ staging) {
+  constexpr int CP = (CIN + 3) / 4 * 4;
+  using O = GnnOff<CP>;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 16 * CP; i += blockDim.x) {
+    const int o = i / CP, c = i - o * CP;
+    const bool in = c < CIN;
+    staging[O::wl + i] = in ? w.lin_l_w[o * CIN + c] : 0.f;
+    staging[O::wr + i] = in ? w.lin_r_w[o * CIN + c] : 0.f;
+    staging[O::w0 + i] = in ? w.self0_w[o * CIN + c] : 0.f;
+  }
+  for (int i = tid; i < 256; i += blockDim.x) staging[O::w2 + i] = w.self2_w[i];
+  if (tid < 16) {
+    staging[O::bl + tid] = w.lin_l_b[tid]; staging[O::b0 + tid] = w.self0_b[tid];
+    staging[O::b2 + tid] = w.self2_b[tid]; staging[O::wc + tid] = w.cls_w[tid];
+  }
+  if (tid == 0) staging[O::cb] = w.cls_b[0];
+}
+
 // CIN = 1 (layer 0: emb = vec(Kp)) or 17 (x1 of the previous layer + its Sinkhorn channel).
 // xprev:   [B, N, 16]   (CIN == 17 only), N = n1max*n2max, p = i2*n1max + i1
 // mprev_t: [B, n2max, n1max]  the matrix channel in p order (Kp^T or Sinkhorn^T)
@@ -67,40 +104,18 @@ __global__ void __launch_bounds__(128, 3)
 gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mprev_t,
                  const int* __restrict__ in_ptr1, const int* __restrict__ in_src1,
                  const int* __restrict__ in_ptr2, const int* __restrict__ in_src2,
-                 const int64_t* __restrict__ n1, const int64_t* __restrict__ n2, GnnWeights w,
+                 const int64_t* __restrict__ n1, const int64_t* __restrict__ n2,
                  float* __restrict__ xout, float* __restrict__ score, int n1max, int n2max, int e1max,
                  int e2max) {
-  // Shared layout: every row is padded to CP floats (a multiple of 4) so that the per-node loops below
-  // read weights and partial sums as 128-bit broadcasts: one LDS.128 per 4 FMAs instead of one LDS per
-  // FMA (the first version of this kernel was LSU-bound: 1256 LDS for 1183 FFMA per node).
+  // Shared layout: the partial sums are padded to CP floats per row (a multiple of 4) and read as 128-bit
+  // broadcasts.
   constexpr int CP = (CIN + 3) / 4 * 4;
   extern __shared__ __align__(16) float sm[];
   float* Rsum = sm;                               // [n1max][CP] sum over In2(j2) rows
-  float* Wsh = sm + (size_t)n1max * CP;           // weights
+  using O = GnnOff<CP>;                             // weights: constant bank c_gnn (see above)
   const int b = blockIdx.y, j2 = blockIdx.x;
   const int N = n1max * n2max;
   const int tid = threadIdx.x;
-
-  float* wl = Wsh;                    // [16][CP]
-  float* wr = wl + kF * CP;           // [16][CP]
-  float* w0 = wr + kF * CP;           // [16][CP]
-  float* w2 = w0 + kF * CP;           // [16][16]
-  float* bl = w2 + kF * kF;           // [16]
-  float* b0 = bl + kF;
-  float* b2 = b0 + kF;
-  float* wc = b2 + kF;                // [16] + bias
-  for (int i = tid; i < kF * CP; i += blockDim.x) {
-    const int o = i / CP, c = i - o * CP;
-    const bool in = c < CIN;
-    wl[i] = in ? w.lin_l_w[o * CIN + c] : 0.f;
-    wr[i] = in ? w.lin_r_w[o * CIN + c] : 0.f;
-    w0[i] = in ? w.self0_w[o * CIN + c] : 0.f;
-  }
-  for (int i = tid; i < kF * kF; i += blockDim.x) w2[i] = w.self2_w[i];
-  if (tid < kF) {
-    bl[tid] = w.lin_l_b[tid]; b0[tid] = w.self0_b[tid]; b2[tid] = w.self2_b[tid]; wc[tid] = w.cls_w[tid];
-  }
-  if (tid == 0) wc[kF] = w.cls_b[0];
 
   // ---- stage 1: Rsum[i1, c] = sum_{i2 in In2(j2)} feat[(i2, i1), c]
   const int* ip2 = in_ptr2 + (size_t)b * (n2max + 1);
@@ -189,40 +204,28 @@ gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mpre
     float h[kF];
 #pragma unroll
     for (int o = 0; o < kF; ++o) {
-      float a = b0[o];
+      float a = c_gnn[O::b0 + o];
 #pragma unroll
-      for (int t = 0; t < CP / 4; ++t) {
-        const float4 wv = *(const float4*)&w0[o * CP + t * 4];
-        a = fmaf(wv.x, own[t * 4], a); a = fmaf(wv.y, own[t * 4 + 1], a);
-        a = fmaf(wv.z, own[t * 4 + 2], a); a = fmaf(wv.w, own[t * 4 + 3], a);
-      }
+      for (int c = 0; c < CP; ++c) a = fmaf(c_gnn[O::w0 + o * CP + c], own[c], a);
       h[o] = fmaxf(a, 0.f);
     }
     float x1[kF];
-    float sc = wc[kF];
+    float sc = c_gnn[O::cb];
 #pragma unroll
     for (int o = 0; o < kF; ++o) {
-      float a = bl[o];
+      float a = c_gnn[O::bl + o];
       float r = 0.f;
 #pragma unroll
-      for (int t = 0; t < CP / 4; ++t) {
-        const float4 lv = *(const float4*)&wl[o * CP + t * 4];
-        const float4 rv = *(const float4*)&wr[o * CP + t * 4];
-        a = fmaf(lv.x, agg[t * 4], a); a = fmaf(lv.y, agg[t * 4 + 1], a);
-        a = fmaf(lv.z, agg[t * 4 + 2], a); a = fmaf(lv.w, agg[t * 4 + 3], a);
-        r = fmaf(rv.x, own[t * 4], r); r = fmaf(rv.y, own[t * 4 + 1], r);
-        r = fmaf(rv.z, own[t * 4 + 2], r); r = fmaf(rv.w, own[t * 4 + 3], r);
+      for (int c = 0; c < CP; ++c) {
+        a = fmaf(c_gnn[O::wl + o * CP + c], agg[c], a);
+        r = fmaf(c_gnn[O::wr + o * CP + c], own[c], r);
       }
-      float s2 = b2[o];
+      float s2 = c_gnn[O::b2 + o];
 #pragma unroll
-      for (int t = 0; t < kF / 4; ++t) {
-        const float4 wv = *(const float4*)&w2[o * kF + t * 4];
-        s2 = fmaf(wv.x, h[t * 4], s2); s2 = fmaf(wv.y, h[t * 4 + 1], s2);
-        s2 = fmaf(wv.z, h[t * 4 + 2], s2); s2 = fmaf(wv.w, h[t * 4 + 3], s2);
-      }
+      for (int c = 0; c < kF; ++c) s2 = fmaf(c_gnn[O::w2 + o * kF + c], h[c], s2);
       const float v = (a + r) + fmaxf(s2, 0.f);
       x1[o] = v;
-      sc = fmaf(wc[o], v, sc);
+      sc = fmaf(c_gnn[O::wc + o], v, sc);
     }
     float4* dst = (float4*)(xout + ((size_t)b * N + p) * kF);
     dst[0] = make_float4(x1[0], x1[1], x1[2], x1[3]);
@@ -586,19 +589,33 @@ extern "C" int fpm_gnn_layer(const float* xprev, const float* mprev_t, const int
                     weights[5], weights[6], weights[7], weights[8]};
   for (int i = 0; i < 9; ++i) FPM_CHECK_ARG(weights[i], "fpm_gnn_layer: null weight");
   const int cp = (cin + 3) / 4 * 4;
-  const size_t smem = ((size_t)n1max * cp + 3 * 16 * cp + 16 * 16 + 4 * 16 + 4) * sizeof(float);
+  const size_t smem = (size_t)n1max * cp * sizeof(float);
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_gnn_layer: n1max too large");
   dim3 grid(n2max, B);
   cudaStream_t st = (cudaStream_t)stream;
+  // weights -> padded staging buffer (device) -> constant bank, all stream ordered
+  static float* staging[16] = {nullptr};
+  int dev = 0;
+  FPM_CUDA(cudaGetDevice(&dev));
+  FPM_CHECK_ARG(dev >= 0 && dev < 16, "fpm_gnn_layer: device index out of range");
+  if (!staging[dev]) FPM_CUDA(cudaMalloc(&staging[dev], fpm::kGnnConstFloats * sizeof(float)));
   if (cin == 1) {
+    fpm::gnn_pack_weights_kernel<1><<<1, 256, 0, st>>>(w, staging[dev]);
+    FPM_LAUNCH_CHECK();
+    FPM_CUDA(cudaMemcpyToSymbolAsync(fpm::c_gnn, staging[dev], fpm::GnnOff<4>::total * sizeof(float), 0,
+                                     cudaMemcpyDeviceToDevice, st));
     FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fpm::gnn_layer_kernel<1><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
-                                                      (const int64_t*)n1, (const int64_t*)n2, w, xout, score,
+                                                      (const int64_t*)n1, (const int64_t*)n2, xout, score,
                                                       n1max, n2max, e1max, e2max);
   } else {
+    fpm::gnn_pack_weights_kernel<17><<<1, 256, 0, st>>>(w, staging[dev]);
+    FPM_LAUNCH_CHECK();
+    FPM_CUDA(cudaMemcpyToSymbolAsync(fpm::c_gnn, staging[dev], fpm::GnnOff<20>::total * sizeof(float), 0,
+                                     cudaMemcpyDeviceToDevice, st));
     FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fpm::gnn_layer_kernel<17><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
-                                                       (const int64_t*)n1, (const int64_t*)n2, w, xout, score,
+                                                       (const int64_t*)n1, (const int64_t*)n2, xout, score,
                                                        n1max, n2max, e1max, e2max);
   }
   FPM_LAUNCH_CHECK();
