@@ -51,7 +51,7 @@ SIGNATURES = {
     "fpm_sinkhorn_log": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "fpm_soft_topk_workspace_bytes": (_LL, [_I, _I, _I]),
     "fpm_soft_topk": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
-    "fpm_afau_attention": (_I, [_P, _P, _P, _P, _LL, _LL, _LL, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_afau_attention": (_I, [_P, _P, _P, _P, _LL, _LL, _LL, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_add_instnorm": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "fpm_onehot_proj": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_k_head": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),

@@ -501,7 +501,7 @@ def soft_topk(scores: Tensor, ks: Tensor, n1: Optional[Tensor], n2: Optional[Ten
 # AFA-U
 # ---------------------------------------------------------------------------------------------------
 def afau_attention(q: Tensor, k: Tensor, v: Tensor, cost: Tensor, transposed_cost: bool, mix1_w: Tensor,
-                   mix1_b: Tensor, mix2_w: Tensor, mix2_b: Tensor) -> Tensor:
+                   mix1_b: Tensor, mix2_w: Tensor, mix2_b: Tensor, q_zero: bool = False) -> Tensor:
     """cost is the ORIGINAL [B, n1, n2] matrix; ``transposed_cost`` makes the kernel read cost^T."""
     B, nr, E = q.shape
     nc = k.shape[1]
@@ -516,7 +516,7 @@ def afau_attention(q: Tensor, k: Tensor, v: Tensor, cost: Tensor, transposed_cos
     rc = _lib.lib().fpm_afau_attention(_chk(q, "q"), _chk(k, "k"), _chk(v, "v"), _chk(cost, "cost"), cs_b, cs_r, cs_c,
                                        _chk(mix1_w, "mix1_weight"), _chk(mix1_b, "mix1_bias"),
                                        _chk(mix2_w, "mix2_weight"), _chk(mix2_b, "mix2_bias"), out.data_ptr(),
-                                       B, nr, nc, _stream())
+                                       B, nr, nc, int(q_zero), _stream())
     _lib.check(rc, "fpm_afau_attention"); _count()
     return out
 

@@ -178,7 +178,8 @@ int fpm_soft_topk(const float* scores, const float* ks, const long long* n1, con
  */
 int fpm_afau_attention(const float* q, const float* k, const float* v, const float* cost, long long cs_b,
                        long long cs_r, long long cs_c, const float* mix1_w, const float* mix1_b,
-                       const float* mix2_w, const float* mix2_b, float* out, int B, int nr, int nc, void* stream);
+                       const float* mix2_w, const float* mix2_b, float* out, int B, int nr, int nc, int q_zero,
+                       void* stream);   /* q_zero = 1: caller guarantees q == 0 (row block of Net.forward): q.k is skipped */
 int fpm_add_instnorm(const float* a, const float* other, int other_mode, const float* gamma, const float* beta,
                      float* out, float* rowmax, int B, int n, int E, float eps, void* stream);
 int fpm_onehot_proj(const float* W, const long long* n, float* out, int B, int nmax, int OUT, int IN,
