@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(128, 2)
 gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ mprev_t,
                      const int* __restrict__ in_ptr1, const int* __restrict__ in_src1,
                      const int* __restrict__ in_ptr2, const int* __restrict__ in_src2,
-                     const int64_t* __restrict__ n1, const int64_t* __restrict__ n2, GnnWeights w,
+                     const int64_t* __restrict__ n1, const int64_t* __restrict__ n2,
                      const float* __restrict__ dxout, const float* __restrict__ dscore,
                      float* __restrict__ dxprev, float* __restrict__ dm, float* __restrict__ gagg,
                      float* __restrict__ grads, int n1max, int n2max, int e1max, int e2max) {
@@ -288,34 +288,13 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
   constexpr int QPT = (NQ + 127) / 128;
   extern __shared__ __align__(16) float sm[];
   float* Rsum = sm;                               // [n1max][CP]
-  float* Wsh = sm + (size_t)n1max * CP;
+  using O = GnnOff<CP>;                             // weights: constant bank c_gnn (packed by the host wrapper)
   const int b = blockIdx.y, j2 = blockIdx.x;
   const int N = n1max * n2max;
   const int tid = threadIdx.x;
-
-  float* wl = Wsh;                    // [16][CP]
-  float* wr = wl + kF * CP;
-  float* w0 = wr + kF * CP;
-  float* w2 = w0 + kF * CP;           // [16][16]
-  float* bl = w2 + kF * kF;
-  float* b0 = bl + kF;
-  float* b2 = b0 + kF;
-  float* wc = b2 + kF;                // [16] + bias (+3 pad)
-  float* V = wc + kF + 4;             // [128][VS]
+  float* V = sm + (size_t)n1max * CP;              // [128][VS]
   short* qlo = (short*)(V + 128 * VS);   // [NQ]
   short* qro = qlo + NQ;
-  for (int i = tid; i < kF * CP; i += blockDim.x) {
-    const int o = i / CP, c = i - o * CP;
-    const bool in = c < CIN;
-    wl[i] = in ? w.lin_l_w[o * CIN + c] : 0.f;
-    wr[i] = in ? w.lin_r_w[o * CIN + c] : 0.f;
-    w0[i] = in ? w.self0_w[o * CIN + c] : 0.f;
-  }
-  for (int i = tid; i < kF * kF; i += blockDim.x) w2[i] = w.self2_w[i];
-  if (tid < kF) {
-    bl[tid] = w.lin_l_b[tid]; b0[tid] = w.self0_b[tid]; b2[tid] = w.self2_b[tid]; wc[tid] = w.cls_w[tid];
-  }
-  if (tid == 0) wc[kF] = w.cls_b[0];
   // weight-gradient task table: entry q = <left vector component, right vector component>
   for (int q = tid; q < NQ; q += blockDim.x) {
     int lo, ro, r = q;
@@ -408,18 +387,18 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
       float h0[kF], s2[kF], x1[kF];
 #pragma unroll
       for (int o = 0; o < kF; ++o) {
-        float a = b0[o];
+        float a = c_gnn[O::b0 + o];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) a = fmaf(w0[o * CP + c], own[c], a);
+        for (int c = 0; c < CP; ++c) a = fmaf(c_gnn[O::w0 + o * CP + c], own[c], a);
         h0[o] = fmaxf(a, 0.f);
       }
 #pragma unroll
       for (int o = 0; o < kF; ++o) {
-        float a = bl[o], r = 0.f, q2 = b2[o];
+        float a = c_gnn[O::bl + o], r = 0.f, q2 = c_gnn[O::b2 + o];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) { a = fmaf(wl[o * CP + c], agg[c], a); r = fmaf(wr[o * CP + c], own[c], r); }
+        for (int c = 0; c < CP; ++c) { a = fmaf(c_gnn[O::wl + o * CP + c], agg[c], a); r = fmaf(c_gnn[O::wr + o * CP + c], own[c], r); }
 #pragma unroll
-        for (int c = 0; c < kF; ++c) q2 = fmaf(w2[o * kF + c], h0[c], q2);
+        for (int c = 0; c < kF; ++c) q2 = fmaf(c_gnn[O::w2 + o * kF + c], h0[c], q2);
         s2[o] = q2;
         x1[o] = (a + r) + fmaxf(q2, 0.f);
       }
@@ -435,7 +414,7 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
         }
       }
 #pragma unroll
-      for (int o = 0; o < kF; ++o) dx1[o] = fmaf(dsc, wc[o], dx1[o]);
+      for (int o = 0; o < kF; ++o) dx1[o] = fmaf(dsc, c_gnn[O::wc + o], dx1[o]);
       float ds2[kF], dh0[kF];
 #pragma unroll
       for (int o = 0; o < kF; ++o) ds2[o] = s2[o] > 0.f ? dx1[o] : 0.f;
@@ -443,7 +422,7 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
       for (int c = 0; c < kF; ++c) {
         float a = 0.f;
 #pragma unroll
-        for (int o = 0; o < kF; ++o) a = fmaf(w2[o * kF + c], ds2[o], a);
+        for (int o = 0; o < kF; ++o) a = fmaf(c_gnn[O::w2 + o * kF + c], ds2[o], a);
         dh0[c] = h0[c] > 0.f ? a : 0.f;
       }
       float down[CP], dagg[CP];
@@ -452,9 +431,9 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
         float a = 0.f, g = 0.f;
 #pragma unroll
         for (int o = 0; o < kF; ++o) {
-          a = fmaf(wr[o * CP + c], dx1[o], a);
-          a = fmaf(w0[o * CP + c], dh0[o], a);
-          g = fmaf(wl[o * CP + c], dx1[o], g);
+          a = fmaf(c_gnn[O::wr + o * CP + c], dx1[o], a);
+          a = fmaf(c_gnn[O::w0 + o * CP + c], dh0[o], a);
+          g = fmaf(c_gnn[O::wl + o * CP + c], dx1[o], g);
         }
         g = g / inv;
         dagg[c] = g;
@@ -559,6 +538,22 @@ assoc_aggregate_add_kernel(const float* __restrict__ gagg, const int* __restrict
 
 }  // namespace fpm
 
+// weights -> padded staging buffer (device) -> constant bank c_gnn, all stream ordered (see the comment at c_gnn)
+template <int CIN>
+static int gnn_publish_weights(const fpm::GnnWeights& w, cudaStream_t st) {
+  static float* staging[16] = {nullptr};
+  int dev = 0;
+  FPM_CUDA(cudaGetDevice(&dev));
+  FPM_CHECK_ARG(dev >= 0 && dev < 16, "fpm_gnn_layer: device index out of range");
+  if (!staging[dev]) FPM_CUDA(cudaMalloc(&staging[dev], fpm::kGnnConstFloats * sizeof(float)));
+  constexpr int CP = (CIN + 3) / 4 * 4;
+  fpm::gnn_pack_weights_kernel<CIN><<<1, 256, 0, st>>>(w, staging[dev]);
+  FPM_LAUNCH_CHECK();
+  FPM_CUDA(cudaMemcpyToSymbolAsync(fpm::c_gnn, staging[dev], fpm::GnnOff<CP>::total * sizeof(float), 0,
+                                   cudaMemcpyDeviceToDevice, st));
+  return FPM_OK;
+}
+
 extern "C" int fpm_assoc_in_csr(const int* edges, int* in_ptr, int* in_src, int B, int nmax, int emax,
                                 void* stream) {
   FPM_CHECK_ARG(edges && in_ptr && in_src, "fpm_assoc_in_csr: null tensor");
@@ -593,26 +588,15 @@ extern "C" int fpm_gnn_layer(const float* xprev, const float* mprev_t, const int
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_gnn_layer: n1max too large");
   dim3 grid(n2max, B);
   cudaStream_t st = (cudaStream_t)stream;
-  // weights -> padded staging buffer (device) -> constant bank, all stream ordered
-  static float* staging[16] = {nullptr};
-  int dev = 0;
-  FPM_CUDA(cudaGetDevice(&dev));
-  FPM_CHECK_ARG(dev >= 0 && dev < 16, "fpm_gnn_layer: device index out of range");
-  if (!staging[dev]) FPM_CUDA(cudaMalloc(&staging[dev], fpm::kGnnConstFloats * sizeof(float)));
+  int rc_pack;
   if (cin == 1) {
-    fpm::gnn_pack_weights_kernel<1><<<1, 256, 0, st>>>(w, staging[dev]);
-    FPM_LAUNCH_CHECK();
-    FPM_CUDA(cudaMemcpyToSymbolAsync(fpm::c_gnn, staging[dev], fpm::GnnOff<4>::total * sizeof(float), 0,
-                                     cudaMemcpyDeviceToDevice, st));
+    if ((rc_pack = gnn_publish_weights<1>(w, st)) != FPM_OK) return rc_pack;
     FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fpm::gnn_layer_kernel<1><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
                                                       (const int64_t*)n1, (const int64_t*)n2, xout, score,
                                                       n1max, n2max, e1max, e2max);
   } else {
-    fpm::gnn_pack_weights_kernel<17><<<1, 256, 0, st>>>(w, staging[dev]);
-    FPM_LAUNCH_CHECK();
-    FPM_CUDA(cudaMemcpyToSymbolAsync(fpm::c_gnn, staging[dev], fpm::GnnOff<20>::total * sizeof(float), 0,
-                                     cudaMemcpyDeviceToDevice, st));
+    if ((rc_pack = gnn_publish_weights<17>(w, st)) != FPM_OK) return rc_pack;
     FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fpm::gnn_layer_kernel<17><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
                                                        (const int64_t*)n1, (const int64_t*)n2, xout, score,
@@ -654,16 +638,17 @@ extern "C" int fpm_gnn_layer_bwd(const float* xprev, const float* mprev_t, const
   const int cp = (cin + 3) / 4 * 4;
   const int nq = 3 * 16 * cin + 16 * 16 + 4 * 16 + 1;
   const int vs = 49 + 2 * cp + 33;
-  const size_t smem = ((size_t)n1max * cp + 3 * 16 * cp + 16 * 16 + 4 * 16 + 4 + (size_t)128 * vs) * sizeof(float) +
-                      (size_t)2 * nq * sizeof(short) + 16;
+  const size_t smem = ((size_t)n1max * cp + (size_t)128 * vs) * sizeof(float) + (size_t)2 * nq * sizeof(short) + 16;
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_gnn_layer_bwd: n1max too large");
   dim3 grid(n2max, B);
   cudaStream_t st = (cudaStream_t)stream;
+  int rc_pack = FPM_OK;
   const size_t smem2 = (size_t)n1max * cp * sizeof(float);
   if (cin == 1) {
     FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((rc_pack = gnn_publish_weights<1>(w, st)) != FPM_OK) return rc_pack;
     fpm::gnn_layer_bwd_kernel<1><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
-                                                          (const int64_t*)n1, (const int64_t*)n2, w, dxout, dscore,
+                                                          (const int64_t*)n1, (const int64_t*)n2, dxout, dscore,
                                                           dxprev, dm, gagg, grads, n1max, n2max, e1max, e2max);
     FPM_LAUNCH_CHECK();
     FPM_CUDA(cudaFuncSetAttribute(fpm::assoc_aggregate_add_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -671,8 +656,9 @@ extern "C" int fpm_gnn_layer_bwd(const float* xprev, const float* mprev_t, const
                                                                 n1max, n2max, e1max, e2max);
   } else {
     FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_bwd_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((rc_pack = gnn_publish_weights<17>(w, st)) != FPM_OK) return rc_pack;
     fpm::gnn_layer_bwd_kernel<17><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
-                                                           (const int64_t*)n1, (const int64_t*)n2, w, dxout, dscore,
+                                                           (const int64_t*)n1, (const int64_t*)n2, dxout, dscore,
                                                            dxprev, dm, gagg, grads, n1max, n2max, e1max, e2max);
     FPM_LAUNCH_CHECK();
     FPM_CUDA(cudaFuncSetAttribute(fpm::assoc_aggregate_add_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
