@@ -223,20 +223,19 @@ affinity_kernel(const float* __restrict__ XA, const float* __restrict__ XB, cons
 // (source and target node of each of its edges) are staged in shared memory; every thread keeps its column's
 // (s2, d2) and walks the k1 rows.  (The first version used one CTA per single k1 row: 742 k tiny CTAs at B = 256,
 // launch-bound at 0.57 ms.)
-constexpr int kKeRows = 16;
+constexpr int kKeRows = 16;            // rows per CTA for small graphs; large ones (Cn > 160) use 4 and all columns
 __global__ void __launch_bounds__(128)
 ke_factored_kernel(const float* __restrict__ P, const int64_t* __restrict__ eidxA,
                    const int64_t* __restrict__ eptrA, const int64_t* __restrict__ ptrA,
                    const int64_t* __restrict__ eidxB, const int64_t* __restrict__ eptrB,
                    const int64_t* __restrict__ ptrB, int EA, int EB, float* __restrict__ out, int Rn, int Cn,
-                   int e1max, int e2max, float scale) {
-  extern __shared__ float rows[];               // [2 * kKeRows][Cn]
-  const int b = blockIdx.z, k1_0 = blockIdx.y * kKeRows;
-  const int k2 = blockIdx.x * blockDim.x + threadIdx.x;
+                   int e1max, int e2max, float scale, int rows_per) {
+  extern __shared__ float rows[];               // [2 * rows_per][Cn]
+  const int b = blockIdx.z, k1_0 = blockIdx.y * rows_per;
   const int e1 = (int)(eptrA[b + 1] - eptrA[b]), e2 = (int)(eptrB[b + 1] - eptrB[b]);
   const float* Pb = P + (size_t)b * Rn * Cn;
   const int64_t pa = ptrA[b], ea0 = eptrA[b];
-  const int nrow = min(kKeRows, e1 - k1_0);     // valid edge rows of this block (<= 0: padding only)
+  const int nrow = min(rows_per, e1 - k1_0);    // valid edge rows of this block (<= 0: padding only)
   for (int r = 0; r < nrow; ++r) {
     const int s1 = (int)(eidxA[ea0 + k1_0 + r] - pa), d1 = (int)(eidxA[(size_t)EA + ea0 + k1_0 + r] - pa);
     for (int j = threadIdx.x; j < Cn; j += blockDim.x) {
@@ -245,23 +244,26 @@ ke_factored_kernel(const float* __restrict__ P, const int64_t* __restrict__ eidx
     }
   }
   __syncthreads();
-  if (k2 >= e2max) return;
-  int s2 = 0, d2 = 0;
-  const bool col_ok = k2 < e2;
-  if (col_ok) {
-    const int64_t eb = eptrB[b] + k2;
-    s2 = (int)(eidxB[eb] - ptrB[b]); d2 = (int)(eidxB[(size_t)EB + eb] - ptrB[b]);
-  }
-  for (int r = 0; r < kKeRows; ++r) {
-    const int k1 = k1_0 + r;
-    if (k1 >= e1max) break;
-    float v = 0.f;
-    if (r < nrow && col_ok) {
-      const float* ps = rows + (2 * r) * Cn; const float* pd = ps + Cn;
-      const float dot = (ps[s2] - ps[d2]) - (pd[s2] - pd[d2]);
-      v = scale * (softplus_torch(dot) - 0.5f);
+  // Columns are walked with a grid stride: small graphs launch one 128-column block per CTA, large ones
+  // (Cn > 160) a single block per row group so that the staged rows are amortised over every column.
+  for (int k2 = blockIdx.x * blockDim.x + threadIdx.x; k2 < e2max; k2 += gridDim.x * blockDim.x) {
+    int s2 = 0, d2 = 0;
+    const bool col_ok = k2 < e2;
+    if (col_ok) {
+      const int64_t eb = eptrB[b] + k2;
+      s2 = (int)(eidxB[eb] - ptrB[b]); d2 = (int)(eidxB[(size_t)EB + eb] - ptrB[b]);
     }
-    out[((size_t)b * e1max + k1) * e2max + k2] = v;
+    for (int r = 0; r < rows_per; ++r) {
+      const int k1 = k1_0 + r;
+      if (k1 >= e1max) break;
+      float v = 0.f;
+      if (r < nrow && col_ok) {
+        const float* ps = rows + (2 * r) * Cn; const float* pd = ps + Cn;
+        const float dot = (ps[s2] - ps[d2]) - (pd[s2] - pd[d2]);
+        v = scale * (softplus_torch(dot) - 0.5f);
+      }
+      out[((size_t)b * e1max + k1) * e2max + k2] = v;
+    }
   }
 }
 
@@ -312,13 +314,16 @@ extern "C" int fpm_affinity_edges_factored(const float* P, const long long* eidx
   FPM_CHECK_ARG(B >= 0 && Rn > 0 && Cn > 0 && e1max > 0 && e2max > 0, "fpm_affinity_edges_factored: bad sizes");
   if (B == 0) return FPM_OK;
   FPM_CHECK_ARG(B <= 65535 && e1max <= 65535, "fpm_affinity_edges_factored: batch or edge count too large");
-  const size_t smem = (size_t)2 * fpm::kKeRows * Cn * sizeof(float);
+  const bool big = Cn > 160;
+  const int rows_per = big ? 4 : fpm::kKeRows;
+  const size_t smem = (size_t)2 * rows_per * Cn * sizeof(float);
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_affinity_edges_factored: too many columns for shared memory");
+  FPM_CHECK_ARG(fpm_cdiv(e1max, rows_per) <= 65535, "fpm_affinity_edges_factored: too many edges");
   FPM_CUDA(cudaFuncSetAttribute(fpm::ke_factored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(fpm_cdiv(e2max, 128), fpm_cdiv(e1max, fpm::kKeRows), B);
+  dim3 grid(big ? 1 : fpm_cdiv(e2max, 128), fpm_cdiv(e1max, rows_per), B);
   fpm::ke_factored_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(
       P, (const int64_t*)eidxA, (const int64_t*)eptrA, (const int64_t*)ptrA, (const int64_t*)eidxB,
-      (const int64_t*)eptrB, (const int64_t*)ptrB, EA, EB, out, Rn, Cn, e1max, e2max, scale);
+      (const int64_t*)eptrB, (const int64_t*)ptrB, EA, EB, out, Rn, Cn, e1max, e2max, scale, rows_per);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

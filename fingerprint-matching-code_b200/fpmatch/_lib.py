@@ -18,6 +18,7 @@ _P = C.c_void_p
 _I = C.c_int
 _F = C.c_float
 _LL = C.c_longlong
+_D = C.c_double
 
 # name -> (restype, argtypes); kept in the order of include/fpmatch.h
 SIGNATURES = {
@@ -81,6 +82,13 @@ SIGNATURES = {
     "fpm_sinkhorn_log_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "fpm_soft_topk_bwd_workspace_bytes": (_LL, [_I, _I, _I]),
     "fpm_soft_topk_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    # keypoint-graph construction
+    "fpm_graph_adjacency": (_I, [_P, _P, _P, _I, _I, _I, _D, _P]),
+    "fpm_graph_row_counts": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "fpm_graph_edges": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _LL, _I, _I, _D, _P]),
+    "fpm_graph_permute": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fpm_graph_incidence": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "fpm_graph_kron_index": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
 }
 
 

@@ -301,6 +301,36 @@ int fpm_soft_topk_bwd(const float* scores, const float* ks, const long long* n1,
                       const float* gout, float* gscores, void* workspace, int B, int R, int C, int max_iter,
                       float tau, void* stream);
 
+/* ---- keypoint-graph construction ---------------------------------------------------
+ * Replaces the per-image host code of /root/reference/utils/build_graphs.py:12-119 (build_graphs,
+ * delaunay_triangulate, fully_connect) and /root/reference/src/gmdataset.py:169-189 (to_pyg_graph), :345-352
+ * (graph 2 of a genuine pair = perm^T graph 1) and :623-642 (Kronecker index lists) for a whole padded batch.
+ *   P [B,nmax,2] fp64 keypoints (x, y), ns [B] valid counts.
+ *   fpm_graph_adjacency: A [B,nmax,nmax] 0/1 fp32, zero padded; stg 0 = 'fc', 1 = 'tri' (Delaunay), 2 = 'near' (thre).
+ *   fpm_graph_row_counts: rowcnt [B*nmax] = nonzeros of each row (columns >= row when upper_only: sym = False).
+ *   fpm_graph_edges: rowoff [B*nmax+1] = exclusive prefix sum of rowcnt; E = total; writes (each nullable)
+ *      edge_index [2,E] int64 (node ids offset by ptr[b]), edge_attr [E,2] = clip(0.5 (P_i-P_j)/rescale + 0.5, 0, 1),
+ *      x [sum(ns),2] = P/rescale, edge_list [B,2,emax] int32 pair-local (src, dst) (caller pre-fills -1).
+ *   fpm_graph_permute: map [B,n1max] int32 (node of graph 2 matched to node i of graph 1, -1 = none):
+ *      A2[map[i],map[j]] = A1[i,j] on a zeroed A2 [B,n2max,n2max]; elist2 = elist1 mapped column by column.
+ *   fpm_graph_incidence: edge_list -> dense one-hot G, H [B,npad,epad] (caller zero-fills).
+ *   fpm_graph_kron_index: idxG/idxH flat int64, pair b at koff[b] (koff = prefix sum of es1*es2), entry
+ *      k2*e1+k1 = i2*n1max + i1 (source nodes for G, target nodes for H).
+ */
+int fpm_graph_adjacency(const double* P, const long long* ns, float* A, int B, int nmax, int stg, double thre,
+                        void* stream);
+int fpm_graph_row_counts(const float* A, const long long* ns, int* rowcnt, int B, int nmax, int upper_only,
+                         void* stream);
+int fpm_graph_edges(const float* A, const double* P, const long long* ns, const long long* ptr,
+                    const long long* rowoff, long long* edge_index, float* edge_attr, float* x, int* edge_list,
+                    int B, int nmax, long long E, int emax, int upper_only, double rescale, void* stream);
+int fpm_graph_permute(const float* A1, const int* map, const int* elist1, float* A2, int* elist2, int B, int n1max,
+                      int n2max, int emax, void* stream);
+int fpm_graph_incidence(const int* edge_list, float* G, float* H, int B, int emax, int npad, int epad, void* stream);
+int fpm_graph_kron_index(const int* elist1, const int* elist2, const long long* es1, const long long* es2,
+                         const long long* koff, long long* idxG, long long* idxH, int B, int e1max, int e2max,
+                         int n1max, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

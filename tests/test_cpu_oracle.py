@@ -141,3 +141,36 @@ def test_oracle_head_runs_and_is_consistent_between_fp32_and_fp64():
     # loop-structured feature_align (what the CPU baseline times) gives the same result
     o32b = head.forward_head(sd, synth.clone_batch(data), data["fmaps"], feature_align_loops=True)
     assert torch.equal(o32["ds_mat"], o32b["ds_mat"])
+
+
+def test_graph_oracle_matches_scipy_delaunay():
+    """oracle/graphs.py: the empty-circle restatement (what the CUDA kernel evaluates) against scipy's Delaunay
+    called the way the reference calls it (utils/build_graphs.py:78-100)."""
+    from oracle import graphs as og
+    rng = np.random.RandomState(0)
+    for t in range(60):
+        n = int(rng.choice([1, 2, 3, 4, 5, 8, 17, 50, 100]))
+        P = np.stack([rng.uniform(0, 320, n), rng.uniform(0, 240, n)], 1)
+        if t % 2:
+            P = P.astype(np.float32)
+        assert (og.delaunay_adjacency(P) == og.delaunay_adjacency_ref(P.astype(np.float64))).all()
+    P = np.stack([rng.uniform(0, 320, 400), rng.uniform(0, 240, 400)], 1)
+    A = og.delaunay_adjacency(P)
+    assert (A == og.delaunay_adjacency_ref(P)).all() and 2300 < A.sum() < 2400
+    # degenerate inputs: collinear -> fully connected, duplicate -> isolated, both as scipy / the reference do
+    col = np.array([[0, 0], [1, 1], [2, 2], [3, 3.0]])
+    assert (og.delaunay_adjacency(col) == og.fully_connect(col)).all()
+    assert (og.delaunay_adjacency_ref(col) == og.fully_connect(col)).all()
+    dup = np.stack([rng.uniform(0, 320, 12), rng.uniform(0, 240, 12)], 1); dup[9] = dup[2]
+    A = og.delaunay_adjacency(dup)
+    assert A[9].sum() == 0 and (A == og.delaunay_adjacency_ref(dup)).all()
+    # build_graphs / to_pyg_graph statements: row-major edge order, G H^T = A, pseudo-coordinates in [0, 1]
+    P = np.stack([rng.uniform(0, 320, 30), rng.uniform(0, 240, 30)], 1)
+    A, G, H, e = og.build_graphs(P, 30, 32, None, "tri", True)
+    assert e == int(A.sum()) and (G[:30] @ H[:30].T == A).all()
+    x, ei, ea = og.pyg_graph(A, P)
+    assert (np.diff(ei[0]) >= 0).all() and ea.min() >= 0 and ea.max() <= 1 and x.dtype == np.float32
+    # genuine pairs: A2 = perm^T A1 perm
+    perm = np.eye(30, dtype=np.float32)[rng.permutation(30)]
+    A2, _, _ = og.permute_adjacency(A, perm)
+    assert (A2 == perm.T @ A @ perm).all()
