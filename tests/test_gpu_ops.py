@@ -235,9 +235,10 @@ def test_hungarian_golden_bit_exact():
     assert torch.equal(out.cpu(), fx["out"])
 
 
-# nmax >= 160: the cost matrix leaves shared memory -> the 8-warp block kernel (lap_topk_block_kernel)
+# nmax >= 160: the cost matrix leaves shared memory -> one CTA per pair: lap_topk_cols_kernel<1|2|4> (column state in
+# registers, up to 1024 columns), beyond that lap_topk_block_kernel (cost row staged per step)
 @pytest.mark.parametrize("nmax,count,seed", [(12, 400, 1), (40, 300, 2), (100, 120, 3), (160, 24, 4), (256, 10, 5),
-                                             (400, 6, 6)])
+                                             (400, 6, 6), (600, 3, 7), (1100, 1, 8)])
 def test_hungarian_matches_scipy_exactly(oo, nmax, count, seed):
     from utils.hungarian import hungarian
     s, n1, n2 = _pack(_tie_heavy(np.random.RandomState(seed), count, nmax))
