@@ -811,6 +811,25 @@ def matching_stats(pred: Tensor, gt: Tensor, ns: Tensor) -> Tensor:
     return out
 
 
+def match_classifier(s: Tensor, perm: Optional[Tensor], w1: Tensor, b1: Tensor, bn1: Sequence[Tensor], w2: Tensor,
+                     b2: Tensor, bn2: Sequence[Tensor], fcw: Tensor, fcb: Tensor, eps: float = 1e-5) -> Tensor:
+    """Logits [B] of the genuine / imposter CNN on ``s * perm`` (MatchClassifier.forward in eval mode, ngm.py:75-106).
+    ``bn1`` / ``bn2`` = (weight, bias, running_mean, running_var) of the two BatchNorm2d layers."""
+    B, H, W = s.shape
+    if tuple(w1.shape) != (16, 1, 3, 3) or tuple(w2.shape) != (32, 16, 3, 3) or fcw.numel() != 32:
+        raise RuntimeError("fpmatch: match_classifier is built for the reference's (16, 32) channel plan")
+    L = _lib.lib()
+    ws = torch.empty(L.fpm_match_classifier_workspace_floats(B, H, W), dtype=torch.float32, device=s.device)
+    out = torch.empty(B, dtype=torch.float32, device=s.device)
+    for t in list(bn1) + list(bn2):
+        _chk(t, "batch-norm tensor")
+    rc = L.fpm_match_classifier(_chk(s, "s"), _chk(perm, "perm"), _chk(w1, "w1"), _chk(b1, "b1"), _ptr_array(bn1),
+                                _chk(w2, "w2"), _chk(b2, "b2"), _ptr_array(bn2), _chk(fcw, "fcw"), _chk(fcb, "fcb"),
+                                float(eps), ws.data_ptr(), out.data_ptr(), B, H, W, _stream())
+    _lib.check(rc, "fpm_match_classifier"); _count(3)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # AFA-U backward (k-branch training, stages 2-5)
 # ---------------------------------------------------------------------------------------------------

@@ -66,7 +66,13 @@ def concat_features(embeddings, num_vertices):
 
 
 class MatchClassifier(nn.Module):
-    """Small CNN over the matched-similarity map (ngm.py:75-106); stock torch."""
+    """Small CNN over the matched-similarity map (ngm.py:75-106).
+
+    ``forward`` is stock torch (training: batch statistics, autograd).  ``forward_product(s, x)`` is what the
+    matching head calls: in eval mode on the GPU the product ``s * x``, both conv blocks, the pools and the
+    linear layer run as three fused fp32 kernels (``csrc/match_cls.cu``); otherwise it falls through to
+    ``forward(s * x)``.
+    """
 
     def __init__(self, channels: tuple = (16, 32)):
         super().__init__()
@@ -85,6 +91,22 @@ class MatchClassifier(nn.Module):
         x = self.conv(x)
         x = self.pool(x).view(x.size(0), -1)
         return self.fc(x).squeeze(-1)
+
+    def _fusable(self, s: torch.Tensor) -> bool:
+        c = self.conv
+        return (not self.training and not torch.is_grad_enabled() and s.is_cuda and len(c) == 8
+                and c[0].out_channels == 16 and c[4].out_channels == 32 and c[2].track_running_stats
+                and c[2].eps == c[6].eps and c[2].affine and c[6].affine
+                and min(s.shape[1], s.shape[2]) >= 4)
+
+    def forward_product(self, s: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        """Logits of ``s * x`` (ngm.py:451-454)."""
+        if not self._fusable(s):
+            return self.forward(s * x)
+        c = self.conv
+        bn = lambda m: (m.weight, m.bias, m.running_mean, m.running_var)
+        return ops.match_classifier(s.contiguous(), x.contiguous(), c[0].weight, c[0].bias, bn(c[2]), c[4].weight,
+                                    c[4].bias, bn(c[6]), self.fc.weight, self.fc.bias, c[2].eps)
 
 
 class Net(CNN):
@@ -348,8 +370,7 @@ class Net(CNN):
         _, x = ops.lap_topk(ss_out, n1, n2, ks=k_scaled, want_hungarian=False, want_perm=True)
 
         # ---- genuine / imposter classifier and losses (ngm.py:451-469)
-        matched_sim = s * x
-        cls_logits = self.match_cls(matched_sim)
+        cls_logits = self.match_cls.forward_product(s, x)
         cls_prob = torch.sigmoid(cls_logits)
         cls_loss = torch.zeros((), device=dev)          # a fill kernel: torch.tensor(0.0, device=...) is a blocking host copy
         if 'label' in data_dict:

@@ -301,6 +301,19 @@ int fpm_soft_topk_bwd(const float* scores, const float* ks, const long long* n1,
                       const float* gout, float* gscores, void* workspace, int B, int R, int C, int max_iter,
                       float tau, void* stream);
 
+/* ---- [A13] genuine / imposter classifier, inference (eval-mode BatchNorm) ------------------------------------------
+ * Replaces MatchClassifier.forward (/root/reference/src/model/ngm.py:75-106) on `s * perm_mat` (ngm.py:451-455):
+ * two blocks of Conv3x3(pad 1) -> ReLU -> BatchNorm2d(running statistics) -> MaxPool2 with 1 -> 16 -> 32 channels,
+ * global average pool, Linear(32 -> 1).  s, perm [B,H,W] (perm nullable: classify s itself); w1 [16,1,3,3], b1 [16],
+ * w2 [32,16,3,3], b2 [32]; bn1 / bn2 = arrays of 4 device pointers {weight, bias, running_mean, running_var};
+ * fcw [32], fcb [1]; workspace = fpm_match_classifier_workspace_floats(B,H,W) floats; logits [B].  H, W >= 4.
+ */
+long long fpm_match_classifier_workspace_floats(int B, int H, int W);
+int fpm_match_classifier(const float* s, const float* perm, const float* w1, const float* b1,
+                         const float* const* bn1, const float* w2, const float* b2, const float* const* bn2,
+                         const float* fcw, const float* fcb, float eps, float* workspace, float* logits, int B, int H,
+                         int W, void* stream);
+
 /* ---- keypoint-graph construction ---------------------------------------------------
  * Replaces the per-image host code of /root/reference/utils/build_graphs.py:12-119 (build_graphs,
  * delaunay_triangulate, fully_connect) and /root/reference/src/gmdataset.py:169-189 (to_pyg_graph), :345-352

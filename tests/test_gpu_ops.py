@@ -546,3 +546,37 @@ def test_permutation_loss_and_matching_metrics_golden():
     assert torch.equal(acc.cpu(), fx["accuracy"])
     with pytest.raises(AssertionError):
         PermutationLoss()(fx["pred"].to(DEV) * 1.5, fx["gt"].to(DEV), fx["n1"].to(DEV), fx["n2"].to(DEV))
+
+
+# ------------------------------------------------------------------------------------- match classifier (A13)
+@pytest.mark.parametrize("B,H,W", [(5, 100, 100), (3, 37, 53), (2, 4, 4), (2, 5, 9), (1, 400, 400)])
+def test_match_classifier_fused_equals_stock_module(ops, B, H, W):
+    """The fused fp32 kernels of csrc/match_cls.cu against the stock torch module (the reference's
+    MatchClassifier, ngm.py:75-106) evaluated on the CPU in fp32, eval-mode BatchNorm with non-trivial statistics."""
+    from src.model.ngm import MatchClassifier
+    torch.manual_seed(3)
+    m = MatchClassifier().eval()
+    with torch.no_grad():
+        for bn in (m.conv[2], m.conv[6]):
+            bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.3, 2.0)
+            bn.weight.normal_(1, 0.5); bn.bias.normal_(0, 0.3)      # negative scales too: BN before the max-pool
+    g = torch.Generator().manual_seed(4)
+    s = torch.rand(B, H, W, generator=g)
+    x = (torch.rand(B, H, W, generator=g) < 0.05).float()
+    with torch.no_grad():
+        ref = m(s * x)
+        ref_dense = m(s)
+    md = MatchClassifier().to(DEV).eval()
+    md.load_state_dict(m.state_dict())
+    with torch.no_grad():
+        out = md.forward_product(s.to(DEV), x.to(DEV))
+        c = md.conv
+        bn = lambda q: (q.weight, q.bias, q.running_mean, q.running_var)
+        dense = ops.match_classifier(s.to(DEV), None, c[0].weight, c[0].bias, bn(c[2]), c[4].weight, c[4].bias,
+                                     bn(c[6]), md.fc.weight, md.fc.bias, c[2].eps)
+    e1 = (out.cpu() - ref).abs().max().item(); e2 = (dense.cpu() - ref_dense).abs().max().item()
+    report("match_classifier", B=B, H=H, W=W, err_product=e1, err_dense=e2)
+    assert e1 <= 2e-5 and e2 <= 2e-5
+    # training mode / autograd keep the stock path
+    md.train()
+    assert md.forward_product(s.to(DEV), x.to(DEV)).requires_grad

@@ -46,6 +46,13 @@ def main():
         ev[1].record()
         torch.cuda.synchronize()
         adj_ms = ev[0].elapsed_time(ev[1]) / reps
+        A = gb.graph_adjacency(P, ns, "tri")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            gb.graph_edges(A, P, ns)
+        torch.cuda.synchronize()
+        edges_wall_ms = (time.perf_counter() - t0) / reps * 1e3
         m = min(B, 16)
         og.delaunay_adjacency_ref(pts[0])                                  # scipy import / first-call cost
         t0 = time.perf_counter()
@@ -55,7 +62,7 @@ def main():
             og.pyg_graph(A, pts[b])
         cpu_ms = (time.perf_counter() - t0) / m * B * 1e3
         rows.append({"n": n, "graphs": B, "edges_total": int(built.graph.edge_index.shape[1]),
-                     "gpu_ms_per_batch": gpu_ms, "gpu_adjacency_ms": adj_ms, "graphs_per_s": B / gpu_ms * 1e3,
+                     "gpu_ms_per_batch": gpu_ms, "gpu_adjacency_ms": adj_ms, "edges_wall_ms": edges_wall_ms, "graphs_per_s": B / gpu_ms * 1e3,
                      "cpu_scipy_numpy_ms_per_batch_1core": cpu_ms, "cpu_sample_graphs": m})
         print(json.dumps(rows[-1]))
     if args.out:
