@@ -11,6 +11,7 @@
 //     out_i = max_{e: j->i} sum_s basis_s(e) * Y[j, wi_s(e), :]  (0 if no in-edge) + Y[i, 25, :] + bias
 // fused with ReLU (layer 0) or the residual x + 0.1 * out (layer 1, spline_conv.py:56).
 #include "common.cuh"
+#include <limits.h>
 
 namespace fpm {
 
@@ -181,6 +182,56 @@ spline_scatter_bwd_kernel(const float* __restrict__ G, const int* __restrict__ a
     *(float4*)(dst + (size_t)k * C + c4 * 4) = *(const float4*)(blk + (size_t)k * C + c4 * 4);
 }
 
+// Column-compacted variant of the scatter (training with the slab plan).  dY is zero outside the (node, slab) blocks
+// some edge reads, and on keypoint graphs most slabs are read by few nodes or none: writing all 26 slabs of every
+// node (1 GB at 64 pairs) and feeding them to the dX / dW GEMMs spends ~60 % of the backward on zeros.  The caller
+// splits the slabs into a WIDE group (read by many nodes, plus the root slab) and a NARROW group (read by the nodes
+// listed in `rowpos`); colmap[k] = g >= 0: column block g of dYd [T, nD, C];  = -(g + 1) < 0: column block g of
+// dYs [nR, nS, C], row rowpos[j];  = INT_MIN: no edge reads slab k (nothing to write).
+__global__ void __launch_bounds__(192)
+spline_scatter_bwd_compact_kernel(const float* __restrict__ G, const int* __restrict__ argmax,
+                                  const int64_t* __restrict__ edge_dst, const float* __restrict__ pseudo,
+                                  const int* __restrict__ out_ptr, const int* __restrict__ out_eid,
+                                  const int* __restrict__ colmap, const int* __restrict__ rowpos,
+                                  float* __restrict__ dYd, float* __restrict__ dYs, int C, int KS, int nD, int nS) {
+  extern __shared__ __align__(16) float blk[];       // [NS][C]
+  const int j = blockIdx.x;
+  const int NS = KS * KS + 1;
+  const int c4 = threadIdx.x;
+  if (c4 * 4 >= C) return;
+  for (int k = 0; k < NS - 1; ++k) *(float4*)(blk + (size_t)k * C + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  *(float4*)(blk + (size_t)(NS - 1) * C + c4 * 4) = *(const float4*)(G + (size_t)j * C + c4 * 4);
+  const int e_beg = out_ptr[j], e_end = out_ptr[j + 1];
+  for (int q = e_beg; q < e_end; ++q) {
+    const int e = out_eid[q];
+    const int i = (int)edge_dst[e];
+    const int4 a = *(const int4*)(argmax + (size_t)i * C + c4 * 4);
+    if (a.x != e && a.y != e && a.z != e && a.w != e) continue;
+    float4 g = *(const float4*)(G + (size_t)i * C + c4 * 4);
+    if (a.x != e) g.x = 0.f;
+    if (a.y != e) g.y = 0.f;
+    if (a.z != e) g.z = 0.f;
+    if (a.w != e) g.w = 0.f;
+    float bas[4]; int wi[4];
+    spline_basis4(pseudo[(size_t)e * 2], pseudo[(size_t)e * 2 + 1], KS, bas, wi);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      float4* d = (float4*)(blk + (size_t)wi[s] * C + c4 * 4);
+      float4 v = *d;
+      v.x = fmaf(bas[s], g.x, v.x); v.y = fmaf(bas[s], g.y, v.y);
+      v.z = fmaf(bas[s], g.z, v.z); v.w = fmaf(bas[s], g.w, v.w);
+      *d = v;
+    }
+  }
+  const int rp = rowpos ? rowpos[j] : -1;
+  for (int k = 0; k < NS; ++k) {
+    const int cm = colmap[k];
+    const float4 v = *(const float4*)(blk + (size_t)k * C + c4 * 4);
+    if (cm >= 0) *(float4*)(dYd + ((size_t)j * nD + cm) * C + c4 * 4) = v;
+    else if (cm != INT_MIN && rp >= 0) *(float4*)(dYs + ((size_t)rp * nS + (-cm - 1)) * C + c4 * 4) = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Slab planner: which (node, weight slab) products does the gather actually read?
 //
@@ -342,6 +393,25 @@ extern "C" int fpm_spline_scatter_bwd(const float* G, const int* argmax, const l
   FPM_CUDA(cudaFuncSetAttribute(fpm::spline_scatter_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fpm::spline_scatter_bwd_kernel<<<total_nodes, 192, smem, (cudaStream_t)stream>>>(
       G, argmax, (const int64_t*)edge_dst, pseudo, out_ptr, out_eid, dY, C, kernel_size);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_spline_scatter_bwd_compact(const float* G, const int* argmax, const long long* edge_dst,
+                                              const float* pseudo, const int* out_ptr, const int* out_eid,
+                                              const int* colmap, const int* rowpos, float* dYd, float* dYs,
+                                              int total_nodes, int C, int kernel_size, int nD, int nS, void* stream) {
+  FPM_CHECK_ARG(G && argmax && edge_dst && pseudo && out_ptr && out_eid && colmap && dYd,
+                "fpm_spline_scatter_bwd_compact: null tensor");
+  FPM_CHECK_ARG(nD >= 1 && nS >= 0 && (nS == 0 || (dYs && rowpos)), "fpm_spline_scatter_bwd_compact: bad groups");
+  FPM_CHECK_ARG(C % 4 == 0 && C <= 768, "fpm_spline_scatter_bwd_compact: C must be a multiple of 4, at most 768");
+  if (total_nodes == 0) return FPM_OK;
+  const size_t smem = (size_t)(kernel_size * kernel_size + 1) * C * sizeof(float);
+  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_spline_scatter_bwd_compact: kernel_size too large");
+  FPM_CUDA(cudaFuncSetAttribute(fpm::spline_scatter_bwd_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  fpm::spline_scatter_bwd_compact_kernel<<<total_nodes, 192, smem, (cudaStream_t)stream>>>(
+      G, argmax, (const int64_t*)edge_dst, pseudo, out_ptr, out_eid, colmap, rowpos, dYd, dYs, C, kernel_size, nD, nS);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

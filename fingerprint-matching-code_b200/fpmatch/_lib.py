@@ -72,6 +72,7 @@ SIGNATURES = {
     "fpm_node_features_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "fpm_fmap_prep_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_spline_scatter_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_spline_scatter_bwd_compact": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "fpm_transpose_f32": (_I, [_P, _P, _I, _I, _I, _P]),
     "fpm_bmm_ragged": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
     "fpm_segment_rowdot": (_I, [_P, _P, _P, _P, _I, _I, _P]),

@@ -624,6 +624,55 @@ def spline_scatter_bwd(G: Tensor, argmax: Tensor, edge_index: Tensor, pseudo: Te
     return dY
 
 
+class SlabGroups:
+    """Column / row compaction of the SplineConv backward for one graph batch (built from the slab plan's per-node
+    slab mask; shared by both conv layers).  Slabs read by at least ``T / wide_div`` nodes - and the root slab - form
+    the WIDE group (all rows); the other slabs that some edge reads form the NARROW group, restricted to the rows
+    ``R`` that read any of them.  Two host reads (slab counts, row list) per graph batch."""
+
+    def __init__(self, plan: "SlabPlan", wide_div: int = 8):
+        dev = plan.mask.device
+        NS, T = plan.NS, plan.T
+        ar = torch.arange(NS - 1, device=dev, dtype=torch.int32)
+        cnt = ((plan.mask.view(-1, 1) >> ar) & 1).sum(0).tolist()              # host read 1
+        self.wide = [k for k in range(NS - 1) if cnt[k] * wide_div >= T and cnt[k] > 0] + [NS - 1]
+        self.narrow = [k for k in range(NS - 1) if 0 < cnt[k] and cnt[k] * wide_div < T]
+        colmap = [-(2 ** 31)] * NS
+        for g, k in enumerate(self.wide):
+            colmap[k] = g
+        for g, k in enumerate(self.narrow):
+            colmap[k] = -(g + 1)
+        self.colmap = torch.tensor(colmap, dtype=torch.int32).to(dev)
+        self.rows = None
+        self.rowpos = None
+        if self.narrow:
+            bits = 0
+            for k in self.narrow:
+                bits |= 1 << k
+            self.rows = torch.nonzero(plan.mask & bits).view(-1)                # host read 2 (output size)
+            self.rowpos = torch.full((T,), -1, dtype=torch.int32, device=dev)
+            self.rowpos[self.rows] = torch.arange(self.rows.numel(), device=dev, dtype=torch.int32)
+            if self.rows.numel() == 0:
+                self.narrow, self.rows, self.rowpos = [], None, None
+        self.NS, self.T = NS, T
+
+
+def spline_scatter_bwd_compact(G: Tensor, argmax: Tensor, edge_index: Tensor, pseudo: Tensor, out_ptr: Tensor,
+                               out_eid: Tensor, groups: SlabGroups, kernel_size: int = 5):
+    """(dYd [total, nD*C], dYs [nR, nS*C] or None): the gradient of the slab products, zero blocks left out."""
+    total, Cc = G.shape
+    nD, nS = len(groups.wide), len(groups.narrow)
+    dYd = torch.empty((total, nD * Cc), dtype=torch.float32, device=G.device)
+    dYs = torch.empty((groups.rows.numel(), nS * Cc), dtype=torch.float32, device=G.device) if nS else None
+    rc = _lib.lib().fpm_spline_scatter_bwd_compact(
+        _chk(G, "G"), _chk(argmax, "argmax", torch.int32), _chk(edge_index[1], "edge_index[1]", torch.int64),
+        _chk(pseudo, "pseudo"), _chk(out_ptr, "out_ptr", torch.int32), _chk(out_eid, "out_eid", torch.int32),
+        _chk(groups.colmap, "colmap", torch.int32), _chk(groups.rowpos, "rowpos", torch.int32), dYd.data_ptr(),
+        dYs.data_ptr() if dYs is not None else None, total, Cc, kernel_size, nD, nS, _stream())
+    _lib.check(rc, "fpm_spline_scatter_bwd_compact"); _count()
+    return dYd, dYs
+
+
 def transpose_pad(x: Tensor, multiple: int = 8) -> Tensor:
     """[R, C] -> [C, ldo] with ldo = R rounded up to `multiple`, zero padded (K-major GEMM operand)."""
     R, Cc = x.shape

@@ -13,6 +13,8 @@ torch / cuDNN (out of scope per BASELINE.json).
 import itertools
 import logging
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -63,6 +65,9 @@ def normalize_over_channels(x):
 def concat_features(embeddings, num_vertices):
     res = torch.cat([embedding[:, :num_v] for embedding, num_v in zip(embeddings, num_vertices)], dim=-1)
     return res.transpose(0, 1)
+
+
+_SIDE_STREAMS = {}     # device index -> side stream of the inference head (process-wide, like torch's stream pool)
 
 
 class MatchClassifier(nn.Module):
@@ -158,6 +163,8 @@ class Net(CNN):
         # (SURVEY.md section 0.4); keep paying for it by default so throughput comparisons are honest.
         self.compute_dead_ke = True
         self.ke_mode = "factored"
+        # inference: run the (unread) edge-affinity kernels beside the main chain (FPMATCH_KE_SIDE=0: same stream)
+        self.ke_side_stream = os.environ.get('FPMATCH_KE_SIDE', '1') != '0'
 
     # ------------------------------------------------------------------------------------------
     def forward(self, data_dict, regression=True):
@@ -287,6 +294,14 @@ class Net(CNN):
         data_dict['_fpm_inter'] = {'node_feat': feats, 'Kp': Kp, 'Ke': Ke, 's': s, 'ss': ss, 'k_scaled': k_scaled}
         return data_dict
 
+    @staticmethod
+    def _ke_stream(dev):
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        st = _SIDE_STREAMS.get(key)
+        if st is None:
+            st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+        return st
+
     @torch.no_grad()
     def matching_head(self, data_dict, fmaps):
         points = data_dict['Ps']
@@ -326,16 +341,26 @@ class Net(CNN):
         coeff_v = self.vertex_affinity.fused_coefficients(gcat)
         Kp, Kp_t = ops.affinity_nodes(feats[0], feats[1], coeff_v, offs[0][0], offs[1][0], n1max, n2max)
         Ke = None
+        ke_join = None
         if self.compute_dead_ke:
-            coeff_e = self.edge_affinity.fused_coefficients(gcat)
-            ei1 = graphs[0].edge_index.to(dev).contiguous()
-            ei2 = graphs[1].edge_index.to(dev).contiguous()
-            if self.ke_mode == "factored":      # same values through linearity, 33x fewer FLOPs
-                Ke = ops.affinity_edges_factored(feats[0], feats[1], coeff_e, offs[0][0], offs[1][0], offs[0][1],
-                                                 offs[1][1], ei1, ei2, n1max, n2max, e1max, e2max, scale=0.5)
-            else:                               # "direct": the reference's e1 x 768 x e2 product
-                Ke = ops.affinity_edges(feats[0], feats[1], coeff_e, offs[0][1], offs[1][1], ei1, ei2,
-                                        e1max, e2max, scale=0.5)
+            # Nothing downstream reads Ke, so its kernels run on a side stream underneath the
+            # latency-bound middle of the forward (association-graph layers, Sinkhorn, LAP); joined before returning.
+            main = torch.cuda.current_stream(dev)
+            side = self._ke_stream(dev) if self.ke_side_stream else main
+            if side is not main:
+                side.wait_stream(main)
+            with torch.cuda.stream(side):
+                coeff_e = self.edge_affinity.fused_coefficients(gcat)
+                ei1 = graphs[0].edge_index.to(dev).contiguous()
+                ei2 = graphs[1].edge_index.to(dev).contiguous()
+                if self.ke_mode == "factored":      # same values through linearity, 33x fewer FLOPs
+                    Ke = ops.affinity_edges_factored(feats[0], feats[1], coeff_e, offs[0][0], offs[1][0], offs[0][1],
+                                                     offs[1][1], ei1, ei2, n1max, n2max, e1max, e2max, scale=0.5)
+                else:                               # "direct": the reference's e1 x 768 x e2 product
+                    Ke = ops.affinity_edges(feats[0], feats[1], coeff_e, offs[0][1], offs[1][1], ei1, ei2,
+                                            e1max, e2max, scale=0.5)
+            if side is not main:
+                ke_join = side
 
         # ---- NGM layers on the factorised association graph (ngm.py:326-362)
         csr1 = ops.assoc_in_csr(tables[0], n1max)
@@ -384,6 +409,8 @@ class Net(CNN):
             ks_loss = 0.0
             ks_error = 0.0
 
+        if ke_join is not None:
+            torch.cuda.current_stream(dev).wait_stream(ke_join)
         data_dict.update({
             'ds_mat': ss_out,
             'perm_mat': x,

@@ -271,6 +271,12 @@ int fpm_fmap_prep_bwd(const float* fmap_nchw, const float* dy_nhwc, float* dx_nc
 int fpm_spline_scatter_bwd(const float* G, const int* argmax, const long long* edge_dst, const float* pseudo,
                            const int* out_ptr, const int* out_eid, float* dY, int total_nodes, int C,
                            int kernel_size, void* stream);
+/* Column-compacted scatter: colmap [KS*KS+1] int32 (>= 0: column block of dYd [total,nD,C]; -(g+1): column block g of
+ * dYs [nR,nS,C], written at row rowpos[node] when that is >= 0; INT_MIN: slab unread, skipped). */
+int fpm_spline_scatter_bwd_compact(const float* G, const int* argmax, const long long* edge_dst, const float* pseudo,
+                                   const int* out_ptr, const int* out_eid, const int* colmap, const int* rowpos,
+                                   float* dYd, float* dYs, int total_nodes, int C, int kernel_size, int nD, int nS,
+                                   void* stream);
 int fpm_transpose_f32(const float* src, float* dst, int R, int C, int ldo, void* stream);
 int fpm_bmm_ragged(const float* Mat, int B, int Rmax, int Cmax, int trans, const float* X, const long long* ptrX,
                    const long long* ptrO, const float* coeff_in, const float* coeff_out, float* Out, int D,

@@ -105,13 +105,23 @@ def test_node_features_backward():
     assert e1 < 1e-5 and e2 < 1e-5
 
 
-def test_spline_conv_backward():
+@pytest.mark.parametrize("pseudo_kind,plan", [("graph", True), ("uniform", True), ("graph", False)])
+def test_spline_conv_backward(pseudo_kind, plan):
+    """plan=True: slab-plan forward + column / row compacted backward (wide and narrow slab groups; "uniform" pseudo-
+    coordinates spread the edges over all 25 slabs so that both groups are populated); plan=False: dense products."""
     from fpmatch import autograd as fa
+    from fpmatch import ops
     from oracle import ops as oo
     net, sd, data = _setup(B=3, n=16, ragged=True)
     graph = data["pyg_graphs"][0]
     total = graph.x.shape[0]
     gen = torch.Generator().manual_seed(2)
+    if pseudo_kind == "uniform":
+        graph.edge_attr = torch.rand(graph.edge_attr.shape, generator=gen)
+    was = ops.slab_plan_enabled()
+    ops.set_slab_plan(plan)
+    floor = fa.GraphCtx.COMPACT_BACKWARD_MIN_NODES
+    fa.GraphCtx.COMPACT_BACKWARD_MIN_NODES = 0          # the test graphs are tiny: force the compacted path
     x = torch.randn(total, 768, generator=gen) * 0.05
     conv = net.message_pass_node_features.mp_network.convs[0]
     with torch.no_grad():
@@ -135,9 +145,16 @@ def test_spline_conv_backward():
         (og * g.to(DEV)).sum().backward()
         errs = {"x": rel_err(xg.grad, xr.grad), "weight": rel_err(convg.weight.grad, w.grad),
                 "root": rel_err(convg.root.grad, r.grad), "bias": rel_err(convg.bias.grad, bb.grad)}
-        report("spline_conv_bwd", mode=mode, fwd=fwd, **errs)
-        assert fwd < 1e-5 and max(errs.values()) < 1e-4, errs
+        grp = gctx.groups(768, 5)
+        report("spline_conv_bwd", mode=mode, pseudo=pseudo_kind, plan=plan, fwd=fwd,
+               wide=len(grp.wide) if grp else None, narrow=len(grp.narrow) if grp else None, **errs)
+        ok = (fwd < 1e-5 and max(errs.values()) < 1e-4 and (grp is not None) == plan
+              and (pseudo_kind != "graph" or not plan or len(grp.narrow) > 0))      # both groups exercised
+        if not ok:
+            ops.set_slab_plan(was); fa.GraphCtx.COMPACT_BACKWARD_MIN_NODES = floor
+        assert ok, (fwd, errs)
         conv = conv.cpu()
+    ops.set_slab_plan(was); fa.GraphCtx.COMPACT_BACKWARD_MIN_NODES = floor
 
 
 def test_affinity_backward():
@@ -234,17 +251,19 @@ def test_ngm_solver_backward():
 
 # ------------------------------------------------------------------------------------------------- whole step
 @pytest.mark.parametrize("with_label", [False, True])
-def test_stage1_loss_gradients_match_oracle(with_label):
-    """d(loss)/d(every trainable parameter and both feature maps) of one stage-1 step.  The bar per tensor is
+def test_stage1_loss_gradients_match_oracle(with_label, monkeypatch):
+    """d(loss)/d(every trainable parameter and both feature maps) of one stage-1 step (with_label=True also forces
+    the compacted SplineConv backward that large batches use).  The bar per tensor is
     max(1e-4 x max|g|, 4 x the fp32 oracle's own distance to an fp64 evaluation of the same formulae): with
     tau = 0.01 Sinkhorn layers the fp32 autograd of the reference is itself only good to ~3e-4 on the GNN
     weights, and every GNN bias gradient is exactly zero in exact arithmetic (the loss only sees s through
     shift-invariant Sinkhorn layers), so fp32 returns pure rounding noise there."""
-    from fpmatch import synth
+    from fpmatch import autograd as fa, synth
     from oracle import train as otrain
     net, sd, data = _setup(B=3, n=14, seed=3)
     if with_label:       # classify-task batches: cls_loss joins the objective and reaches s through s * perm_mat
         data["label"] = torch.ones(3)
+        monkeypatch.setattr(fa.GraphCtx, "COMPACT_BACKWARD_MIN_NODES", 0)
     loss_ref, g32, f32, _ = otrain.loss_and_grads(sd, synth.clone_batch(data), data["fmaps"], fmap_grads=True)
     loss64, g64, f64, _ = otrain.loss_and_grads(sd, synth.clone_batch(data), data["fmaps"], fmap_grads=True,
                                                 dtype=torch.float64)
