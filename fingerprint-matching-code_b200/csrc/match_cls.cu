@@ -7,9 +7,9 @@
 //   logit = Linear(32 -> 1)(mean over pixels)                         [B]
 // Stock torch runs this as ~12 cuDNN / elementwise launches (9 % of the 256-pair step, every intermediate through HBM).
 // Here: stage 1 fuses the product, conv, bias, ReLU, BatchNorm (running statistics) and the pool into one pass;
-// stage 2 does the same for the second block with the 16-channel input tile and the weights in shared memory and
-// 128 fp32 accumulators per thread (one pooled pixel x 32 channels x 2x2 pre-pool positions), and reduces the
-// average pool to per-tile partial sums; stage 3 adds the tiles in a fixed order and applies the linear layer.
+// stage 2 does the same for the second block with the weights in shared memory and 128 fp32 accumulators per thread
+// (one pooled pixel x 32 channels x 2x2 pre-pool positions), and reduces the average pool to per-chunk partial
+// sums; stage 3 adds the chunks in a fixed order and applies the linear layer.
 // Everything is fp32 FMA (cuDNN's default for this conv is TF32); results are deterministic.
 // Training mode (batch statistics, autograd) stays on stock torch.
 #include "common.cuh"
@@ -30,9 +30,17 @@ __device__ __forceinline__ void bn_affine(const BnParams& bn, int c, float eps, 
 __global__ void __launch_bounds__(256)
 match_cls_stage1_kernel(const float* __restrict__ s, const float* __restrict__ perm, const float* __restrict__ w1,
                         const float* __restrict__ b1, BnParams bn1, float eps,
-                        float* __restrict__ p1, int H, int W, int H1, int W1) {
+                        float* __restrict__ p1, int H, int W, int H1, int W1, const float* __restrict__ w2,
+                        float* __restrict__ wpack) {
   __shared__ float sw[kC1 * 9], sb[kC1], ssc[kC1], ssh[kC1];
   const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    // second conv's weights [32][16][3][3] -> [16 ic][32 oc][12] for stage 2 (one CTA, 24 KB)
+    for (int idx = tid; idx < kC1 * kC2 * 12; idx += 256) {
+      const int ic = idx / (kC2 * 12), oc = (idx / 12) % kC2, k = idx % 12;
+      wpack[idx] = k < 9 ? w2[((size_t)oc * kC1 + ic) * 9 + k] : 0.f;
+    }
+  }
   if (tid < kC1 * 9) sw[tid] = w1[tid];
   if (tid < kC1) {
     sb[tid] = b1[tid];
@@ -77,34 +85,34 @@ match_cls_stage1_kernel(const float* __restrict__ s, const float* __restrict__ p
   }
 }
 
-// grid (cdiv(W2, 8), cdiv(H2, 8), B), block 64: thread = one pooled output pixel, 32 channels x 4 pre-pool positions.
-constexpr int kT2 = 8;                       // pooled pixels per tile side
-constexpr int kIn2 = 2 * kT2 + 2;            // input tile side (pre-pool 16 + halo)
+// grid (cdiv(H2 * W2, 64), B), block 64: thread = one pooled output pixel (pixels taken in raster order, so that
+// only the last chunk of a map has idle threads), 32 channels x 4 pre-pool positions = 128 accumulators.  The 4 x 4
+// input patch of every channel comes straight from P1 (L1 / L2 resident; neighbouring threads share most of it); the
+// weights are copied from the [ic][oc][12] repack stage 1 left in the workspace and read back as 128-bit broadcasts.
+constexpr int kChunk = 64;                   // pooled pixels per CTA
 constexpr int kWpad = 12;                    // 9 taps padded to 12 floats (three 128-bit loads)
 
-__global__ void __launch_bounds__(kT2 * kT2)
-match_cls_stage2_kernel(const float* __restrict__ p1, const float* __restrict__ w2, const float* __restrict__ b2,
-                        BnParams bn2, float eps, float* __restrict__ partial, int H1, int W1,
-                        int H2, int W2) {
+__global__ void __launch_bounds__(kChunk)
+match_cls_stage2_kernel(const float* __restrict__ p1, const float* __restrict__ wpack, const float* __restrict__ b2,
+                        BnParams bn2, float eps, float* __restrict__ partial, int H1, int W1, int H2, int W2) {
   extern __shared__ __align__(16) float sm2[];
-  float* tile = sm2;                                   // [16][kIn2][kIn2]
-  float* sw = tile + kC1 * kIn2 * kIn2;                // [16 ic][32 oc][kWpad]
+  float* sw = sm2;                                     // [16 ic][32 oc][kWpad]
   float* red = sw + kC1 * kC2 * kWpad;                 // [2 warps][32]
-  const int tid = threadIdx.x, b = blockIdx.z;
-  const int ty0 = blockIdx.y * kT2, tx0 = blockIdx.x * kT2;
-  const int gy0 = 2 * ty0 - 1, gx0 = 2 * tx0 - 1;      // P1 coordinates of tile element (0, 0)
-  for (int idx = tid; idx < kC1 * kIn2 * kIn2; idx += kT2 * kT2) {
-    const int ic = idx / (kIn2 * kIn2), r = (idx / kIn2) % kIn2, c = idx % kIn2;
-    const int y = gy0 + r, x = gx0 + c;
-    tile[idx] = (y >= 0 && y < H1 && x >= 0 && x < W1) ? p1[(((size_t)b * kC1 + ic) * H1 + y) * W1 + x] : 0.f;
-  }
-  for (int idx = tid; idx < kC1 * kC2 * kWpad; idx += kT2 * kT2) {
-    const int ic = idx / (kC2 * kWpad), oc = (idx / kWpad) % kC2, k = idx % kWpad;
-    sw[idx] = k < 9 ? w2[((size_t)oc * kC1 + ic) * 9 + k] : 0.f;
-  }
+  const int tid = threadIdx.x, b = blockIdx.y;
+  for (int idx = tid; idx < kC1 * kC2 * kWpad / 4; idx += kChunk)
+    reinterpret_cast<float4*>(sw)[idx] = reinterpret_cast<const float4*>(wpack)[idx];
   __syncthreads();
 
-  const int ty = tid / kT2, tx = tid % kT2;
+  const int npix = H2 * W2;
+  const int pix = blockIdx.x * kChunk + tid;
+  const bool valid = pix < npix;
+  const int pc = valid ? pix : npix - 1;               // idle threads shadow the last pixel
+  const int y2 = pc / W2, x2 = pc - y2 * W2;
+  const int y0 = 2 * y2 - 1, x0 = 2 * x2 - 1;          // P1 coordinates of patch element (0, 0)
+  // rows / columns 1, 2 of the patch are always inside P1; 0 and 3 are the conv's zero padding at the borders
+  const bool top = y0 >= 0, bottom = y0 + 3 < H1, left = x0 >= 0, right = x0 + 3 < W1;
+  const float* base = p1 + (size_t)b * kC1 * H1 * W1 + (size_t)(y0 + 1) * W1 + (x0 + 1);
+
   float acc[kC2][4];
 #pragma unroll
   for (int oc = 0; oc < kC2; ++oc)
@@ -112,13 +120,16 @@ match_cls_stage2_kernel(const float* __restrict__ p1, const float* __restrict__ 
     for (int d = 0; d < 4; ++d) acc[oc][d] = 0.f;
 
   for (int ic = 0; ic < kC1; ++ic) {
+    const float* t = base + (size_t)ic * H1 * W1;      // patch element (1, 1)
     float p[4][4];
-    const float* t = tile + (ic * kIn2 + 2 * ty) * kIn2 + 2 * tx;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const float2 a = *reinterpret_cast<const float2*>(t + r * kIn2);
-      const float2 c = *reinterpret_cast<const float2*>(t + r * kIn2 + 2);
-      p[r][0] = a.x; p[r][1] = a.y; p[r][2] = c.x; p[r][3] = c.y;
+      const bool rok = (r == 0) ? top : (r == 3) ? bottom : true;
+      const float* row = t + (r - 1) * W1;
+      p[r][0] = (rok && left) ? __ldg(row - 1) : 0.f;
+      p[r][1] = rok ? __ldg(row) : 0.f;
+      p[r][2] = rok ? __ldg(row + 1) : 0.f;
+      p[r][3] = (rok && right) ? __ldg(row + 2) : 0.f;
     }
     const float4* wv = reinterpret_cast<const float4*>(sw + ic * kC2 * kWpad);
 #pragma unroll
@@ -137,7 +148,6 @@ match_cls_stage2_kernel(const float* __restrict__ p1, const float* __restrict__ 
     }
   }
 
-  const bool valid = (ty0 + ty) < H2 && (tx0 + tx) < W2;
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int oc = 0; oc < kC2; ++oc) {
@@ -152,33 +162,33 @@ match_cls_stage2_kernel(const float* __restrict__ p1, const float* __restrict__ 
     if (lane == 0) red[warp * kC2 + oc] = v;
   }
   __syncthreads();
-  if (tid < kC2) {
-    const int tiles = gridDim.x * gridDim.y, tix = blockIdx.y * gridDim.x + blockIdx.x;
-    partial[((size_t)b * tiles + tix) * kC2 + tid] = red[tid] + red[kC2 + tid];
-  }
+  if (tid < kC2) partial[((size_t)b * gridDim.x + blockIdx.x) * kC2 + tid] = red[tid] + red[kC2 + tid];
 }
 
-// grid (cdiv(B, 128)), block 128: fixed-order sum of the tile partials, mean, linear layer.
+// grid (cdiv(B, 4)), block 128: one warp per pair, lane = channel; fixed-order sum of the chunk partials, mean,
+// linear layer.
 __global__ void __launch_bounds__(128)
 match_cls_stage3_kernel(const float* __restrict__ partial, const float* __restrict__ fcw, const float* __restrict__ fcb,
-                        float* __restrict__ logits, int B, int tiles, float inv_pixels) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+                        float* __restrict__ logits, int B, int chunks, float inv_pixels) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), oc = threadIdx.x & 31;
   if (b >= B) return;
-  float out = 0.f;
-  for (int oc = 0; oc < kC2; ++oc) {
-    float sum = 0.f;
-    for (int t = 0; t < tiles; ++t) sum += partial[((size_t)b * tiles + t) * kC2 + oc];
-    out = fmaf(sum * inv_pixels, fcw[oc], out);
-  }
-  logits[b] = out + fcb[0];
+  float sum = 0.f;
+  for (int t = 0; t < chunks; ++t) sum += partial[((size_t)b * chunks + t) * kC2 + oc];
+  const float out = warp_sum(sum * inv_pixels * fcw[oc]);
+  if (oc == 0) logits[b] = out + fcb[0];
 }
 
 }  // namespace fpm
 
+static inline long long match_cls_chunks(int H, int W) {
+  const long long H2 = H / 4, W2 = W / 4;
+  return (H2 * W2 + fpm::kChunk - 1) / fpm::kChunk;
+}
+
 extern "C" long long fpm_match_classifier_workspace_floats(int B, int H, int W) {
-  const long long H1 = H / 2, W1 = W / 2, H2 = H1 / 2, W2 = W1 / 2;
-  const long long tiles = (long long)fpm_cdiv(W2 > 0 ? W2 : 1, fpm::kT2) * fpm_cdiv(H2 > 0 ? H2 : 1, fpm::kT2);
-  return (long long)B * fpm::kC1 * H1 * W1 + (long long)B * tiles * fpm::kC2;
+  const long long H1 = H / 2, W1 = W / 2;
+  return (long long)B * fpm::kC1 * H1 * W1 + (long long)B * match_cls_chunks(H, W) * fpm::kC2 +
+         (long long)fpm::kC1 * fpm::kC2 * fpm::kWpad;
 }
 
 extern "C" int fpm_match_classifier(const float* s, const float* perm, const float* w1, const float* b1,
@@ -193,18 +203,18 @@ extern "C" int fpm_match_classifier(const float* s, const float* perm, const flo
   if (B == 0) return FPM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int H1 = H / 2, W1 = W / 2, H2 = H1 / 2, W2 = W1 / 2;
+  const int chunks = (int)match_cls_chunks(H, W);
   float* p1 = workspace;
-  float* partial = workspace + (size_t)B * fpm::kC1 * H1 * W1;
+  float* partial = p1 + (size_t)B * fpm::kC1 * H1 * W1;
+  float* wpack = partial + (size_t)B * chunks * fpm::kC2;
   fpm::match_cls_stage1_kernel<<<dim3(fpm_cdiv(W1, 32), fpm_cdiv(H1, 8), B), dim3(32, 8), 0, st>>>(
-      s, perm, w1, b1, q1, eps, p1, H, W, H1, W1);
+      s, perm, w1, b1, q1, eps, p1, H, W, H1, W1, w2, wpack);
   FPM_LAUNCH_CHECK();
-  const dim3 g2(fpm_cdiv(W2, fpm::kT2), fpm_cdiv(H2, fpm::kT2), B);
-  const size_t smem2 = sizeof(float) * ((size_t)fpm::kC1 * fpm::kIn2 * fpm::kIn2 + (size_t)fpm::kC1 * fpm::kC2 * fpm::kWpad +
-                                        2 * fpm::kC2);
-  FPM_CUDA(cudaFuncSetAttribute(fpm::match_cls_stage2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  fpm::match_cls_stage2_kernel<<<g2, fpm::kT2 * fpm::kT2, smem2, st>>>(p1, w2, b2, q2, eps, partial, H1, W1, H2, W2);
+  const size_t smem2 = sizeof(float) * ((size_t)fpm::kC1 * fpm::kC2 * fpm::kWpad + 2 * fpm::kC2);
+  fpm::match_cls_stage2_kernel<<<dim3(chunks, B), fpm::kChunk, smem2, st>>>(p1, wpack, b2, q2, eps, partial, H1, W1,
+                                                                          H2, W2);
   FPM_LAUNCH_CHECK();
-  fpm::match_cls_stage3_kernel<<<fpm_cdiv(B, 128), 128, 0, st>>>(partial, fcw, fcb, logits, B, (int)(g2.x * g2.y),
+  fpm::match_cls_stage3_kernel<<<fpm_cdiv(B, 4), 128, 0, st>>>(partial, fcw, fcb, logits, B, chunks,
                                                                 1.0f / ((float)H2 * (float)W2));
   FPM_LAUNCH_CHECK();
   return FPM_OK;

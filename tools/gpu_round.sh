@@ -17,6 +17,6 @@ $CMD > $O/${TAG}_plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_launch.log 2>&1
 echo "ncu launches rc=$?"
 $CMD > $O/${TAG}_plain2.log 2>&1 &&
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_pair_kernel|gemm_tc_kernel|gnn_layer_kernel|lap_topk|ke_factored|spline_gather|afau_attention|sinkhorn_log" -s 50 -c 25 -o $O/${TAG}_prof $CMD > $O/${TAG}_ncu_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_pair_kernel|gemm_tc_kernel|gnn_layer_kernel|lap_topk|ke_factored|spline_gather|afau_attention|sinkhorn_log|match_cls|affinity_kernel" -s 50 -c 25 -o $O/${TAG}_prof $CMD > $O/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la $O | tail -20
