@@ -604,29 +604,34 @@ lap_topk_cols_kernel(const float* __restrict__ ds, const int64_t* __restrict__ n
           sc[c] = 0.f;
           if (live[c]) sc[c] = kCostSmem ? rowp[joff[c]] : __ldg(rowp + joff[c]);
         }
-        double best = INFINITY;
-        int ucode = -1;            // packed (position, column) of the last minimal unassigned column
-        int fcode = INT_MAX;       // ... of the first minimal column
+        // Relax every owned column (independent fp64 chains, no branches: one warp alone has to cover their latency),
+        // then fold the columns' (value, first-position code, last-unassigned-position code) triples.
+        double cur[kCols];
+        int fc[kCols], uc[kCols];
 #pragma unroll
         for (int c = 0; c < kCols; ++c) {
-          if (!live[c]) continue;
           const int j = tid + c * T;
           const double cst = -(double)sc[c];
           double r = minVal + cst;
           r = r - ui;
           r = r - v[c];
-          if (r < spc[c]) {
-            spc[c] = r;
-            sm.path[j] = i;
-          }
-          const double cur = spc[c];
+          const bool better = live[c] && r < spc[c];
+          spc[c] = better ? r : spc[c];
+          if (better) sm.path[j] = i;
           const int code = (pos[c] << 10) | j;
-          if (cur < best) {
-            best = cur; fcode = code; ucode = unassigned[c] ? code : -1;
-          } else if (cur == best) {
-            fcode = min(fcode, code);
-            if (unassigned[c]) ucode = max(ucode, code);
-          }
+          cur[c] = live[c] ? spc[c] : INFINITY;
+          fc[c] = live[c] ? code : INT_MAX;
+          uc[c] = (live[c] && unassigned[c]) ? code : -1;
+        }
+        double best = cur[0];
+        int fcode = fc[0];         // packed (position, column) of the first minimal column
+        int ucode = uc[0];         // ... of the last minimal unassigned column
+#pragma unroll
+        for (int c = 1; c < kCols; ++c) {
+          const bool lt = cur[c] < best, eq = cur[c] == best;
+          fcode = lt ? fc[c] : (eq ? min(fcode, fc[c]) : fcode);
+          ucode = lt ? uc[c] : (eq ? max(ucode, uc[c]) : ucode);
+          best = lt ? cur[c] : best;
         }
         const unsigned long long key = ordered_key(best);
         const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
