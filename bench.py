@@ -271,10 +271,10 @@ def main():
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape, from the committed
     # `ncu --set full` capture profiles/r1c_ncu_full_gemm_pair.md (algorithmic bytes: 2.185e9)
     # (dense product: profiles/r1c_ncu_full_gemm_pair.md, 2.644e9 for 2.185e9 algorithmic; tile-table launch at
-    # 6084 tiles: profiles/r1d_ncu_full.md, 1.047e9 for 0.90e9 algorithmic)
+    # 6084 tiles: profiles/r1i_ncu_full.md, 1.056e9 for 0.90e9 algorithmic; r1d measured 1.047e9)
     traffic = None
     if mode == "3xf16" and (big[1], big[2], big[3]) == (25600, 19968, 768):
-        traffic = 2.644e9 if kernel_label is None else 1.047e9
+        traffic = 2.644e9 if kernel_label is None else 1.056e9
     achieved = flops / (gemm_ms / 1e3) / 1e12
     gemm_share = gemm_ms * len(same) / args.steps / ms_step
 

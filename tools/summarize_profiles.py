@@ -67,13 +67,18 @@ def full():
     out = [f"# ncu --set full, one launch of each hot kernel inside bench.py (B=256, n=100) - {tag}", "",
            "`ncu --set full --clock-control none --import-source on`; values are per launch (ncu replays each kernel ~39 passes; "
            "durations here are under the profiler - bench numbers come from CUDA events, not from this file).", ""]
-    seen = {}
+    # one entry per (kernel, grid size): the longest launch of that shape (several GEMMs share the persistent grid)
+    def dur(d):
+        try:
+            return float(d[idx["gpu__time_duration.sum"]].replace(",", ""))
+        except Exception:
+            return 0.0
+    best = {}
     for d in data:
-        name = short(d[idx["Kernel Name"]])
-        key = (name, d[idx["launch__grid_size"]] if "launch__grid_size" in idx else "")
-        if key in seen:
-            continue
-        seen[key] = 1
+        key = (short(d[idx["Kernel Name"]]), d[idx["launch__grid_size"]] if "launch__grid_size" in idx else "")
+        if key not in best or dur(d) > dur(best[key]):
+            best[key] = d
+    for (name, _), d in best.items():
         out.append(f"## `{name}`  grid {d[idx['Grid Size']] if 'Grid Size' in idx else ''} block {d[idx['Block Size']] if 'Block Size' in idx else ''}")
         out.append("")
         out.append("| metric | value | unit |"); out.append("|---|---|---|")
