@@ -167,7 +167,9 @@ node_features_kernel(const float* __restrict__ nodes, const float* __restrict__ 
 }
 
 // coeff[b, :] = tanh(A * normalize([g_src[b]; g_tgt[b]]) + a)   (ngm.py:262-268, affinity_layer.py:13)
-// One CTA per pair; the 2*G-vector sits in shared memory; one warp per output row of A.
+// grid (B, cdiv(OUT, 64)): one CTA per (pair, 64 output rows of A) - the first version gave a pair's 768 rows to one CTA
+// and took 0.2 ms whatever the batch; the 2*G-vector sits in shared memory; one warp per output row.
+constexpr int kCoeffRows = 64;
 __global__ void __launch_bounds__(256)
 affinity_coeff_kernel(const float* __restrict__ gcat, const float* __restrict__ W,
                       const float* __restrict__ bias, float* __restrict__ coeff, int IN, int OUT) {
@@ -185,7 +187,8 @@ affinity_coeff_kernel(const float* __restrict__ gcat, const float* __restrict__ 
   __syncthreads();
   for (int i = threadIdx.x; i < IN; i += blockDim.x) g[i] = g[i] / nrm;
   __syncthreads();
-  for (int o = warp; o < OUT; o += (blockDim.x >> 5)) {
+  const int o_end = min(OUT, (int)(blockIdx.y + 1) * kCoeffRows);
+  for (int o = blockIdx.y * kCoeffRows + warp; o < o_end; o += (blockDim.x >> 5)) {
     const float* w = W + (size_t)o * IN;
     float acc = 0.f;
     for (int i = lane; i < IN; i += 32) acc = fmaf(w[i], g[i], acc);
@@ -338,7 +341,7 @@ extern "C" int fpm_affinity_coeff(const float* gcat, const float* W, const float
                                   int B, int IN, int OUT, void* stream) {
   FPM_CHECK_ARG(gcat && W && bias && coeff, "fpm_affinity_coeff: null tensor");
   if (B == 0) return FPM_OK;
-  fpm::affinity_coeff_kernel<<<B, 256, (size_t)IN * sizeof(float), (cudaStream_t)stream>>>(
+  fpm::affinity_coeff_kernel<<<dim3(B, fpm_cdiv(OUT, fpm::kCoeffRows)), 256, (size_t)IN * sizeof(float), (cudaStream_t)stream>>>(
       gcat, W, bias, coeff, IN, OUT);
   FPM_LAUNCH_CHECK();
   return FPM_OK;

@@ -33,6 +33,7 @@ transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int
 // One CTA per (pair, 128-channel chunk): the pair's matrix sits in shared memory; every thread owns one channel
 // and walks the output rows in blocks of 8 (the matrix entries are shared-memory broadcasts).
 constexpr int BR = 8;
+constexpr int kRowsPerCta = 32;
 __global__ void __launch_bounds__(128)
 bmm_ragged_kernel(const float* __restrict__ Mat, int Rmax, int Cmax, int trans, const float* __restrict__ X,
                   const int64_t* __restrict__ ptrX, const int64_t* __restrict__ ptrO,
@@ -50,7 +51,9 @@ bmm_ragged_kernel(const float* __restrict__ Mat, int Rmax, int Cmax, int trans, 
   float* ob = Out + (size_t)ptrO[b] * D + d;
   const float ci = coeff_in ? coeff_in[(size_t)b * D + d] : 1.f;
   const float co = coeff_out ? coeff_out[(size_t)b * D + d] : 1.f;
-  for (int i0 = 0; i0 < nO; i0 += BR) {
+  // blockIdx.z splits the output rows in chunks of kRowsPerCta: a small batch still fills the machine
+  const int i_end = min(nO, (int)(blockIdx.z + 1) * kRowsPerCta);
+  for (int i0 = blockIdx.z * kRowsPerCta; i0 < i_end; i0 += BR) {
     float acc[BR];
 #pragma unroll
     for (int u = 0; u < BR; ++u) acc[u] = 0.f;
@@ -103,7 +106,8 @@ extern "C" int fpm_bmm_ragged(const float* Mat, int B, int Rmax, int Cmax, int t
   const size_t smem = (size_t)Rmax * Cmax * sizeof(float);
   FPM_CHECK_ARG(smem <= 200 * 1024 && B <= 65535, "fpm_bmm_ragged: matrix or batch too large");
   FPM_CUDA(cudaFuncSetAttribute(fpm::bmm_ragged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fpm::bmm_ragged_kernel<<<dim3(fpm_cdiv(D, 128), B), 128, smem, (cudaStream_t)stream>>>(
+  const int Omax = trans ? Cmax : Rmax;               // output rows of a pair never exceed the matrix side
+  fpm::bmm_ragged_kernel<<<dim3(fpm_cdiv(D, 128), B, fpm_cdiv(Omax, fpm::kRowsPerCta)), 128, smem, (cudaStream_t)stream>>>(
       Mat, Rmax, Cmax, trans, X, (const int64_t*)ptrX, (const int64_t*)ptrO, coeff_in, coeff_out, Out, D);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
