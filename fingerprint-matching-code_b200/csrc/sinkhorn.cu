@@ -8,6 +8,7 @@
 // HBM-bound by design: algorithmic traffic is one read and one write of the n1 x n2 matrix per call
 // (SURVEY.md section 8d); all 10/20 iterations run on chip.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fpm {
 
@@ -371,6 +372,158 @@ soft_topk_kernel(const float* __restrict__ scores, const float* __restrict__ ks,
     const int i = idx / C, j = idx - i * C;
     ob[idx] = (i < n1b && j < n2b) ? expf(L1[(size_t)i * n2b + j]) : 0.f;
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// soft-top-k for plans beyond one CTA's shared memory (n = 400: 2 x 640 KB): a cluster of kSkCluster CTAs per pair,
+// each keeping a contiguous slice of the flattened [n1_b * n2_b, 2] log-plan in its own shared memory for all
+// iterations.  The row half-steps are element-wise; the column half-steps and the anchors need four scalars over the
+// whole plan: every CTA publishes its slice's partials, one cluster barrier, every CTA combines the eight partials in
+// rank order through distributed shared memory.  Same shift (global column maximum) as the single-CTA kernel; only
+// the association of the final eight-term sums differs.  (The global-workspace path this replaces for such sizes
+// walks 2.5 MB of L2 per pair and half-step from one CTA: 1.66 ms for 32 pairs at n = 400.)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stk_publish(float* part, int& slot, float a, float b_) {
+  // part: [2 slots][2]; a slot is rewritten two publishes later, after every peer has passed the barrier in between
+  if (threadIdx.x == 0) { part[slot * 2] = a; part[slot * 2 + 1] = b_; }
+  sk_cluster_sync();
+}
+
+__global__ void __launch_bounds__(512)
+soft_topk_cluster_kernel(const float* __restrict__ scores, const float* __restrict__ ks,
+                         const int64_t* __restrict__ n1, const int64_t* __restrict__ n2,
+                         float* __restrict__ out, int R, int C, int max_iter, float tau, int slice_cap) {
+  extern __shared__ float smem[];
+  __shared__ float red[64];
+  __shared__ float part[4];
+  const int b = blockIdx.x / kSkCluster;
+  const uint32_t rank = sk_cluster_rank();
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  int n1b = n1 ? (int)n1[b] : R;
+  int n2b = n2 ? (int)n2[b] : C;
+  n1b = min(max(n1b, 0), R);
+  n2b = min(max(n2b, 0), C);
+  const int N = n1b * n2b;
+  const int S = (N + kSkCluster - 1) / kSkCluster;              // <= slice_cap
+  const int p0 = min(N, (int)rank * S), p1 = min(N, p0 + S);
+  const int mine = p1 - p0;
+  float* L0 = smem;
+  float* L1 = smem + slice_cap;
+  const float* sb = scores + (size_t)b * R * C;
+  int slot = 0;
+
+  // anchors = (min, max) over the valid block
+  float mn = INFINITY, mx = kNegInf;
+  for (int q = tid; q < mine; q += nthreads) {
+    const int p = p0 + q, i = p / n2b, j = p - i * n2b;
+    const float v = sb[(size_t)i * C + j];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  mn = block_min(mn, red);
+  mx = block_max(mx, red + 32);
+  stk_publish(part, slot, mn, mx);
+  mn = INFINITY; mx = kNegInf;
+#pragma unroll
+  for (int c = 0; c < kSkCluster; ++c) {
+    mn = fminf(mn, sk_ld_remote(&part[slot * 2], (uint32_t)c));
+    mx = fmaxf(mx, sk_ld_remote(&part[slot * 2 + 1], (uint32_t)c));
+  }
+  slot ^= 1;
+  for (int q = tid; q < mine; q += nthreads) {
+    const int p = p0 + q, i = p / n2b, j = p - i * n2b;
+    const float v = sb[(size_t)i * C + j];
+    L0[q] = (-fabsf(v - mn)) / tau;
+    L1[q] = (-fabsf(v - mx)) / tau;
+  }
+  const float k = ks[b];
+  const float lc0 = logf((float)((long long)n1b * (long long)n2b) - k);
+  const float lc1 = logf(k);
+  __syncthreads();
+
+  int it = 0;
+  while (true) {
+    if (it >= max_iter) {
+      int pos = 0;
+      for (int q = tid; q < mine; q += nthreads) pos |= (L0[q] > 0.f) | (L1[q] > 0.f);
+      pos = __syncthreads_or(pos);
+      stk_publish(part, slot, pos ? 1.f : 0.f, 0.f);
+      float any = 0.f;
+#pragma unroll
+      for (int c = 0; c < kSkCluster; ++c) any = fmaxf(any, sk_ld_remote(&part[slot * 2], (uint32_t)c));
+      slot ^= 1;
+      if (any == 0.f) break;
+    }
+    if ((it & 1) == 0) {
+      for (int q = tid; q < mine; q += nthreads) {
+        const float a = L0[q], c = L1[q];
+        const float m = fmaxf(a, c);
+        const float sh = (m == kNegInf || m == INFINITY) ? 0.f : m;
+        const float lse = logf(expf(a - sh) + expf(c - sh)) + sh;
+        float na = a - lse + 0.0f, nc_ = c - lse + 0.0f;
+        L0[q] = isnan(na) ? kNegInf : na;
+        L1[q] = isnan(nc_) ? kNegInf : nc_;
+      }
+      __syncthreads();
+    } else {
+      float m0 = kNegInf, m1 = kNegInf;
+      for (int q = tid; q < mine; q += nthreads) {
+        m0 = fmaxf(m0, L0[q]);
+        m1 = fmaxf(m1, L1[q]);
+      }
+      m0 = block_max(m0, red);
+      m1 = block_max(m1, red + 32);
+      stk_publish(part, slot, m0, m1);
+      m0 = kNegInf; m1 = kNegInf;
+#pragma unroll
+      for (int c = 0; c < kSkCluster; ++c) {
+        m0 = fmaxf(m0, sk_ld_remote(&part[slot * 2], (uint32_t)c));
+        m1 = fmaxf(m1, sk_ld_remote(&part[slot * 2 + 1], (uint32_t)c));
+      }
+      slot ^= 1;
+      const float sh0 = (m0 == kNegInf || m0 == INFINITY) ? 0.f : m0;
+      const float sh1 = (m1 == kNegInf || m1 == INFINITY) ? 0.f : m1;
+      float s0 = 0.f, s1 = 0.f;
+      for (int q = tid; q < mine; q += nthreads) {
+        s0 += expf(L0[q] - sh0);
+        s1 += expf(L1[q] - sh1);
+      }
+      s0 = block_sum(s0, red);
+      s1 = block_sum(s1, red + 32);
+      stk_publish(part, slot, s0, s1);
+      s0 = 0.f; s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kSkCluster; ++c) {
+        s0 += sk_ld_remote(&part[slot * 2], (uint32_t)c);
+        s1 += sk_ld_remote(&part[slot * 2 + 1], (uint32_t)c);
+      }
+      slot ^= 1;
+      const float lse0 = logf(s0) + sh0, lse1 = logf(s1) + sh1;
+      for (int q = tid; q < mine; q += nthreads) {
+        float na = L0[q] - lse0 + lc0, nc_ = L1[q] - lse1 + lc1;
+        L0[q] = isnan(na) ? kNegInf : na;
+        L1[q] = isnan(nc_) ? kNegInf : nc_;
+      }
+      __syncthreads();
+    }
+    ++it;
+    if (it > max_iter + 64) break;   // cannot happen (a row step makes every entry <= 0)
+  }
+
+  // every CTA writes the outputs of its slice; rank 0 also writes the zero padding of the frame
+  float* ob = out + (size_t)b * R * C;
+  for (int q = tid; q < mine; q += nthreads) {
+    const int p = p0 + q, i = p / n2b, j = p - i * n2b;
+    ob[(size_t)i * C + j] = expf(L1[q]);
+  }
+  if (rank == 0) {
+    for (int idx = tid; idx < R * C; idx += nthreads) {
+      const int i = idx / C, j = idx - i * C;
+      if (!(i < n1b && j < n2b)) ob[idx] = 0.f;
+    }
+  }
+  sk_cluster_sync();                                 // no CTA may exit while a peer can still read its partials
 }
 
 
@@ -827,6 +980,25 @@ extern "C" int fpm_soft_topk(const float* scores, const float* ks, const long lo
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     fpm::soft_topk_kernel<false><<<B, threads, need, st>>>(
         scores, ks, (const int64_t*)n1, (const int64_t*)n2, out, nullptr, R, C, max_iter, tau);
+  } else if ((size_t)2 * fpm_cdiv((long long)R * C, fpm::kSkCluster) * sizeof(float) <= kSmemLimit - 1024 &&
+             (long long)B * fpm::kSkCluster <= 0x7fffffffLL && !getenv("FPMATCH_STK_GLOBAL")) {
+    // cluster of 8 CTAs per pair, one slice of the flattened plan per CTA (scalars exchanged through DSMEM)
+    const int slice_cap = fpm_cdiv((long long)R * C, fpm::kSkCluster);
+    const size_t sm_slice = (size_t)2 * slice_cap * sizeof(float);
+    FPM_CUDA(cudaFuncSetAttribute(fpm::soft_topk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sm_slice));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * fpm::kSkCluster));
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = sm_slice;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = fpm::kSkCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FPM_CUDA(cudaLaunchKernelEx(&cfg, fpm::soft_topk_cluster_kernel, scores, ks, (const int64_t*)n1,
+                                (const int64_t*)n2, out, R, C, max_iter, tau, slice_cap));
   } else {
     FPM_CHECK_ARG(workspace, "fpm_soft_topk: matrix exceeds shared memory, workspace required");
     fpm::soft_topk_kernel<true><<<B, threads, 0, st>>>(

@@ -19,9 +19,14 @@ def report(name, **kv):
         f.write(json.dumps({"test": name, **kv}) + "\n")
 
 
-def test_soft_topk_beyond_shared_memory():
+@pytest.mark.parametrize("path", ["cluster", "global"])
+def test_soft_topk_beyond_shared_memory(path, monkeypatch):
+    """Plans beyond one CTA's shared memory: the 8-CTA cluster kernel (slices in distributed shared memory) and the
+    global-workspace kernel it falls back to for still larger plans (forced here through FPMATCH_STK_GLOBAL)."""
     from fpmatch import ops
     from oracle import ops as oo
+    if path == "global":
+        monkeypatch.setenv("FPMATCH_STK_GLOBAL", "1")
     g = torch.Generator().manual_seed(0)
     B, n = 3, 260
     n1 = torch.tensor([260, 200, 230]); n2 = torch.tensor([260, 260, 190])
@@ -30,7 +35,7 @@ def test_soft_topk_beyond_shared_memory():
     ref = oo.soft_topk_prob(ss, ks, 10, 0.01, n1, n2)
     out = ops.soft_topk(ss.to(DEV), ks.to(DEV), n1.to(DEV), n2.to(DEV), 10, 0.01)
     err = (out.cpu() - ref).abs().max().item()
-    report("soft_topk_global_scratch", max_abs=err)
+    report("soft_topk_beyond_smem", path=path, max_abs=err)
     assert err < 1e-4
 
 
