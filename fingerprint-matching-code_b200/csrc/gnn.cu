@@ -18,33 +18,56 @@
 namespace fpm {
 
 // In-neighbour lists from the per-pair edge tables [B, 2, emax] (int32, -1 padded; row 0 = G-node
-// (source), row 1 = H-node (target) of every G/H column).  Thread per destination node, edges scanned in
-// column order -> deterministic.  in_ptr: [B, nmax + 1] (offsets local to the pair), in_src: [B, emax].
-__global__ void assoc_in_csr_kernel(const int* __restrict__ edges, int* __restrict__ in_ptr,
-                                    int* __restrict__ in_src, int nmax, int emax) {
+// (source), row 1 = H-node (target) of every G/H column).  One CTA per pair, one WARP per destination node: the edge
+// table is walked 32 columns at a time and the hits are compacted in column order with a ballot -> deterministic.
+// (Thread-per-destination full scans took 0.27 ms per launch at 400 keypoints.)
+// in_ptr: [B, nmax + 1] (offsets local to the pair), in_src: [B, emax].
+constexpr int kAssocThreads = 512;
+__global__ void __launch_bounds__(kAssocThreads)
+assoc_in_csr_kernel(const int* __restrict__ edges, int* __restrict__ in_ptr, int* __restrict__ in_src, int nmax,
+                    int emax) {
   extern __shared__ int sh[];            // [2 * emax] edge table, then [nmax + 1] counts
   int* ssrc = sh; int* sdst = sh + emax; int* cnt = sh + 2 * emax;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int* eb = edges + (size_t)b * 2 * emax;
   for (int k = threadIdx.x; k < emax; k += blockDim.x) { ssrc[k] = eb[k]; sdst[k] = eb[emax + k]; }
   __syncthreads();
-  for (int j = threadIdx.x; j < nmax; j += blockDim.x) {
+  for (int j = warp; j < nmax; j += nwarps) {
     int c = 0;
-    for (int k = 0; k < emax; ++k) c += (sdst[k] == j);
-    cnt[j] = c;
+    for (int k0 = 0; k0 < emax; k0 += 32) {
+      const int k = k0 + lane;
+      c += __popc(__ballot_sync(0xffffffffu, k < emax && sdst[k] == j));
+    }
+    if (lane == 0) cnt[j] = c;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int j = 0; j < nmax; ++j) { const int c = cnt[j]; cnt[j] = run; run += c; }
-    cnt[nmax] = run;
+  if (warp == 0) {                       // exclusive scan, 32 nodes at a time
+    int base = 0;
+    for (int j0 = 0; j0 < nmax; j0 += 32) {
+      const int j = j0 + lane;
+      const int c = j < nmax ? cnt[j] : 0;
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (j < nmax) cnt[j] = base + inc - c;
+      base += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) cnt[nmax] = base;
   }
   __syncthreads();
   for (int j = threadIdx.x; j <= nmax; j += blockDim.x) in_ptr[(size_t)b * (nmax + 1) + j] = cnt[j];
-  for (int j = threadIdx.x; j < nmax; j += blockDim.x) {
+  for (int j = warp; j < nmax; j += nwarps) {
     int w = cnt[j];
-    for (int k = 0; k < emax; ++k)
-      if (sdst[k] == j) in_src[(size_t)b * emax + (w++)] = ssrc[k];
+    for (int k0 = 0; k0 < emax; k0 += 32) {
+      const int k = k0 + lane;
+      const bool hit = k < emax && sdst[k] == j;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) in_src[(size_t)b * emax + w + __popc(m & ((1u << lane) - 1u))] = ssrc[k];
+      w += __popc(m);
+    }
   }
 }
 
@@ -563,7 +586,7 @@ extern "C" int fpm_assoc_in_csr(const int* edges, int* in_ptr, int* in_src, int 
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_assoc_in_csr: graph too large for one CTA");
   FPM_CUDA(cudaFuncSetAttribute(fpm::assoc_in_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
-  fpm::assoc_in_csr_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(edges, in_ptr, in_src, nmax, emax);
+  fpm::assoc_in_csr_kernel<<<B, fpm::kAssocThreads, smem, (cudaStream_t)stream>>>(edges, in_ptr, in_src, nmax, emax);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

@@ -16,55 +16,56 @@
 namespace fpm {
 
 // In-edge lists of a PyG-style batch graph: for every node, the ids of the edges that end in it, in
-// ascending edge order (deterministic).  One CTA per pair; one thread per destination node scans the
-// pair's edges.  in_ptr has [total_nodes + 1] entries (global offsets into in_eid).
-__global__ void csr_by_dst_kernel(const int64_t* __restrict__ edge_dst, const int64_t* __restrict__ ptr,
-                                  const int64_t* __restrict__ eptr, int* __restrict__ in_ptr,
-                                  int* __restrict__ in_eid, int total_nodes) {
-  extern __shared__ int sdst[];
-  __shared__ int wsum[32];
-  const int b = blockIdx.x;
+// ascending edge order (deterministic).  One CTA per pair; one WARP per destination node walks the pair's edge list
+// 32 edges at a time and compacts the hits in order with a ballot (the first version gave every destination to one
+// thread that scanned all edges twice: 0.24 ms per launch at 400 keypoints, 2 400 edges).
+// in_ptr has [total_nodes + 1] entries (global offsets into in_eid).
+constexpr int kCsrThreads = 512;
+__global__ void __launch_bounds__(kCsrThreads)
+csr_by_dst_kernel(const int64_t* __restrict__ edge_dst, const int64_t* __restrict__ ptr,
+                  const int64_t* __restrict__ eptr, int* __restrict__ in_ptr, int* __restrict__ in_eid,
+                  int total_nodes) {
+  extern __shared__ int sdst[];                   // [e] local destinations
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int n0 = (int)ptr[b], n = (int)ptr[b + 1] - n0;
   const int e0 = (int)eptr[b], e = (int)eptr[b + 1] - e0;
+  int* cnt = in_ptr + n0;                         // counts, then offsets, live in the output itself (this CTA's rows)
   for (int k = threadIdx.x; k < e; k += blockDim.x) sdst[k] = (int)edge_dst[e0 + k] - n0;
   __syncthreads();
-  // count, then exclusive scan over nodes (nodes are processed in chunks of blockDim)
-  int base = 0;
-  for (int c0 = 0; c0 < n; c0 += blockDim.x) {
-    const int j = c0 + threadIdx.x;
-    int cnt = 0;
-    if (j < n)
-      for (int k = 0; k < e; ++k) cnt += (sdst[k] == j);
-    // block exclusive scan of cnt
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
+  for (int j = warp; j < n; j += nwarps) {
+    int c = 0;
+    for (int k0 = 0; k0 < e; k0 += 32) {
+      const int k = k0 + lane;
+      c += __popc(__ballot_sync(0xffffffffu, k < e && sdst[k] == j));
     }
-    if (lane == 31) wsum[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-      int w = (lane < (int)(blockDim.x >> 5)) ? wsum[lane] : 0;
+    if (lane == 0) cnt[j] = c;
+  }
+  __syncthreads();
+  if (warp == 0) {                                // exclusive scan of the counts, 32 nodes at a time
+    int base = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      const int c = j < n ? cnt[j] : 0;
+      int inc = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += t;
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
       }
-      wsum[lane] = w;
+      if (j < n) cnt[j] = e0 + base + inc - c;
+      base += __shfl_sync(0xffffffffu, inc, 31);
     }
-    __syncthreads();
-    const int woff = wid ? wsum[wid - 1] : 0;
-    const int excl = base + woff + inc - cnt;
-    if (j < n) {
-      in_ptr[n0 + j] = e0 + excl;
-      int w = e0 + excl;
-      for (int k = 0; k < e; ++k)
-        if (sdst[k] == j) in_eid[w++] = e0 + k;
+  }
+  __syncthreads();
+  for (int j = warp; j < n; j += nwarps) {
+    int w = cnt[j];
+    for (int k0 = 0; k0 < e; k0 += 32) {
+      const int k = k0 + lane;
+      const bool hit = k < e && sdst[k] == j;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) in_eid[w + __popc(m & ((1u << lane) - 1u))] = e0 + k;
+      w += __popc(m);
     }
-    base += wsum[(blockDim.x >> 5) - 1];
-    __syncthreads();
   }
   if (b == (int)gridDim.x - 1 && threadIdx.x == 0) in_ptr[total_nodes] = e0 + e;
 }
@@ -362,7 +363,7 @@ extern "C" int fpm_csr_by_dst(const long long* edge_dst, const long long* ptr, c
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_csr_by_dst: too many edges per graph");
   FPM_CUDA(cudaFuncSetAttribute(fpm::csr_by_dst_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
-  fpm::csr_by_dst_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(
+  fpm::csr_by_dst_kernel<<<B, fpm::kCsrThreads, smem, (cudaStream_t)stream>>>(
       (const int64_t*)edge_dst, (const int64_t*)ptr, (const int64_t*)eptr, in_ptr, in_eid, total_nodes);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
