@@ -187,3 +187,28 @@ def test_full_forward_with_backbone_runs():
         out = net(synth.batch_to(data, DEV))
     assert out["ds_mat"].shape == (2, 12, 12) and out["perm_mat"].shape == (2, 12, 12)
     assert torch.isfinite(out["ds_mat"]).all() and out["cls_prob"].shape == (2,)
+
+
+def test_channels_last_backbone_option():
+    """Net.backbone_channels_last(): same stock cuDNN backbone in NHWC; the maps agree with the NCHW run to cuDNN's
+    TF32 noise and the head consumes them unchanged (opt-in)."""
+    from fpmatch import synth
+    data = synth.make_batch(2, 12, seed=3, with_fmaps=False)
+    g = torch.Generator().manual_seed(0)
+    data["images"] = [torch.randn(2, 3, 240, 320, generator=g) for _ in range(2)]
+    net = make_net().to(DEV)
+    dev = synth.batch_to(data, DEV)
+    with torch.no_grad():
+        ref_nodes = net.node_layers(dev["images"][0])
+        net.backbone_channels_last(True)
+        out = net(synth.batch_to(synth.clone_batch(data), DEV))
+        cl_nodes = net.node_layers(dev["images"][0].contiguous(memory_format=torch.channels_last))
+    assert cl_nodes.is_contiguous(memory_format=torch.channels_last)
+    rel = ((cl_nodes - ref_nodes).abs().max() / ref_nodes.abs().max()).item()
+    report("channels_last_backbone", rel_err_nodes=rel)
+    assert rel < 2e-2
+    assert out["ds_mat"].shape == (2, 12, 12) and torch.isfinite(out["ds_mat"]).all()
+    net.backbone_channels_last(False)
+    with torch.no_grad():
+        back = net.node_layers(dev["images"][0])
+    assert back.is_contiguous() and ((back - ref_nodes).abs().max() / ref_nodes.abs().max()).item() < 2e-2
