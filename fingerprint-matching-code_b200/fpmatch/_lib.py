@@ -85,6 +85,8 @@ SIGNATURES = {
     "fpm_soft_topk_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "fpm_match_classifier_workspace_floats": (_LL, [_I, _I, _I]),
     "fpm_match_classifier": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _P]),
+    "fpm_fgm_aggregate": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "fpm_fgm_aggregate_dw": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     # keypoint-graph construction
     "fpm_graph_adjacency": (_I, [_P, _P, _P, _I, _I, _I, _D, _P]),
     "fpm_graph_row_counts": (_I, [_P, _P, _P, _I, _I, _I, _P]),

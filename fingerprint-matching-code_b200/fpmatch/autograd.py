@@ -145,6 +145,26 @@ class SplineConvFn(Function):
         return dx, dweight, droot, dbias, dxin, None, None, None, None
 
 
+class FgmAggregateFn(Function):
+    """x2[b,i,:] = sum_j normalize(A)[i,j] W[i,j,:] x1[j,:] of the dense NGM-v1 layer (gnn.py:54-68).  Gradients reach
+    the edge tensor W and x1; the 0/1 adjacency A carries none."""
+
+    @staticmethod
+    def forward(ctx, A: Tensor, W: Tensor, x1: Tensor, norm: bool):
+        A = A.contiguous(); W = W.contiguous(); x1 = x1.contiguous()
+        out, inv = ops.fgm_aggregate(A, W, x1, norm)
+        ctx.save_for_backward(A, W, x1, inv)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        A, W, x1, inv = ctx.saved_tensors
+        gout = gout.contiguous()
+        dW = ops.fgm_aggregate_dw(A, inv, gout, x1, W.shape[-1]) if ctx.needs_input_grad[1] else None
+        dx1 = ops.fgm_aggregate(A, W, gout, trans=True, inv=inv) if ctx.needs_input_grad[2] else None
+        return None, dW, dx1, None
+
+
 class AffinityFn(Function):
     """Kp = softplus((X1 (.) c) X2^T) - 0.5, padded, with its transpose (affinity_layer.py:11-19, ngm.py:317-321)."""
 

@@ -860,6 +860,30 @@ def matching_stats(pred: Tensor, gt: Tensor, ns: Tensor) -> Tensor:
     return out
 
 
+def fgm_aggregate(A: Tensor, W: Tensor, X: Tensor, norm: bool = True, trans: bool = False,
+                  inv: Optional[Tensor] = None):
+    """Dense NGM-v1 aggregation (GNNLayer.forward, gnn.py:54-68).  Forward: returns (out [B,N,F], inv [B,N] or None);
+    ``trans=True`` evaluates the transposed product with the given row scales (backward of the forward)."""
+    B, N, F_ = X.shape
+    fe = W.shape[-1]
+    out = torch.empty((B, N, F_), dtype=torch.float32, device=X.device)
+    if not trans:
+        inv = torch.empty((B, N), dtype=torch.float32, device=X.device) if norm else None
+    rc = _lib.lib().fpm_fgm_aggregate(_chk(A, "A"), _chk(W, "W"), _chk(X, "X"), _chk(inv, "inv"), out.data_ptr(), B, N,
+                                      F_, fe, int(norm), int(trans), _stream())
+    _lib.check(rc, "fpm_fgm_aggregate"); _count()
+    return (out, inv) if not trans else out
+
+
+def fgm_aggregate_dw(A: Tensor, inv: Optional[Tensor], dx2: Tensor, x1: Tensor, fe: int) -> Tensor:
+    B, N, F_ = x1.shape
+    dW = torch.empty((B, N, N, fe), dtype=torch.float32, device=x1.device)
+    rc = _lib.lib().fpm_fgm_aggregate_dw(_chk(A, "A"), _chk(inv, "inv"), _chk(dx2, "dx2"), _chk(x1, "x1"),
+                                         dW.data_ptr(), B, N, F_, fe, _stream())
+    _lib.check(rc, "fpm_fgm_aggregate_dw"); _count()
+    return dW
+
+
 def match_classifier(s: Tensor, perm: Optional[Tensor], w1: Tensor, b1: Tensor, bn1: Sequence[Tensor], w2: Tensor,
                      b2: Tensor, bn2: Sequence[Tensor], fcw: Tensor, fcb: Tensor, eps: float = 1e-5) -> Tensor:
     """Logits [B] of the genuine / imposter CNN on ``s * perm`` (MatchClassifier.forward in eval mode, ngm.py:75-106).

@@ -320,6 +320,19 @@ int fpm_match_classifier(const float* s, const float* perm, const float* w1, con
                          const float* fcw, const float* fcb, float eps, float* workspace, float* logits, int B, int H,
                          int W, void* stream);
 
+/* ---- dense NGM-v1 message passing --------------------------------------------------
+ * Replaces the aggregation of GNNLayer.forward (/root/reference/src/model/gnn.py:54-68): A [B,N,N] 0/1 adjacency,
+ * W [B,N,N,fe] edge tensor (fe = 1 or F), X [B,N,F] (F in {1,2,4,8,16,32}).
+ *   trans = 0: out[b,i,:] = sum_j A[i,j] s_i W[i,j,:] X[j,:],  s_i = 1 / max(sum_j |A[i,j]|, 1e-12) when norm (written to
+ *              inv [B,N] when non-null), else 1;
+ *   trans = 1: out[b,j,:] = sum_i A[i,j] inv[i] W[i,j,:] X[i,:]  (the backward's dx1; inv nullable = 1).
+ * fpm_fgm_aggregate_dw: dW[b,i,j,c'] = A[i,j] inv[i] (fe == 1 ? sum_c dx2[i,c] x1[j,c] : dx2[i,c'] x1[j,c']).
+ */
+int fpm_fgm_aggregate(const float* A, const float* W, const float* X, float* inv, float* out, int B, int N, int F,
+                      int fe, int norm, int trans, void* stream);
+int fpm_fgm_aggregate_dw(const float* A, const float* inv, const float* dx2, const float* x1, float* dW, int B, int N,
+                         int F, int fe, void* stream);
+
 /* ---- keypoint-graph construction ---------------------------------------------------
  * Replaces the per-image host code of /root/reference/utils/build_graphs.py:12-119 (build_graphs,
  * delaunay_triangulate, fully_connect) and /root/reference/src/gmdataset.py:169-189 (to_pyg_graph), :345-352

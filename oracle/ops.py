@@ -481,3 +481,34 @@ def match_classifier(m: Tensor, p: dict, training: bool = False, prefix: str = "
         x = F.max_pool2d(x, 2)
     x = F.adaptive_avg_pool2d(x, 1).view(x.size(0), -1)
     return F.linear(x, p[f"{prefix}.fc.weight"], p[f"{prefix}.fc.bias"]).squeeze(-1)
+
+
+def gnn_layer_dense(p: dict, A: Tensor, W: Tensor, x: Tensor, n1: Tensor, n2: Tensor, norm: bool = True,
+                    sk_iter: int = 20, sk_tau: float = 0.05) -> tuple:
+    """GNNLayer.forward of the dense NGM-v1 path (/root/reference/src/model/gnn.py:54-87), with the reference's own
+    permute + matmul formulation of the aggregation.  ``p``: the layer's state_dict (e_func.* optional)."""
+    lin = torch.nn.functional.linear
+    mlp = lambda name, t: torch.relu(lin(torch.relu(lin(t, p[name + ".0.weight"], p[name + ".0.bias"])),
+                                         p[name + ".2.weight"], p[name + ".2.bias"]))
+    if "e_func.0.weight" in p:
+        W1 = torch.mul(A.unsqueeze(-1), x.unsqueeze(1))
+        W_new = mlp("e_func", torch.cat((W, W1), dim=-1))
+    else:
+        W_new = W
+    if norm:
+        A = torch.nn.functional.normalize(A, p=1, dim=2)
+    x1 = mlp("n_func", x)
+    x2 = torch.matmul((A.unsqueeze(-1) * W_new).permute(0, 3, 1, 2),
+                      x1.unsqueeze(2).permute(0, 3, 1, 2)).squeeze(-1).transpose(1, 2)
+    x2 = x2 + mlp("n_self_func", x)
+    if "classifier.weight" in p:
+        skc = p["classifier.weight"].shape[0]
+        x3 = lin(x2, p["classifier.weight"], p["classifier.bias"])
+        n1_rep = torch.repeat_interleave(n1, skc, dim=0)
+        n2_rep = torch.repeat_interleave(n2, skc, dim=0)
+        n1m, n2m = int(n1.max()), int(n2.max())
+        x4 = x3.permute(0, 2, 1).reshape(x.shape[0] * skc, n2m, n1m).transpose(1, 2)
+        x5 = sinkhorn(x4, n1_rep, n2_rep, dummy_row=True, max_iter=sk_iter, tau=sk_tau).transpose(2, 1).contiguous()
+        x6 = x5.reshape(x.shape[0], skc, n1m * n2m).permute(0, 2, 1)
+        return W_new, torch.cat((x2, x6), dim=-1)
+    return W_new, x2

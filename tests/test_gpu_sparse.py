@@ -89,3 +89,42 @@ def test_construct_aff_mat_forward_backward(n, ragged):
     eg = (generic.cpu() + torch.diag_embed(Kp.transpose(1, 2).reshape(B, -1)) - Kref.detach()).abs().max().item()
     report("construct_aff_mat", n=n, ragged=ragged, forward=ef, dKe=eke, dKp=ekp, generic_route=eg)
     assert max(ef, eke, ekp, eg) < 1e-5
+
+
+@pytest.mark.parametrize("edge_emb,sk", [(False, 1), (True, 0), (False, 0)])
+def test_dense_gnn_layer_matches_reference_formulation(edge_emb, sk):
+    """GNNLayer (dense NGM-v1 message passing, gnn.py:11-87): forward and gradients of the
+    fused row kernels against the reference's permute + matmul formulation evaluated on the CPU (oracle/ops.py)."""
+    from oracle import ops as oo
+    from src.model.gnn import GNNLayer
+    torch.manual_seed(1)
+    in_n, out_e = (1, 16) if not edge_emb else (8, 8)
+    layer = GNNLayer(in_n, 1, out_e + sk, out_e, sk_channel=sk, sk_iter=20, sk_tau=0.05, edge_emb=edge_emb)
+    g = torch.Generator().manual_seed(2)
+    b, n1m, n2m = 3, 6, 7
+    N = n1m * n2m
+    n1 = torch.tensor([6, 4, 5]); n2 = torch.tensor([7, 7, 3])
+    A = (torch.rand(b, N, N, generator=g) < 0.25).float()
+    A[0, 5] = 0                                                     # an isolated node: row sum 0 -> normalised to 0
+    W = (torch.rand(b, N, N, 1, generator=g) - 0.3) * A.unsqueeze(-1)
+    x = torch.rand(b, N, in_n, generator=g)
+    up = torch.randn(b, N, out_e + sk, generator=g)
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+    Wc = W.clone().requires_grad_(True); xc = x.clone().requires_grad_(True)
+    Wn_ref, xn_ref = oo.gnn_layer_dense(p, A, Wc, xc, n1, n2, True, 20, 0.05)
+    (xn_ref * up).sum().backward()
+    layer = layer.to(DEV)
+    Wd = W.to(DEV).requires_grad_(True); xd = x.to(DEV).requires_grad_(True)
+    Wn, xn = layer(A.to(DEV), Wd, xd, n1.to(DEV), n2.to(DEV), norm=True)
+    (xn * up.to(DEV)).sum().backward()
+    rel = lambda a, r: ((a.detach().cpu() - r.detach()).abs().max() / r.detach().abs().max().clamp_min(1e-12)).item()
+    errs = {"x_new": rel(xn, xn_ref), "W_new": rel(Wn, Wn_ref), "dx": rel(xd.grad, xc.grad), "dW": rel(Wd.grad, Wc.grad)}
+    for k, q in layer.named_parameters():
+        if p[k].grad is not None and p[k].grad.abs().max() > 0:
+            errs["d" + k] = rel(q.grad, p[k].grad)
+    report("dense_gnn_layer", edge_emb=edge_emb, sk=sk, **errs)
+    tol = 2e-3 if sk else 1e-4            # tau = 0.05 Sinkhorn amplifies fp32 rounding of its input
+    assert max(errs.values()) < tol, errs
+    with torch.no_grad():                 # inference path (no autograd) gives the same values
+        _, xn2 = layer(A.to(DEV), W.to(DEV), x.to(DEV), n1.to(DEV), n2.to(DEV))
+    assert (xn2 - xn.detach()).abs().max().item() < 1e-5
