@@ -103,4 +103,12 @@ __device__ __forceinline__ float softplus_torch(float x) {   // beta = 1, thresh
   return x > 20.f ? x : log1pf(expf(x));
 }
 
+// softplus for values nobody reads back at full precision (the dead edge affinities Ke): fast exp / log, absolute
+// error < 3e-6 (x > 8: x + log1p(e^-x) by its series; tiny e^x: series; otherwise log(1 + e^x) with __logf).
+__device__ __forceinline__ float softplus_fast(float x) {
+  if (x > 8.f) { const float u = __expf(-x); return x + u * (1.f - 0.5f * u); }
+  const float t = __expf(x);
+  return t < 1e-3f ? t * (1.f - 0.5f * t) : __logf(1.f + t);
+}
+
 }  // namespace fpm

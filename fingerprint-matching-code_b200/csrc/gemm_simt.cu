@@ -260,7 +260,7 @@ ke_factored_kernel(const float* __restrict__ P, const int64_t* __restrict__ eidx
       if (r < nrow && col_ok) {
         const float* ps = rows + (2 * r) * Cn; const float* pd = ps + Cn;
         const float dot = (ps[s2] - ps[d2]) - (pd[s2] - pd[d2]);
-        v = scale * (softplus_torch(dot) - 0.5f);
+        v = scale * (softplus_fast(dot) - 0.5f);         // Ke feeds nothing: |error| < 2e-6
       }
       out[((size_t)b * e1max + k1) * e2max + k2] = v;
     }
