@@ -5,6 +5,7 @@ reference file (``sbmm``, ``sdd_bmm_torch`` ...) are unreachable from the matchi
 import torch
 
 from fpmatch import ops
+from fpmatch.legacy_ext import bilinear_diag       # noqa: F401  (the reference binds its extension under this name, :12)
 from src.sparse_torch import CSCMatrix3d, CSRMatrix3d
 
 

@@ -13,6 +13,7 @@ import scipy.sparse as ssp
 import torch
 
 from fpmatch import ops
+from fpmatch.legacy_ext import sparse_dot          # noqa: F401  (the reference binds its extension under this name, :10)
 
 
 def _to_tensor(x, dtype, device):

@@ -207,3 +207,21 @@ def test_data_to_cuda_walks_every_container_type():
     assert out["KGHs"][0].shape == (2, 3, 3) and len(seen) > 20
     with pytest.raises(TypeError):
         data_to_cuda({"bad": object()}, device="cpu")
+
+
+def test_legacy_extension_namespaces_and_device_rules():
+    """src.sparse_torch.csx_matrix.sparse_dot / src.sparse.bilinear_diag: the reference's extension objects
+    (csx_matrix.py:10, sparse.py:12) exist with their function names and raise like the originals on the wrong device
+    (sparse_dot.cpp:204,225,242)."""
+    from src.sparse import bilinear_diag
+    from src.sparse_torch.csx_matrix import sparse_dot
+    for name in ("csr_dot_csc_to_csr", "csr_dot_csc_to_dense", "dense_dot_csc_to_dense", "csr_dot_diag_to_csr"):
+        assert callable(getattr(sparse_dot, name))
+    assert callable(bilinear_diag.bilinear_diag)
+    i = torch.zeros(1, dtype=torch.long); d = torch.zeros(1)
+    with pytest.raises(RuntimeError, match="Unexpected cpu tensor in sparse dot sparse -> dense"):
+        sparse_dot.csr_dot_csc_to_dense(i, i, d, i, i, d, 1, 1, 1)
+    with pytest.raises(RuntimeError, match="Unexpected cpu tensor in dense dot sparse -> dense"):
+        sparse_dot.dense_dot_csc_to_dense(torch.zeros(1, 1, 1), i, i, d, 1, 1, 1, 1)
+    with pytest.raises(RuntimeError):
+        sparse_dot.csr_dot_csc_to_csr(i, i, d, i, i, d, 1, 1, 1)

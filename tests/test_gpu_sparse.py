@@ -128,3 +128,31 @@ def test_dense_gnn_layer_matches_reference_formulation(edge_emb, sk):
     with torch.no_grad():                 # inference path (no autograd) gives the same values
         _, xn2 = layer(A.to(DEV), W.to(DEV), x.to(DEV), n1.to(DEV), n2.to(DEV))
     assert (xn2 - xn.detach()).abs().max().item() < 1e-5
+
+
+def test_legacy_extension_namespaces_match_containers():
+    """The reference's raw-tensor entry points (sparse_dot.*, bilinear_diag.bilinear_diag) against the container
+    methods that the parity tests above pin to scipy."""
+    from src.sparse import bilinear_diag, bilinear_diag_torch
+    from src.sparse_torch import CSCMatrix3d, CSRMatrix3d, dot
+    from src.sparse_torch.csx_matrix import sparse_dot
+    B, h, k, w = 3, 13, 19, 7
+    a = CSRMatrix3d(rand_mats(B, h, k, 0.3, 10), shape=(B, h, k)).cuda()
+    b = CSCMatrix3d(rand_mats(B, k, w, 0.3, 11), shape=(B, k, w)).cuda()
+    got = sparse_dot.csr_dot_csc_to_dense(a.indices, a.indptr, a.data, b.indices, b.indptr, b.data, B, h, w)
+    assert torch.equal(got, dot(a, b, dense_output=True))
+    D = torch.randn(B, h, k, generator=torch.Generator().manual_seed(12)).to(DEV)
+    got = sparse_dot.dense_dot_csc_to_dense(D, b.indices, b.indptr, b.data, B, h, w, k)
+    assert torch.equal(got, dot(D, b, dense_output=True))
+    diag = torch.randn(B, k, generator=torch.Generator().manual_seed(13)).to(DEV)
+    ind, ptr, dat = sparse_dot.csr_dot_diag_to_csr(a.indices, a.indptr, a.data, diag, B, h, k)
+    ref = a.dotdiag(diag)
+    assert torch.equal(ind, ref.indices) and torch.equal(ptr, ref.indptr) and torch.equal(dat, ref.data)
+    with pytest.raises(RuntimeError, match="Unexpected cuda tensor"):
+        sparse_dot.csr_dot_csc_to_csr(a.indices, a.indptr, a.data, b.indices, b.indptr, b.data, B, h, w)
+    x, f = 11, 9
+    s1 = CSRMatrix3d(rand_mats(B, x, f, 0.4, 14), shape=(B, x, f)).cuda()
+    s3 = CSCMatrix3d(rand_mats(B, f, x, 0.4, 15), shape=(B, f, x)).cuda()
+    T = torch.randn(B, f, f, generator=torch.Generator().manual_seed(16)).to(DEV)
+    got = bilinear_diag.bilinear_diag(s1.indices, s1.indptr, s1.data, T, s3.indices, s3.indptr, s3.data, B, x)
+    assert torch.equal(got, bilinear_diag_torch(s1, T, s3))
