@@ -54,3 +54,31 @@ class Sinkhorn(nn.Module):
         if matrix_input:
             out = out.squeeze(0)
         return out
+
+
+class GumbelSinkhorn(nn.Module):
+    """
+    Gumbel-Sinkhorn layer (``/root/reference/src/model/sinkhorn.py:172-233``): ``sample_num`` Gumbel-perturbed copies of
+    every score matrix go through the log-domain Sinkhorn above as one batch of ``b * sample_num`` problems.  The noise
+    is drawn with the reference's own expression from torch's generator, so a seeded run sees the same perturbation.
+
+    :param max_iter: maximum iterations (default: ``10``)
+    :param tau: temperature (default: ``1``)
+    :param epsilon: kept for signature compatibility
+    :param batched_operation: accepted and ignored (see ``Sinkhorn``)
+    """
+    def __init__(self, max_iter=10, tau=1., epsilon=1e-4, batched_operation=False):
+        super(GumbelSinkhorn, self).__init__()
+        self.sinkhorn = Sinkhorn(max_iter, tau, epsilon, batched_operation=batched_operation)
+
+    def forward(self, s: Tensor, nrows: Tensor = None, ncols: Tensor = None, sample_num=5, dummy_row=False) -> Tensor:
+        """:return: ``(b * sample_num, n1, n2)`` doubly-stochastic matrices, the samples of one input adjacent."""
+        def sample_gumbel(t_like, eps=1e-20):
+            u = torch.empty_like(t_like).uniform_()
+            return -torch.log(-torch.log(u + eps) + eps)
+
+        s_rep = torch.repeat_interleave(s, sample_num, dim=0)
+        s_rep = s_rep + sample_gumbel(s_rep)
+        nrows_rep = torch.repeat_interleave(nrows, sample_num, dim=0) if nrows is not None else None
+        ncols_rep = torch.repeat_interleave(ncols, sample_num, dim=0) if ncols is not None else None
+        return self.sinkhorn(s_rep, nrows_rep, ncols_rep, dummy_row)

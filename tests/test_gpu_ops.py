@@ -580,3 +580,22 @@ def test_match_classifier_fused_equals_stock_module(ops, B, H, W):
     # training mode / autograd keep the stock path
     md.train()
     assert md.forward_product(s.to(DEV), x.to(DEV)).requires_grad
+
+
+def test_gumbel_sinkhorn_matches_seeded_reference_expression(oo):
+    """GumbelSinkhorn (sinkhorn.py:172-233): the same seeded Gumbel noise pushed through the oracle's Sinkhorn."""
+    from src.model.sinkhorn import GumbelSinkhorn
+    g = torch.Generator().manual_seed(5)
+    s = torch.randn(3, 9, 11, generator=g).to(DEV)
+    n1 = torch.tensor([9, 7, 5]); n2 = torch.tensor([11, 11, 8])
+    layer = GumbelSinkhorn(max_iter=10, tau=0.5)
+    torch.manual_seed(123)
+    out = layer(s, n1.to(DEV), n2.to(DEV), sample_num=4, dummy_row=True)
+    torch.manual_seed(123)
+    s_rep = torch.repeat_interleave(s, 4, dim=0)
+    u = torch.empty_like(s_rep).uniform_()
+    s_rep = s_rep - torch.log(-torch.log(u + 1e-20) + 1e-20)
+    ref = oo.sinkhorn(s_rep.cpu(), torch.repeat_interleave(n1, 4), torch.repeat_interleave(n2, 4), dummy_row=True,
+                      max_iter=10, tau=0.5)
+    assert out.shape == (12, 9, 11)
+    assert (out.cpu() - ref).abs().max().item() < 1e-5
