@@ -174,3 +174,26 @@ def test_graph_oracle_matches_scipy_delaunay():
     perm = np.eye(30, dtype=np.float32)[rng.permutation(30)]
     A2, _, _ = og.permute_adjacency(A, perm)
     assert (A2 == perm.T @ A @ perm).all()
+
+
+def test_dense_gnn_layer_oracle_equals_einsum():
+    """oracle.ops.gnn_layer_dense keeps the reference's permute + matmul expression (gnn.py:66); an independent einsum
+    of the same sum must agree, for the single-channel edge tensor and for one channel per node feature."""
+    torch.manual_seed(0)
+    b, N, F_ = 2, 12, 4
+    A = (torch.rand(b, N, N) < 0.3).float()
+    x = torch.rand(b, N, 3)
+    lin = lambda i, o: (torch.randn(o, i) * 0.3, torch.randn(o) * 0.1)
+    p = {}
+    for name, i in (("n_func", 3), ("n_self_func", 3)):
+        p[name + ".0.weight"], p[name + ".0.bias"] = lin(i, F_)
+        p[name + ".2.weight"], p[name + ".2.bias"] = lin(F_, F_)
+    mlp = lambda name, t: torch.relu(torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(
+        t, p[name + ".0.weight"], p[name + ".0.bias"])), p[name + ".2.weight"], p[name + ".2.bias"]))
+    An = torch.nn.functional.normalize(A, p=1, dim=2)
+    for fe in (1, F_):
+        W = torch.rand(b, N, N, fe)
+        _, out = oo.gnn_layer_dense(p, A, W, x, torch.tensor([3, 3]), torch.tensor([4, 4]), True)
+        x1 = mlp("n_func", x)
+        ref = torch.einsum("bij,bijc,bjc->bic", An, W.expand(b, N, N, F_), x1) + mlp("n_self_func", x)
+        assert (out - ref).abs().max() < 1e-5
