@@ -17,20 +17,101 @@
 
 namespace fpm {
 
-// In-neighbour lists from the per-pair edge tables [B, 2, emax] (int32, -1 padded; row 0 = G-node
-// (source), row 1 = H-node (target) of every G/H column).  One CTA per pair, one WARP per destination node: the edge
-// table is walked 32 columns at a time and the hits are compacted in column order with a ballot -> deterministic.
-// (Thread-per-destination full scans took 0.27 ms per launch at 400 keypoints.)
-// in_ptr: [B, nmax + 1] (offsets local to the pair), in_src: [B, emax].
+// ------------------------------------------------------------------------------------------
+// Effective association structure of a pair (what the reference's index lists actually describe).
+//
+// gmdataset.py:623-642 hands the model idxG = CSC indices of kron(G2, G1) and idxH = those of kron(H2, H1): one entry
+// per NON-ZERO column, each matrix eliminating its own zero columns.  With a complete edge table the t-th entries of
+// both lists belong to the same column t = k2*e1 + k1 and the association edge is (src2[k2], src1[k1]) ->
+// (dst2[k2], dst1[k1]).  With a PARTIAL ground-truth permutation (gmdataset.py:345-352: G2 = perm^T G1, H2 = perm^T H1)
+// G2 loses the columns whose source keypoint has no counterpart and H2 those whose target has none, so the t-th
+// entries pair the a-th surviving G2 column with the a-th surviving H2 column: still a Kronecker structure, over the
+// "effective" edge list (src2[gv(a)], dst2[hv(a)]).  ngm.py:333-342 then cuts [idx; 0..n1 n2-1] to
+// common_len = min(len(row), len(col), e1_pyg*e2_pyg + n1*n2) (K_value is built from the PyG edge lists), which can
+// drop the tail of the diagonal block and, if the lists are long enough, end inside a Kronecker column block.
+// Per pair this kernel emits
+//   eff1 / eff2 [2, emax]  effective edge tables (sources and targets compacted independently, -1 padded); eff2 holds
+//                          only the column blocks that survive the cut completely,
+//   part = (ps2, pd2, ccut, 0): the block the cut ends in - graph-2 edge ps2 -> pd2 combined with the graph-1 edges
+//                          c < ccut only (ccut = 0: none),
+//   ndiag                  number of diagonal (self-loop) entries that survive: association nodes p < ndiag,
+//   status bit 0           the G / H lists of a graph have different lengths (asymmetric adjacency): the reference's
+//                          pairing is then not a Kronecker structure; min(len) columns are used and the bit is set.
+// For complete tables eff == edges, ndiag = n1*n2, ccut = 0.  One CTA per pair, one warp per list.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+assoc_effective_kernel(const int* __restrict__ edges1, const int* __restrict__ edges2,
+                       const int64_t* __restrict__ eptr1, const int64_t* __restrict__ eptr2,
+                       const int64_t* __restrict__ n1, const int64_t* __restrict__ n2, int* __restrict__ eff1,
+                       int* __restrict__ eff2, int64_t* __restrict__ ndiag, int* __restrict__ part,
+                       int* __restrict__ status, int e1max, int e2max) {
+  extern __shared__ int sh[];            // gs1[e1max] hd1[e1max] gs2[e2max] hd2[e2max]
+  __shared__ int cnt[4];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* lists[4] = {sh, sh + e1max, sh + 2 * e1max, sh + 2 * e1max + e2max};
+  {
+    const int emax = warp < 2 ? e1max : e2max;
+    const int* src = (warp < 2 ? edges1 + (size_t)b * 2 * e1max : edges2 + (size_t)b * 2 * e2max) + (warp & 1) * emax;
+    int* out = lists[warp];
+    int w = 0;
+    for (int k0 = 0; k0 < emax; k0 += 32) {
+      const int k = k0 + lane;
+      const int v = k < emax ? src[k] : -1;
+      const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+      if (v >= 0) out[w + __popc(m & ((1u << lane) - 1u))] = v;
+      w += __popc(m);
+    }
+    if (lane == 0) cnt[warp] = w;
+  }
+  __syncthreads();
+  const int E1 = min(cnt[0], cnt[1]), E2 = min(cnt[2], cnt[3]);
+  const long long L = (long long)E1 * E2;
+  const long long nd = (long long)n1[b] * (long long)n2[b];
+  const long long lval = (eptr1[b + 1] - eptr1[b]) * (eptr2[b + 1] - eptr2[b]) + nd;
+  const long long common = min(L + nd, lval);
+  const long long cut = min(L, common);
+  const int afull = E1 > 0 ? (int)(cut / E1) : 0;
+  const int ccut = E1 > 0 ? (int)(cut % E1) : 0;
+  for (int k = threadIdx.x; k < e1max; k += blockDim.x) {
+    const bool in = k < E1;
+    eff1[(size_t)b * 2 * e1max + k] = in ? lists[0][k] : -1;
+    eff1[(size_t)b * 2 * e1max + e1max + k] = in ? lists[1][k] : -1;
+  }
+  for (int k = threadIdx.x; k < e2max; k += blockDim.x) {
+    const bool in = k < afull;
+    eff2[(size_t)b * 2 * e2max + k] = in ? lists[2][k] : -1;
+    eff2[(size_t)b * 2 * e2max + e2max + k] = in ? lists[3][k] : -1;
+  }
+  if (threadIdx.x == 0) {
+    long long d = common - L;
+    ndiag[b] = d < 0 ? 0 : (d > nd ? nd : d);
+    const bool has = afull < E2 && ccut > 0;
+    part[b * 4 + 0] = has ? lists[2][afull] : -1;
+    part[b * 4 + 1] = has ? lists[3][afull] : -1;
+    part[b * 4 + 2] = has ? ccut : 0;
+    part[b * 4 + 3] = 0;
+    if (cnt[0] != cnt[1] || cnt[2] != cnt[3]) atomicOr(status, 1);
+  }
+}
+
+// In-neighbour lists from per-pair edge tables [B, 2, emax] (int32, -1 padded; row 0 = G-node (source), row 1 =
+// H-node (target) of every column; a column counts only if BOTH ends are present).  One CTA per pair, one WARP per
+// destination node: the edge table is walked 32 columns at a time and the hits are compacted in column order with a
+// ballot -> deterministic, ascending column ids inside every list.
+// in_ptr: [B, nmax + 1] (offsets local to the pair), in_src: [B, emax], in_col (optional): [B, emax] column ids.
 constexpr int kAssocThreads = 512;
 __global__ void __launch_bounds__(kAssocThreads)
-assoc_in_csr_kernel(const int* __restrict__ edges, int* __restrict__ in_ptr, int* __restrict__ in_src, int nmax,
-                    int emax) {
+assoc_in_csr_kernel(const int* __restrict__ edges, int* __restrict__ in_ptr, int* __restrict__ in_src,
+                    int* __restrict__ in_col, int nmax, int emax) {
   extern __shared__ int sh[];            // [2 * emax] edge table, then [nmax + 1] counts
   int* ssrc = sh; int* sdst = sh + emax; int* cnt = sh + 2 * emax;
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int* eb = edges + (size_t)b * 2 * emax;
-  for (int k = threadIdx.x; k < emax; k += blockDim.x) { ssrc[k] = eb[k]; sdst[k] = eb[emax + k]; }
+  for (int k = threadIdx.x; k < emax; k += blockDim.x) {
+    const int s_ = eb[k], d_ = eb[emax + k];
+    ssrc[k] = s_;
+    sdst[k] = (s_ >= 0 && s_ < nmax) ? d_ : -1;      // a column without a valid source end is no edge
+  }
   __syncthreads();
   for (int j = warp; j < nmax; j += nwarps) {
     int c = 0;
@@ -65,7 +146,11 @@ assoc_in_csr_kernel(const int* __restrict__ edges, int* __restrict__ in_ptr, int
       const int k = k0 + lane;
       const bool hit = k < emax && sdst[k] == j;
       const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) in_src[(size_t)b * emax + w + __popc(m & ((1u << lane) - 1u))] = ssrc[k];
+      if (hit) {
+        const size_t o = (size_t)b * emax + w + __popc(m & ((1u << lane) - 1u));
+        in_src[o] = ssrc[k];
+        if (in_col) in_col[o] = k;
+      }
       w += __popc(m);
     }
   }
@@ -82,13 +167,13 @@ struct GnnWeights {
 constexpr int kF = 16;   // GNN_FEAT, ngm.py:47
 
 // The layer's weights live in CONSTANT memory during the forward: every thread of a warp multiplies by the same
-// weight, so the FMAs take it as a constant-bank operand and stage 2 issues no load at all for it.  (With the
-// weights in shared memory the kernel spent 27 % of its warp samples waiting on LDS and 18 % on the dependent
-// FMAs behind them, at 12 warps per SM - r1c ncu source view.)  Layout for row padding CP (4 or 20):
+// weight, so the FMAs take it as a constant-bank operand and issue no load at all for it.  (With the weights in
+// shared memory the kernel spent 27 % of its warp samples waiting on LDS and 18 % on the dependent FMAs behind
+// them - r1c ncu source view.)  Layout for row padding CP (4 or 20):
 //   wl[16][CP] wr[16][CP] w0[16][CP] w2[16][16] bl[16] b0[16] b2[16] wc[16] cb
 // gnn_pack_weights_kernel writes that layout into a device staging buffer and one cudaMemcpyToSymbolAsync
-// (device to device, stream ordered) publishes it before the layer kernel; calls on one stream are ordered,
-// concurrent forwards on different streams of one process are not supported.
+// (device to device, stream ordered) publishes it before the layer kernel.  The bank is one per device: launches
+// from different streams are serialised against each other with an event (gnn_publish_weights).
 constexpr int kGnnConstFloats = 3 * 16 * 20 + 16 * 16 + 4 * 16 + 4;
 __constant__ float c_gnn[kGnnConstFloats];
 
@@ -118,49 +203,29 @@ __global__ void gnn_pack_weights_kernel(GnnWeights w, float* __restrict__ stagin
   if (tid == 0) staging[O::cb] = w.cls_b[0];
 }
 
-// CIN = 1 (layer 0: emb = vec(Kp)) or 17 (x1 of the previous layer + its Sinkhorn channel).
-// xprev:   [B, N, 16]   (CIN == 17 only), N = n1max*n2max, p = i2*n1max + i1
-// mprev_t: [B, n2max, n1max]  the matrix channel in p order (Kp^T or Sinkhorn^T)
-// xout:    [B, N, 16];  score: [B, n1max, n2max] (classifier output, Sinkhorn-ready layout)
+// Stage 1 of a (pair, j2) CTA, shared by the forward and backward kernels:
+//   Rsum[i1, c] = sum_{i2 in In2(j2)} feat[(i2, i1), c]     (feat = 16 channels of xprev + the matrix channel)
+//   Rp[i1, c]   = feat[(ps2, i1), c]  when the pair's cut-off block targets this j2 (see assoc_effective_kernel)
+// Each source row (i2, :) is contiguous ([n1max][16] floats + [n1max] for the matrix channel): it is streamed with
+// independent 128-bit loads, accumulated over In2(j2) in registers.
 template <int CIN>
-__global__ void __launch_bounds__(128, 3)
-gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mprev_t,
-                 const int* __restrict__ in_ptr1, const int* __restrict__ in_src1,
-                 const int* __restrict__ in_ptr2, const int* __restrict__ in_src2,
-                 const int64_t* __restrict__ n1, const int64_t* __restrict__ n2,
-                 float* __restrict__ xout, float* __restrict__ score, int n1max, int n2max, int e1max,
-                 int e2max) {
-  // Shared layout: the partial sums are padded to CP floats per row (a multiple of 4) and read as 128-bit
-  // broadcasts.
+__device__ __forceinline__ void gnn_stage1(const float* __restrict__ xb, const float* __restrict__ mb,
+                                           const int* __restrict__ is2, int beg2, int end2, int ps2,
+                                           float* __restrict__ Rsum, float* __restrict__ Rp, int n1max) {
   constexpr int CP = (CIN + 3) / 4 * 4;
-  extern __shared__ __align__(16) float sm[];
-  float* Rsum = sm;                               // [n1max][CP] sum over In2(j2) rows
-  using O = GnnOff<CP>;                             // weights: constant bank c_gnn (see above)
-  const int b = blockIdx.y, j2 = blockIdx.x;
-  const int N = n1max * n2max;
-  const int tid = threadIdx.x;
-
-  // ---- stage 1: Rsum[i1, c] = sum_{i2 in In2(j2)} feat[(i2, i1), c]
-  const int* ip2 = in_ptr2 + (size_t)b * (n2max + 1);
-  const int beg2 = ip2[j2], end2 = ip2[j2 + 1];
-  const int* is2 = in_src2 + (size_t)b * e2max;
-  const float* xb = (CIN > 1) ? xprev + (size_t)b * N * kF : nullptr;
-  const float* mb = mprev_t + (size_t)b * N;
-  // Each source row (i2, :) is contiguous ([n1max][16] floats + [n1max] for the matrix channel): stream it
-  // with independent 128-bit loads, 4 per thread in flight, accumulating over In2(j2) in registers.  (The
-  // first version walked In2 per element with dependent scalar loads and was latency-bound: 1.6 ms/layer.)
+  const int tid = threadIdx.x, nt = blockDim.x;
   if (CIN > 1) {
     const int nvec = n1max * (kF / 4);
-    for (int f0 = 0; f0 < nvec; f0 += 4 * blockDim.x) {
-      float4 acc[4];
+    for (int f0 = 0; f0 < nvec; f0 += 2 * nt) {
+      float4 acc[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
+      for (int u = 0; u < 2; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 3
       for (int q = beg2; q < end2; ++q) {
         const float4* row = (const float4*)(xb + (size_t)is2[q] * n1max * kF);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int f = f0 + u * blockDim.x + tid;
+        for (int u = 0; u < 2; ++u) {
+          const int f = f0 + u * nt + tid;
           if (f < nvec) {
             const float4 v = row[f];
             acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
@@ -168,94 +233,254 @@ gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mpre
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int f = f0 + u * blockDim.x + tid;
+      for (int u = 0; u < 2; ++u) {
+        const int f = f0 + u * nt + tid;
         if (f < nvec) *(float4*)&Rsum[(size_t)(f >> 2) * CP + (f & 3) * 4] = acc[u];
       }
     }
+    if (ps2 >= 0) {
+      const float4* row = (const float4*)(xb + (size_t)ps2 * n1max * kF);
+      for (int f = tid; f < nvec; f += nt) *(float4*)&Rp[(size_t)(f >> 2) * CP + (f & 3) * 4] = row[f];
+    }
   }
-  for (int i1 = tid; i1 < n1max; i1 += blockDim.x) {
+  for (int i1 = tid; i1 < n1max; i1 += nt) {
     float a = 0.f;
 #pragma unroll 4
     for (int q = beg2; q < end2; ++q) a += mb[(size_t)is2[q] * n1max + i1];
     Rsum[(size_t)i1 * CP + (CIN - 1)] = a;
 #pragma unroll
     for (int c = CIN; c < CP; ++c) Rsum[(size_t)i1 * CP + c] = 0.f;
+    if (ps2 >= 0) {
+      Rp[(size_t)i1 * CP + (CIN - 1)] = mb[(size_t)ps2 * n1max + i1];
+#pragma unroll
+      for (int c = CIN; c < CP; ++c) Rp[(size_t)i1 * CP + c] = 0.f;
+    }
   }
-  __syncthreads();
+}
 
-  // ---- stage 2: one thread per node (j2, j1)
-  const int n1b = (int)n1[b], n2b = (int)n2[b];
-  const long long ndiag = (long long)n1b * (long long)n2b;
+// own[] (the node's input features) and agg[] (mean over its association in-neighbours) of node (j2, j1); returns
+// the divisor and whether the node carries a self loop.  Shared by the forward and backward kernels.
+template <int CIN>
+__device__ __forceinline__ float gnn_node_inputs(const float* __restrict__ xb, const float* __restrict__ mb,
+                                                 const float* __restrict__ Rsum, const float* __restrict__ Rp,
+                                                 const int* __restrict__ ip1, const int* __restrict__ is1,
+                                                 const int* __restrict__ ic1, int j1, size_t p, int d2, int ccut,
+                                                 long long ndiag, float* own, float* agg, bool& self) {
+  constexpr int CP = (CIN + 3) / 4 * 4;
+#pragma unroll
+  for (int c = 0; c < CP; ++c) { own[c] = 0.f; agg[c] = 0.f; }
+  if (CIN > 1) {
+    const float4* xp = (const float4*)(xb + p * kF);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float4 v = xp[t];
+      own[t * 4] = v.x; own[t * 4 + 1] = v.y; own[t * 4 + 2] = v.z; own[t * 4 + 3] = v.w;
+    }
+  }
+  own[CIN - 1] = mb[p];
+  const int beg1 = ip1[j1], end1 = ip1[j1 + 1];
+  for (int q = beg1; q < end1; ++q) {
+    const float4* r = (const float4*)(Rsum + (size_t)is1[q] * CP);
+#pragma unroll
+    for (int t = 0; t < CP / 4; ++t) {
+      const float4 v = r[t];
+      agg[t * 4] += v.x; agg[t * 4 + 1] += v.y; agg[t * 4 + 2] += v.z; agg[t * 4 + 3] += v.w;
+    }
+  }
+  long long cnt = (long long)d2 * (long long)(end1 - beg1);
+  if (ccut > 0) {                                   // CTA-uniform: the cut-off block of this pair targets j2
+    for (int q = beg1; q < end1; ++q) {
+      if (ic1[q] < ccut) {
+        const float4* r = (const float4*)(Rp + (size_t)is1[q] * CP);
+#pragma unroll
+        for (int t = 0; t < CP / 4; ++t) {
+          const float4 v = r[t];
+          agg[t * 4] += v.x; agg[t * 4 + 1] += v.y; agg[t * 4 + 2] += v.z; agg[t * 4 + 3] += v.w;
+        }
+        cnt += 1;
+      }
+    }
+  }
+  self = (long long)p < ndiag;
+  if (self) {
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) agg[c] += own[c];
+    cnt += 1;
+  }
+  const float inv = cnt > 0 ? (float)cnt : 1.f;
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) agg[c] = agg[c] / inv;
+  return inv;
+}
+
+// One NGM layer.  CIN = 1 (layer 0: emb = vec(Kp)) or 17 (x1 of the previous layer + its Sinkhorn channel).
+// xprev:   [B, N, 16]   (CIN == 17 only), N = n1max*n2max, p = i2*n1max + i1
+// mprev_t: [B, n2max, n1max]  the matrix channel in p order (Kp^T or Sinkhorn^T)
+// xout:    [B, N, 16];  score: [B, n1max, n2max] (classifier output, Sinkhorn-ready layout)
+// One CTA per (pair, j2), 256 threads = 4 node warps x 2 halves: warp w works on nodes 32*(w>>1) .. +31 and
+// computes output channels 8*(w&1) .. +7 of them, so a node's 1 216 FMAs are split over two threads of two different
+// warps (the half index is warp-uniform -> constant-bank weight operands keep compile-time offsets).  Order:
+//   A  own features -> this half of h0 = relu(W0 own + b0) -> shared memory          (does not depend on stage 1)
+//   B  stage 1: row sums over In2(j2) into shared memory                             (L2 reads)
+//   C  barrier;  D  aggregate over In1(j1), the 8 outputs, half of the classifier dot product
+// The first version ran one thread per node with all 16 outputs: 128 registers, 12 warps per SM, stage 1 and the
+// FMAs of a CTA strictly one after the other (0.49 ms per layer at 256 pairs x 100 keypoints).
+constexpr int kGnnThreads = 256;
+constexpr int kGnnNodes = 128;       // nodes per pass = kGnnThreads / 2
+
+template <int CIN, int H>
+__device__ __forceinline__ void gnn_half_h0(const float* own, float* hx_slot) {
+  constexpr int CP = (CIN + 3) / 4 * 4;
+  using O = GnnOff<CP>;
+  float hh[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    float a = c_gnn[O::b0 + 8 * H + o];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) a = fmaf(c_gnn[O::w0 + (8 * H + o) * CP + c], own[c], a);
+    hh[o] = fmaxf(a, 0.f);
+  }
+  *(float4*)(hx_slot + 8 * H) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+  *(float4*)(hx_slot + 8 * H + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
+}
+
+template <int CIN, int H>
+__device__ __forceinline__ float gnn_half_out(const float* own, const float* agg, const float* hx_slot,
+                                              float* __restrict__ xo) {
+  constexpr int CP = (CIN + 3) / 4 * 4;
+  using O = GnnOff<CP>;
+  float h[kF];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float4 v = *(const float4*)(hx_slot + 4 * t);
+    h[4 * t] = v.x; h[4 * t + 1] = v.y; h[4 * t + 2] = v.z; h[4 * t + 3] = v.w;
+  }
+  float x1[8];
+  float sc = 0.f;
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    float a = c_gnn[O::bl + 8 * H + o];
+    float r = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      a = fmaf(c_gnn[O::wl + (8 * H + o) * CP + c], agg[c], a);
+      r = fmaf(c_gnn[O::wr + (8 * H + o) * CP + c], own[c], r);
+    }
+    float s2 = c_gnn[O::b2 + 8 * H + o];
+#pragma unroll
+    for (int c = 0; c < kF; ++c) s2 = fmaf(c_gnn[O::w2 + (8 * H + o) * kF + c], h[c], s2);
+    const float v = (a + r) + fmaxf(s2, 0.f);
+    x1[o] = v;
+    sc = fmaf(c_gnn[O::wc + 8 * H + o], v, sc);
+  }
+  *(float4*)(xo + 8 * H) = make_float4(x1[0], x1[1], x1[2], x1[3]);
+  *(float4*)(xo + 8 * H + 4) = make_float4(x1[4], x1[5], x1[6], x1[7]);
+  return sc;
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(kGnnThreads, 3)
+gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mprev_t,
+                 const int* __restrict__ in_ptr1, const int* __restrict__ in_src1, const int* __restrict__ in_col1,
+                 const int* __restrict__ in_ptr2, const int* __restrict__ in_src2,
+                 const int64_t* __restrict__ ndiag_p, const int* __restrict__ part,
+                 float* __restrict__ xout, float* __restrict__ score, int n1max, int n2max, int e1max,
+                 int e2max) {
+  constexpr int CP = (CIN + 3) / 4 * 4;
+  using O = GnnOff<CP>;
+  extern __shared__ __align__(16) float sm[];
+  float* Rsum = sm;                               // [n1max][CP] sum over In2(j2) rows
+  float* Rp = Rsum + (size_t)n1max * CP;          // [n1max][CP] row of the cut-off block (rarely used)
+  float* hx = Rp + (size_t)n1max * CP;            // [kGnnNodes][16] h0 exchange between the two halves
+  float* sx = hx + kGnnNodes * kF;                // [kGnnNodes] partial classifier dot products of half 1
+  const int b = blockIdx.y, j2 = blockIdx.x;
+  const int N = n1max * n2max;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp & 1;
+  const int slot = (warp >> 1) * 32 + lane;       // node slot of this thread inside a pass
+
+  const int* ip2 = in_ptr2 + (size_t)b * (n2max + 1);
+  const int beg2 = ip2[j2], end2 = ip2[j2 + 1];
+  const int* is2 = in_src2 + (size_t)b * e2max;
+  const float* xb = (CIN > 1) ? xprev + (size_t)b * N * kF : nullptr;
+  const float* mb = mprev_t + (size_t)b * N;
+  int ps2 = -1, ccut = 0;
+  if (part != nullptr && part[b * 4 + 1] == j2) { ps2 = part[b * 4]; ccut = part[b * 4 + 2]; }
+  if (ccut <= 0) ps2 = -1;
+  const long long ndiag = ndiag_p[b];
   const int* ip1 = in_ptr1 + (size_t)b * (n1max + 1);
   const int* is1 = in_src1 + (size_t)b * e1max;
+  const int* ic1 = in_col1 != nullptr ? in_col1 + (size_t)b * e1max : nullptr;
   const int d2 = end2 - beg2;
-  for (int j1 = tid; j1 < n1max; j1 += blockDim.x) {
-    const size_t p = (size_t)j2 * n1max + j1;
-    float own[CP], agg[CP];
-#pragma unroll
-    for (int c = 0; c < CP; ++c) { own[c] = 0.f; agg[c] = 0.f; }
-    if (CIN > 1) {
-      const float4* xp = (const float4*)(xb + p * kF);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float4 v = xp[t];
-        own[t * 4] = v.x; own[t * 4 + 1] = v.y; own[t * 4 + 2] = v.z; own[t * 4 + 3] = v.w;
-      }
-    }
-    own[CIN - 1] = mb[p];
-    const int beg1 = ip1[j1], end1 = ip1[j1 + 1];
-    for (int q = beg1; q < end1; ++q) {
-      const float4* r = (const float4*)(Rsum + (size_t)is1[q] * CP);
-#pragma unroll
-      for (int t = 0; t < CP / 4; ++t) {
-        const float4 v = r[t];
-        agg[t * 4] += v.x; agg[t * 4 + 1] += v.y; agg[t * 4 + 2] += v.z; agg[t * 4 + 3] += v.w;
-      }
-    }
-    long long cnt = (long long)d2 * (long long)(end1 - beg1);
-    if ((long long)p < ndiag) {
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) agg[c] += own[c];
-      cnt += 1;
-    }
-    const float inv = cnt > 0 ? (float)cnt : 1.f;
-#pragma unroll
-    for (int c = 0; c < CIN; ++c) agg[c] = agg[c] / inv;
 
-    // padded lanes (c >= CIN) multiply zeros: fmaf(0, 0, a) == a, so the sums keep their c-order value
-    float h[kF];
+  for (int base = 0; base < n1max; base += kGnnNodes) {
+    const int j1 = base + slot;
+    const bool live = j1 < n1max;
+    const size_t p = (size_t)j2 * n1max + (live ? j1 : 0);
+    float own[CP];
+    // ---- A: own features, this half of h0
 #pragma unroll
-    for (int o = 0; o < kF; ++o) {
-      float a = c_gnn[O::b0 + o];
+    for (int c = 0; c < CP; ++c) own[c] = 0.f;
+    if (live) {
+      if (CIN > 1) {
+        const float4* xp = (const float4*)(xb + p * kF);
 #pragma unroll
-      for (int c = 0; c < CP; ++c) a = fmaf(c_gnn[O::w0 + o * CP + c], own[c], a);
-      h[o] = fmaxf(a, 0.f);
-    }
-    float x1[kF];
-    float sc = c_gnn[O::cb];
-#pragma unroll
-    for (int o = 0; o < kF; ++o) {
-      float a = c_gnn[O::bl + o];
-      float r = 0.f;
-#pragma unroll
-      for (int c = 0; c < CP; ++c) {
-        a = fmaf(c_gnn[O::wl + o * CP + c], agg[c], a);
-        r = fmaf(c_gnn[O::wr + o * CP + c], own[c], r);
+        for (int t = 0; t < 4; ++t) {
+          const float4 v = xp[t];
+          own[t * 4] = v.x; own[t * 4 + 1] = v.y; own[t * 4 + 2] = v.z; own[t * 4 + 3] = v.w;
+        }
       }
-      float s2 = c_gnn[O::b2 + o];
-#pragma unroll
-      for (int c = 0; c < kF; ++c) s2 = fmaf(c_gnn[O::w2 + o * kF + c], h[c], s2);
-      const float v = (a + r) + fmaxf(s2, 0.f);
-      x1[o] = v;
-      sc = fmaf(c_gnn[O::wc + o], v, sc);
+      own[CIN - 1] = mb[p];
+      if (half == 0) gnn_half_h0<CIN, 0>(own, hx + slot * kF); else gnn_half_h0<CIN, 1>(own, hx + slot * kF);
     }
-    float4* dst = (float4*)(xout + ((size_t)b * N + p) * kF);
-    dst[0] = make_float4(x1[0], x1[1], x1[2], x1[3]);
-    dst[1] = make_float4(x1[4], x1[5], x1[6], x1[7]);
-    dst[2] = make_float4(x1[8], x1[9], x1[10], x1[11]);
-    dst[3] = make_float4(x1[12], x1[13], x1[14], x1[15]);
-    score[((size_t)b * n1max + j1) * n2max + j2] = sc;
+    // ---- B: stage 1 (once per CTA)
+    if (base == 0) gnn_stage1<CIN>(xb, mb, is2, beg2, end2, ps2, Rsum, Rp, n1max);
+    __syncthreads();
+    // ---- D: aggregate, outputs
+    float sc = 0.f;
+    if (live) {
+      float agg[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) agg[c] = 0.f;
+      const int beg1 = ip1[j1], end1 = ip1[j1 + 1];
+      for (int q = beg1; q < end1; ++q) {
+        const float4* r = (const float4*)(Rsum + (size_t)is1[q] * CP);
+#pragma unroll
+        for (int t = 0; t < CP / 4; ++t) {
+          const float4 v = r[t];
+          agg[t * 4] += v.x; agg[t * 4 + 1] += v.y; agg[t * 4 + 2] += v.z; agg[t * 4 + 3] += v.w;
+        }
+      }
+      long long cnt = (long long)d2 * (long long)(end1 - beg1);
+      if (ps2 >= 0) {                               // CTA-uniform, rare: the cut-off block targets this j2
+        for (int q = beg1; q < end1; ++q) {
+          if (ic1[q] < ccut) {
+            const float4* r = (const float4*)(Rp + (size_t)is1[q] * CP);
+#pragma unroll
+            for (int t = 0; t < CP / 4; ++t) {
+              const float4 v = r[t];
+              agg[t * 4] += v.x; agg[t * 4 + 1] += v.y; agg[t * 4 + 2] += v.z; agg[t * 4 + 3] += v.w;
+            }
+            cnt += 1;
+          }
+        }
+      }
+      if ((long long)p < ndiag) {
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) agg[c] += own[c];
+        cnt += 1;
+      }
+      const float inv = cnt > 0 ? (float)cnt : 1.f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) agg[c] = agg[c] / inv;
+      float* xo = xout + ((size_t)b * N + p) * kF;
+      if (half == 0) sc = gnn_half_out<CIN, 0>(own, agg, hx + slot * kF, xo);
+      else sc = gnn_half_out<CIN, 1>(own, agg, hx + slot * kF, xo);
+      if (half == 1) sx[slot] = sc;
+    }
+    __syncthreads();
+    if (live && half == 0)
+      score[((size_t)b * n1max + j1) * n2max + j2] = (c_gnn[O::cb] + sc) + sx[slot];
   }
 }
 
@@ -298,8 +523,9 @@ template <int CIN>
 __global__ void __launch_bounds__(128, 2)
 gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ mprev_t,
                      const int* __restrict__ in_ptr1, const int* __restrict__ in_src1,
+                     const int* __restrict__ in_col1,
                      const int* __restrict__ in_ptr2, const int* __restrict__ in_src2,
-                     const int64_t* __restrict__ n1, const int64_t* __restrict__ n2,
+                     const int64_t* __restrict__ ndiag_p, const int* __restrict__ part,
                      const float* __restrict__ dxout, const float* __restrict__ dscore,
                      float* __restrict__ dxprev, float* __restrict__ dm, float* __restrict__ gagg,
                      float* __restrict__ grads, int n1max, int n2max, int e1max, int e2max) {
@@ -315,7 +541,8 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
   const int b = blockIdx.y, j2 = blockIdx.x;
   const int N = n1max * n2max;
   const int tid = threadIdx.x;
-  float* V = sm + (size_t)n1max * CP;              // [128][VS]
+  float* Rp = sm + (size_t)n1max * CP;             // [n1max][CP] row of the cut-off block
+  float* V = sm + (size_t)2 * n1max * CP;          // [128][VS]
   short* qlo = (short*)(V + 128 * VS);   // [NQ]
   short* qro = qlo + NQ;
   // weight-gradient task table: entry q = <left vector component, right vector component>
@@ -340,30 +567,16 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
   const int* is2 = in_src2 + (size_t)b * e2max;
   const float* xb = (CIN > 1) ? xprev + (size_t)b * N * kF : nullptr;
   const float* mb = mprev_t + (size_t)b * N;
-  if (CIN > 1) {
-    const int nvec = n1max * (kF / 4);
-    for (int f = tid; f < nvec; f += blockDim.x) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = beg2; q < end2; ++q) {
-        const float4 v = ((const float4*)(xb + (size_t)is2[q] * n1max * kF))[f];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
-      *(float4*)&Rsum[(size_t)(f >> 2) * CP + (f & 3) * 4] = acc;
-    }
-  }
-  for (int i1 = tid; i1 < n1max; i1 += blockDim.x) {
-    float a = 0.f;
-    for (int q = beg2; q < end2; ++q) a += mb[(size_t)is2[q] * n1max + i1];
-    Rsum[(size_t)i1 * CP + (CIN - 1)] = a;
-#pragma unroll
-    for (int c = CIN; c < CP; ++c) Rsum[(size_t)i1 * CP + c] = 0.f;
-  }
+  int ps2 = -1, ccut = 0;
+  if (part != nullptr && part[b * 4 + 1] == j2) { ps2 = part[b * 4]; ccut = part[b * 4 + 2]; }
+  if (ccut <= 0) { ps2 = -1; ccut = 0; }
+  gnn_stage1<CIN>(xb, mb, is2, beg2, end2, ps2, Rsum, Rp, n1max);
   __syncthreads();
 
-  const int n1b = (int)n1[b], n2b = (int)n2[b];
-  const long long ndiag = (long long)n1b * (long long)n2b;
+  const long long ndiag = ndiag_p[b];
   const int* ip1 = in_ptr1 + (size_t)b * (n1max + 1);
   const int* is1 = in_src1 + (size_t)b * e1max;
+  const int* ic1 = in_col1 != nullptr ? in_col1 + (size_t)b * e1max : nullptr;
   const int d2 = end2 - beg2;
   float wacc[QPT];
 #pragma unroll
@@ -375,36 +588,8 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
     if (j1 < n1max) {
       const size_t p = (size_t)j2 * n1max + j1;
       float own[CP], agg[CP];
-#pragma unroll
-      for (int c = 0; c < CP; ++c) { own[c] = 0.f; agg[c] = 0.f; }
-      if (CIN > 1) {
-        const float4* xp = (const float4*)(xb + p * kF);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float4 q4 = xp[t];
-          own[t * 4] = q4.x; own[t * 4 + 1] = q4.y; own[t * 4 + 2] = q4.z; own[t * 4 + 3] = q4.w;
-        }
-      }
-      own[CIN - 1] = mb[p];
-      const int beg1 = ip1[j1], end1 = ip1[j1 + 1];
-      for (int q = beg1; q < end1; ++q) {
-        const float4* r = (const float4*)(Rsum + (size_t)is1[q] * CP);
-#pragma unroll
-        for (int t = 0; t < CP / 4; ++t) {
-          const float4 q4 = r[t];
-          agg[t * 4] += q4.x; agg[t * 4 + 1] += q4.y; agg[t * 4 + 2] += q4.z; agg[t * 4 + 3] += q4.w;
-        }
-      }
-      long long cnt = (long long)d2 * (long long)(end1 - beg1);
-      const bool self = (long long)p < ndiag;
-      if (self) {
-#pragma unroll
-        for (int c = 0; c < CIN; ++c) agg[c] += own[c];
-        cnt += 1;
-      }
-      const float inv = cnt > 0 ? (float)cnt : 1.f;
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) agg[c] = agg[c] / inv;
+      bool self;
+      const float inv = gnn_node_inputs<CIN>(xb, mb, Rsum, Rp, ip1, is1, ic1, j1, p, d2, ccut, ndiag, own, agg, self);
 
       // forward recompute: h0 = relu(W0 own + b0), s2 = W2 h0 + b2, x1 = Wl agg + bl + Wr own + relu(s2)
       float h0[kF], s2[kF], x1[kF];
@@ -510,12 +695,20 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
 template <int CIN>
 __global__ void __launch_bounds__(128, 4)
 assoc_aggregate_add_kernel(const float* __restrict__ gagg, const int* __restrict__ out_ptr1,
-                           const int* __restrict__ out_dst1, const int* __restrict__ out_ptr2,
-                           const int* __restrict__ out_dst2, float* __restrict__ dxprev,
+                           const int* __restrict__ out_dst1, const int* __restrict__ out_col1,
+                           const int* __restrict__ out_ptr2,
+                           const int* __restrict__ out_dst2, const int* __restrict__ part,
+                           float* __restrict__ dxprev,
                            float* __restrict__ dm, int n1max, int n2max, int e1max, int e2max) {
   constexpr int CP = (CIN + 3) / 4 * 4;
-  extern __shared__ __align__(16) float Rs[];       // [n1max][CP]
+  extern __shared__ __align__(16) float Rs[];       // [n1max][CP], then [n1max][CP] for the cut-off block
   const int b = blockIdx.y, i2 = blockIdx.x, tid = threadIdx.x;
+  // the cut-off block (assoc_effective_kernel) is the association edge set (ps2, src1[c]) -> (pd2, dst1[c]), c < ccut:
+  // its gradient flows from row pd2 of gagg to the sources in row ps2
+  int pd2 = -1, ccut = 0;
+  if (part != nullptr && part[b * 4] == (int)blockIdx.x) { pd2 = part[b * 4 + 1]; ccut = part[b * 4 + 2]; }
+  if (ccut <= 0) pd2 = -1;
+  float* Rq = Rs + (size_t)n1max * CP;
   const int N = n1max * n2max;
   const int* op2 = out_ptr2 + (size_t)b * (n2max + 1);
   const int beg2 = op2[i2], end2 = op2[i2 + 1];
@@ -529,10 +722,12 @@ assoc_aggregate_add_kernel(const float* __restrict__ gagg, const int* __restrict
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     ((float4*)Rs)[f] = acc;
+    if (pd2 >= 0) ((float4*)Rq)[f] = ((const float4*)(gb + (size_t)pd2 * n1max * CP))[f];
   }
   __syncthreads();
   const int* op1 = out_ptr1 + (size_t)b * (n1max + 1);
   const int* od1 = out_dst1 + (size_t)b * e1max;
+  const int* oc1 = out_col1 != nullptr ? out_col1 + (size_t)b * e1max : nullptr;
   for (int i1 = tid; i1 < n1max; i1 += blockDim.x) {
     float acc[CP];
 #pragma unroll
@@ -543,6 +738,18 @@ assoc_aggregate_add_kernel(const float* __restrict__ gagg, const int* __restrict
       for (int t = 0; t < CP / 4; ++t) {
         const float4 v = r[t];
         acc[t * 4] += v.x; acc[t * 4 + 1] += v.y; acc[t * 4 + 2] += v.z; acc[t * 4 + 3] += v.w;
+      }
+    }
+    if (pd2 >= 0) {
+      for (int q = op1[i1]; q < op1[i1 + 1]; ++q) {
+        if (oc1[q] < ccut) {
+          const float4* r = (const float4*)(Rq + (size_t)od1[q] * CP);
+#pragma unroll
+          for (int t = 0; t < CP / 4; ++t) {
+            const float4 v = r[t];
+            acc[t * 4] += v.x; acc[t * 4 + 1] += v.y; acc[t * 4 + 2] += v.z; acc[t * 4 + 3] += v.w;
+          }
+        }
       }
     }
     const size_t p = (size_t)i2 * n1max + i1;
@@ -561,23 +768,83 @@ assoc_aggregate_add_kernel(const float* __restrict__ gagg, const int* __restrict
 
 }  // namespace fpm
 
-// weights -> padded staging buffer (device) -> constant bank c_gnn, all stream ordered (see the comment at c_gnn)
-template <int CIN>
-static int gnn_publish_weights(const fpm::GnnWeights& w, cudaStream_t st) {
-  static float* staging[16] = {nullptr};
+// weights -> padded staging buffer (device) -> constant bank c_gnn, all stream ordered (see the comment at c_gnn).
+// The bank and the staging buffer exist once per device, so a (publish, layer kernel) sequence must not interleave
+// with one issued on ANOTHER stream: gnn_bank_acquire makes the caller's stream wait for the last layer kernel that
+// read the bank from a different stream, gnn_bank_release records that kernel's completion event.  Launches from
+// several host threads are serialised by the mutex for the duration of the enqueue.
+#include <mutex>
+namespace {
+struct GnnBank {
+  std::mutex mu;
+  float* staging = nullptr;
+  cudaEvent_t last_use = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool used = false;
+};
+GnnBank g_bank[16];
+}  // namespace
+
+static int gnn_bank_acquire(int* dev_out, cudaStream_t st) {
   int dev = 0;
   FPM_CUDA(cudaGetDevice(&dev));
   FPM_CHECK_ARG(dev >= 0 && dev < 16, "fpm_gnn_layer: device index out of range");
-  if (!staging[dev]) FPM_CUDA(cudaMalloc(&staging[dev], fpm::kGnnConstFloats * sizeof(float)));
+  GnnBank& k = g_bank[dev];
+  k.mu.lock();
+  *dev_out = dev;
+  cudaError_t e = cudaSuccess;
+  if (!k.staging) e = cudaMalloc(&k.staging, fpm::kGnnConstFloats * sizeof(float));
+  if (e == cudaSuccess && !k.last_use) e = cudaEventCreateWithFlags(&k.last_use, cudaEventDisableTiming);
+  if (e == cudaSuccess && k.used && k.last_stream != st) e = cudaStreamWaitEvent(st, k.last_use, 0);
+  if (e != cudaSuccess) {
+    k.mu.unlock();
+    fpm_set_error(cudaGetErrorString(e));
+    return (int)e;
+  }
+  return FPM_OK;
+}
+
+static int gnn_bank_release(int dev, cudaStream_t st, int rc) {
+  GnnBank& k = g_bank[dev];
+  if (rc == FPM_OK) {
+    cudaError_t e = cudaEventRecord(k.last_use, st);
+    if (e == cudaSuccess) { k.used = true; k.last_stream = st; }
+    else { fpm_set_error(cudaGetErrorString(e)); rc = (int)e; }
+  }
+  k.mu.unlock();
+  return rc;
+}
+
+template <int CIN>
+static int gnn_publish_weights(const fpm::GnnWeights& w, int dev, cudaStream_t st) {
   constexpr int CP = (CIN + 3) / 4 * 4;
-  fpm::gnn_pack_weights_kernel<CIN><<<1, 256, 0, st>>>(w, staging[dev]);
+  float* staging = g_bank[dev].staging;
+  fpm::gnn_pack_weights_kernel<CIN><<<1, 256, 0, st>>>(w, staging);
   FPM_LAUNCH_CHECK();
-  FPM_CUDA(cudaMemcpyToSymbolAsync(fpm::c_gnn, staging[dev], fpm::GnnOff<CP>::total * sizeof(float), 0,
+  FPM_CUDA(cudaMemcpyToSymbolAsync(fpm::c_gnn, staging, fpm::GnnOff<CP>::total * sizeof(float), 0,
                                    cudaMemcpyDeviceToDevice, st));
   return FPM_OK;
 }
 
-extern "C" int fpm_assoc_in_csr(const int* edges, int* in_ptr, int* in_src, int B, int nmax, int emax,
+extern "C" int fpm_assoc_effective(const int* edges1, const int* edges2, const long long* eptr1,
+                                   const long long* eptr2, const long long* n1, const long long* n2, int* eff1,
+                                   int* eff2, long long* ndiag, int* part, int* status, int B, int e1max, int e2max,
+                                   void* stream) {
+  FPM_CHECK_ARG(edges1 && edges2 && eptr1 && eptr2 && n1 && n2 && eff1 && eff2 && ndiag && part && status,
+                "fpm_assoc_effective: null tensor");
+  FPM_CHECK_ARG(B >= 0 && e1max >= 0 && e2max >= 0, "fpm_assoc_effective: bad sizes");
+  if (B == 0) return FPM_OK;
+  const size_t smem = (size_t)(2 * e1max + 2 * e2max + 4) * sizeof(int);
+  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_assoc_effective: graphs too large for one CTA");
+  FPM_CUDA(cudaFuncSetAttribute(fpm::assoc_effective_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fpm::assoc_effective_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(
+      edges1, edges2, (const int64_t*)eptr1, (const int64_t*)eptr2, (const int64_t*)n1, (const int64_t*)n2, eff1, eff2,
+      (int64_t*)ndiag, part, status, e1max, e2max);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+extern "C" int fpm_assoc_in_csr(const int* edges, int* in_ptr, int* in_src, int* in_col, int B, int nmax, int emax,
                                 void* stream) {
   FPM_CHECK_ARG(edges && in_ptr && in_src, "fpm_assoc_in_csr: null tensor");
   FPM_CHECK_ARG(B >= 0 && nmax > 0 && emax >= 0, "fpm_assoc_in_csr: bad sizes");
@@ -586,47 +853,59 @@ extern "C" int fpm_assoc_in_csr(const int* edges, int* in_ptr, int* in_src, int 
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_assoc_in_csr: graph too large for one CTA");
   FPM_CUDA(cudaFuncSetAttribute(fpm::assoc_in_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
-  fpm::assoc_in_csr_kernel<<<B, fpm::kAssocThreads, smem, (cudaStream_t)stream>>>(edges, in_ptr, in_src, nmax, emax);
+  fpm::assoc_in_csr_kernel<<<B, fpm::kAssocThreads, smem, (cudaStream_t)stream>>>(edges, in_ptr, in_src, in_col, nmax,
+                                                                                  emax);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }
 
-// weights: 9 device pointers in the order of GnnWeights.
+template <int CIN>
+static int gnn_layer_launch(const fpm::GnnWeights& w, int dev, const float* xprev, const float* mprev_t,
+                            const int* in_ptr1, const int* in_src1, const int* in_col1, const int* in_ptr2,
+                            const int* in_src2, const long long* ndiag, const int* part, float* xout, float* score,
+                            int B, int n1max, int n2max, int e1max, int e2max, cudaStream_t st) {
+  constexpr int CP = (CIN + 3) / 4 * 4;
+  const size_t smem = ((size_t)2 * n1max * CP + fpm::kGnnNodes * (fpm::kF + 1)) * sizeof(float);
+  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_gnn_layer: n1max too large");
+  int rc = gnn_publish_weights<CIN>(w, dev, st);
+  if (rc != FPM_OK) return rc;
+  FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(n2max, B);
+  fpm::gnn_layer_kernel<CIN><<<grid, fpm::kGnnThreads, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_col1, in_ptr2,
+                                                                  in_src2, (const int64_t*)ndiag, part, xout, score,
+                                                                  n1max, n2max, e1max, e2max);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+// weights: 9 device pointers in the order of GnnWeights.  ndiag [B] int64 and part [B,4] int32 come from
+// fpm_assoc_effective (part may be NULL = no cut-off block; in_col1 is only read for pairs that have one).
 extern "C" int fpm_gnn_layer(const float* xprev, const float* mprev_t, const int* in_ptr1,
-                             const int* in_src1, const int* in_ptr2, const int* in_src2,
-                             const long long* n1, const long long* n2, const float* const* weights,
+                             const int* in_src1, const int* in_col1, const int* in_ptr2, const int* in_src2,
+                             const long long* ndiag, const int* part, const float* const* weights,
                              float* xout, float* score, int B, int n1max, int n2max, int e1max, int e2max,
                              int cin, void* stream) {
-  FPM_CHECK_ARG(mprev_t && in_ptr1 && in_src1 && in_ptr2 && in_src2 && n1 && n2 && weights && xout && score,
+  FPM_CHECK_ARG(mprev_t && in_ptr1 && in_src1 && in_ptr2 && in_src2 && ndiag && weights && xout && score,
                 "fpm_gnn_layer: null tensor");
+  FPM_CHECK_ARG(part == nullptr || in_col1 != nullptr, "fpm_gnn_layer: part needs in_col1");
   FPM_CHECK_ARG(cin == 1 || (cin == 17 && xprev), "fpm_gnn_layer: cin must be 1 or 17 (with xprev)");
   FPM_CHECK_ARG(B >= 0 && n1max > 0 && n2max > 0, "fpm_gnn_layer: bad sizes");
   if (B == 0) return FPM_OK;
   FPM_CHECK_ARG(B <= 65535, "fpm_gnn_layer: batch too large");
+  for (int i = 0; i < 9; ++i) FPM_CHECK_ARG(weights[i], "fpm_gnn_layer: null weight");
   fpm::GnnWeights w{weights[0], weights[1], weights[2], weights[3], weights[4],
                     weights[5], weights[6], weights[7], weights[8]};
-  for (int i = 0; i < 9; ++i) FPM_CHECK_ARG(weights[i], "fpm_gnn_layer: null weight");
-  const int cp = (cin + 3) / 4 * 4;
-  const size_t smem = (size_t)n1max * cp * sizeof(float);
-  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_gnn_layer: n1max too large");
-  dim3 grid(n2max, B);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc_pack;
-  if (cin == 1) {
-    if ((rc_pack = gnn_publish_weights<1>(w, st)) != FPM_OK) return rc_pack;
-    FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fpm::gnn_layer_kernel<1><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
-                                                      (const int64_t*)n1, (const int64_t*)n2, xout, score,
-                                                      n1max, n2max, e1max, e2max);
-  } else {
-    if ((rc_pack = gnn_publish_weights<17>(w, st)) != FPM_OK) return rc_pack;
-    FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fpm::gnn_layer_kernel<17><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
-                                                       (const int64_t*)n1, (const int64_t*)n2, xout, score,
-                                                       n1max, n2max, e1max, e2max);
-  }
-  FPM_LAUNCH_CHECK();
-  return FPM_OK;
+  int dev = 0;
+  int rc = gnn_bank_acquire(&dev, st);
+  if (rc != FPM_OK) return rc;
+  if (cin == 1)
+    rc = gnn_layer_launch<1>(w, dev, xprev, mprev_t, in_ptr1, in_src1, in_col1, in_ptr2, in_src2, ndiag, part, xout,
+                             score, B, n1max, n2max, e1max, e2max, st);
+  else
+    rc = gnn_layer_launch<17>(w, dev, xprev, mprev_t, in_ptr1, in_src1, in_col1, in_ptr2, in_src2, ndiag, part, xout,
+                              score, B, n1max, n2max, e1max, e2max, st);
+  return gnn_bank_release(dev, st, rc);
 }
 
 extern "C" int fpm_final_classifier(const float* x1, const float* sk_t, const float* cw, const float* cb,
@@ -640,54 +919,67 @@ extern "C" int fpm_final_classifier(const float* x1, const float* sk_t, const fl
   return FPM_OK;
 }
 
-// Backward of fpm_gnn_layer.  out_ptr*/out_dst*: OUT-neighbour lists (fpm_assoc_in_csr on the edge tables with
-// the two rows swapped).  gagg: scratch [B, N, CP] floats (CP = 4 for cin 1, 20 for cin 17).  grads: see the
-// kernel comment; the caller zeroes it.  dxprev may be NULL for cin = 1.
+// Backward of fpm_gnn_layer.  out_ptr*/out_dst*/out_col1: OUT-neighbour lists (fpm_assoc_in_csr on the effective edge
+// tables with the two rows swapped).  gagg: scratch [B, N, CP] floats (CP = 4 for cin 1, 20 for cin 17).  grads: see
+// the kernel comment; the caller zeroes it.  dxprev may be NULL for cin = 1.
+template <int CIN>
+static int gnn_layer_bwd_launch(const fpm::GnnWeights& w, int dev, const float* xprev, const float* mprev_t,
+                                const int* in_ptr1, const int* in_src1, const int* in_col1, const int* in_ptr2,
+                                const int* in_src2, const int* out_ptr1, const int* out_dst1, const int* out_col1,
+                                const int* out_ptr2, const int* out_dst2, const long long* ndiag, const int* part,
+                                const float* dxout, const float* dscore, float* dxprev, float* dm, float* gagg,
+                                float* grads, int B, int n1max, int n2max, int e1max, int e2max, cudaStream_t st) {
+  constexpr int CP = (CIN + 3) / 4 * 4;
+  constexpr int NQ = 3 * 16 * CIN + 16 * 16 + 4 * 16 + 1;
+  constexpr int VS = 49 + 2 * CP + 33;
+  const size_t smem = ((size_t)2 * n1max * CP + (size_t)128 * VS) * sizeof(float) + (size_t)2 * NQ * sizeof(short) + 16;
+  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_gnn_layer_bwd: n1max too large");
+  const size_t smem2 = (size_t)2 * n1max * CP * sizeof(float);
+  dim3 grid(n2max, B);
+  FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_bwd_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int rc = gnn_publish_weights<CIN>(w, dev, st);
+  if (rc != FPM_OK) return rc;
+  fpm::gnn_layer_bwd_kernel<CIN><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_col1, in_ptr2, in_src2,
+                                                         (const int64_t*)ndiag, part, dxout, dscore, dxprev, dm, gagg,
+                                                         grads, n1max, n2max, e1max, e2max);
+  FPM_LAUNCH_CHECK();
+  FPM_CUDA(cudaFuncSetAttribute(fpm::assoc_aggregate_add_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem2));
+  fpm::assoc_aggregate_add_kernel<CIN><<<grid, 128, smem2, st>>>(gagg, out_ptr1, out_dst1, out_col1, out_ptr2, out_dst2,
+                                                                part, dxprev, dm, n1max, n2max, e1max, e2max);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
 extern "C" int fpm_gnn_layer_bwd(const float* xprev, const float* mprev_t, const int* in_ptr1, const int* in_src1,
-                                 const int* in_ptr2, const int* in_src2, const int* out_ptr1, const int* out_dst1,
-                                 const int* out_ptr2, const int* out_dst2, const long long* n1, const long long* n2,
-                                 const float* const* weights, const float* dxout, const float* dscore,
-                                 float* dxprev, float* dm, float* gagg, float* grads, int B, int n1max, int n2max,
-                                 int e1max, int e2max, int cin, void* stream) {
+                                 const int* in_col1, const int* in_ptr2, const int* in_src2, const int* out_ptr1,
+                                 const int* out_dst1, const int* out_col1, const int* out_ptr2, const int* out_dst2,
+                                 const long long* ndiag, const int* part, const float* const* weights,
+                                 const float* dxout, const float* dscore, float* dxprev, float* dm, float* gagg,
+                                 float* grads, int B, int n1max, int n2max, int e1max, int e2max, int cin,
+                                 void* stream) {
   FPM_CHECK_ARG(mprev_t && in_ptr1 && in_src1 && in_ptr2 && in_src2 && out_ptr1 && out_dst1 && out_ptr2 && out_dst2 &&
-                n1 && n2 && weights && dxout && dscore && dm && gagg && grads, "fpm_gnn_layer_bwd: null tensor");
+                ndiag && weights && dxout && dscore && dm && gagg && grads, "fpm_gnn_layer_bwd: null tensor");
+  FPM_CHECK_ARG(part == nullptr || (in_col1 != nullptr && out_col1 != nullptr),
+                "fpm_gnn_layer_bwd: part needs in_col1 and out_col1");
   FPM_CHECK_ARG(cin == 1 || (cin == 17 && xprev && dxprev), "fpm_gnn_layer_bwd: cin must be 1 or 17 (with xprev, dxprev)");
   FPM_CHECK_ARG(B >= 0 && n1max > 0 && n2max > 0, "fpm_gnn_layer_bwd: bad sizes");
   if (B == 0) return FPM_OK;
   FPM_CHECK_ARG(B <= 65535, "fpm_gnn_layer_bwd: batch too large");
+  for (int i = 0; i < 9; ++i) FPM_CHECK_ARG(weights[i], "fpm_gnn_layer_bwd: null weight");
   fpm::GnnWeights w{weights[0], weights[1], weights[2], weights[3], weights[4],
                     weights[5], weights[6], weights[7], weights[8]};
-  for (int i = 0; i < 9; ++i) FPM_CHECK_ARG(weights[i], "fpm_gnn_layer_bwd: null weight");
-  const int cp = (cin + 3) / 4 * 4;
-  const int nq = 3 * 16 * cin + 16 * 16 + 4 * 16 + 1;
-  const int vs = 49 + 2 * cp + 33;
-  const size_t smem = ((size_t)n1max * cp + (size_t)128 * vs) * sizeof(float) + (size_t)2 * nq * sizeof(short) + 16;
-  FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_gnn_layer_bwd: n1max too large");
-  dim3 grid(n2max, B);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc_pack = FPM_OK;
-  const size_t smem2 = (size_t)n1max * cp * sizeof(float);
-  if (cin == 1) {
-    FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if ((rc_pack = gnn_publish_weights<1>(w, st)) != FPM_OK) return rc_pack;
-    fpm::gnn_layer_bwd_kernel<1><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
-                                                          (const int64_t*)n1, (const int64_t*)n2, dxout, dscore,
-                                                          dxprev, dm, gagg, grads, n1max, n2max, e1max, e2max);
-    FPM_LAUNCH_CHECK();
-    FPM_CUDA(cudaFuncSetAttribute(fpm::assoc_aggregate_add_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    fpm::assoc_aggregate_add_kernel<1><<<grid, 128, smem2, st>>>(gagg, out_ptr1, out_dst1, out_ptr2, out_dst2, dxprev, dm,
-                                                                n1max, n2max, e1max, e2max);
-  } else {
-    FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_bwd_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if ((rc_pack = gnn_publish_weights<17>(w, st)) != FPM_OK) return rc_pack;
-    fpm::gnn_layer_bwd_kernel<17><<<grid, 128, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_ptr2, in_src2,
-                                                           (const int64_t*)n1, (const int64_t*)n2, dxout, dscore,
-                                                           dxprev, dm, gagg, grads, n1max, n2max, e1max, e2max);
-    FPM_LAUNCH_CHECK();
-    FPM_CUDA(cudaFuncSetAttribute(fpm::assoc_aggregate_add_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    fpm::assoc_aggregate_add_kernel<17><<<grid, 128, smem2, st>>>(gagg, out_ptr1, out_dst1, out_ptr2, out_dst2, dxprev, dm,
-                                                                 n1max, n2max, e1max, e2max);
-  }
-  FPM_LAUNCH_CHECK();
-  return FPM_OK;
+  int dev = 0;
+  int rc = gnn_bank_acquire(&dev, st);
+  if (rc != FPM_OK) return rc;
+  if (cin == 1)
+    rc = gnn_layer_bwd_launch<1>(w, dev, xprev, mprev_t, in_ptr1, in_src1, in_col1, in_ptr2, in_src2, out_ptr1,
+                                 out_dst1, out_col1, out_ptr2, out_dst2, ndiag, part, dxout, dscore, dxprev, dm, gagg,
+                                 grads, B, n1max, n2max, e1max, e2max, st);
+  else
+    rc = gnn_layer_bwd_launch<17>(w, dev, xprev, mprev_t, in_ptr1, in_src1, in_col1, in_ptr2, in_src2, out_ptr1,
+                                  out_dst1, out_col1, out_ptr2, out_dst2, ndiag, part, dxout, dscore, dxprev, dm, gagg,
+                                  grads, B, n1max, n2max, e1max, e2max, st);
+  return gnn_bank_release(dev, st, rc);
 }

@@ -45,8 +45,9 @@ SIGNATURES = {
     "fpm_spline_gather_max": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_affinity": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "fpm_affinity_edges_factored": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _F, _P]),
-    "fpm_assoc_in_csr": (_I, [_P, _P, _P, _I, _I, _I, _P]),
-    "fpm_gnn_layer": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "fpm_assoc_effective": (_I, [_P] * 11 + [_I, _I, _I, _P]),
+    "fpm_assoc_in_csr": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_gnn_layer": (_I, [_P] * 12 + [_I] * 6 + [_P]),
     "fpm_final_classifier": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_sinkhorn_workspace_bytes": (_LL, [_I, _I, _I, _I]),
     "fpm_sinkhorn_log": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
@@ -76,7 +77,7 @@ SIGNATURES = {
     "fpm_transpose_f32": (_I, [_P, _P, _I, _I, _I, _P]),
     "fpm_bmm_ragged": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
     "fpm_segment_rowdot": (_I, [_P, _P, _P, _P, _I, _I, _P]),
-    "fpm_gnn_layer_bwd": (_I, [_P] * 19 + [_I] * 6 + [_P]),
+    "fpm_gnn_layer_bwd": (_I, [_P] * 21 + [_I] * 6 + [_P]),
     "fpm_afau_attention_bwd": (_I, [_P, _P, _P, _P, _LL, _LL, _LL] + [_P] * 10 + [_I, _I, _I, _P]),
     "fpm_add_instnorm_bwd": (_I, [_P, _P, _I] + [_P] * 7 + [_I, _I, _I, _F, _P]),
     "fpm_sinkhorn_bwd_workspace_bytes": (_LL, [_I, _I, _I, _I]),
@@ -108,8 +109,8 @@ def lib() -> C.CDLL:
     global _LIB
     if _LIB is None:
         path = _build.LIB_PATH
-        if not path.exists():
-            _build.build()
+        if not path.exists() or _build.stale():     # sources edited since the library was linked: rebuild, never
+            _build.build()                          # run an out-of-date binary silently
         handle = C.CDLL(str(path))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError = the library is stale: fail loudly

@@ -231,8 +231,8 @@ class NgmSolverFn(Function):
 
     @staticmethod
     def forward(ctx, Kp_t: Tensor, meta: dict, *params: Tensor):
-        csr1, csr2, n1, n2 = meta["csr1"], meta["csr2"], meta["n1"], meta["n2"]
-        n1max, n2max, e1max, e2max = meta["n1max"], meta["n2max"], meta["e1max"], meta["e2max"]
+        st, n1, n2 = meta["assoc"], meta["n1"], meta["n2"]
+        n1max, n2max = meta["n1max"], meta["n2max"]
         nl = meta["layers"]
         det = lambda t: t.detach().contiguous()
         lw = [[det(params[9 * i + j]).reshape(-1) if j == 7 else det(params[9 * i + j]) for j in range(9)]
@@ -241,7 +241,7 @@ class NgmSolverFn(Function):
         xprev, m_t = None, Kp_t.contiguous()
         saved = []
         for i in range(nl):
-            x1, score = ops.gnn_layer(xprev, m_t, csr1, csr2, n1, n2, lw[i], n1max, n2max, e1max, e2max)
+            x1, score = ops.gnn_layer(xprev, m_t, st, lw[i])
             _, sk_t = ops.sinkhorn_log(score, n1, n2, meta["sk_iter"], meta["sk_tau"], True, want_t=True)
             saved.append((xprev, m_t, score))
             xprev, m_t = x1, sk_t
@@ -254,9 +254,8 @@ class NgmSolverFn(Function):
     @staticmethod
     def backward(ctx, ds: Tensor):
         meta = ctx.meta
-        csr1, csr2, ocsr1, ocsr2 = meta["csr1"], meta["csr2"], meta["ocsr1"], meta["ocsr2"]
-        n1, n2 = meta["n1"], meta["n2"]
-        n1max, n2max, e1max, e2max = meta["n1max"], meta["n2max"], meta["e1max"], meta["e2max"]
+        st, n1, n2 = meta["assoc"], meta["n1"], meta["n2"]
+        n1max, n2max = meta["n1max"], meta["n2max"]
         nl = meta["layers"]
         B = ds.shape[0]
         N = n1max * n2max
@@ -274,8 +273,7 @@ class NgmSolverFn(Function):
         for i in range(nl - 1, -1, -1):
             xprev, m_t, score = ctx.saved[i]
             dscore = ops.sinkhorn_log_bwd(score, n1, n2, dsk, meta["sk_iter"], meta["sk_tau"], True)
-            dxprev, dm, wg = ops.gnn_layer_bwd(xprev, m_t, csr1, csr2, ocsr1, ocsr2, n1, n2, ctx.lw[i], dx1, dscore,
-                                               n1max, n2max, e1max, e2max)
+            dxprev, dm, wg = ops.gnn_layer_bwd(xprev, m_t, st, ctx.lw[i], dx1, dscore)
             for j in range(9):
                 grads[9 * i + j] = wg[j].reshape(ctx.pshapes[9 * i + j])
             dx1, dsk = dxprev, dm

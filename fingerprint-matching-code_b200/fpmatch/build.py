@@ -42,6 +42,30 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
+MANIFEST = LIB_PATH.with_suffix(".manifest")
+
+
+def _inputs():
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted((PKG_DIR.parent / "include").glob("*.h"))
+
+
+def source_digest() -> str:
+    """Content hash of everything the library is compiled from (robust against copied trees with fresh mtimes)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in _inputs():
+        h.update(f.name.encode()); h.update(f.read_bytes())
+    return h.hexdigest()
+
+
+def stale() -> bool:
+    """True when the sources differ from the ones the existing library was built from."""
+    try:
+        return MANIFEST.read_text().strip() != source_digest()
+    except OSError:
+        return not LIB_PATH.exists()        # a library without a manifest (older build) is taken as it is
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     BUILD.mkdir(parents=True, exist_ok=True)
@@ -75,6 +99,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")
+    MANIFEST.write_text(source_digest() + "\n")
     return LIB_PATH
 
 

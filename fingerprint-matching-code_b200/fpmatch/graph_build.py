@@ -126,9 +126,24 @@ def incidence_dense(edge_list: Tensor, n_pad: int, edge_pad: Optional[int] = Non
 
 def kron_index_lists(edge_list1: Tensor, edge_list2: Tensor, es1: Sequence[int], es2: Sequence[int], n1max: int):
     """``KGHs_sparse``: per pair ``(idxG, idxH)``, the row of the single one in every column of
-    ``kron(G2, G1)`` / ``kron(H2, H1)`` (gmdataset.py:623-642).  Views into two flat int64 buffers."""
+    ``kron(G2, G1)`` / ``kron(H2, H1)`` (gmdataset.py:623-642).  Views into two flat int64 buffers.
+
+    Each Kronecker product drops its own all-zero columns (csx_matrix.py:39-41), so with a partial permutation
+    (``-1`` ends in ``edge_list2``) the sources and the targets are compacted independently, exactly as the
+    reference's lists are; ``es1`` / ``es2`` are then ignored in favour of the surviving column counts."""
     B = edge_list1.shape[0]
     dev = edge_list1.device
+    if bool(((edge_list1[:, 0] < 0) != (edge_list1[:, 1] < 0)).any()) or \
+            bool(((edge_list2[:, 0] < 0) != (edge_list2[:, 1] < 0)).any()):
+        def compact(t):
+            order = torch.argsort((t < 0).to(torch.int8), dim=-1, stable=True)
+            return torch.gather(t, -1, order)
+        edge_list1, edge_list2 = compact(edge_list1).contiguous(), compact(edge_list2).contiguous()
+        c1, c2 = (edge_list1 >= 0).sum(-1), (edge_list2 >= 0).sum(-1)              # [B, 2] surviving G / H columns
+        if not (torch.equal(c1[:, 0], c1[:, 1]) and torch.equal(c2[:, 0], c2[:, 1])):
+            raise NotImplementedError("kron_index_lists: G and H keep different numbers of columns (asymmetric "
+                                      "adjacency); the reference's two lists then have different lengths")
+        es1, es2 = c1[:, 0].tolist(), c2[:, 0].tolist()
     sizes = [a * b for a, b in zip(es1, es2)]
     koff_host = [0]
     for s in sizes:

@@ -420,19 +420,59 @@ def affinity_edges_factored(XA: Tensor, XB: Tensor, coeff: Tensor, ptrA: Tensor,
 # ---------------------------------------------------------------------------------------------------
 # association-graph GNN
 # ---------------------------------------------------------------------------------------------------
-def assoc_in_csr(edges: Tensor, nmax: int):
+def assoc_in_csr(edges: Tensor, nmax: int, want_col: bool = False):
+    """In-neighbour lists of a [B, 2, emax] edge table (a column is an edge only if both its ends are >= 0).
+    Returns (in_ptr [B,nmax+1], in_src [B,emax]) and, with ``want_col``, the column id of every list entry."""
     B, _, emax = edges.shape
     in_ptr = torch.empty((B, nmax + 1), dtype=torch.int32, device=edges.device)
     in_src = torch.empty((B, max(emax, 1)), dtype=torch.int32, device=edges.device)
+    in_col = torch.empty((B, max(emax, 1)), dtype=torch.int32, device=edges.device) if want_col else None
     rc = _lib.lib().fpm_assoc_in_csr(_chk(edges, "edges", torch.int32), in_ptr.data_ptr(), in_src.data_ptr(),
-                                     B, nmax, emax, _stream())
+                                     in_col.data_ptr() if want_col else None, B, nmax, emax, _stream())
     _lib.check(rc, "fpm_assoc_in_csr"); _count()
-    return in_ptr, in_src
+    return (in_ptr, in_src, in_col) if want_col else (in_ptr, in_src)
 
 
-def gnn_layer(xprev: Optional[Tensor], mprev_t: Tensor, csr1, csr2, n1: Tensor, n2: Tensor, weights,
-              n1max: int, n2max: int, e1max: int, e2max: int):
+class AssocStructure:
+    """The association graph of a batch of pairs, kept factorised (csrc/gnn.cu).
+
+    Built from the two per-pair edge tables ``[B, 2, emax]`` (the (G-node, H-node) of every G / H column, -1 where
+    the column is all-zero) exactly as the reference's index lists describe it: kron(G2,G1) and kron(H2,H1) drop
+    their zero columns independently (gmdataset.py:623-642) and ngm.py:333-342 cuts [idx; diag] to the length of
+    K_value.  For complete tables this is the plain Kronecker structure; for the partial permutations of real
+    genuine pairs it reproduces the reference's (mis-paired, truncated) lists - see ``assoc_effective_kernel``.
+    ``csr1`` / ``csr2`` = (in_ptr, in_src, in_col) of the effective tables, ``ocsr*`` the out-neighbour lists
+    (training), ``ndiag`` [B] int64, ``part`` [B,4] int32, ``status`` [1] int32."""
+
+    def __init__(self, edges1: Tensor, edges2: Tensor, eptr1: Tensor, eptr2: Tensor, n1: Tensor, n2: Tensor,
+                 n1max: int, n2max: int, with_out: bool = False):
+        B, _, e1max = edges1.shape
+        e2max = edges2.shape[2]
+        dev = edges1.device
+        self.eff1 = torch.empty_like(edges1)
+        self.eff2 = torch.empty_like(edges2)
+        self.ndiag = torch.empty((B,), dtype=torch.int64, device=dev)
+        self.part = torch.empty((B, 4), dtype=torch.int32, device=dev)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        rc = _lib.lib().fpm_assoc_effective(_chk(edges1, "edges1", torch.int32), _chk(edges2, "edges2", torch.int32),
+                                            _chk(eptr1, "eptr1", torch.int64), _chk(eptr2, "eptr2", torch.int64),
+                                            _chk(n1, "n1", torch.int64), _chk(n2, "n2", torch.int64),
+                                            self.eff1.data_ptr(), self.eff2.data_ptr(), self.ndiag.data_ptr(),
+                                            self.part.data_ptr(), self.status.data_ptr(), B, e1max, e2max, _stream())
+        _lib.check(rc, "fpm_assoc_effective"); _count()
+        self.csr1 = assoc_in_csr(self.eff1, n1max, want_col=True)
+        self.csr2 = assoc_in_csr(self.eff2, n2max)
+        self.ocsr1 = self.ocsr2 = None
+        if with_out:
+            swap = lambda t: torch.stack((t[:, 1], t[:, 0]), 1).contiguous()
+            self.ocsr1 = assoc_in_csr(swap(self.eff1), n1max, want_col=True)
+            self.ocsr2 = assoc_in_csr(swap(self.eff2), n2max)
+        self.n1max, self.n2max, self.e1max, self.e2max = n1max, n2max, e1max, e2max
+
+
+def gnn_layer(xprev: Optional[Tensor], mprev_t: Tensor, st: AssocStructure, weights):
     B = mprev_t.shape[0]
+    n1max, n2max = st.n1max, st.n2max
     N = n1max * n2max
     dev = mprev_t.device
     xout = torch.empty((B, N, 16), dtype=torch.float32, device=dev)
@@ -441,12 +481,11 @@ def gnn_layer(xprev: Optional[Tensor], mprev_t: Tensor, csr1, csr2, n1: Tensor, 
         _chk(w, f"gnn weight {i}")
     wp = _ptr_array(weights)
     rc = _lib.lib().fpm_gnn_layer(_chk(xprev, "xprev"), _chk(mprev_t, "mprev_t"),
-                                  _chk(csr1[0], "in_ptr1", torch.int32), _chk(csr1[1], "in_src1", torch.int32),
-                                  _chk(csr2[0], "in_ptr2", torch.int32), _chk(csr2[1], "in_src2", torch.int32),
-                                  _chk(n1, "n1", torch.int64), _chk(n2, "n2", torch.int64), wp,
-                                  xout.data_ptr(), score.data_ptr(), B, n1max, n2max, e1max, e2max,
-                                  1 if xprev is None else 17, _stream())
-    _lib.check(rc, "fpm_gnn_layer"); _count()
+                                  st.csr1[0].data_ptr(), st.csr1[1].data_ptr(), st.csr1[2].data_ptr(),
+                                  st.csr2[0].data_ptr(), st.csr2[1].data_ptr(), st.ndiag.data_ptr(),
+                                  st.part.data_ptr(), wp, xout.data_ptr(), score.data_ptr(), B, n1max, n2max,
+                                  st.e1max, st.e2max, 1 if xprev is None else 17, _stream())
+    _lib.check(rc, "fpm_gnn_layer"); _count(3)
     return xout, score
 
 
@@ -708,10 +747,12 @@ def segment_rowdot(X: Tensor, Y: Tensor, ptr: Tensor) -> Tensor:
 GNN_GRAD_SIZES = lambda cin: [16 * cin, 16, 16 * cin, 16 * cin, 16, 256, 16, 16, 1]
 
 
-def gnn_layer_bwd(xprev: Optional[Tensor], mprev_t: Tensor, csr1, csr2, ocsr1, ocsr2, n1: Tensor, n2: Tensor,
-                  weights, dxout: Tensor, dscore: Tensor, n1max: int, n2max: int, e1max: int, e2max: int):
+def gnn_layer_bwd(xprev: Optional[Tensor], mprev_t: Tensor, st: AssocStructure, weights, dxout: Tensor,
+                  dscore: Tensor):
     """Returns (dxprev [B,N,16] or None, dm [B,n1max,n2max], list of the 9 weight gradients)."""
+    assert st.ocsr1 is not None, "AssocStructure was built without the out-neighbour lists (with_out=True)"
     B = mprev_t.shape[0]
+    n1max, n2max = st.n1max, st.n2max
     N = n1max * n2max
     dev = mprev_t.device
     cin = 1 if xprev is None else 17
@@ -725,14 +766,12 @@ def gnn_layer_bwd(xprev: Optional[Tensor], mprev_t: Tensor, csr1, csr2, ocsr1, o
         _chk(w, f"gnn weight {i}")
     rc = _lib.lib().fpm_gnn_layer_bwd(
         _chk(xprev, "xprev"), _chk(mprev_t, "mprev_t"),
-        _chk(csr1[0], "in_ptr1", torch.int32), _chk(csr1[1], "in_src1", torch.int32),
-        _chk(csr2[0], "in_ptr2", torch.int32), _chk(csr2[1], "in_src2", torch.int32),
-        _chk(ocsr1[0], "out_ptr1", torch.int32), _chk(ocsr1[1], "out_dst1", torch.int32),
-        _chk(ocsr2[0], "out_ptr2", torch.int32), _chk(ocsr2[1], "out_dst2", torch.int32),
-        _chk(n1, "n1", torch.int64), _chk(n2, "n2", torch.int64), _ptr_array(weights),
+        st.csr1[0].data_ptr(), st.csr1[1].data_ptr(), st.csr1[2].data_ptr(), st.csr2[0].data_ptr(), st.csr2[1].data_ptr(),
+        st.ocsr1[0].data_ptr(), st.ocsr1[1].data_ptr(), st.ocsr1[2].data_ptr(), st.ocsr2[0].data_ptr(),
+        st.ocsr2[1].data_ptr(), st.ndiag.data_ptr(), st.part.data_ptr(), _ptr_array(weights),
         _chk(dxout, "dxout"), _chk(dscore, "dscore"), dxprev.data_ptr() if cin > 1 else None, dm.data_ptr(),
-        gagg.data_ptr(), grads.data_ptr(), B, n1max, n2max, e1max, e2max, cin, _stream())
-    _lib.check(rc, "fpm_gnn_layer_bwd"); _count(2)
+        gagg.data_ptr(), grads.data_ptr(), B, n1max, n2max, st.e1max, st.e2max, cin, _stream())
+    _lib.check(rc, "fpm_gnn_layer_bwd"); _count(4)
     return dxprev, dm, list(torch.split(grads, sizes))
 
 

@@ -80,8 +80,15 @@ def _pad_stack(arrs, dtype=torch.float32):
 def make_batch(batch_size: int, n: int, seed: int = 1234, imposter_every: int = 2,
                ragged: bool = False, n_min: Optional[int] = None, with_kron: bool = False,
                with_dense_gh: bool = True, with_fmaps: bool = True, jitter: float = 1.5,
-               fmap_seed: Optional[int] = None, fmap_noise: Optional[float] = None) -> dict:
+               fmap_seed: Optional[int] = None, fmap_noise: Optional[float] = None, partial: int = 0) -> dict:
     """Build one batch.
+
+    ``partial = d`` turns every genuine pair into a PARTIAL match, the normal case of the reference's real data
+    (``get_pair``: keypoints of one print without a counterpart in the other): ``d`` keypoints of image 1 have no
+    match, image 2 carries the matched ones in shuffled order plus ``d`` keypoints of its own, ``gt_perm`` is a partial
+    permutation and graph 2 = ``perm^T G1`` / ``perm^T H1`` keeps only what the permutation carries over
+    (gmdataset.py:345-352) - so G2 and H2 have DIFFERENT all-zero columns and the Kronecker index lists of
+    gmdataset.py:623-642 lose their pairing (ngm.py:333-342 truncates them to a common length).
 
     ``imposter_every = k`` makes every k-th pair (b % k == k-1) an imposter; 0 = all genuine.
     ``ragged`` draws n1_b, n2_b uniformly from [n_min, n] (imposters get independent sizes).
@@ -99,7 +106,22 @@ def make_batch(batch_size: int, n: int, seed: int = 1234, imposter_every: int = 
         P1 = np.stack([rng.uniform(0, RESCALE[0], n1), rng.uniform(0, RESCALE[1], n1)], 1)
         A1 = delaunay_adjacency(P1)
         s1, d1, G1, H1 = incidence_from_adjacency(A1)
-        if genuine:
+        if genuine and partial:
+            d = min(int(partial), max(n1 - 3, 0))
+            keep = np.sort(rng.permutation(n1)[:n1 - d])                # matched keypoints of image 1
+            n2 = n1
+            pos = rng.permutation(n2)                                   # their positions in image 2
+            P2 = np.stack([rng.uniform(0, RESCALE[0], n2), rng.uniform(0, RESCALE[1], n2)], 1)
+            P2[pos[:len(keep)]] = P1[keep] + rng.normal(0, jitter, (len(keep), 2))
+            P2[:, 0] = np.clip(P2[:, 0], 0, RESCALE[0] - 1e-3)
+            P2[:, 1] = np.clip(P2[:, 1], 0, RESCALE[1] - 1e-3)
+            perm = np.zeros((n1, n2), dtype=np.float32)
+            perm[keep, pos[:len(keep)]] = 1
+            G2, H2 = perm.T @ G1, perm.T @ H1           # gmdataset.py:349-350
+            A2 = G2 @ H2.T
+            colnode = lambda M: np.where(M.sum(0) > 0, M.argmax(0), -1)
+            s2g, d2g = colnode(G2).astype(np.int64), colnode(H2).astype(np.int64)   # -1: all-zero column
+        elif genuine:
             n2 = n1
             P2 = P1 + rng.normal(0, jitter, P1.shape)
             P2[:, 0] = np.clip(P2[:, 0], 0, RESCALE[0] - 1e-3)
@@ -154,13 +176,7 @@ def make_batch(batch_size: int, n: int, seed: int = 1234, imposter_every: int = 
     else:
         data["As"] = [None, None]
     if with_kron:
-        # CSC .indices of kron(G2,G1) / kron(H2,H1): column t = k2*e1 + k1 -> row i2*n1max + i1
-        for b in range(batch_size):
-            (s1, d1), (s2g, d2g) = edges1[b], edges2[b]
-            idxG = (torch.from_numpy(s2g)[:, None] * n1max + torch.from_numpy(s1)[None, :]).reshape(-1)
-            idxH = (torch.from_numpy(d2g)[:, None] * n1max + torch.from_numpy(d1)[None, :]).reshape(-1)
-            kgh.append((idxG.long(), idxH.long()))
-        data["KGHs_sparse"] = kgh
+        add_kron(data)
     if with_fmaps:
         g = torch.Generator().manual_seed(seed + 77 if fmap_seed is None else fmap_seed)
         data["fmaps"] = [
@@ -171,6 +187,24 @@ def make_batch(batch_size: int, n: int, seed: int = 1234, imposter_every: int = 
         if fmap_noise is not None:
             a, b = data["fmaps"][0]
             data["fmaps"][1] = (a + fmap_noise * data["fmaps"][1][0], b + fmap_noise * data["fmaps"][1][1])
+    return data
+
+
+def add_kron(data: dict) -> dict:
+    """Attach ``KGHs_sparse`` (the CSC ``.indices`` of kron(G2,G1) / kron(H2,H1), gmdataset.py:623-642) computed from the
+    batch's edge tables - for batches that were generated or sharded without it (only the CPU oracle reads it)."""
+    t1, t2 = data["edge_lists"]
+    n1max = data["Ps"][0].shape[1]
+    kgh = []
+    for b in range(t1.shape[0]):
+        # CSC .indices of kron(G2,G1): one entry per NON-ZERO column t = k2*e1max + k1 (G2 column k2 and G1 column k1
+        # both non-zero), in column order, value = row i2*n1max + i1; kron(H2,H1) likewise with ITS OWN non-zero
+        # columns (csx_matrix.py:39-41 eliminates zeros per matrix) - the two lists pair up only if the same
+        # columns survive in G and H
+        s1, d1 = t1[b, 0][t1[b, 0] >= 0].long(), t1[b, 1][t1[b, 1] >= 0].long()
+        s2, d2 = t2[b, 0][t2[b, 0] >= 0].long(), t2[b, 1][t2[b, 1] >= 0].long()
+        kgh.append(((s2[:, None] * n1max + s1[None, :]).reshape(-1), (d2[:, None] * n1max + d1[None, :]).reshape(-1)))
+    data["KGHs_sparse"] = kgh
     return data
 
 

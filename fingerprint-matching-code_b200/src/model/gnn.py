@@ -76,12 +76,12 @@ class PYGNNLayer(nn.Module):
                 d(self.n_self_func[2].weight), d(self.n_self_func[2].bias),
                 d(self.classifier.weight).reshape(-1), d(self.classifier.bias)]
 
-    def forward_factorised(self, xprev, mprev_t, csr1, csr2, n1, n2, n1max, n2max, e1max, e2max):
-        """One NGM layer for the whole batch.  Returns (x1 [B,N,16], sinkhorn [B,n1max,n2max],
+    def forward_factorised(self, xprev, mprev_t, assoc, n1, n2):
+        """One NGM layer for the whole batch on the factorised association graph ``assoc``
+        (``fpmatch.ops.AssocStructure``).  Returns (x1 [B,N,16], sinkhorn [B,n1max,n2max],
         sinkhorn^T [B,n2max,n1max]); the layer's 17-channel output is (x1, vec(sinkhorn^T))."""
         assert self.sk_channel == 1 and self.out_nfeat == 16
-        x1, score = ops.gnn_layer(xprev, mprev_t, csr1, csr2, n1, n2, self.kernel_weights(),
-                                  n1max, n2max, e1max, e2max)
+        x1, score = ops.gnn_layer(xprev, mprev_t, assoc, self.kernel_weights())
         sk, sk_t = ops.sinkhorn_log(score, n1, n2, self.sk.max_iter, self.sk.tau, True, want_t=True)
         return x1, sk, sk_t
 

@@ -198,15 +198,17 @@ class Net(CNN):
 
     @staticmethod
     def _edge_tables(data_dict, dev):
-        """[B, 2, emax] int32 (G-node, H-node) per G/H column, -1 padded, for both graphs."""
+        """[B, 2, emax] int32 (G-node, H-node) per G/H column for both graphs; -1 where the column of G (row 0) or of
+        H (row 1) is all-zero - padding, or an end without a counterpart under a partial permutation
+        (gmdataset.py:345-352), which G and H lose independently."""
         if 'edge_lists' in data_dict:
             return [t.to(dev, torch.int32).contiguous() for t in data_dict['edge_lists']]
         tables = []
         for G, H in zip(data_dict['Gs'], data_dict['Hs']):
             G, H = G.to(dev), H.to(dev)
-            valid = G.sum(dim=1) > 0
-            src = torch.where(valid, G.argmax(dim=1), torch.full_like(valid, -1, dtype=torch.long))
-            dst = torch.where(valid, H.argmax(dim=1), torch.full_like(valid, -1, dtype=torch.long))
+            none = torch.full(G.shape[:1] + G.shape[2:], -1, dtype=torch.long, device=dev)
+            src = torch.where(G.sum(dim=1) > 0, G.argmax(dim=1), none)
+            dst = torch.where(H.sum(dim=1) > 0, H.argmax(dim=1), none)
             tables.append(torch.stack([src, dst], 1).to(torch.int32).contiguous())
         return tables
 
@@ -261,10 +263,8 @@ class Net(CNN):
                                                  graphs[1].edge_index.to(dev).contiguous(), n1max, n2max, e1max,
                                                  e2max, scale=0.5)
 
-        swap = lambda t: torch.stack((t[:, 1], t[:, 0]), 1).contiguous()
-        meta = {"csr1": ops.assoc_in_csr(tables[0], n1max), "csr2": ops.assoc_in_csr(tables[1], n2max),
-                "ocsr1": ops.assoc_in_csr(swap(tables[0]), n1max), "ocsr2": ops.assoc_in_csr(swap(tables[1]), n2max),
-                "n1": n1, "n2": n2, "n1max": n1max, "n2max": n2max, "e1max": e1max, "e2max": e2max,
+        assoc = ops.AssocStructure(tables[0], tables[1], offs[0][1], offs[1][1], n1, n2, n1max, n2max, with_out=True)
+        meta = {"assoc": assoc, "n1": n1, "n2": n2, "n1max": n1max, "n2max": n2max,
                 "layers": self.gnn_layer, "sk_iter": self.gnn_layer_0.sk.max_iter, "sk_tau": self.gnn_layer_0.sk.tau}
         params = []
         for i in range(self.gnn_layer):
@@ -305,7 +305,8 @@ class Net(CNN):
             cls_loss = torch.nn.functional.binary_cross_entropy_with_logits(cls_logits, label_tensor)
         data_dict.update({'ds_mat': ss_out, 'perm_mat': x, 'ks_loss': ks_loss, 'ks_error': ks_error,
                           'cls_loss': cls_loss, 'cls_prob': cls_prob, 'k_prob': ks})
-        data_dict['_fpm_inter'] = {'node_feat': feats, 'Kp': Kp, 'Ke': Ke, 's': s, 'ss': ss, 'k_scaled': k_scaled}
+        data_dict['_fpm_inter'] = {'node_feat': feats, 'Kp': Kp, 'Ke': Ke, 's': s, 'ss': ss, 'k_scaled': k_scaled,
+                                   'assoc_status': assoc.status}
         return data_dict
 
     @staticmethod
@@ -377,12 +378,11 @@ class Net(CNN):
                 ke_join = side
 
         # ---- NGM layers on the factorised association graph (ngm.py:326-362)
-        csr1 = ops.assoc_in_csr(tables[0], n1max)
-        csr2 = ops.assoc_in_csr(tables[1], n2max)
+        assoc = ops.AssocStructure(tables[0], tables[1], offs[0][1], offs[1][1], n1, n2, n1max, n2max)
         xprev, m_t = None, Kp_t
         for i in range(self.gnn_layer):
             layer = getattr(self, 'gnn_layer_{}'.format(i))
-            xprev, _, m_t = layer.forward_factorised(xprev, m_t, csr1, csr2, n1, n2, n1max, n2max, e1max, e2max)
+            xprev, _, m_t = layer.forward_factorised(xprev, m_t, assoc, n1, n2)
         s = ops.final_classifier(xprev, m_t, self.classifier.weight.detach().reshape(-1).contiguous(),
                                  self.classifier.bias.detach().contiguous(), n1max, n2max)     # :368-369
         ss = ops.sinkhorn_log(s, n1, n2, self.sinkhorn.max_iter, self.sinkhorn.tau, True)      # :371
@@ -436,5 +436,5 @@ class Net(CNN):
         })
         # stage outputs kept for the parity tests (cheap references, no copies)
         data_dict['_fpm_inter'] = {'node_feat': feats, 'Kp': Kp, 'Ke': Ke, 's': s, 'ss': ss, 'x1': xprev,
-                                   'k_scaled': k_scaled}
+                                   'k_scaled': k_scaled, 'assoc_status': assoc.status}
         return data_dict

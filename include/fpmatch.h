@@ -145,12 +145,25 @@ int fpm_affinity_edges_factored(const float* P, const long long* eidxA, const lo
  * n_self_func.2.weight, .2.bias, classifier.weight, classifier.bias.
  * xprev [B,N,16] (cin = 17) or NULL (cin = 1); mprev_t [B,n2max,n1max]; xout [B,N,16]; score [B,n1max,n2max].
  * fpm_final_classifier: s[b,i1,i2] = classifier([x1, sinkhorn channel])  (ngm.py:368-369).
+ *
+ * fpm_assoc_effective: the structure the reference's index lists really describe (gmdataset.py:623-642 eliminates the
+ * zero columns of kron(G2,G1) and kron(H2,H1) SEPARATELY, ngm.py:333-342 cuts [idx; diag] to the length of K_value =
+ * e1_pyg*e2_pyg + n1*n2).  edges1/edges2 as above; eptr1/eptr2 [B+1] int64 edge offsets of the two PyG batches;
+ * outputs: eff1/eff2 [B,2,emax] effective edge tables, ndiag [B] int64 surviving self-loop count (n1*n2 for complete
+ * tables), part [B,4] int32 = (ps2, pd2, ccut, 0) the column block the cut ends in (ccut = 0: none), status [1] int32
+ * (bit 0: G / H lists of different length, i.e. an asymmetric adjacency; accumulated with atomicOr, caller zeroes).
+ * fpm_assoc_in_csr: in-neighbour lists of an edge table; in_col (optional) = column id of every list entry.
+ * fpm_gnn_layer: in_*1 / in_*2 from fpm_assoc_in_csr on eff1 / eff2; part may be NULL (no cut-off block anywhere).
  */
-int fpm_assoc_in_csr(const int* edges, int* in_ptr, int* in_src, int B, int nmax, int emax, void* stream);
+int fpm_assoc_effective(const int* edges1, const int* edges2, const long long* eptr1, const long long* eptr2,
+                        const long long* n1, const long long* n2, int* eff1, int* eff2, long long* ndiag, int* part,
+                        int* status, int B, int e1max, int e2max, void* stream);
+int fpm_assoc_in_csr(const int* edges, int* in_ptr, int* in_src, int* in_col, int B, int nmax, int emax,
+                     void* stream);
 int fpm_gnn_layer(const float* xprev, const float* mprev_t, const int* in_ptr1, const int* in_src1,
-                  const int* in_ptr2, const int* in_src2, const long long* n1, const long long* n2,
-                  const float* const* weights, float* xout, float* score, int B, int n1max, int n2max,
-                  int e1max, int e2max, int cin, void* stream);
+                  const int* in_col1, const int* in_ptr2, const int* in_src2, const long long* ndiag,
+                  const int* part, const float* const* weights, float* xout, float* score, int B, int n1max,
+                  int n2max, int e1max, int e2max, int cin, void* stream);
 int fpm_final_classifier(const float* x1, const float* sk_t, const float* cw, const float* cb, float* s, int B,
                          int n1max, int n2max, void* stream);
 
@@ -258,7 +271,8 @@ int fpm_fgm_rebuild(const long long* indg, const long long* ptrg, const float* d
  * [A7] fpm_gnn_layer_bwd: backward of fpm_gnn_layer (forward recomputed from its inputs); grads = flat fp32 buffer
  *      lin_l.weight[16*cin] lin_l.bias[16] lin_r.weight[16*cin] n_self_func.0.weight[16*cin] .0.bias[16]
  *      n_self_func.2.weight[256] .2.bias[16] classifier.weight[16] classifier.bias[1], accumulated (caller zeroes);
- *      out_ptr/out_dst: out-neighbour lists (fpm_assoc_in_csr on the edge table with its two rows swapped);
+ *      out_ptr/out_dst/out_col: out-neighbour lists (fpm_assoc_in_csr on the EFFECTIVE edge table with its two rows
+ *      swapped); ndiag / part as in fpm_gnn_layer;
  *      gagg: scratch [B,N,4] (cin 1) / [B,N,20] (cin 17); dxprev [B,N,16], dm [B,n1max,n2max] are overwritten.
  * [A8] fpm_sinkhorn_log_bwd: gout [B,R,C] -> gs [B,R,C] through the unrolled iterations (forward replayed on chip).
  * [A10] fpm_soft_topk_bwd: gout [B,R,C] -> gscores [B,R,C]; anchors and k carry no gradient (soft_topk.py:27).
@@ -283,11 +297,11 @@ int fpm_bmm_ragged(const float* Mat, int B, int Rmax, int Cmax, int trans, const
                    void* stream);
 int fpm_segment_rowdot(const float* X, const float* Y, const long long* ptr, float* out, int B, int D, void* stream);
 int fpm_gnn_layer_bwd(const float* xprev, const float* mprev_t, const int* in_ptr1, const int* in_src1,
-                      const int* in_ptr2, const int* in_src2, const int* out_ptr1, const int* out_dst1,
-                      const int* out_ptr2, const int* out_dst2, const long long* n1, const long long* n2,
-                      const float* const* weights, const float* dxout, const float* dscore, float* dxprev,
-                      float* dm, float* gagg, float* grads, int B, int n1max, int n2max, int e1max, int e2max,
-                      int cin, void* stream);
+                      const int* in_col1, const int* in_ptr2, const int* in_src2, const int* out_ptr1,
+                      const int* out_dst1, const int* out_col1, const int* out_ptr2, const int* out_dst2,
+                      const long long* ndiag, const int* part, const float* const* weights, const float* dxout,
+                      const float* dscore, float* dxprev, float* dm, float* gagg, float* grads, int B, int n1max,
+                      int n2max, int e1max, int e2max, int cin, void* stream);
 /* [A9] fpm_afau_attention_bwd: backward of fpm_afau_attention (out = its forward output); dq is overwritten, dk / dv and
  *      dmix [16 heads x 65: mix1_weight[h,0,:], mix1_weight[h,1,:], mix1_bias[h,:], mix2_weight[h,:], mix2_bias[h]] are
  *      accumulated (caller zero-fills).  fpm_add_instnorm_bwd: dy [B,n,E] and / or drowmax [B,E] -> dx [B,n,E] (gradient of

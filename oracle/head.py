@@ -96,6 +96,12 @@ def forward_head(p: Dict[str, Tensor], data: dict, fmaps, regression: bool = Tru
         n1b, n2b = int(n_points[0][b]), int(n_points[1][b])
         diag = torch.arange(n1b * n2b, dtype=torch.long)     # linspace(...).long() of factorize_graph_matching.py:93-94
         row = torch.cat((idxG.long(), diag)); col = torch.cat((idxH.long(), diag))
+        # ngm.py:333-342: K_value = [Ke_b.flatten(); Kp_b.flatten()] (Ke_b is e1 x e2 of the PyG edge lists) and all
+        # three tensors are cut to the smallest length.  With a partial gt permutation G2 / H2 lose different
+        # columns, the lists are longer than the value vector and the cut removes the tail of the diagonal block.
+        e1b = int(graphs[0].eptr[b + 1] - graphs[0].eptr[b]); e2b = int(graphs[1].eptr[b + 1] - graphs[1].eptr[b])
+        common_len = min(row.numel(), col.numel(), e1b * e2b + n1b * n2b)
+        row, col = row[:common_len], col[:common_len]
         t = emb[b]
         for i in range(GNN_LAYERS):
             t = ops.pygnn_layer(t, row, col, n1b, n2b, n1max, n2max, p, f"gnn_layer_{i}",

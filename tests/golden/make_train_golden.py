@@ -29,7 +29,28 @@ from fpmatch import synth  # noqa: E402
 from oracle import head, train as otrain  # noqa: E402
 from src.model.ngm import Net  # noqa: E402
 
-B, N_KPTS, STEPS = 3, 14, 100
+import argparse
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--fp64", action="store_true")
+ap.add_argument("--config", default="n14", choices=["n14", "n100"],
+                help="n14: 3 pairs x 14 keypoints, fresh unrelated pairs (flat loss, long history); "
+                     "n100: BASELINE.json config 3's per-GPU share, 8 genuine pairs x 100 keypoints, image-2 maps = "
+                     "image-1 maps + noise on a fixed cycle of 4 batches (the loss falls)")
+ap.add_argument("--steps", type=int, default=100)
+ap.add_argument("--noise", type=float, default=None)
+ap.add_argument("--cycle", type=int, default=None)
+ap.add_argument("--out", default=None)
+ARGS = ap.parse_args()
+if ARGS.config == "n14":
+    B, N_KPTS, FMAP_NOISE, CYCLE = 3, 14, None, 0
+else:
+    B, N_KPTS, FMAP_NOISE, CYCLE = 8, 100, 1.0, 4
+if ARGS.noise is not None:
+    FMAP_NOISE = ARGS.noise
+if ARGS.cycle is not None:
+    CYCLE = ARGS.cycle
+STEPS = ARGS.steps
 BASE_LR, WARMUP_EPOCHS, STEPS_PER_EPOCH = 1e-3, 10, 75
 
 
@@ -38,7 +59,10 @@ def lr_at(t):
 
 
 def batch(t):
-    d = synth.make_batch(B, N_KPTS, seed=1000 + t, imposter_every=0, with_kron=True)
+    """Step t's batch: a fresh one (CYCLE = 0) or batch t % CYCLE of a fixed cycle."""
+    seed = 1000 + (t % CYCLE if CYCLE else t)
+    d = synth.make_batch(B, N_KPTS, seed=seed, imposter_every=0, with_kron=True, with_dense_gh=False,
+                         fmap_noise=FMAP_NOISE)
     d.pop("label")
     return d
 
@@ -52,8 +76,13 @@ def run(dtype):
     params = [p[k].requires_grad_(True) for k in names]
     opt = torch.optim.AdamW(params, lr=lr_at(0), weight_decay=1e-4)
     losses = []
+    cache = {}
     for t in range(STEPS):
-        d = batch(t)
+        key = t % CYCLE if CYCLE else t
+        d = cache[key] if key in cache else batch(t)
+        if CYCLE:
+            cache[key] = d
+        d = synth.clone_batch(d)
         for gp in opt.param_groups:
             gp["lr"] = lr_at(t)
         opt.zero_grad()
@@ -64,22 +93,24 @@ def run(dtype):
         torch.nn.utils.clip_grad_norm_([q for q in params if q.grad is not None], max_norm=5.0)
         opt.step()
         losses.append(float(loss.detach()))
-        if t % 10 == 0:
+        if t % 10 == 0 or STEPS <= 30:
             print(t, losses[-1], flush=True)
     return losses
 
 
 if __name__ == "__main__":
-    out = ROOT / "tests" / "golden" / "train_trajectory.json"
+    name = "train_trajectory.json" if ARGS.config == "n14" else "train_trajectory_n100.json"
+    out = Path(ARGS.out) if ARGS.out else ROOT / "tests" / "golden" / name
     rec = json.loads(out.read_text()) if out.exists() else {}
-    rec.update({"B": B, "n": N_KPTS, "steps": STEPS, "seed_base": 1000, "fmap_noise": None, "lr": BASE_LR,
+    rec.update({"B": B, "n": N_KPTS, "steps": STEPS, "seed_base": 1000, "fmap_noise": FMAP_NOISE, "cycle": CYCLE,
+                "lr": BASE_LR,
                 "warmup_epochs": WARMUP_EPOCHS, "steps_per_epoch": STEPS_PER_EPOCH,
                 "weight_decay": 1e-4, "clip": 5.0, "torch": torch.__version__})
     t0 = time.time()
-    if "--fp64" in sys.argv:
+    if ARGS.fp64:
         rec["loss_fp64"] = run(torch.float64)
     else:
         rec["loss_fp32"] = run(torch.float32)
-    rec["seconds_" + ("fp64" if "--fp64" in sys.argv else "fp32")] = time.time() - t0
+    rec["seconds_" + ("fp64" if ARGS.fp64 else "fp32")] = time.time() - t0
     out.write_text(json.dumps(rec))
     print("wrote", out)

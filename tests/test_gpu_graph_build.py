@@ -167,6 +167,25 @@ def test_genuine_pair_topology_transfer():
         assert ((H2.argmax(0) == d) | ((H2.sum(0) == 0) & (d == -1))).all()
 
 
+def test_collate_pairs_partial_permutation_index_lists():
+    """Partial ground-truth permutations: collate_pairs' edge tables carry -1 ends and its KGHs_sparse are the
+    reference's independently compacted lists (scipy kron + CSC indices, gmdataset.py:623-642)."""
+    import scipy.sparse as ssp
+    from fpmatch import graph_build as gb
+    from fpmatch.synth import batch_to, clone_batch, make_batch
+    host = make_batch(4, 18, seed=5, imposter_every=0, partial=3, with_kron=True, with_dense_gh=True)
+    dev_host = batch_to(clone_batch(host), DEV)
+    data = gb.collate_pairs(dev_host["Ps"][0], dev_host["Ps"][1], dev_host["ns"][0], dev_host["ns"][1],
+                            gt_perm_mat=dev_host["gt_perm_mat"], fmaps=dev_host["fmaps"], with_dense_gh=True,
+                            with_kron=True)
+    assert torch.equal(data["edge_lists"][1], dev_host["edge_lists"][1])
+    for b, (a, c) in enumerate(data["KGHs_sparse"]):
+        kg = ssp.kron(ssp.coo_matrix(host["Gs"][1][b].numpy()), ssp.coo_matrix(host["Gs"][0][b].numpy()))
+        kh = ssp.kron(ssp.coo_matrix(host["Hs"][1][b].numpy()), ssp.coo_matrix(host["Hs"][0][b].numpy()))
+        kg.eliminate_zeros(); kh.eliminate_zeros()
+        assert np.array_equal(kg.tocsc().indices, a.cpu().numpy()) and np.array_equal(kh.tocsc().indices, c.cpu().numpy())
+
+
 def test_collate_pairs_reproduces_host_pipeline():
     """collate_pairs on the device == the scipy / numpy pipeline of fpmatch.synth (which follows the reference's
     dataset code), down to the Kronecker index lists and the outputs of the matching head."""
