@@ -259,22 +259,26 @@ def main():
         kernel_label = None
     gemm_ms = sum(e[4].elapsed_time(e[5]) for e in same) / len(same)
     peaks, peak_kind = measured_peaks()
-    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
     mode = big[0]
     if mode == "fp32":
         # CUDA-core path: bounded by the fp32 FMA pipe, 148 SMs x 128 lanes x 2 flop x max clock
         peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
         peak_note = "fp32 CUDA-core FMA peak at max SM clock (nominal; no measured figure)"
     else:
-        peak = tf32_peak
-        peak_note = f"TF32 dense = {peak_kind} sustained bf16 cuBLAS peak / 2 (no TF32 figure is measured)"
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape, from the committed
-    # `ncu --set full` capture profiles/r1c_ncu_full_gemm_pair.md (algorithmic bytes: 2.185e9)
-    # (dense product: profiles/r1c_ncu_full_gemm_pair.md, 2.644e9 for 2.185e9 algorithmic; tile-table launch at
-    # 6084 tiles: profiles/r1i_ncu_full.md, 1.056e9 for 0.90e9 algorithmic; r1d measured 1.047e9)
-    traffic = None
-    if mode == "3xf16" and (big[1], big[2], big[3]) == (25600, 19968, 768):
-        traffic = 2.644e9 if kernel_label is None else 1.056e9
+        # the kernel is timed inside a long step -> the SUSTAINED measured dense bf16 figure of MEASURED_PEAKS.json
+        peak = peaks["bf16_tflops_sustained"]
+        peak_note = (f"{peak_kind} MEASURED_PEAKS.json bf16_tflops_sustained = {peaks['bf16_tflops_sustained']} "
+                     f"(burst {peaks['bf16_tflops']}); fp16 and bf16 MMAs run at the same rate")
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape: read from the summary
+    # of the last `ncu --set full` capture of THIS workload (tools/summarize_profiles.py writes profiles/LATEST_NCU.json
+    # next to profiles/<tag>_ncu_full.md); null when no capture of this kernel at this grid is on file
+    traffic, traffic_src = None, None
+    latest = ROOT / "profiles" / "LATEST_NCU.json"
+    if latest.exists() and kernel_label is not None and B == BATCH:
+        rec = json.loads(latest.read_text())
+        g = rec.get("slab_gemm")
+        if g:
+            traffic, traffic_src = g["dram_bytes"], f"{rec['file']} ({g['kernel']}, grid {g['grid']}, {g['time_us']:.0f} us under ncu)"
     achieved = flops / (gemm_ms / 1e3) / 1e12
     gemm_share = gemm_ms * len(same) / args.steps / ms_step
 
@@ -340,8 +344,14 @@ def main():
                        "l2": "inputs + intermediates per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "dead_ke_computed": True, "parallelism": f"dp{world} (independent pairs, no data-path collective)"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel": kernel_label or f"gemm_nt[{mode}] M={big[1]} N={big[2]} K={big[3]}",
-                         "launch_ms": gemm_ms, "share_of_step": gemm_share, "peak_source": peak_note},
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": kernel_label or f"gemm_nt[{mode}] M={big[1]} N={big[2]} K={big[3]}",
+                         "launch_ms": gemm_ms, "share_of_step": gemm_share, "peak_source": peak_note,
+                         "flops_per_launch": flops,
+                         "note": ("achieved = algorithmic 2*M*N*K of the executed tiles / live CUDA-event time of the launch. "
+                                  "fp32-faithful results need 3 fp16 MMAs per product (hi*hi, hi*lo, lo*hi), which are NOT "
+                                  "counted as work: the scheme's own ceiling is frac = 1/3; issued-MMA rate = 3 x achieved = "
+                                  f"{3 * achieved:.0f} TFLOP/s = {3 * achieved / peak:.2f} of the peak") if mode == "3xf16" else None},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "h2d_link_gbs_measured": h2d_gbs, "h2d_ms_per_step_at_that_rate": h2d / h2d_gbs / 1e6},

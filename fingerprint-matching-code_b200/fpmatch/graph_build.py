@@ -18,7 +18,7 @@ from torch import Tensor
 
 from . import _lib
 from .graph import GraphBatch
-from .ops import _chk, _count, _i64, _stream
+from .ops import _chk, _count, _i64, _stream, on_tensor_device
 
 RESCALE = 320.0                       # max(RESCALE), /root/reference/src/gmdataset.py:36-48,171
 _STG = {"fc": 0, "tri": 1, "near": 2}
@@ -32,6 +32,7 @@ def _points64(P: Tensor) -> Tensor:
     return P.to(torch.float64).contiguous()
 
 
+@on_tensor_device
 def graph_adjacency(P: Tensor, ns: Tensor, stg: str = "tri", thre: float = 0.0) -> Tensor:
     """``A [B,nmax,nmax]`` fp32 0/1: ``delaunay_triangulate`` / ``fully_connect`` (build_graphs.py:78-119)."""
     assert stg in _STG, "No strategy named {} found.".format(stg)      # build_graphs.py:43
@@ -58,6 +59,7 @@ class EdgeSet:
     es: List[int]           # edges per graph (host)
 
 
+@on_tensor_device
 def graph_edges(A: Tensor, P: Tensor, ns: Tensor, upper_only: bool = False, emax: Optional[int] = None) -> EdgeSet:
     """Edge list, pseudo-coordinates and node coordinates of ``to_pyg_graph`` (gmdataset.py:169-189) plus the
     (src, dst) table that stands for the one-hot ``G``/``H`` columns (build_graphs.py:60-72; ``upper_only`` =
@@ -92,6 +94,7 @@ def graph_edges(A: Tensor, P: Tensor, ns: Tensor, upper_only: bool = False, emax
     return EdgeSet(edge_index, edge_attr, x, ptr, eptr, edge_list, es)
 
 
+@on_tensor_device
 def permute_graph(A1: Tensor, perm: Tensor, edge_list1: Optional[Tensor], n2max: Optional[int] = None):
     """Graph 2 of a genuine pair: ``G2 = perm^T G1``, ``H2 = perm^T H1``, ``A2 = G2 H2^T`` (gmdataset.py:345-352).
     ``perm [B,n1max,n2max]`` is a (partial) permutation; returns ``(A2, edge_list2)`` with unmatched ends = -1."""
@@ -110,6 +113,7 @@ def permute_graph(A1: Tensor, perm: Tensor, edge_list1: Optional[Tensor], n2max:
     return A2, el2
 
 
+@on_tensor_device
 def incidence_dense(edge_list: Tensor, n_pad: int, edge_pad: Optional[int] = None):
     """Dense one-hot ``G, H [B, n_pad, edge_pad]`` from the (src, dst) table (build_graphs.py:60-72)."""
     B, emax = edge_list.shape[0], edge_list.shape[2]
@@ -124,6 +128,7 @@ def incidence_dense(edge_list: Tensor, n_pad: int, edge_pad: Optional[int] = Non
     return G, H
 
 
+@on_tensor_device
 def kron_index_lists(edge_list1: Tensor, edge_list2: Tensor, es1: Sequence[int], es2: Sequence[int], n1max: int):
     """``KGHs_sparse``: per pair ``(idxG, idxH)``, the row of the single one in every column of
     ``kron(G2, G1)`` / ``kron(H2, H1)`` (gmdataset.py:623-642).  Views into two flat int64 buffers.
@@ -170,6 +175,7 @@ class BuiltGraphs:
     es: List[int]
 
 
+@on_tensor_device
 def build_graph_batch(P: Tensor, ns: Tensor, stg: str = "tri", sym: bool = True, thre: float = 0.0) -> BuiltGraphs:
     """``build_graphs`` + ``to_pyg_graph`` for a padded batch ``P [B,nmax,2]``, ``ns [B]``."""
     A = graph_adjacency(P, ns, stg, thre)
@@ -181,6 +187,7 @@ def build_graph_batch(P: Tensor, ns: Tensor, stg: str = "tri", sym: bool = True,
     return BuiltGraphs(A, gb, half.edge_list, half.es)
 
 
+@on_tensor_device
 def collate_pairs(P1: Tensor, P2: Tensor, ns1: Tensor, ns2: Tensor, gt_perm_mat: Optional[Tensor] = None,
                   label: Optional[Tensor] = None, fmaps=None, images=None, stg: str = "tri",
                   tgt_stg: str = "same", with_dense_gh: bool = False, with_kron: bool = False) -> dict:

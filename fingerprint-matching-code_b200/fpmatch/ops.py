@@ -74,11 +74,46 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _first_cuda_index(args):
+    for x in args:
+        if isinstance(x, Tensor):
+            if x.is_cuda:
+                return x.device.index
+        elif isinstance(x, (list, tuple)):
+            r = _first_cuda_index(x)
+            if r is not None:
+                return r
+    return None
+
+
+def on_tensor_device(fn):
+    """The C ABI launches into the calling thread's CURRENT CUDA device and takes that device's current stream.  torch
+    ops work on whatever device their tensors live on, and so must these (the reference's extension had no device guard
+    at all): every public wrapper runs under ``torch.cuda.device(<device of its first CUDA
+    tensor>)`` when that is not the current one.  ``_chk`` then refuses any tensor that is not on the current device,
+    so a mixed-device call fails loudly instead of launching into the wrong context."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        idx = _first_cuda_index(args)
+        if idx is None and kwargs:
+            idx = _first_cuda_index(kwargs.values())
+        if idx is None or idx == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(idx):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def _chk(t: Optional[Tensor], name: str, dtype=torch.float32) -> Optional[int]:
     if t is None:
         return None
     if not isinstance(t, Tensor) or not t.is_cuda:
         raise RuntimeError(f"fpmatch: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"fpmatch: {name} is on {t.device} but the op runs on cuda:{torch.cuda.current_device()} "
+                           "(all tensors of one op must live on one device)")
     if t.dtype != dtype:
         raise RuntimeError(f"fpmatch: {name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -601,19 +636,24 @@ def k_head(g_row: Tensor, g_col: Tensor, weights, n1: Tensor, n2: Tensor, mean_k
 # LAP + greedy
 # ---------------------------------------------------------------------------------------------------
 def lap_topk(ds: Tensor, n1: Optional[Tensor], n2: Optional[Tensor], ks: Optional[Tensor] = None,
-             want_hungarian: bool = True, want_perm: bool = False):
+             want_hungarian: bool = True, want_perm: bool = False, want_status: bool = False):
+    """(hungarian, perm_mat[, status]).  ``status [B]`` int32 is 1 where the pair's cost matrix was infeasible (NaN /
+    inf entries): the outputs of that pair are all-zero and scipy's ``linear_sum_assignment`` would have raised
+    ``ValueError`` (utils/hungarian.py:63)."""
     B, R, Cc = ds.shape
     hung = torch.empty_like(ds) if want_hungarian else None
     perm = torch.empty_like(ds) if want_perm else None
+    status = torch.empty((B,), dtype=torch.int32, device=ds.device) if want_status else None
     n1 = _i64(n1) if n1 is not None else None
     n2 = _i64(n2) if n2 is not None else None
     if ks is not None:
         ks = ks.to(torch.float32).contiguous()
     rc = _lib.lib().fpm_lap_topk(_chk(ds, "s"), _chk(n1, "n1", torch.int64), _chk(n2, "n2", torch.int64),
                                  _chk(ks, "ks"), hung.data_ptr() if want_hungarian else None,
-                                 perm.data_ptr() if want_perm else None, None, B, R, Cc, _stream())
+                                 perm.data_ptr() if want_perm else None,
+                                 status.data_ptr() if want_status else None, B, R, Cc, _stream())
     _lib.check(rc, "fpm_lap_topk"); _count()
-    return hung, perm
+    return (hung, perm, status) if want_status else (hung, perm)
 
 
 def greedy_perm(x: Tensor, top_indices: Tensor, ks: Tensor) -> Tensor:
@@ -988,3 +1028,24 @@ def add_instnorm_bwd(a: Tensor, other: Optional[Tensor], gamma: Tensor, dy: Opti
                                          float(eps), _stream())
     _lib.check(rc, "fpm_add_instnorm_bwd"); _count()
     return dx, dgamma, dbeta, dvec
+
+
+# ---------------------------------------------------------------------------------------------------
+# device guard: every public wrapper (and the constructors of the plan / structure classes) runs on the device of its
+# tensors - see on_tensor_device
+# ---------------------------------------------------------------------------------------------------
+def _install_device_guards():
+    import types
+    g = globals()
+    skip = {"set_gemm_mode", "gemm_mode", "set_gemm_pair", "gemm_pair_enabled", "set_slab_plan", "slab_plan_enabled",
+            "launch_count", "gemm_profile_start", "gemm_profile_stop", "on_tensor_device"}
+    for name, obj in list(g.items()):
+        if name.startswith("_") or name in skip:
+            continue
+        if isinstance(obj, types.FunctionType) and obj.__module__ == __name__:
+            g[name] = on_tensor_device(obj)
+    for cls in (SlabPlan, SlabGroups, AssocStructure):
+        cls.__init__ = on_tensor_device(cls.__init__)
+
+
+_install_device_guards()

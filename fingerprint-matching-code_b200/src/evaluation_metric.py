@@ -35,10 +35,11 @@ def matching_recall(pmat_pred: Tensor, pmat_gt: Tensor, ns: Tensor) -> Tensor:
 
 
 def matching_precision(pmat_pred: Tensor, pmat_gt: Tensor, ns: Tensor) -> Tensor:
-    r""":math:`tr(X {X^{gt}}^\top) / \sum X` per pair; 0 where nothing was predicted (evaluation_metric.py:93-131)."""
+    r""":math:`tr(X {X^{gt}}^\top) / \sum X` per pair; 1 where nothing was predicted - 0/0 = NaN -> 1 as the reference
+    sets it (evaluation_metric.py:93-125; only its ``*_varied`` variants use 0)."""
     st = _stats(pmat_pred, pmat_gt, ns)
     precision = st[:, 0] / st[:, 2]
-    precision[torch.isnan(precision)] = 0
+    precision[torch.isnan(precision)] = 1
     return precision
 
 

@@ -37,18 +37,26 @@ class InnerProductWithWeightsAffinity(nn.Module):
             assert X.shape[1] == Y.shape[1] == self.d, (X.shape[1], Y.shape[1], self.d)
         dev = Xs[0].device
         Ws = Ws if isinstance(Ws, torch.Tensor) else torch.stack(list(Ws), 0)
+        # differentiable like the reference's matmul / tanh / softplus chain whenever something upstream wants a gradient
+        differentiable = torch.is_grad_enabled() and (
+            any(t.requires_grad for t in Xs + Ys) or Ws.requires_grad
+            or (use_global and (self.A.weight.requires_grad or self.A.bias.requires_grad)))
+        det = (lambda t: t) if differentiable else (lambda t: t.detach())
         if use_global:
-            W32 = Ws.detach().to(torch.float32)
-            coeff = torch.tanh(torch.nn.functional.linear(W32, self.A.weight.detach(), self.A.bias.detach()))
+            coeff = torch.tanh(torch.nn.functional.linear(det(Ws).to(torch.float32), det(self.A.weight), det(self.A.bias)))
         else:
             coeff = torch.ones((B, self.d), dtype=torch.float32, device=dev)
         nA = torch.tensor([x.shape[0] for x in Xs], dtype=torch.int64)
         nB = torch.tensor([y.shape[0] for y in Ys], dtype=torch.int64)
         ptrA = torch.zeros(B + 1, dtype=torch.int64); ptrA[1:] = torch.cumsum(nA, 0)
         ptrB = torch.zeros(B + 1, dtype=torch.int64); ptrB[1:] = torch.cumsum(nB, 0)
-        XA = torch.cat([x.detach().to(torch.float32) for x in Xs], 0).contiguous()
-        XB = torch.cat([y.detach().to(torch.float32) for y in Ys], 0).contiguous()
+        XA = torch.cat([det(x).to(torch.float32) for x in Xs], 0).contiguous()
+        XB = torch.cat([det(y).to(torch.float32) for y in Ys], 0).contiguous()
         Rmax, Cmax = int(nA.max()), int(nB.max())
-        out, _ = ops.affinity_nodes(XA, XB, coeff.contiguous(), ptrA.to(dev), ptrB.to(dev), Rmax, Cmax,
-                                    scale=1.0, want_t=False)
+        if differentiable:
+            from fpmatch import autograd as fa
+            out, _ = fa.AffinityFn.apply(XA, XB, coeff, ptrA.to(dev), ptrB.to(dev), Rmax, Cmax)
+        else:
+            out, _ = ops.affinity_nodes(XA, XB, coeff.contiguous(), ptrA.to(dev), ptrB.to(dev), Rmax, Cmax,
+                                        scale=1.0, want_t=False)
         return [out[b, :int(nA[b]), :int(nB[b])] for b in range(B)]

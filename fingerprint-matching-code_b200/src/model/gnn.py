@@ -57,8 +57,16 @@ class PYGNNLayer(nn.Module):
             self.out_nfeat = out_node_features
             self.sk = self.classifier = None
         if edge_emb:
-            raise NotImplementedError("edge_emb=True is not used by the matching head (ngm.py:49)")
-        self.e_func = None
+            # gnn.py:188-196: the reference creates this edge MLP (so its parameters exist in checkpoints) and its
+            # PYGNNLayer.forward never calls it (gnn.py:207-226) - same here
+            self.e_func = nn.Sequential(
+                nn.Linear(self.in_efeat + self.in_nfeat, self.out_efeat),
+                nn.ReLU(),
+                nn.Linear(self.out_efeat, self.out_efeat),
+                nn.ReLU()
+            )
+        else:
+            self.e_func = None
         self.conv = _GCNParams(self.in_nfeat, self.out_nfeat)
         self.conv2 = _SAGEParams(self.in_nfeat, self.out_nfeat)
         self.n_self_func = nn.Sequential(

@@ -166,6 +166,7 @@ class Net(CNN):
         # inference: run the (unread) edge-affinity kernels beside the main chain (FPMATCH_KE_SIDE=0: same stream)
         self.ke_side_stream = os.environ.get('FPMATCH_KE_SIDE', '1') != '0'
         self._backbone_channels_last = False
+        self._lap_pending = None          # pinned ring of LAP status flags, see _note_lap_status
 
     def backbone_channels_last(self, on: bool = True):
         """Opt-in: keep the stock ResNet-18 chunks in channels-last memory format so that
@@ -180,6 +181,10 @@ class Net(CNN):
 
     # ------------------------------------------------------------------------------------------
     def forward(self, data_dict, regression=True):
+        dev = next(self.parameters()).device
+        if dev.type == 'cuda' and dev.index is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):   # kernels launch into the current device: make it the model's
+                return self.forward(data_dict, regression)
         if 'fmaps' in data_dict:           # head-only entry: backbone maps supplied by the caller
             fmaps = data_dict['fmaps']
         else:
@@ -295,7 +300,9 @@ class Net(CNN):
         k_scaled = ks.detach() * min_point_tensor
         ss_out = fa.SoftTopkFn.apply(ss, gt_ks, n1, n2, SK_ITER_NUM, self.tau)
         with torch.no_grad():
-            _, x = ops.lap_topk(ss_out.detach(), n1, n2, ks=k_scaled, want_hungarian=False, want_perm=True)
+            _, x, lap_status = ops.lap_topk(ss_out.detach(), n1, n2, ks=k_scaled, want_hungarian=False,
+                                            want_perm=True, want_status=True)
+            self._note_lap_status(lap_status)
         matched_sim = s * x
         cls_logits = self.match_cls(matched_sim)
         cls_prob = torch.sigmoid(cls_logits)
@@ -308,6 +315,43 @@ class Net(CNN):
         data_dict['_fpm_inter'] = {'node_feat': feats, 'Kp': Kp, 'Ke': Ke, 's': s, 'ss': ss, 'k_scaled': k_scaled,
                                    'assoc_status': assoc.status}
         return data_dict
+
+    def _note_lap_status(self, status):
+        """NaN / inf scores (diverged training) make the assignment infeasible: scipy raises ``ValueError`` inside the
+        reference's forward (hungarian.py:63).  The GPU solver flags the pair instead and zeroes its outputs; to keep
+        the forward free of host synchronisation the flag travels to a pinned host word asynchronously (a ring of 8,
+        because the host runs ahead of the device) and is looked at by a LATER call - or by ``check_lap_status()`` -
+        which raises the same ``ValueError``."""
+        self.check_lap_status(block=False)
+        if self._lap_pending is None:
+            self._lap_pending = {"flags": torch.zeros(8, dtype=torch.int32).pin_memory(), "queue": [], "next": 0}
+        ring = self._lap_pending
+        if len(ring["queue"]) == 8:                       # ring full: wait for the oldest entry
+            self._lap_check_entry(ring["queue"].pop(0), wait=True)
+        slot = ring["next"]
+        ring["next"] = (slot + 1) % 8
+        ring["flags"][slot:slot + 1].copy_(status.max().view(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        ring["queue"].append((slot, ev))
+
+    def _lap_check_entry(self, entry, wait):
+        slot, ev = entry
+        if wait:
+            ev.synchronize()
+        if int(self._lap_pending["flags"][slot]) != 0:
+            self._lap_pending["queue"].clear()
+            raise ValueError('matrix contains invalid numeric entries (the scores of an earlier forward held NaN or '
+                             'inf: scipy.optimize.linear_sum_assignment raises here, utils/hungarian.py:63)')
+
+    def check_lap_status(self, block: bool = True):
+        """Raise ``ValueError`` if a previous forward met a score matrix with NaN / inf entries.  ``block=True`` waits
+        for every forward issued so far; ``block=False`` only looks at those that have already finished."""
+        ring = self._lap_pending
+        if ring is None:
+            return
+        while ring["queue"] and (block or ring["queue"][0][1].query()):
+            self._lap_check_entry(ring["queue"].pop(0), wait=block)
 
     @staticmethod
     def _ke_stream(dev):
@@ -406,7 +450,9 @@ class Net(CNN):
         # ---- soft top-k, exact LAP, greedy top-k (ngm.py:418-449)
         k_topk = gt_ks if self.training else k_scaled
         ss_out = ops.soft_topk(ss, k_topk, n1, n2, SK_ITER_NUM, self.tau)
-        _, x = ops.lap_topk(ss_out, n1, n2, ks=k_scaled, want_hungarian=False, want_perm=True)
+        _, x, lap_status = ops.lap_topk(ss_out, n1, n2, ks=k_scaled, want_hungarian=False, want_perm=True,
+                                        want_status=True)
+        self._note_lap_status(lap_status)
 
         # ---- genuine / imposter classifier and losses (ngm.py:451-469)
         cls_logits = self.match_cls.forward_product(s, x)

@@ -29,6 +29,7 @@ def soft_topk(scores, ks, max_iter=10, tau=1., nrows=None, ncols=None, return_pr
     """
     x = scores.detach().to(torch.float32).contiguous()
     dev = x.device
+    differentiable = torch.is_grad_enabled() and scores.requires_grad
     B, R, C = x.shape
     if nrows is None:
         nrows = torch.full((B,), R, dtype=torch.int64, device=dev)
@@ -36,9 +37,13 @@ def soft_topk(scores, ks, max_iter=10, tau=1., nrows=None, ncols=None, return_pr
         ncols = torch.full((B,), C, dtype=torch.int64, device=dev)
     nrows, ncols = nrows.to(dev), ncols.to(dev)
     ks = torch.as_tensor(ks, dtype=torch.float32, device=dev).reshape(-1)
-    output_s = ops.soft_topk(x, ks, nrows, ncols, max_iter, tau)
+    if differentiable:        # the soft matrix carries gradients back to `scores`, as the reference's does
+        from fpmatch import autograd as fa
+        output_s = fa.SoftTopkFn.apply(scores.to(torch.float32), ks, nrows, ncols, max_iter, tau)
+    else:
+        output_s = ops.soft_topk(x, ks, nrows, ncols, max_iter, tau)
     # hard selection: candidates ranked over the flattened (n1_b x n2_b block of the) soft matrix
-    top_indices = _rank_valid_block(output_s, nrows, ncols)
+    top_indices = _rank_valid_block(output_s.detach(), nrows, ncols)
     hard = ops.greedy_perm(torch.zeros_like(x), top_indices, ks)
     if return_prob:
         return hard, output_s

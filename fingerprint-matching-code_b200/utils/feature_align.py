@@ -22,10 +22,53 @@ def feature_align(raw_feature: Tensor, P: Tensor, ns_t: Tensor, ori_size: tuple,
     if device is None:
         device = raw_feature.device
     ori = tuple(float(v) for v in (ori_size.tolist() if isinstance(ori_size, Tensor) else ori_size))
-    F = ops.feature_align(raw_feature.detach().to(torch.float32).contiguous(),
-                          P.to(raw_feature.device, torch.float32).contiguous(),
-                          ns_t.to(raw_feature.device), ori)
+    Pd = P.to(raw_feature.device, torch.float32).contiguous()
+    nsd = ns_t.to(raw_feature.device)
+    if torch.is_grad_enabled() and raw_feature.requires_grad:
+        # the reference backpropagates into the feature map through its slice assignments (feature_align.py:62)
+        F = _FeatureAlignFn.apply(raw_feature.to(torch.float32), Pd, nsd, ori)
+    else:
+        F = ops.feature_align(raw_feature.detach().to(torch.float32).contiguous(), Pd, nsd, ori)
     return F.to(device)
+
+
+class _FeatureAlignFn(torch.autograd.Function):
+    """``feature_align`` with a gradient for the feature map (none for the keypoints, as in the reference, whose
+    coordinates pass through ``floor`` / integer indexing).  Forward = the bit-exact kernel; backward = the transposed
+    4-tap gather: every output column scatters its gradient to its four taps with the interpolation weights
+    (``feature_align.py:98-125``), as one batched ``index_add`` on the device."""
+
+    @staticmethod
+    def forward(ctx, raw_feature, P, ns, ori):
+        raw = raw_feature.contiguous()
+        ctx.save_for_backward(P, ns)
+        ctx.meta = (tuple(raw.shape), ori)
+        return ops.feature_align(raw, P, ns, ori)
+
+    @staticmethod
+    def backward(ctx, g):
+        P, ns = ctx.saved_tensors
+        (B, C, Hf, Wf), ori = ctx.meta
+        dev = g.device
+        n = P.shape[1]
+        ori_t = torch.tensor(ori, dtype=torch.float32, device=dev)
+        feat = torch.tensor([Hf, Wf], dtype=torch.float32, device=dev)      # (sic) feature_align.py:30,57-61
+        step = ori_t / feat
+        pt = (P - step / 2) / ori_t * feat
+        x, y = pt[..., 0], pt[..., 1]
+        x0 = torch.floor(x); x1 = x0 + 1; y0 = torch.floor(y); y1 = y0 + 1
+        x0 = x0.clamp(0, Wf - 1); x1 = x1.clamp(0, Wf - 1); y0 = y0.clamp(0, Hf - 1); y1 = y1.clamp(0, Hf - 1)
+        xi0, xi1, yi0, yi1 = x0.long(), x1.long(), y0.long(), y1.long()
+        eqx, eqy = xi0 == xi1, yi0 == yi1                                    # edge rule applied AFTER the fetch (:104-113)
+        x0 = torch.where(eqx & (xi0 == 0), x0 - 1, x0); x1 = torch.where(eqx & (xi0 != 0), x1 + 1, x1)
+        y0 = torch.where(eqy & (yi0 == 0), y0 - 1, y0); y1 = torch.where(eqy & (yi0 != 0), y1 + 1, y1)
+        valid = (torch.arange(n, device=dev)[None, :] < ns.view(-1, 1)).to(g.dtype)
+        w = [(x1 - x) * (y1 - y), (x1 - x) * (y - y0), (x - x0) * (y1 - y), (x - x0) * (y - y0)]
+        taps = [yi0 * Wf + xi0, yi1 * Wf + xi0, yi0 * Wf + xi1, yi1 * Wf + xi1]
+        d = torch.zeros((B, C, Hf * Wf), dtype=g.dtype, device=dev)
+        for wk, tk in zip(w, taps):
+            d.scatter_add_(2, tk[:, None, :].expand(B, C, n), g * (wk * valid)[:, None, :])
+        return d.view(B, C, Hf, Wf), None, None, None
 
 
 def interp_2d(z: Tensor, P: Tensor, ori_size: Tensor, feat_size: Tensor, out=None, device=None) -> Tensor:

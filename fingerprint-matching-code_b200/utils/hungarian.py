@@ -36,7 +36,12 @@ def hungarian(s: Tensor, n1: Tensor = None, n2: Tensor = None, nproc: int = 1) -
     dev = x.device
     n1 = n1.to(dev) if n1 is not None else None
     n2 = n2.to(dev) if n2 is not None else None
-    perm_mat, _ = ops.lap_topk(x, n1, n2, want_hungarian=True, want_perm=False)
+    perm_mat, _, status = ops.lap_topk(x, n1, n2, want_hungarian=True, want_perm=False, want_status=True)
+    # scipy raises for NaN / inf entries (the reference reaches it at hungarian.py:63); the reference call is
+    # synchronous anyway (it copies the scores to the host, hungarian.py:34)
+    if bool(status.any()):
+        bad = torch.nonzero(status).view(-1).tolist()
+        raise ValueError('matrix contains invalid numeric entries (pairs {})'.format(bad))
     if matrix_input:
         perm_mat = perm_mat.squeeze(0)
     return perm_mat

@@ -59,6 +59,14 @@ for b in range(B):
 rec = met_mod.matching_recall(hard, gt, n1)
 prec = met_mod.matching_precision(hard, gt, n1)
 acc = met_mod.matching_accuracy(hard, gt, [n1, n2], 0)
+# second case: pairs WITHOUT any predicted match (imposter pairs with k = 0 predict nothing): 0/0 -> the reference's
+# NaN rule (matching_precision sets 1, evaluation_metric.py:123)
+hard2 = hard.clone()
+hard2[1] = 0; hard2[3] = 0; hard2[4] = 0
+rec2 = met_mod.matching_recall(hard2, gt, n1)
+prec2 = met_mod.matching_precision(hard2, gt, n1)
 torch.save({"pred": pred, "gt": gt, "n1": n1, "n2": n2, "loss": loss.detach(), "grad": p.grad, "hard": hard,
-            "recall": rec, "precision": prec, "accuracy": acc}, ROOT / "tests" / "golden" / "loss_metric.pt")
+            "recall": rec, "precision": prec, "accuracy": acc, "hard_empty": hard2, "recall_empty": rec2,
+            "precision_empty": prec2}, ROOT / "tests" / "golden" / "loss_metric.pt")
+print("empty-prediction case: recall", rec2.tolist(), "precision", prec2.tolist())
 print("loss", float(loss), "recall", rec.tolist(), "precision", prec.tolist())

@@ -225,3 +225,88 @@ def test_legacy_extension_namespaces_and_device_rules():
         sparse_dot.dense_dot_csc_to_dense(torch.zeros(1, 1, 1), i, i, d, 1, 1, 1, 1)
     with pytest.raises(RuntimeError):
         sparse_dot.csr_dot_csc_to_csr(i, i, d, i, i, d, 1, 1, 1)
+
+
+def test_sinkhorn_forward_ori_matches_reference_golden():
+    """`Sinkhorn(log_forward=False)` (reference sinkhorn.py:89-169, deprecated but part of the class): values and
+    gradients against vectors produced by the reference's own `forward_ori` (tests/golden/make_sinkhorn_ori_golden.py).
+    The path is batched torch ops, so it runs wherever the input lives - here on the CPU."""
+    from src.model.sinkhorn import Sinkhorn
+    fx = torch.load(ROOT / "tests" / "golden" / "sinkhorn_ori.pt")
+    for tag, c in fx.items():
+        sk = Sinkhorn(max_iter=c["max_iter"], tau=c["tau"], epsilon=1e-4, log_forward=False)
+        s = c["s"].clone().requires_grad_(True)
+        out = sk(s, c["nrows"], c["ncols"], dummy_row=c["dummy_row"])
+        assert out.shape == c["out"].shape, tag
+        assert (out - c["out"]).abs().max() < 1e-6, (tag, (out - c["out"]).abs().max())
+        (out * c["w"]).sum().backward()
+        assert (s.grad - c["grad"]).abs().max() < 1e-5 * max(1.0, c["grad"].abs().max().item()), tag
+
+
+OVERLAY_PROBE = r"""
+import sys
+sys.path[:0] = [{pkg!r}, {ref!r}]
+import utils.hungarian, utils.feature_align, src.model.ngm, src.sparse_torch            # ours (first on the path)
+assert utils.hungarian.__file__.startswith({pkg!r}) and src.model.ngm.__file__.startswith({pkg!r})
+assert src.sparse_torch.__file__.startswith({pkg!r})
+import utils.models_sl, utils.scheduler, src.dataset, src.train.training_loop, src.model.gcn   # the reference's own
+for m in (utils.models_sl, utils.scheduler, src.dataset, src.train.training_loop, src.model.gcn):
+    assert m.__file__.startswith({ref!r}), m.__file__
+print("OVERLAY_OK")
+"""
+
+
+def _run_overlay_probe(ref_root):
+    import subprocess
+    code = OVERLAY_PROBE.format(pkg=str(ROOT / "fingerprint-matching-code_b200"), ref=str(ref_root))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OVERLAY_OK" in r.stdout, r.stderr[-3000:]
+
+
+def test_package_overlays_the_reference_tree(tmp_path):
+    """with this package FIRST and the reference root SECOND on sys.path the reference's
+    scripts find the rebuilt hot-path modules here and everything else (models_sl, scheduler, dataset, the training
+    loop...) in their own tree (train.py:14-26, evaluate_binary_classifier.py:27-34).  Fake reference root with the
+    reference's package layout: `src/` and `src/model/` WITHOUT __init__.py, `utils/` and `src/train/` with one."""
+    ref = tmp_path / "reference"
+    for d in ("utils", "src/train", "src/model", "src/sparse_torch"):
+        (ref / d).mkdir(parents=True)
+    for f in ("utils/__init__.py", "src/train/__init__.py", "src/sparse_torch/__init__.py"):
+        (ref / f).write_text("")
+    for f in ("utils/models_sl.py", "utils/scheduler.py", "utils/hungarian.py", "src/dataset.py", "src/model/gcn.py",
+              "src/model/ngm.py", "src/train/training_loop.py"):
+        (ref / f).write_text("MARK = 'reference'\n")
+    _run_overlay_probe(ref)
+
+
+@pytest.mark.skipif(not Path("/root/reference/utils/models_sl.py").exists(), reason="reference tree not present")
+def test_real_reference_host_modules_import_through_the_overlay():
+    """The same with the real reference tree (present in the build container only): its importable host-side modules
+    resolve through the overlay while the hot path resolves here."""
+    import subprocess
+    code = r"""
+import sys
+sys.path[:0] = [{pkg!r}, '/root/reference']
+import utils.models_sl, utils.scheduler
+assert utils.models_sl.__file__.startswith('/root/reference'), utils.models_sl.__file__
+from utils.models_sl import save_model, load_model
+from utils.hungarian import hungarian
+import utils.hungarian
+assert utils.hungarian.__file__.startswith({pkg!r})
+import src.model.ngm
+assert src.model.ngm.__file__.startswith({pkg!r})
+print("OVERLAY_OK")
+""".format(pkg=str(ROOT / "fingerprint-matching-code_b200"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OVERLAY_OK" in r.stdout, r.stderr[-3000:]
+
+
+def test_pygnn_layer_edge_emb_creates_the_unused_edge_mlp():
+    """PYGNNLayer(edge_emb=True) (gnn.py:188-196): the reference builds `e_func` and never calls it; the mirror must
+    accept the flag and expose the same state_dict keys."""
+    from src.model.gnn import PYGNNLayer
+    a = PYGNNLayer(17, 16, 17, 16, sk_channel=1, sk_tau=0.01, edge_emb=True)
+    b = PYGNNLayer(17, 16, 17, 16, sk_channel=1, sk_tau=0.01, edge_emb=False)
+    extra = sorted(set(a.state_dict()) - set(b.state_dict()))
+    assert extra == ["e_func.0.bias", "e_func.0.weight", "e_func.2.bias", "e_func.2.weight"]
+    assert a.e_func[0].in_features == 16 + 17 and a.e_func[0].out_features == 16

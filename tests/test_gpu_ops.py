@@ -544,6 +544,11 @@ def test_permutation_loss_and_matching_metrics_golden():
     assert e_loss < 1e-6 and e_grad < 1e-6
     assert torch.equal(rec.cpu(), fx["recall"]) and torch.equal(prec.cpu(), fx["precision"])
     assert torch.equal(acc.cpu(), fx["accuracy"])
+    # pairs without any predicted match: 0/0 -> 1 in the reference's matching_precision (evaluation_metric.py:123)
+    rec2 = matching_recall(fx["hard_empty"].to(DEV), fx["gt"].to(DEV), fx["n1"].to(DEV))
+    prec2 = matching_precision(fx["hard_empty"].to(DEV), fx["gt"].to(DEV), fx["n1"].to(DEV))
+    assert torch.equal(rec2.cpu(), fx["recall_empty"]) and torch.equal(prec2.cpu(), fx["precision_empty"])
+    assert prec2[4].item() == 1.0
     with pytest.raises(AssertionError):
         PermutationLoss()(fx["pred"].to(DEV) * 1.5, fx["gt"].to(DEV), fx["n1"].to(DEV), fx["n2"].to(DEV))
 
@@ -599,3 +604,139 @@ def test_gumbel_sinkhorn_matches_seeded_reference_expression(oo):
                       max_iter=10, tau=0.5)
     assert out.shape == (12, 9, 11)
     assert (out.cpu() - ref).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------- module-level APIs are differentiable (boundary)
+def _rel(a, b):
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()
+
+
+def test_module_level_sinkhorn_is_differentiable(oo):
+    """`Sinkhorn.forward` must stay autograd-transparent like the reference's pygmtools call (sinkhorn.py:85-87, used in
+    training at gnn.py:219): gradient of the module call against torch autograd through the oracle."""
+    from src.model.sinkhorn import GumbelSinkhorn, Sinkhorn
+    g = torch.Generator().manual_seed(4)
+    s = torch.randn(3, 9, 11, generator=g) * 0.3
+    n1 = torch.tensor([9, 6, 8]); n2 = torch.tensor([11, 10, 8])
+    w = torch.randn(3, 9, 11, generator=g)
+    sr = s.clone().requires_grad_(True)
+    (oo.sinkhorn(sr, n1, n2, dummy_row=True, max_iter=10, tau=0.05) * w).sum().backward()
+    sg = s.to(DEV).requires_grad_(True)
+    out = Sinkhorn(max_iter=10, tau=0.05)(sg, n1.to(DEV), n2.to(DEV), dummy_row=True)
+    assert out.requires_grad
+    (out * w.to(DEV)).sum().backward()
+    err = _rel(sg.grad, sr.grad)
+    report("module_sinkhorn_grad", rel=err)
+    assert err < 2e-4
+    with torch.no_grad():                      # inference path unchanged, no graph
+        assert not Sinkhorn(max_iter=10, tau=0.05)(sg, n1.to(DEV), n2.to(DEV), dummy_row=True).requires_grad
+    sg2 = s.to(DEV).requires_grad_(True)       # GumbelSinkhorn rides on the same module
+    GumbelSinkhorn(max_iter=10, tau=0.05)(sg2, n1.to(DEV), n2.to(DEV), sample_num=2, dummy_row=True).sum().backward()
+    assert sg2.grad is not None and torch.isfinite(sg2.grad).all()
+
+
+def test_module_level_soft_topk_is_differentiable(oo):
+    from src.model.soft_topk import soft_topk
+    g = torch.Generator().manual_seed(6)
+    n1 = torch.tensor([10, 7]); n2 = torch.tensor([10, 9])
+    ss = oo.sinkhorn(torch.randn(2, 10, 10, generator=g), n1, n2, dummy_row=True, max_iter=10, tau=0.05)
+    ks = torch.tensor([4.0, 2.5])
+    w = torch.randn(2, 10, 10, generator=g)
+    sr = ss.clone().requires_grad_(True)
+    (oo.soft_topk_prob(sr, ks, 10, 0.01, n1, n2) * w).sum().backward()
+    sg = ss.to(DEV).requires_grad_(True)
+    hard, prob = soft_topk(sg, ks.to(DEV), 10, 0.01, n1.to(DEV), n2.to(DEV), return_prob=True)
+    assert prob.requires_grad and not hard.requires_grad
+    (prob * w.to(DEV)).sum().backward()
+    err = _rel(sg.grad, sr.grad)
+    report("module_soft_topk_grad", rel=err)
+    assert err < 2e-4
+
+
+def test_module_level_feature_align_is_differentiable(oo):
+    from utils.feature_align import feature_align
+    g = torch.Generator().manual_seed(8)
+    fm = torch.randn(2, 16, 15, 20, generator=g)
+    P = torch.stack([torch.rand(2, 13, generator=g) * 320, torch.rand(2, 13, generator=g) * 240], -1)
+    P[0, 0] = torch.tensor([0.0, 0.0]); P[0, 1] = torch.tensor([319.0, 239.0]); P[1, 0] = torch.tensor([319.9, 0.1])
+    ns = torch.tensor([13, 9])
+    w = torch.randn(2, 16, 13, generator=g)
+    fr = fm.clone().requires_grad_(True)
+    (oo.feature_align(fr, P, ns, (320, 240)) * w).sum().backward()
+    fg = fm.to(DEV).requires_grad_(True)
+    out = feature_align(fg, P.to(DEV), ns.to(DEV), (320, 240))
+    assert out.requires_grad
+    (out * w.to(DEV)).sum().backward()
+    err = _rel(fg.grad, fr.grad)
+    report("module_feature_align_grad", rel=err)
+    assert err < 1e-6
+
+
+def test_module_level_affinity_is_differentiable(oo):
+    from src.model.affinity_layer import InnerProductWithWeightsAffinity
+    g = torch.Generator().manual_seed(9)
+    torch.manual_seed(1)
+    layer = InnerProductWithWeightsAffinity(32, 24)
+    Xs = [torch.randn(n, 24, generator=g) * 0.4 for n in (7, 5)]
+    Ys = [torch.randn(n, 24, generator=g) * 0.4 for n in (6, 9)]
+    Ws = torch.randn(2, 32, generator=g)
+    ws = [torch.randn(7, 6, generator=g), torch.randn(5, 9, generator=g)]
+    xr = [x.clone().requires_grad_(True) for x in Xs]; yr = [y.clone().requires_grad_(True) for y in Ys]
+    A_w = layer.A.weight.detach().clone().requires_grad_(True); A_b = layer.A.bias.detach().clone().requires_grad_(True)
+    sum(((oo.affinity(x, y, wv, A_w, A_b)) * q).sum() for x, y, wv, q in zip(xr, yr, Ws, ws)).backward()
+    layer = layer.to(DEV)
+    xg = [x.to(DEV).requires_grad_(True) for x in Xs]; yg = [y.to(DEV).requires_grad_(True) for y in Ys]
+    outs = layer(xg, yg, Ws.to(DEV))
+    assert all(o.requires_grad for o in outs)
+    sum((o * q.to(DEV)).sum() for o, q in zip(outs, ws)).backward()
+    errs = {"X": max(_rel(a.grad, b.grad) for a, b in zip(xg, xr)), "Y": max(_rel(a.grad, b.grad) for a, b in zip(yg, yr)),
+            "A.weight": _rel(layer.A.weight.grad, A_w.grad), "A.bias": _rel(layer.A.bias.grad, A_b.grad)}
+    report("module_affinity_grad", **errs)
+    assert max(errs.values()) < 1e-4, errs
+
+
+def test_lap_on_non_finite_scores_raises_like_scipy(ops):
+    """scipy.optimize.linear_sum_assignment raises ValueError for NaN / inf entries (the reference reaches it at
+    utils/hungarian.py:63); the GPU solver must not return an all-zero assignment silently."""
+    from utils.hungarian import hungarian
+    s = torch.rand(3, 6, 6)
+    s[1, 2, 3] = float("nan")
+    with pytest.raises(ValueError):
+        hungarian(s.to(DEV))
+    hungarian(torch.rand(3, 6, 6).to(DEV))      # finite input: no error
+    _, _, st = ops.lap_topk(s.to(DEV), None, None, want_hungarian=True, want_status=True)
+    assert st.tolist() == [0, 1, 0]
+
+
+def test_net_reports_non_finite_scores_lazily():
+    """Inside Net.forward the flag is not read synchronously (no host sync on the hot path): check_lap_status() - or a
+    later forward - raises."""
+    from fpmatch import synth
+    from src.model.ngm import Net
+    torch.manual_seed(0)
+    net = Net(regression=True).eval().to(DEV)
+    data = synth.make_batch(2, 12, seed=1)
+    with torch.no_grad():
+        net(synth.batch_to(synth.clone_batch(data), DEV))
+    net.check_lap_status()                                   # finite scores: nothing to report
+    with torch.no_grad():
+        net.classifier.bias.fill_(float("nan"))              # a diverged parameter
+        net(synth.batch_to(synth.clone_batch(data), DEV))
+    with pytest.raises(ValueError):
+        net.check_lap_status()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_ops_follow_their_tensors_device(ops, oo):
+    """Tensors on cuda:1 while the current device is cuda:0: the wrappers switch to the tensors' device (the
+    reference's extension launched into whatever context was current)."""
+    g = torch.Generator().manual_seed(0)
+    s = torch.randn(2, 8, 8, generator=g)
+    ref = oo.sinkhorn(s, None, None, dummy_row=False, max_iter=10, tau=0.1)
+    assert torch.cuda.current_device() == 0
+    out = ops.sinkhorn_log(s.to("cuda:1"), None, None, 10, 0.1, False)
+    assert out.device.index == 1 and torch.cuda.current_device() == 0
+    assert (out.cpu() - ref).abs().max() < 1e-5
+    with pytest.raises(RuntimeError):
+        ops.sinkhorn_log(s.to("cuda:1"), torch.tensor([8, 8], device="cuda:0"), None, 10, 0.1, False)

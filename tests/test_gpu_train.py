@@ -322,8 +322,15 @@ def gpu_permutation_loss(ds, gt, n1, n2):
     return (bce * mask).sum() / n1.sum().to(torch.float32)
 
 
-def test_stage1_loss_trajectory_100_steps():
+@pytest.mark.parametrize("gold_name", ["train_trajectory.json", "train_trajectory_n100.json"])
+def test_stage1_loss_trajectory_100_steps(gold_name):
     """North-star bar: training loss within 1e-3 relative of the reference after 100 steps.
+
+    Two committed trajectories: `train_trajectory.json` (3 pairs x 14 keypoints, a fresh unrelated batch per step: the
+    loss stays O(1), so step t depends on the whole update history) and `train_trajectory_n100.json` = BASELINE.json
+    config 3's per-GPU share (8 genuine pairs x 100 keypoints, image-2 maps = image-1 maps + noise, a fixed cycle of 4
+    batches: the loss FALLS from 5.6 to 1.7, and the n = 100 kernels - slab planner, compacted backward, the
+    column-resident LAP - are the ones that run).
 
     Set-up = the first 100 steps of the reference's stage-1 recipe (tests/golden/make_train_golden.py): a fresh batch
     of 3 genuine pairs x 14 keypoints per step, AdamW(wd 1e-4) with the LR warm-up of train.py (1e-4 for steps 0-74,
@@ -335,23 +342,31 @@ def test_stage1_loss_trajectory_100_steps():
     from fpmatch import synth
     from oracle import train as otrain
     from src.model.ngm import Net
-    gold = json.loads((ROOT / "tests" / "golden" / "train_trajectory.json").read_text())
+    gold = json.loads((ROOT / "tests" / "golden" / gold_name).read_text())
     ref = gold["loss_fp32"]
     B, n, steps = gold["B"], gold["n"], gold["steps"]
+    cycle = gold.get("cycle", 0)
     lr_at = lambda t: otrain.warmup_lr(t, gold["lr"], gold["warmup_epochs"], gold["steps_per_epoch"])
+    cache = {}
 
     def batch(t):
-        d = synth.make_batch(B, n, seed=gold["seed_base"] + t, imposter_every=0, with_kron=True,
-                             fmap_noise=gold["fmap_noise"])
-        d.pop("label")
-        return d
+        key = t % cycle if cycle else t
+        if key not in cache:
+            d = synth.make_batch(B, n, seed=gold["seed_base"] + key, imposter_every=0, with_kron=True,
+                                 with_dense_gh=False, fmap_noise=gold["fmap_noise"])
+            d.pop("label")
+            if not cycle:
+                return d
+            cache[key] = d
+        return synth.clone_batch(cache[key])
 
     torch.manual_seed(0)
     net = Net(regression=False)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    live = otrain.train_trajectory(sd, [batch(t) for t in range(3)], 3, lr=gold["lr"], weight_decay=gold["weight_decay"],
-                                   clip=gold["clip"], lr_schedule=lr_at)
-    assert max(abs(a - b) / abs(b) for a, b in zip(live, ref[:3])) < 1e-5, (live, ref[:3])
+    nlive = 3 if n <= 20 else 2          # the live oracle costs ~5 s per step at 8 pairs x 100 keypoints
+    live = otrain.train_trajectory(sd, [batch(t) for t in range(nlive)], nlive, lr=gold["lr"],
+                                   weight_decay=gold["weight_decay"], clip=gold["clip"], lr_schedule=lr_at)
+    assert max(abs(a - b) / abs(b) for a, b in zip(live, ref[:nlive])) < 1e-5, (live, ref[:nlive])
 
     net = net.to(DEV).train()
     names = set(otrain.trainable_names(sd))
@@ -378,7 +393,7 @@ def test_stage1_loss_trajectory_100_steps():
         rec["oracle32_vs_fp64_rel_max"] = max(abs(a - b) / abs(b) for a, b in zip(ref, r64))
         rec["gpu_vs_fp64_rel_last"] = abs(got[-1] - r64[-1]) / abs(r64[-1])
         rec["gpu_vs_fp64_rel_max"] = max(abs(a - b) / abs(b) for a, b in zip(got, r64))
-    report("stage1_trajectory", **rec)
+    report("stage1_trajectory", gold=gold_name, B=B, n=n, cycle=cycle, **rec)
     assert rel[0] < 1e-5
     assert rel[-1] < 1e-3, rec
     assert max(rel) < 1e-3, rec

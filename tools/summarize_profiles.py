@@ -94,6 +94,29 @@ def full():
         out.append("")
     (PR / f"{tag}_ncu_full.md").write_text("\n".join(out) + "\n")
     print("\n".join(out[:60]))
+    # machine-readable pointer for bench.py's roofline.traffic: the slab GEMM = the longest persistent-grid launch of
+    # gemm_tc_pair_kernel in the capture
+    import json
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tmul = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+
+    def val(d, m, table):
+        return float(d[idx[m]].replace(",", "")) * table[units[idx[m]]]
+    gemms = [d for (name, _), d in best.items() if "gemm_tc_pair_kernel" in name]
+    rec = {"tag": tag, "file": f"profiles/{tag}_ncu_full.md", "kernels": {}}
+    for (name, grid), d in best.items():
+        try:
+            rec["kernels"][f"{name} grid={grid}"] = {
+                "time_us": val(d, "gpu__time_duration.sum", tmul),
+                "dram_bytes": val(d, "dram__bytes_read.sum", mult) + val(d, "dram__bytes_write.sum", mult)}
+        except Exception:
+            pass
+    if gemms:
+        d = max(gemms, key=dur)
+        rec["slab_gemm"] = {"kernel": short(d[idx["Kernel Name"]]), "grid": d[idx["launch__grid_size"]],
+                            "time_us": val(d, "gpu__time_duration.sum", tmul),
+                            "dram_bytes": val(d, "dram__bytes_read.sum", mult) + val(d, "dram__bytes_write.sum", mult)}
+    (PR / "LATEST_NCU.json").write_text(json.dumps(rec, indent=1) + "\n")
 
 
 launches()
