@@ -44,6 +44,9 @@ SIGNATURES = {
     "fpm_csr_by_dst": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_spline_gather_max": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_affinity": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "fpm_f16_split_rows_scaled": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P]),
+    "fpm_affinity_tiles": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "fpm_affinity_finish": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "fpm_affinity_edges_factored": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _F, _P]),
     "fpm_assoc_effective": (_I, [_P] * 11 + [_I, _I, _I, _P]),
     "fpm_assoc_in_csr": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),

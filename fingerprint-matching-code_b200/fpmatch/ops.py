@@ -408,11 +408,51 @@ def spline_gather_max(Y: Tensor, xin: Optional[Tensor], edge_index: Tensor, pseu
 # ---------------------------------------------------------------------------------------------------
 # affinities
 # ---------------------------------------------------------------------------------------------------
+_AFFINITY_TC = os.environ.get("FPMATCH_AFFINITY_TC", "1") != "0"
+
+
+def set_affinity_tc(on: bool) -> None:
+    """True (default): node affinities on the tcgen05 tile-table GEMM (csrc/affinity_tc.cu); False: CUDA-core kernel."""
+    global _AFFINITY_TC
+    _AFFINITY_TC = bool(on)
+
+
 def affinity_nodes(XA: Tensor, XB: Tensor, coeff: Tensor, ptrA: Tensor, ptrB: Tensor, Rmax: int, Cmax: int,
                    scale: float = 1.0, want_t: bool = True, raw: bool = False):
+    """softplus((XA_b (.) coeff_b) XB_b^T) - 0.5 per pair, zero padded to [B,Rmax,Cmax] (+ the transposed copy)."""
     B = coeff.shape[0]
     out = torch.empty((B, Rmax, Cmax), dtype=torch.float32, device=XA.device)
     out_t = torch.empty((B, Cmax, Rmax), dtype=torch.float32, device=XA.device) if want_t else None
+    K = XA.shape[1]
+    if _AFFINITY_TC and _GEMM_MODE == "3xf16" and _GEMM_PAIR and K % 64 == 0 and B > 0 and XA.shape[0] > 0 \
+            and XB.shape[0] > 0:
+        L = _lib.lib()
+        dev = XA.device
+        tA, tB = (Rmax + 255) // 256, (Cmax + 127) // 128
+        a_hi = torch.empty((XA.shape[0], K), dtype=torch.float16, device=dev)
+        a_lo = torch.empty_like(a_hi)
+        a_inv = torch.empty((XA.shape[0],), dtype=torch.float32, device=dev)
+        rc = L.fpm_f16_split_rows_scaled(_chk(XA, "XA"), _chk(coeff, "coeff"), _chk(ptrA, "ptrA", torch.int64), B,
+                                         a_hi.data_ptr(), a_lo.data_ptr(), a_inv.data_ptr(), XA.shape[0], K, _stream())
+        _lib.check(rc, "fpm_f16_split_rows_scaled"); _count()
+        b_hi, b_lo, b_inv = f16_split_rows(XB)
+        ntile = B * tA * tB
+        tab = torch.empty((ntile, 4), dtype=torch.int32, device=dev)
+        meta = torch.empty((1,), dtype=torch.int32, device=dev)
+        rowmap = torch.empty((B * tA * 256,), dtype=torch.int32, device=dev)
+        rc = L.fpm_affinity_tiles(ptrA.data_ptr(), _chk(ptrB, "ptrB", torch.int64), B, Rmax, Cmax, tab.data_ptr(),
+                                  meta.data_ptr(), rowmap.data_ptr(), _stream())
+        _lib.check(rc, "fpm_affinity_tiles"); _count()
+        ldp = 128 * tB
+        P = torch.empty((B * Rmax, ldp), dtype=torch.float32, device=dev)
+        rc = L.fpm_gemm_nt_f16x3_tiles(a_hi.data_ptr(), a_lo.data_ptr(), a_inv.data_ptr(), b_hi.data_ptr(),
+                                       b_lo.data_ptr(), b_inv.data_ptr(), P.data_ptr(), XA.shape[0], XB.shape[0], K, K, K,
+                                       ldp, tab.data_ptr(), meta.data_ptr(), rowmap.data_ptr(), ntile, 0, _stream())
+        _lib.check(rc, "fpm_gemm_nt_f16x3_tiles"); _count()
+        rc = L.fpm_affinity_finish(P.data_ptr(), ptrA.data_ptr(), ptrB.data_ptr(), out.data_ptr(),
+                                   out_t.data_ptr() if want_t else None, B, Rmax, Cmax, ldp, scale, int(raw), _stream())
+        _lib.check(rc, "fpm_affinity_finish"); _count()
+        return out, out_t
     rc = _lib.lib().fpm_affinity(_chk(XA, "XA"), _chk(XB, "XB"), _chk(coeff, "coeff"),
                                  _chk(ptrA, "ptrA", torch.int64), _chk(ptrB, "ptrB", torch.int64),
                                  None, None, None, None, 0, 0, out.data_ptr(),
@@ -1037,7 +1077,7 @@ def add_instnorm_bwd(a: Tensor, other: Optional[Tensor], gamma: Tensor, dy: Opti
 def _install_device_guards():
     import types
     g = globals()
-    skip = {"set_gemm_mode", "gemm_mode", "set_gemm_pair", "gemm_pair_enabled", "set_slab_plan", "slab_plan_enabled",
+    skip = {"set_gemm_mode", "gemm_mode", "set_affinity_tc", "set_gemm_pair", "gemm_pair_enabled", "set_slab_plan", "slab_plan_enabled",
             "launch_count", "gemm_profile_start", "gemm_profile_stop", "on_tensor_device"}
     for name, obj in list(g.items()):
         if name.startswith("_") or name in skip:

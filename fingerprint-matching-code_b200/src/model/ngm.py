@@ -167,6 +167,7 @@ class Net(CNN):
         self.ke_side_stream = os.environ.get('FPMATCH_KE_SIDE', '1') != '0'
         self._backbone_channels_last = False
         self._lap_pending = None          # pinned ring of LAP status flags, see _note_lap_status
+        self.track_lap_status = True      # False: no status traffic at all (e.g. while capturing a CUDA graph)
 
     def backbone_channels_last(self, on: bool = True):
         """Opt-in: keep the stock ResNet-18 chunks in channels-last memory format so that
@@ -322,6 +323,8 @@ class Net(CNN):
         the forward free of host synchronisation the flag travels to a pinned host word asynchronously (a ring of 8,
         because the host runs ahead of the device) and is looked at by a LATER call - or by ``check_lap_status()`` -
         which raises the same ``ValueError``."""
+        if not self.track_lap_status:
+            return
         self.check_lap_status(block=False)
         if self._lap_pending is None:
             self._lap_pending = {"flags": torch.zeros(8, dtype=torch.int32).pin_memory(), "queue": [], "next": 0}

@@ -132,6 +132,17 @@ int fpm_affinity(const float* XA, const float* XB, const float* coeff, const lon
 /* Ke through linearity: with P = raw node products (X1 (.) c_edge) X2^T [B,Rn,Cn] (fpm_affinity, raw = 1),
  * out[b,k1,k2] = scale * (softplus(P[s1,s2] - P[s1,d2] - P[d1,s2] + P[d1,d2]) - 0.5); 33x fewer FLOPs than
  * the reference's e1 x 768 x e2 product (ngm.py:282-287). */
+/* Tensor-core route of the same affinity (csrc/affinity_tc.cu): fpm_f16_split_rows_scaled = error-compensated fp16 split
+ * of X rows times their pair's coefficient vector (ptr [B+1] = row offsets of the pairs); fpm_affinity_tiles = tile
+ * table + row map for fpm_gemm_nt_f16x3_tiles (tab [B*tA*tB,4], tA = ceil(Rmax/256), tB = ceil(Cmax/128); rowmap
+ * [B*tA*256]); the GEMM writes raw products into P [B*Rmax, ldp = 128*tB]; fpm_affinity_finish applies
+ * scale * (softplus - 0.5) (raw = 0) and the zero padding -> out [B,Rmax,Cmax] (+ out_t [B,Cmax,Rmax] optional). */
+int fpm_f16_split_rows_scaled(const float* src, const float* coeff, const long long* ptr, int B, void* hi, void* lo,
+                              float* inv_scale, int rows, int K, void* stream);
+int fpm_affinity_tiles(const long long* ptrA, const long long* ptrB, int B, int Rmax, int Cmax, int* tab,
+                       int* tab_count, int* rowmap, void* stream);
+int fpm_affinity_finish(const float* P, const long long* ptrA, const long long* ptrB, float* out, float* out_t, int B,
+                        int Rmax, int Cmax, int ldp, float scale, int raw, void* stream);
 int fpm_affinity_edges_factored(const float* P, const long long* eidxA, const long long* eptrA,
                                 const long long* ptrA, const long long* eidxB, const long long* eptrB,
                                 const long long* ptrB, int EA, int EB, float* out, int B, int Rn, int Cn,

@@ -740,3 +740,41 @@ def test_ops_follow_their_tensors_device(ops, oo):
     assert (out.cpu() - ref).abs().max() < 1e-5
     with pytest.raises(RuntimeError):
         ops.sinkhorn_log(s.to("cuda:1"), torch.tensor([8, 8], device="cuda:0"), None, 10, 0.1, False)
+
+
+@pytest.mark.parametrize("ns1,ns2", [((100, 100, 100), (100, 100, 100)), ((57, 100, 3), (100, 64, 91)),
+                                     ((300, 257, 129), (260, 128, 300))])
+def test_affinity_tensor_core_route(ops, oo, ns1, ns2):
+    """Node affinity on the tcgen05 tile-table GEMM (csrc/affinity_tc.cu) against an fp64 evaluation of
+    affinity_layer.py:11-19 and against the CUDA-core kernel: ragged pairs, several 256 x 128 tiles per pair, padding."""
+    g = torch.Generator().manual_seed(sum(ns1) + sum(ns2))
+    D = 768
+    B = len(ns1)
+    X1 = torch.randn(sum(ns1), D, generator=g) * 0.2; X2 = torch.randn(sum(ns2), D, generator=g) * 0.2
+    coeff = torch.tanh(torch.randn(B, D, generator=g))
+    p1 = torch.tensor([0] + list(ns1)).cumsum(0); p2 = torch.tensor([0] + list(ns2)).cumsum(0)
+    Rmax, Cmax = max(ns1), max(ns2)
+    args = (X1.to(DEV), X2.to(DEV), coeff.to(DEV), p1.to(DEV), p2.to(DEV), Rmax, Cmax)
+    assert ops.gemm_mode() == "3xf16"
+    ops.set_affinity_tc(True)
+    l0 = ops.launch_count()
+    Kt, Kt_t = ops.affinity_nodes(*args)
+    assert ops.launch_count() - l0 == 5              # scaled split, split, tile table, GEMM, finish
+    Pt, _ = ops.affinity_nodes(*args, want_t=False, raw=True)
+    ops.set_affinity_tc(False)
+    try:
+        Ks, _ = ops.affinity_nodes(*args)
+    finally:
+        ops.set_affinity_tc(True)
+    worst = worst_raw = 0.0
+    for b in range(B):
+        a = (X1[p1[b]:p1[b + 1]] * coeff[b]).double() @ X2[p2[b]:p2[b + 1]].double().T
+        ref = torch.nn.functional.softplus(a) - 0.5
+        got = Kt[b, :ns1[b], :ns2[b]].cpu().double()
+        worst = max(worst, (got - ref).abs().max().item())
+        worst_raw = max(worst_raw, (Pt[b, :ns1[b], :ns2[b]].cpu().double() - a).abs().max().item())
+        assert (Kt[b, ns1[b]:].cpu() == 0).all() and (Kt[b, :, ns2[b]:].cpu() == 0).all()
+    simt = (Kt - Ks).abs().max().item()
+    report("affinity_tensor_core", ns1=list(ns1), max_abs_vs_fp64=worst, raw_max_abs_vs_fp64=worst_raw, vs_cuda_core=simt)
+    assert torch.equal(Kt_t, Kt.transpose(1, 2))
+    assert worst < 2e-6 and worst_raw < 2e-6 and simt < 2e-6

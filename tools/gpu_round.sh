@@ -1,22 +1,27 @@
 #!/bin/bash
 # One GPU-box visit: GPU tests (as the driver runs them), smoke, bench lines, ncu launch list and full captures.
-# Usage (under gpurun): bash tools/gpu_round.sh <tag>
+# Usage (under gpurun): bash tools/gpu_round.sh <tag> [notests] [noncu]
 TAG=${1:-rX}
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 O=gpurun_out
+rm -f $O/parity_report.jsonl
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${TAG}_smi.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/${TAG}_pytest_gpu.log
-tail -3 $O/${TAG}_pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/${TAG}_smoke.log
+if [[ "$*" != *notests* ]]; then
+  timeout 1500 python -m pytest tests -m gpu -x -q --durations=15 > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/${TAG}_pytest_gpu.log
+  tail -25 $O/${TAG}_pytest_gpu.log
+  cp $O/parity_report.jsonl $O/${TAG}_parity_report.jsonl 2>/dev/null
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/${TAG}_smoke.log
+fi
 timeout 600 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench rc=$?"; tail -1 $O/${TAG}_bench.json
-timeout 300 python bench.py --gemm 3xtf32 --steps 5 --no-cpu-baseline > $O/${TAG}_bench_3xtf32.json 2> $O/${TAG}_bench_3xtf32.err; tail -1 $O/${TAG}_bench_3xtf32.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err; tail -1 $O/${TAG}_bench_reference.json
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
-$CMD > $O/${TAG}_plain.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_launch.log 2>&1
-echo "ncu launches rc=$?"
-$CMD > $O/${TAG}_plain2.log 2>&1 &&
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_pair_kernel|gemm_tc_kernel|gnn_layer_kernel|lap_topk|ke_factored|spline_gather|afau_attention|sinkhorn_log|match_cls|affinity_kernel" -s 50 -c 25 -o $O/${TAG}_prof $CMD > $O/${TAG}_ncu_full.log 2>&1
-echo "ncu full rc=$?"
-ls -la $O | tail -20
+if [[ "$*" != *noncu* ]]; then
+  CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+  $CMD > $O/${TAG}_plain.log 2>&1 &&
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_launch.log 2>&1
+  echo "ncu launches rc=$?"
+  $CMD > $O/${TAG}_plain2.log 2>&1 &&
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_pair_kernel|gnn_layer_kernel|lap_topk|ke_factored|spline_gather|afau_attention|sinkhorn_log|match_cls_stage2|affinity_kernel|soft_topk|add_instnorm|fmap_prep|f16_split" -s 70 -c 44 -o $O/${TAG}_prof $CMD > $O/${TAG}_ncu_full.log 2>&1
+  echo "ncu full rc=$?"
+fi
+ls -la $O | tail -12
