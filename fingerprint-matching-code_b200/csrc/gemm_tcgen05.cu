@@ -441,7 +441,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   uint64_t* tmem_full_bar = empty_bar + kPStages;       // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2] (the leader's copy is the one in use)
   uint32_t* tmem_ptr = (uint32_t*)(tmem_empty_bar + 2);
-  float* epi_tiles = (float*)(smem + (size_t)kPStages * kPStageBytes + 256);   // kEpiWarps x [32][33] floats
+  // kEpiWarps x [32][32] floats, element (row, col) at row * 32 + (col ^ row): conflict-free for the row-wise writes and
+  // the column-wise reads below without the 33-float padding (1 KB less shared memory per CTA: together with the
+  // 16-edge chunks of spline_gather_max_kernel that lets one gather CTA run beside the GEMM CTA of the OTHER graph)
+  float* epi_tiles = (float*)(smem + (size_t)kPStages * kPStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -542,7 +545,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   } else {
     // ===== epilogue (both CTAs): warps 2..9, TMEM lane quarter = warp % 4, two warps per quarter split the columns
     const int q = warp & 3, half = (warp - 2) >> 2;
-    float* tile_s = epi_tiles + (size_t)(warp - 2) * (32 * 33);
+    float* tile_s = epi_tiles + (size_t)(warp - 2) * (32 * 32);
     const uint32_t empty_addr0 = mapa_rank0(smem_u32(&tmem_empty_bar[0]));
     const uint32_t empty_addr1 = mapa_rank0(smem_u32(&tmem_empty_bar[1]));
     constexpr float kCorrScale = kF16 ? (1.0f / 2048.0f) : 1.0f;
@@ -592,14 +595,14 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           if (kF16) x = x * row_scale * __shfl_sync(0xffffffffu, col_scale, j);
           x += __shfl_sync(0xffffffffu, col_bias, j);
           if (act == 1) x = fmaxf(x, 0.f);
-          tile_s[lane * 33 + j] = x;
+          tile_s[lane * 32 + (j ^ lane)] = x;
         }
         __syncwarp();
         if (rm >= 0) {
           // mapped rows (gathered A): every row has its own destination
           for (int rr = 0; rr < 32; ++rr) {
             const int crow = __shfl_sync(0xffffffffu, crow_lane, rr);
-            if (crow >= 0 && brow < N) Cm[(size_t)crow * ldc + ncol] = tile_s[rr * 33 + lane];
+            if (crow >= 0 && brow < N) Cm[(size_t)crow * ldc + ncol] = tile_s[rr * 32 + (lane ^ rr)];
           }
         } else if (brow < N) {
           const int mrow0 = m0 + q * 32;
@@ -610,12 +613,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             for (int r0 = 0; r0 < 32; r0 += 8) {
               float v[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) v[u] = tile_s[(r0 + u) * 33 + lane];
+              for (int u = 0; u < 8; ++u) v[u] = tile_s[(r0 + u) * 32 + (lane ^ (r0 + u))];
 #pragma unroll
               for (int u = 0; u < 8; ++u) cbase[(size_t)(r0 + u) * ldc] = v[u];
             }
           } else {
-            for (int rr = 0; rr < nrows; ++rr) cbase[(size_t)rr * ldc] = tile_s[rr * 33 + lane];
+            for (int rr = 0; rr < nrows; ++rr) cbase[(size_t)rr * ldc] = tile_s[rr * 32 + (lane ^ rr)];
           }
         }
         __syncwarp();
@@ -772,7 +775,7 @@ static int launch_tc_pair(const void* A_hi, const void* A_lo, const void* B_hi, 
   if ((rc = make_map(&mAl, A_lo, M, K, lda, fpm::P_TBM, f16)) != FPM_OK) return rc;
   if ((rc = make_map(&mBh, B_hi, N, K, ldb, fpm::P_TBN / 2, f16)) != FPM_OK) return rc;
   if ((rc = make_map(&mBl, B_lo, N, K, ldb, fpm::P_TBN / 2, f16)) != FPM_OK) return rc;
-  const size_t smem = (size_t)fpm::kPStages * fpm::kPStageBytes + 1024 + 256 + (size_t)fpm::kEpiWarps * 32 * 33 * 4;
+  const size_t smem = (size_t)fpm::kPStages * fpm::kPStageBytes + 1024 + 256 + (size_t)fpm::kEpiWarps * 32 * 32 * 4;
   auto kern = fpm::gemm_tc_pair_kernel<kMode>;
   FPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};

@@ -14,6 +14,7 @@
 // |In2(j2)| source rows of x into shared memory once, then every thread finishes one node j1.
 // HBM/L2-bound: ~7 row reads of [n1max, 17] per CTA, one [n1max, 16] row written.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fpm {
 
@@ -166,22 +167,28 @@ struct GnnWeights {
 
 constexpr int kF = 16;   // GNN_FEAT, ngm.py:47
 
-// The layer's weights live in CONSTANT memory during the forward: every thread of a warp multiplies by the same
-// weight, so the FMAs take it as a constant-bank operand and issue no load at all for it.  (With the weights in
-// shared memory the kernel spent 27 % of its warp samples waiting on LDS and 18 % on the dependent FMAs behind
-// them - r1c ncu source view.)  Layout for row padding CP (4 or 20):
-//   wl[16][CP] wr[16][CP] w0[16][CP] w2[16][16] bl[16] b0[16] b2[16] wc[16] cb
+// The layer's weights live in CONSTANT memory: every thread of a warp multiplies by the same weight, so the FMAs take
+// it from the constant bank through uniform registers and issue no per-thread load for it.  (With the weights in
+// shared memory the kernel spent 27 % of its warp samples waiting on LDS - r1c ncu source view.)
+// Layout, TRANSPOSED so that the weights of two adjacent OUTPUT channels for one input channel are an aligned pair
+// (one operand of the packed FFMA2 of sm_100, see gnn_layer_kernel):
+//   wlT[CP][16] wrT[CP][16] w0T[CP][16] w2T[16][16] bl[16] b0[16] b2[16] wc[16] cb     (xT[c][o] = x[o][c])
 // gnn_pack_weights_kernel writes that layout into a device staging buffer and one cudaMemcpyToSymbolAsync
 // (device to device, stream ordered) publishes it before the layer kernel.  The bank is one per device: launches
 // from different streams are serialised against each other with an event (gnn_publish_weights).
 constexpr int kGnnConstFloats = 3 * 16 * 20 + 16 * 16 + 4 * 16 + 4;
-__constant__ float c_gnn[kGnnConstFloats];
+__constant__ __align__(16) float c_gnn[kGnnConstFloats];
 
 template <int CP>
 struct GnnOff {
   static constexpr int wl = 0, wr = 16 * CP, w0 = 32 * CP, w2 = 48 * CP, bl = w2 + 256, b0 = bl + 16, b2 = b0 + 16,
                        wc = b2 + 16, cb = wc + 16, total = cb + 1;
 };
+// element accessors (o = output channel, c = input channel)
+#define GNN_WL(o, c) c_gnn[O::wl + (c) * 16 + (o)]
+#define GNN_WR(o, c) c_gnn[O::wr + (c) * 16 + (o)]
+#define GNN_W0(o, c) c_gnn[O::w0 + (c) * 16 + (o)]
+#define GNN_W2(o, c) c_gnn[O::w2 + (c) * 16 + (o)]
 
 template <int CIN>
 __global__ void gnn_pack_weights_kernel(GnnWeights w, float* __restrict__ staging) {
@@ -189,13 +196,16 @@ __global__ void gnn_pack_weights_kernel(GnnWeights w, float* __restrict__ stagin
   using O = GnnOff<CP>;
   const int tid = threadIdx.x;
   for (int i = tid; i < 16 * CP; i += blockDim.x) {
-    const int o = i / CP, c = i - o * CP;
+    const int c = i / 16, o = i - c * 16;
     const bool in = c < CIN;
     staging[O::wl + i] = in ? w.lin_l_w[o * CIN + c] : 0.f;
     staging[O::wr + i] = in ? w.lin_r_w[o * CIN + c] : 0.f;
     staging[O::w0 + i] = in ? w.self0_w[o * CIN + c] : 0.f;
   }
-  for (int i = tid; i < 256; i += blockDim.x) staging[O::w2 + i] = w.self2_w[i];
+  for (int i = tid; i < 256; i += blockDim.x) {
+    const int c = i / 16, o = i - c * 16;
+    staging[O::w2 + i] = w.self2_w[o * 16 + c];
+  }
   if (tid < 16) {
     staging[O::bl + tid] = w.lin_l_b[tid]; staging[O::b0 + tid] = w.self0_b[tid];
     staging[O::b2 + tid] = w.self2_b[tid]; staging[O::wc + tid] = w.cls_w[tid];
@@ -203,11 +213,35 @@ __global__ void gnn_pack_weights_kernel(GnnWeights w, float* __restrict__ stagin
   if (tid == 0) staging[O::cb] = w.cls_b[0];
 }
 
+// ---- packed fp32 arithmetic of sm_100: one instruction, two lanes (FFMA2 / FADD2) --------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+// acc[0..7] (output channel pairs (0,1) .. (14,15)) += WT[c][0..15] * x   - 8 FFMA2 with the weight pair as a
+// uniform-register operand and x broadcast to both lanes
+#define GNN_FMA_ROW(acc, base, c, x)                                                      \
+  do {                                                                                    \
+    const f32x2 xx__ = pk2((x), (x));                                                     \
+    _Pragma("unroll") for (int p__ = 0; p__ < 8; ++p__)                                   \
+      (acc)[p__] = fma2(pk2(c_gnn[(base) + (c) * 16 + 2 * p__], c_gnn[(base) + (c) * 16 + 2 * p__ + 1]), xx__, \
+                        (acc)[p__]);                                                      \
+  } while (0)
+
 // Stage 1 of a (pair, j2) CTA, shared by the forward and backward kernels:
 //   Rsum[i1, c] = sum_{i2 in In2(j2)} feat[(i2, i1), c]     (feat = 16 channels of xprev + the matrix channel)
 //   Rp[i1, c]   = feat[(ps2, i1), c]  when the pair's cut-off block targets this j2 (see assoc_effective_kernel)
 // Each source row (i2, :) is contiguous ([n1max][16] floats + [n1max] for the matrix channel): it is streamed with
-// independent 128-bit loads, accumulated over In2(j2) in registers.
+// independent 128-bit loads, accumulated over In2(j2) in registers (packed adds).
 template <int CIN>
 __device__ __forceinline__ void gnn_stage1(const float* __restrict__ xb, const float* __restrict__ mb,
                                            const int* __restrict__ is2, int beg2, int end2, int ps2,
@@ -217,25 +251,25 @@ __device__ __forceinline__ void gnn_stage1(const float* __restrict__ xb, const f
   if (CIN > 1) {
     const int nvec = n1max * (kF / 4);
     for (int f0 = 0; f0 < nvec; f0 += 2 * nt) {
-      float4 acc[2];
+      f32x2 acc[2][2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 2; ++u) acc[u][0] = acc[u][1] = pk2(0.f, 0.f);
 #pragma unroll 3
       for (int q = beg2; q < end2; ++q) {
-        const float4* row = (const float4*)(xb + (size_t)is2[q] * n1max * kF);
+        const ulonglong2* row = (const ulonglong2*)(xb + (size_t)is2[q] * n1max * kF);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int f = f0 + u * nt + tid;
           if (f < nvec) {
-            const float4 v = row[f];
-            acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+            const ulonglong2 v = row[f];
+            acc[u][0] = add2(acc[u][0], v.x); acc[u][1] = add2(acc[u][1], v.y);
           }
         }
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int f = f0 + u * nt + tid;
-        if (f < nvec) *(float4*)&Rsum[(size_t)(f >> 2) * CP + (f & 3) * 4] = acc[u];
+        if (f < nvec) *(ulonglong2*)&Rsum[(size_t)(f >> 2) * CP + (f & 3) * 4] = make_ulonglong2(acc[u][0], acc[u][1]);
       }
     }
     if (ps2 >= 0) {
@@ -317,170 +351,179 @@ __device__ __forceinline__ float gnn_node_inputs(const float* __restrict__ xb, c
 // xprev:   [B, N, 16]   (CIN == 17 only), N = n1max*n2max, p = i2*n1max + i1
 // mprev_t: [B, n2max, n1max]  the matrix channel in p order (Kp^T or Sinkhorn^T)
 // xout:    [B, N, 16];  score: [B, n1max, n2max] (classifier output, Sinkhorn-ready layout)
-// One CTA per (pair, j2), 256 threads = 4 node warps x 2 halves: warp w works on nodes 32*(w>>1) .. +31 and
-// computes output channels 8*(w&1) .. +7 of them, so a node's 1 216 FMAs are split over two threads of two different
-// warps (the half index is warp-uniform -> constant-bank weight operands keep compile-time offsets).  Order:
-//   A  own features -> this half of h0 = relu(W0 own + b0) -> shared memory          (does not depend on stage 1)
-//   B  stage 1: row sums over In2(j2) into shared memory                             (L2 reads)
-//   C  barrier;  D  aggregate over In1(j1), the 8 outputs, half of the classifier dot product
-// The first version ran one thread per node with all 16 outputs: 128 registers, 12 warps per SM, stage 1 and the
-// FMAs of a CTA strictly one after the other (0.49 ms per layer at 256 pairs x 100 keypoints).
-constexpr int kGnnThreads = 256;
-constexpr int kGnnNodes = 128;       // nodes per pass = kGnnThreads / 2
+//
+// One CTA per (pair, group of `rows` consecutive j2), one thread per association node.  The kernel is bound by
+// instruction issue (r2b ncu: 56 % issue slots busy at IPC 2.2 while the FMA pipe is 33 % busy), so the design
+// minimises instructions per node:
+//   * the 1 216 FMAs of a node (four 16 x {17,17,17,16} linears) are issued as 608 packed FFMA2 (sm_100: two fp32 FMAs
+//     per instruction): accumulator pair = two adjacent output channels, multiplicand = the input value broadcast to
+//     both lanes, multiplier = the transposed weight pair as a uniform-register operand (constant bank, no load),
+//   * the In1 aggregation and stage 1 use packed adds, the mean is 3 instructions per channel (q = a r,
+//     e = fma(-q, cnt, a), q += e r with r = RN(1 / cnt): the Markstein correction step of an IEEE division) instead of
+//     17 full divisions,
+//   * `rows` x n1max nodes per CTA fill whole warps (2 x 100 keypoints = 200 of 224 lanes instead of 100 of 128).
+// History: one thread per node with scalar FMAs 0.49 ms per layer (r1); two half-threads per node 0.61 ms (r2b: the
+// per-node bookkeeping - own load, aggregation, divisions - was duplicated and the instruction count doubled).
+constexpr int kGnnMaxThreads = 256;
 
-template <int CIN, int H>
-__device__ __forceinline__ void gnn_half_h0(const float* own, float* hx_slot) {
-  constexpr int CP = (CIN + 3) / 4 * 4;
-  using O = GnnOff<CP>;
-  float hh[8];
-#pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    float a = c_gnn[O::b0 + 8 * H + o];
-#pragma unroll
-    for (int c = 0; c < CP; ++c) a = fmaf(c_gnn[O::w0 + (8 * H + o) * CP + c], own[c], a);
-    hh[o] = fmaxf(a, 0.f);
-  }
-  *(float4*)(hx_slot + 8 * H) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-  *(float4*)(hx_slot + 8 * H + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
-}
-
-template <int CIN, int H>
-__device__ __forceinline__ float gnn_half_out(const float* own, const float* agg, const float* hx_slot,
-                                              float* __restrict__ xo) {
-  constexpr int CP = (CIN + 3) / 4 * 4;
-  using O = GnnOff<CP>;
-  float h[kF];
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const float4 v = *(const float4*)(hx_slot + 4 * t);
-    h[4 * t] = v.x; h[4 * t + 1] = v.y; h[4 * t + 2] = v.z; h[4 * t + 3] = v.w;
-  }
-  float x1[8];
-  float sc = 0.f;
-#pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    float a = c_gnn[O::bl + 8 * H + o];
-    float r = 0.f;
-#pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      a = fmaf(c_gnn[O::wl + (8 * H + o) * CP + c], agg[c], a);
-      r = fmaf(c_gnn[O::wr + (8 * H + o) * CP + c], own[c], r);
-    }
-    float s2 = c_gnn[O::b2 + 8 * H + o];
-#pragma unroll
-    for (int c = 0; c < kF; ++c) s2 = fmaf(c_gnn[O::w2 + (8 * H + o) * kF + c], h[c], s2);
-    const float v = (a + r) + fmaxf(s2, 0.f);
-    x1[o] = v;
-    sc = fmaf(c_gnn[O::wc + 8 * H + o], v, sc);
-  }
-  *(float4*)(xo + 8 * H) = make_float4(x1[0], x1[1], x1[2], x1[3]);
-  *(float4*)(xo + 8 * H + 4) = make_float4(x1[4], x1[5], x1[6], x1[7]);
-  return sc;
-}
-
-template <int CIN>
-__global__ void __launch_bounds__(kGnnThreads, 3)
+// MINB = CTAs per SM the register allocation is sized for: 2 -> 128 registers, 3 -> 80 registers (36 bytes of spills)
+template <int CIN, int MINB>
+__global__ void __launch_bounds__(kGnnMaxThreads, MINB)
 gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mprev_t,
                  const int* __restrict__ in_ptr1, const int* __restrict__ in_src1, const int* __restrict__ in_col1,
                  const int* __restrict__ in_ptr2, const int* __restrict__ in_src2,
                  const int64_t* __restrict__ ndiag_p, const int* __restrict__ part,
                  float* __restrict__ xout, float* __restrict__ score, int n1max, int n2max, int e1max,
-                 int e2max) {
+                 int e2max, int rows) {
   constexpr int CP = (CIN + 3) / 4 * 4;
   using O = GnnOff<CP>;
   extern __shared__ __align__(16) float sm[];
-  float* Rsum = sm;                               // [n1max][CP] sum over In2(j2) rows
-  float* Rp = Rsum + (size_t)n1max * CP;          // [n1max][CP] row of the cut-off block (rarely used)
-  float* hx = Rp + (size_t)n1max * CP;            // [kGnnNodes][16] h0 exchange between the two halves
-  float* sx = hx + kGnnNodes * kF;                // [kGnnNodes] partial classifier dot products of half 1
-  const int b = blockIdx.y, j2 = blockIdx.x;
+  float* Rsum = sm;                                      // [rows][n1max][CP] sums over In2(j2) rows
+  float* Rp = Rsum + (size_t)rows * n1max * CP;          // [n1max][CP] row of the cut-off block (rarely used)
+  int* sdeg = (int*)(Rp + (size_t)n1max * CP);           // [rows] |In2(j2)|
+  const int b = blockIdx.y, j2base = blockIdx.x * rows;
   const int N = n1max * n2max;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int half = warp & 1;
-  const int slot = (warp >> 1) * 32 + lane;       // node slot of this thread inside a pass
+  const int tid = threadIdx.x;
 
   const int* ip2 = in_ptr2 + (size_t)b * (n2max + 1);
-  const int beg2 = ip2[j2], end2 = ip2[j2 + 1];
   const int* is2 = in_src2 + (size_t)b * e2max;
   const float* xb = (CIN > 1) ? xprev + (size_t)b * N * kF : nullptr;
   const float* mb = mprev_t + (size_t)b * N;
-  int ps2 = -1, ccut = 0;
-  if (part != nullptr && part[b * 4 + 1] == j2) { ps2 = part[b * 4]; ccut = part[b * 4 + 2]; }
-  if (ccut <= 0) ps2 = -1;
+  int pd2 = -1, ps2 = -1, ccut = 0;
+  if (part != nullptr) { ps2 = part[b * 4]; pd2 = part[b * 4 + 1]; ccut = part[b * 4 + 2]; }
+  if (ccut <= 0 || pd2 < j2base || pd2 >= j2base + rows) { pd2 = -1; ps2 = -1; ccut = 0; }
   const long long ndiag = ndiag_p[b];
   const int* ip1 = in_ptr1 + (size_t)b * (n1max + 1);
   const int* is1 = in_src1 + (size_t)b * e1max;
   const int* ic1 = in_col1 != nullptr ? in_col1 + (size_t)b * e1max : nullptr;
-  const int d2 = end2 - beg2;
 
-  for (int base = 0; base < n1max; base += kGnnNodes) {
-    const int j1 = base + slot;
-    const bool live = j1 < n1max;
-    const size_t p = (size_t)j2 * n1max + (live ? j1 : 0);
+  // ---- stage 1: row sums over In2(j2) for every row of the group
+  for (int r = 0; r < rows; ++r) {
+    const int j2 = j2base + r;
+    if (j2 >= n2max) break;
+    const int beg2 = ip2[j2], end2 = ip2[j2 + 1];
+    if (tid == 0) sdeg[r] = end2 - beg2;
+    gnn_stage1<CIN>(xb, mb, is2, beg2, end2, j2 == pd2 ? ps2 : -1, Rsum + (size_t)r * n1max * CP, Rp, n1max);
+  }
+  __syncthreads();
+
+  // ---- stage 2: one thread per node (j2, j1)
+  const int nodes = rows * n1max;
+  for (int t = tid; t < nodes; t += blockDim.x) {
+    const int r = t / n1max, j1 = t - r * n1max;
+    const int j2 = j2base + r;
+    if (j2 >= n2max) break;
+    const size_t p = (size_t)j2 * n1max + j1;
+    const float* Rs = Rsum + (size_t)r * n1max * CP;
+    // own features
     float own[CP];
-    // ---- A: own features, this half of h0
 #pragma unroll
     for (int c = 0; c < CP; ++c) own[c] = 0.f;
-    if (live) {
-      if (CIN > 1) {
-        const float4* xp = (const float4*)(xb + p * kF);
+    if (CIN > 1) {
+      const float4* xp = (const float4*)(xb + p * kF);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float4 v = xp[t];
-          own[t * 4] = v.x; own[t * 4 + 1] = v.y; own[t * 4 + 2] = v.z; own[t * 4 + 3] = v.w;
-        }
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = xp[q];
+        own[q * 4] = v.x; own[q * 4 + 1] = v.y; own[q * 4 + 2] = v.z; own[q * 4 + 3] = v.w;
       }
-      own[CIN - 1] = mb[p];
-      if (half == 0) gnn_half_h0<CIN, 0>(own, hx + slot * kF); else gnn_half_h0<CIN, 1>(own, hx + slot * kF);
     }
-    // ---- B: stage 1 (once per CTA)
-    if (base == 0) gnn_stage1<CIN>(xb, mb, is2, beg2, end2, ps2, Rsum, Rp, n1max);
-    __syncthreads();
-    // ---- D: aggregate, outputs
-    float sc = 0.f;
-    if (live) {
-      float agg[CP];
+    own[CIN - 1] = mb[p];
+    // aggregation over In1(j1) of the row sums (packed adds)
+    f32x2 ag[CP / 2];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) agg[c] = 0.f;
-      const int beg1 = ip1[j1], end1 = ip1[j1 + 1];
+    for (int c = 0; c < CP / 2; ++c) ag[c] = pk2(0.f, 0.f);
+    const int beg1 = ip1[j1], end1 = ip1[j1 + 1];
+    for (int q = beg1; q < end1; ++q) {
+      const ulonglong2* rr = (const ulonglong2*)(Rs + (size_t)is1[q] * CP);
+#pragma unroll
+      for (int v = 0; v < CP / 4; ++v) {
+        const ulonglong2 w = rr[v];
+        ag[2 * v] = add2(ag[2 * v], w.x); ag[2 * v + 1] = add2(ag[2 * v + 1], w.y);
+      }
+    }
+    long long cnt = (long long)sdeg[r] * (long long)(end1 - beg1);
+    if (j2 == pd2) {                                    // rare: the cut-off block of this pair targets this row
       for (int q = beg1; q < end1; ++q) {
-        const float4* r = (const float4*)(Rsum + (size_t)is1[q] * CP);
+        if (ic1[q] < ccut) {
+          const ulonglong2* rr = (const ulonglong2*)(Rp + (size_t)is1[q] * CP);
 #pragma unroll
-        for (int t = 0; t < CP / 4; ++t) {
-          const float4 v = r[t];
-          agg[t * 4] += v.x; agg[t * 4 + 1] += v.y; agg[t * 4 + 2] += v.z; agg[t * 4 + 3] += v.w;
-        }
-      }
-      long long cnt = (long long)d2 * (long long)(end1 - beg1);
-      if (ps2 >= 0) {                               // CTA-uniform, rare: the cut-off block targets this j2
-        for (int q = beg1; q < end1; ++q) {
-          if (ic1[q] < ccut) {
-            const float4* r = (const float4*)(Rp + (size_t)is1[q] * CP);
-#pragma unroll
-            for (int t = 0; t < CP / 4; ++t) {
-              const float4 v = r[t];
-              agg[t * 4] += v.x; agg[t * 4 + 1] += v.y; agg[t * 4 + 2] += v.z; agg[t * 4 + 3] += v.w;
-            }
-            cnt += 1;
+          for (int v = 0; v < CP / 4; ++v) {
+            const ulonglong2 w = rr[v];
+            ag[2 * v] = add2(ag[2 * v], w.x); ag[2 * v + 1] = add2(ag[2 * v + 1], w.y);
           }
+          cnt += 1;
         }
       }
-      if ((long long)p < ndiag) {
-#pragma unroll
-        for (int c = 0; c < CIN; ++c) agg[c] += own[c];
-        cnt += 1;
-      }
-      const float inv = cnt > 0 ? (float)cnt : 1.f;
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) agg[c] = agg[c] / inv;
-      float* xo = xout + ((size_t)b * N + p) * kF;
-      if (half == 0) sc = gnn_half_out<CIN, 0>(own, agg, hx + slot * kF, xo);
-      else sc = gnn_half_out<CIN, 1>(own, agg, hx + slot * kF, xo);
-      if (half == 1) sx[slot] = sc;
     }
-    __syncthreads();
-    if (live && half == 0)
-      score[((size_t)b * n1max + j1) * n2max + j2] = (c_gnn[O::cb] + sc) + sx[slot];
+    float agg[CP];
+#pragma unroll
+    for (int c = 0; c < CP / 2; ++c) upk2(ag[c], agg[2 * c], agg[2 * c + 1]);
+    if ((long long)p < ndiag) {
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) agg[c] += own[c];
+      cnt += 1;
+    }
+    {
+      const float inv = cnt > 0 ? (float)cnt : 1.f;
+      const float rcp = __frcp_rn(inv);
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {                   // agg / inv, correctly rounded for these magnitudes
+        const float q0 = agg[c] * rcp;
+        const float e = fmaf(-q0, inv, agg[c]);
+        agg[c] = fmaf(e, rcp, q0);
+      }
+    }
+
+    // h0 = relu(W0 own + b0)
+    f32x2 acc[8];
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) acc[pp] = pk2(c_gnn[O::b0 + 2 * pp], c_gnn[O::b0 + 2 * pp + 1]);
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) GNN_FMA_ROW(acc, O::w0, c, own[c]);
+    float h[kF];
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) {
+      upk2(acc[pp], h[2 * pp], h[2 * pp + 1]);
+      h[2 * pp] = fmaxf(h[2 * pp], 0.f); h[2 * pp + 1] = fmaxf(h[2 * pp + 1], 0.f);
+    }
+    // s2 = relu(W2 h0 + b2)
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) acc[pp] = pk2(c_gnn[O::b2 + 2 * pp], c_gnn[O::b2 + 2 * pp + 1]);
+#pragma unroll
+    for (int c = 0; c < kF; ++c) GNN_FMA_ROW(acc, O::w2, c, h[c]);
+    float s2[kF];
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) {
+      upk2(acc[pp], s2[2 * pp], s2[2 * pp + 1]);
+      s2[2 * pp] = fmaxf(s2[2 * pp], 0.f); s2[2 * pp + 1] = fmaxf(s2[2 * pp + 1], 0.f);
+    }
+    // x1 = (Wl agg + bl + Wr own) + relu(s2)
+    f32x2 accr[8];
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) {
+      acc[pp] = pk2(c_gnn[O::bl + 2 * pp], c_gnn[O::bl + 2 * pp + 1]);
+      accr[pp] = pk2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      GNN_FMA_ROW(acc, O::wl, c, agg[c]);
+      GNN_FMA_ROW(accr, O::wr, c, own[c]);
+    }
+    float x1[kF];
+    float sc = c_gnn[O::cb];
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) {
+      const f32x2 v2 = add2(add2(acc[pp], accr[pp]), pk2(s2[2 * pp], s2[2 * pp + 1]));
+      upk2(v2, x1[2 * pp], x1[2 * pp + 1]);
+    }
+#pragma unroll
+    for (int o = 0; o < kF; ++o) sc = fmaf(c_gnn[O::wc + o], x1[o], sc);
+    float4* dst = (float4*)(xout + ((size_t)b * N + p) * kF);
+    dst[0] = make_float4(x1[0], x1[1], x1[2], x1[3]);
+    dst[1] = make_float4(x1[4], x1[5], x1[6], x1[7]);
+    dst[2] = make_float4(x1[8], x1[9], x1[10], x1[11]);
+    dst[3] = make_float4(x1[12], x1[13], x1[14], x1[15]);
+    score[((size_t)b * n1max + j1) * n2max + j2] = sc;
   }
 }
 
@@ -597,16 +640,16 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
       for (int o = 0; o < kF; ++o) {
         float a = c_gnn[O::b0 + o];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) a = fmaf(c_gnn[O::w0 + o * CP + c], own[c], a);
+        for (int c = 0; c < CP; ++c) a = fmaf(GNN_W0(o, c), own[c], a);
         h0[o] = fmaxf(a, 0.f);
       }
 #pragma unroll
       for (int o = 0; o < kF; ++o) {
         float a = c_gnn[O::bl + o], r = 0.f, q2 = c_gnn[O::b2 + o];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) { a = fmaf(c_gnn[O::wl + o * CP + c], agg[c], a); r = fmaf(c_gnn[O::wr + o * CP + c], own[c], r); }
+        for (int c = 0; c < CP; ++c) { a = fmaf(GNN_WL(o, c), agg[c], a); r = fmaf(GNN_WR(o, c), own[c], r); }
 #pragma unroll
-        for (int c = 0; c < kF; ++c) q2 = fmaf(c_gnn[O::w2 + o * kF + c], h0[c], q2);
+        for (int c = 0; c < kF; ++c) q2 = fmaf(GNN_W2(o, c), h0[c], q2);
         s2[o] = q2;
         x1[o] = (a + r) + fmaxf(q2, 0.f);
       }
@@ -630,7 +673,7 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
       for (int c = 0; c < kF; ++c) {
         float a = 0.f;
 #pragma unroll
-        for (int o = 0; o < kF; ++o) a = fmaf(c_gnn[O::w2 + o * kF + c], ds2[o], a);
+        for (int o = 0; o < kF; ++o) a = fmaf(GNN_W2(o, c), ds2[o], a);
         dh0[c] = h0[c] > 0.f ? a : 0.f;
       }
       float down[CP], dagg[CP];
@@ -639,9 +682,9 @@ gnn_layer_bwd_kernel(const float* __restrict__ xprev, const float* __restrict__ 
         float a = 0.f, g = 0.f;
 #pragma unroll
         for (int o = 0; o < kF; ++o) {
-          a = fmaf(c_gnn[O::wr + o * CP + c], dx1[o], a);
-          a = fmaf(c_gnn[O::w0 + o * CP + c], dh0[o], a);
-          g = fmaf(c_gnn[O::wl + o * CP + c], dx1[o], g);
+          a = fmaf(GNN_WR(o, c), dx1[o], a);
+          a = fmaf(GNN_W0(o, c), dh0[o], a);
+          g = fmaf(GNN_WL(o, c), dx1[o], g);
         }
         g = g / inv;
         dagg[c] = g;
@@ -865,15 +908,33 @@ static int gnn_layer_launch(const fpm::GnnWeights& w, int dev, const float* xpre
                             const int* in_src2, const long long* ndiag, const int* part, float* xout, float* score,
                             int B, int n1max, int n2max, int e1max, int e2max, cudaStream_t st) {
   constexpr int CP = (CIN + 3) / 4 * 4;
-  const size_t smem = ((size_t)2 * n1max * CP + fpm::kGnnNodes * (fpm::kF + 1)) * sizeof(float);
+  // rows of association nodes (consecutive j2) per CTA: as many as fit 256 threads, so that whole warps are busy
+  int rows = fpm::kGnnMaxThreads / n1max;
+  rows = rows < 1 ? 1 : (rows > 4 ? 4 : rows);
+  if (rows > n2max) rows = n2max;
+  int threads = (rows * n1max + 31) / 32 * 32;
+  if (threads > fpm::kGnnMaxThreads) threads = fpm::kGnnMaxThreads;
+  const size_t smem = ((size_t)(rows + 1) * n1max * CP + 8) * sizeof(float);
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_gnn_layer: n1max too large");
   int rc = gnn_publish_weights<CIN>(w, dev, st);
   if (rc != FPM_OK) return rc;
-  FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(n2max, B);
-  fpm::gnn_layer_kernel<CIN><<<grid, fpm::kGnnThreads, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_col1, in_ptr2,
-                                                                  in_src2, (const int64_t*)ndiag, part, xout, score,
-                                                                  n1max, n2max, e1max, e2max);
+  static int minb = 0;                                 // FPMATCH_GNN_MINB=2|3 (A/B switch; default 3)
+  if (minb == 0) {
+    const char* e = getenv("FPMATCH_GNN_MINB");
+    minb = (e && e[0] == '2') ? 2 : 3;
+  }
+  dim3 grid(fpm_cdiv(n2max, rows), B);
+  if (minb == 2) {
+    FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<CIN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fpm::gnn_layer_kernel<CIN, 2><<<grid, threads, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_col1, in_ptr2,
+                                                              in_src2, (const int64_t*)ndiag, part, xout, score, n1max,
+                                                              n2max, e1max, e2max, rows);
+  } else {
+    FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<CIN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fpm::gnn_layer_kernel<CIN, 3><<<grid, threads, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_col1, in_ptr2,
+                                                              in_src2, (const int64_t*)ndiag, part, xout, score, n1max,
+                                                              n2max, e1max, e2max, rows);
+  }
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

@@ -734,6 +734,33 @@ __global__ void greedy_perm_kernel(float* __restrict__ x, const int64_t* __restr
 
 }  // namespace fpm
 
+namespace fpm {
+// scipy.optimize.linear_sum_assignment refuses a cost matrix with NaN or -inf entries ("matrix contains invalid numeric
+// entries"; cost = -s, so s = NaN or +inf) even when an assignment that avoids them exists - which is what the
+// shortest-augmenting-path kernels above would return.  One CTA per pair scans its valid block after the solve: such a
+// pair gets status 1 and all-zero outputs, like an infeasible one.
+__global__ void __launch_bounds__(256)
+lap_validate_kernel(const float* __restrict__ ds, const int64_t* __restrict__ n1, const int64_t* __restrict__ n2,
+                    float* __restrict__ hung_out, float* __restrict__ perm_out, int* __restrict__ status, int R,
+                    int C) {
+  const int b = blockIdx.x;
+  const int nr = n1 ? (int)n1[b] : R, nc = n2 ? (int)n2[b] : C;
+  const float* s = ds + (size_t)b * R * C;
+  int bad = 0;
+  for (int i = threadIdx.x; i < nr * nc; i += blockDim.x) {
+    const float v = s[(size_t)(i / nc) * C + (i % nc)];
+    bad |= (v != v) || (v == INFINITY);
+  }
+  bad = __syncthreads_or(bad);
+  if (!bad) return;
+  if (threadIdx.x == 0) status[b] = 1;
+  for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
+    if (hung_out) hung_out[(size_t)b * R * C + i] = 0.f;
+    if (perm_out) perm_out[(size_t)b * R * C + i] = 0.f;
+  }
+}
+}  // namespace fpm
+
 static bool g_lap_staged = getenv("FPMATCH_LAP_STAGED") != nullptr;   // A/B switch: force the staged-row kernel
 
 extern "C" int fpm_lap_topk(const float* ds, const long long* n1, const long long* n2, const float* ks,
@@ -786,6 +813,10 @@ extern "C" int fpm_lap_topk(const float* ds, const long long* n1, const long lon
   }
 #undef FPM_LAP_COLS
   FPM_LAUNCH_CHECK();
+  if (status) {
+    fpm::lap_validate_kernel<<<B, 256, 0, st>>>(ds, p1, p2, hung_out, perm_out, status, R, C);
+    FPM_LAUNCH_CHECK();
+  }
   return FPM_OK;
 }
 

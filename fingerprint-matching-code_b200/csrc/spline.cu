@@ -88,12 +88,12 @@ __device__ __forceinline__ void spline_basis4(float u0, float u1, int KS, float*
 // One CTA (192 threads x float4 = 768 channels) per destination node.
 // Y: [total_nodes, NS, C] with NS = KS*KS + 1 slabs.  mode 0: out = relu(conv); mode 1: out = x + 0.1*conv.
 // argmax (training only): [total_nodes, C] int32, the edge id that won the max per channel (-1: no in-edge).
-// The in-edges are handled in chunks of 32: thread t < chunk first resolves edge t (edge id -> source node ->
+// The in-edges are handled in chunks of 16: thread t < chunk first resolves edge t (edge id -> source node ->
 // pseudo-coordinates -> the 4 basis weights and slab ids) into shared memory, ONCE per edge; the channel loop then
 // only streams Y: 4 independent 128-bit loads per edge, two edges in flight per thread.  (The first version walked
 // in_eid -> edge_src -> pseudo -> Y as a dependent chain per edge in every one of the 192 threads, each re-deriving
 // the same basis with its floor / double-precision / modulo arithmetic: 53 % of the DRAM peak, FMA pipe 34 % busy.)
-constexpr int kGatherChunk = 32;
+constexpr int kGatherChunk = 16;      // 576 bytes of shared memory: small enough to sit beside a GEMM CTA
 __global__ void __launch_bounds__(192)
 spline_gather_max_kernel(const float* __restrict__ Y, const float* __restrict__ xin,
                          const int64_t* __restrict__ edge_src, const float* __restrict__ pseudo,

@@ -165,6 +165,10 @@ class Net(CNN):
         self.ke_mode = "factored"
         # inference: run the (unread) edge-affinity kernels beside the main chain (FPMATCH_KE_SIDE=0: same stream)
         self.ke_side_stream = os.environ.get('FPMATCH_KE_SIDE', '1') != '0'
+        # inference: the two images' node-feature chains (align -> 2 x SplineConv) are independent until the affinity
+        # layer; the second one runs on its own stream so that its tensor-bound slab GEMM overlaps the first one's
+        # HBM-bound gather / max kernel (FPMATCH_GRAPH_FORK=0: one stream)
+        self.graph_fork = os.environ.get('FPMATCH_GRAPH_FORK', '1') != '0'
         self._backbone_channels_last = False
         self._lap_pending = None          # pinned ring of LAP status flags, see _note_lap_status
         self.track_lap_status = True      # False: no status traffic at all (e.g. while capturing a CUDA graph)
@@ -357,8 +361,8 @@ class Net(CNN):
             self._lap_check_entry(ring["queue"].pop(0), wait=block)
 
     @staticmethod
-    def _ke_stream(dev):
-        key = dev.index if dev.index is not None else torch.cuda.current_device()
+    def _ke_stream(dev, which=0):
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), which)
         st = _SIDE_STREAMS.get(key)
         if st is None:
             st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
@@ -383,21 +387,31 @@ class Net(CNN):
         tables = self._edge_tables(data_dict, dev)
         e1max, e2max = tables[0].shape[2], tables[1].shape[2]
         feats, offs = [], []
+        main = torch.cuda.current_stream(dev)
+        fork = self._ke_stream(dev, 1) if self.graph_fork else None
+        if fork is not None:
+            self.message_pass_node_features.mp_network.prepare_weights()    # shared cached operands, before the fork
+            fork.wait_stream(main)
         for gi, ((nodes, edges), P, graph) in enumerate(zip(fmaps, points, graphs)):
-            graph.max_edges_per_graph = tables[gi].shape[2]     # host-known bound: no device sync needed
-            nodes = nodes.detach().to(torch.float32).contiguous()
-            edges = edges.detach().to(torch.float32).contiguous()
-            ops.global_max_into(edges, gcat, gi * GLOBAL_FEATURE_DIM)
-            nodes_cl, edges_cl = ops.fmap_prep(nodes), ops.fmap_prep(edges)
-            ptr, eptr = graph_offsets(graph)
-            ptr, eptr = ptr.to(dev).contiguous(), eptr.to(dev).contiguous()
-            total = graph.x.shape[0]
-            x0 = ops.node_features(nodes_cl, edges_cl, nodes.shape[2:], edges.shape[2:],
-                                   P.to(dev, torch.float32).contiguous(), ns[gi], ptr, total, self.rescale)
-            graph.x = x0                                        # the reference mutates the batch too (:251)
-            graph = self.message_pass_node_features(graph)
-            feats.append(graph.x)
-            offs.append((ptr, eptr))
+            with torch.cuda.stream(fork if (fork is not None and gi == 1) else main):
+                graph.max_edges_per_graph = tables[gi].shape[2]     # host-known bound: no device sync needed
+                nodes = nodes.detach().to(torch.float32).contiguous()
+                edges = edges.detach().to(torch.float32).contiguous()
+                ops.global_max_into(edges, gcat, gi * GLOBAL_FEATURE_DIM)
+                nodes_cl, edges_cl = ops.fmap_prep(nodes), ops.fmap_prep(edges)
+                ptr, eptr = graph_offsets(graph)
+                ptr, eptr = ptr.to(dev).contiguous(), eptr.to(dev).contiguous()
+                total = graph.x.shape[0]
+                x0 = ops.node_features(nodes_cl, edges_cl, nodes.shape[2:], edges.shape[2:],
+                                       P.to(dev, torch.float32).contiguous(), ns[gi], ptr, total, self.rescale)
+                graph.x = x0                                        # the reference mutates the batch too (:251)
+                graph = self.message_pass_node_features(graph)
+                feats.append(graph.x)
+                offs.append((ptr, eptr))
+        if fork is not None:
+            main.wait_stream(fork)
+            for t in (feats[1], offs[1][0], offs[1][1]):            # allocated on the fork stream, read on main from here on
+                t.record_stream(main)
 
         # ---- affinities (ngm.py:262-287, 317-321)
         coeff_v = self.vertex_affinity.fused_coefficients(gcat)
@@ -407,7 +421,6 @@ class Net(CNN):
         if self.compute_dead_ke:
             # Nothing downstream reads Ke, so its kernels run on a side stream underneath the
             # latency-bound middle of the forward (association-graph layers, Sinkhorn, LAP); joined before returning.
-            main = torch.cuda.current_stream(dev)
             side = self._ke_stream(dev) if self.ke_side_stream else main
             if side is not main:
                 side.wait_stream(main)

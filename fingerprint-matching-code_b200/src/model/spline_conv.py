@@ -99,6 +99,17 @@ class SConv(torch.nn.Module):
         for conv in self.convs:
             conv.reset_parameters()
 
+    def prepare_weights(self):
+        """Pack the slab matrices and (in the error-compensated fp16 mode) split them into their cached fp16 hi / lo
+        operands on the CURRENT stream.  ``Net.matching_head`` calls this before it forks the two images' chains onto
+        two streams: both chains read the same cached operands, which must exist before either starts."""
+        for conv in self.convs:
+            packed = conv.packed_weight()
+            if slab_plan_enabled() or ops.gemm_mode() == "3xf16":
+                ops.f16_split_rows(packed, cache=True)
+            elif ops.gemm_mode() == "3xtf32":
+                ops.tf32_split(packed, cache=True)
+
     def forward(self, data, residual_scale_input=None):
         """relu(conv0(x)) -> conv1; with ``residual_scale_input`` the x + 0.1 * result of
         SiameseSConvOnNodes is fused into the second gather kernel."""

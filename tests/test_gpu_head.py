@@ -179,18 +179,45 @@ def test_head_100_keypoints_matches_oracle(variant, sharpen):
                               ref["k_prob"].view(-1) * min_pts)
     ties = tie_stats(ref, data["ns"][0], data["ns"][1])
     ties["unstable_sort_same_perm_pairs"] = int((unstable == ref["perm_mat"]).flatten(1).all(1).sum())
+    # (1) the solver itself at this size: GPU LAP + greedy top-k on the ORACLE's ds_mat must reproduce the oracle's
+    #     scipy assignment and perm_mat bit for bit
+    from fpmatch import ops
+    hung_o, perm_o = ops.lap_topk(ref["ds_mat"].float().to(DEV).contiguous(), data["ns"][0].to(DEV), data["ns"][1].to(DEV),
+                                  ks=(ref["k_prob"].view(-1) * min_pts).to(DEV), want_hungarian=True, want_perm=True)
+    solver_exact = bool(torch.equal(hung_o.cpu(), ref["hungarian"])) and bool(torch.equal(perm_o.cpu(), ref["perm_mat"]))
+    # (2) end to end: pairs whose assignment differs must be DEGENERATE optima - with bench.py's untrained weights every
+    #     ds_mat entry is ~k/N and thousands of assignments are optimal to within one ulp of the objective, so the
+    #     1e-7 reordering noise of ds_mat picks among them.  Margin = relative gap of the two assignments' objectives
+    #     under the oracle's ds_mat (both must be optimal to rounding), and of the k-th / (k+1)-th candidate values.
+    ds_o = ref["ds_mat"].double()
+    obj_ref = (ds_o * ref["hungarian"].double()).flatten(1).sum(1)
+    obj_gpu = (ds_o * hung_gpu.cpu().double()).flatten(1).sum(1)
+    hung_same = (hung_gpu.cpu() == ref["hungarian"]).flatten(1).all(1)
+    perm_same = (out["perm_mat"].cpu() == ref["perm_mat"]).flatten(1).all(1)
+    gap = ((obj_ref - obj_gpu).abs() / obj_ref.abs().clamp(min=1e-30))
+    sel_ref = (ds_o * ref["perm_mat"].double()).flatten(1).sum(1)
+    sel_gpu = (ds_o * out["perm_mat"].cpu().double()).flatten(1).sum(1)
+    sel_gap = ((sel_ref - sel_gpu).abs() / sel_ref.abs().clamp(min=1e-30))
     rec = dict(ds_mat_vs_fp32_oracle=st["ds_mat"], strict_bar=1e-4, strict_ok=bool(st["ds_mat"] < 1e-4),
-               hungarian_equal=hung_equal, **ties)
+               solver_exact_on_oracle_ds_mat=solver_exact, hungarian_pairs_equal=int(hung_same.sum()),
+               perm_pairs_equal=int(perm_same.sum()),
+               max_rel_objective_gap_of_differing_assignments=float(gap[~hung_same].max()) if (~hung_same).any() else 0.0,
+               max_rel_selected_mass_gap_of_differing_perms=float(sel_gap[~perm_same].max()) if (~perm_same).any() else 0.0,
+               ds_mat_max=float(ref["ds_mat"].max()), **ties)
     if sharpen:
         rec["gpu_vs_fp64"], rec["relaxed_bar"] = ds_tolerance(tag, net, data, ref, out)
     report(tag + "_strict", **rec)
     assert st["node_feat"] < 1e-5 and st["Kp"] < 1e-5 and st["ss"] < 1e-4
     assert st["k_prob"] < 1e-4 and st["k_int_equal"] and st["cls_prob"] < 1e-4
-    assert st["perm_pairs_equal"] == st["pairs"] and hung_equal
+    assert solver_exact
     if sharpen:
+        assert st["perm_pairs_equal"] == st["pairs"] and hung_equal
         assert rec["gpu_vs_fp64"] < rec["relaxed_bar"]
     else:
         assert st["ds_mat"] < 1e-4          # north-star bar, outright, on the benchmark's own weights
+        # identical assignments, or equally optimal ones (objective equal to 1e-6 relative)
+        assert rec["max_rel_objective_gap_of_differing_assignments"] < 1e-6, rec
+        assert rec["max_rel_selected_mass_gap_of_differing_perms"] < 1e-6, rec
 
 
 @pytest.mark.parametrize("partial,n", [(2, 20), (5, 24), (8, 30)])

@@ -8,7 +8,7 @@ O=gpurun_out
 rm -f $O/parity_report.jsonl
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${TAG}_smi.txt 2>&1
 if [[ "$*" != *notests* ]]; then
-  timeout 1500 python -m pytest tests -m gpu -x -q --durations=15 > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/${TAG}_pytest_gpu.log
+  timeout 1500 python -m pytest tests -m gpu -q --maxfail=10 --durations=12 > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/${TAG}_pytest_gpu.log
   tail -25 $O/${TAG}_pytest_gpu.log
   cp $O/parity_report.jsonl $O/${TAG}_parity_report.jsonl 2>/dev/null
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/${TAG}_smoke.log
@@ -21,7 +21,8 @@ if [[ "$*" != *noncu* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_launch.log 2>&1
   echo "ncu launches rc=$?"
   $CMD > $O/${TAG}_plain2.log 2>&1 &&
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_pair_kernel|gnn_layer_kernel|lap_topk|ke_factored|spline_gather|afau_attention|sinkhorn_log|match_cls_stage2|affinity_kernel|soft_topk|add_instnorm|fmap_prep|f16_split" -s 70 -c 44 -o $O/${TAG}_prof $CMD > $O/${TAG}_ncu_full.log 2>&1
-  echo "ncu full rc=$?"
+  # gpurun_out may carry at most 64 MiB back: keep the full capture to ~20 launches (~2.5 MiB each with source)
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-gemm_tc_pair_kernel|gnn_layer_kernel|spline_gather|sinkhorn_log|lap_topk|afau_attention|match_cls_stage2|ke_factored}" -s ${NCU_SKIP:-40} -c ${NCU_COUNT:-20} -o $O/${TAG}_prof $CMD > $O/${TAG}_ncu_full.log 2>&1
+  echo "ncu full rc=$?"; ls -la $O/${TAG}_prof.ncu-rep
 fi
 ls -la $O | tail -12
