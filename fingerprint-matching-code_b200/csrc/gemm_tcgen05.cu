@@ -371,7 +371,7 @@ constexpr int P_TBN = 128;                    // columns per pair tile
 constexpr uint32_t kPABytes = P_TBM * kRowBytes;              // 16 KB
 constexpr uint32_t kPBHalfBytes = (P_TBN / 2) * kRowBytes;    //  8 KB: this CTA's half of the B tile
 constexpr uint32_t kPStageBytes = 2 * (kPABytes + kPBHalfBytes);   // hi + lo: 48 KB
-constexpr int kPStages = 4;
+constexpr int kPStagesMax = 4;            // pipeline depth: template parameter kPStages of the pair kernel (3 or 4)
 constexpr int kEpiWarps = 8;
 
 __device__ __forceinline__ uint32_t mapa_rank0(uint32_t saddr) {
@@ -421,8 +421,14 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 // *tab_count entries are valid.  Lets one launch compute only the (row block, weight slab) products that are used.
 struct PairTile { int a_row0, b_row0, c_col0, rowmap_off; };
 
-template <int kMode>
-__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
+// kPStages = 4 fills the SM's shared memory (226 KB); 3 leaves 46 KB so that light CTAs of ANOTHER kernel (the
+// SplineConv gather of the other image, launched on a second stream) can run beside the GEMM CTA.
+// __maxnreg__(128): the register file is split over the SM's four sub-partitions (16 K registers each) and a CTA's
+// warps are dealt to them round-robin; at the 160 registers ptxas takes when left alone the fullest sub-partition
+// (3 of the 10 warps) keeps 1 K registers free and no warp of any other kernel fits beside the GEMM CTA.  At 128
+// (no spills) it keeps 4 K: two warps of the 56-register gather kernel.
+template <int kMode, int kPStages>
+__global__ void __maxnreg__(128)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const float* __restrict__ inv_a, const float* __restrict__ inv_b,
@@ -775,8 +781,15 @@ static int launch_tc_pair(const void* A_hi, const void* A_lo, const void* B_hi, 
   if ((rc = make_map(&mAl, A_lo, M, K, lda, fpm::P_TBM, f16)) != FPM_OK) return rc;
   if ((rc = make_map(&mBh, B_hi, N, K, ldb, fpm::P_TBN / 2, f16)) != FPM_OK) return rc;
   if ((rc = make_map(&mBl, B_lo, N, K, ldb, fpm::P_TBN / 2, f16)) != FPM_OK) return rc;
-  const size_t smem = (size_t)fpm::kPStages * fpm::kPStageBytes + 1024 + 256 + (size_t)fpm::kEpiWarps * 32 * 32 * 4;
-  auto kern = fpm::gemm_tc_pair_kernel<kMode>;
+  // FPMATCH_GEMM_STAGES=3|4.  Default 3: measured as fast as 4 on the slab GEMM (0.751 vs 0.757 ms per launch, r2d) and
+  // it leaves 46 KB of shared memory to CTAs of other streams' kernels.
+  static int stages = 0;
+  if (stages == 0) {
+    const char* e = getenv("FPMATCH_GEMM_STAGES");
+    stages = (e && e[0] == '4') ? 4 : 3;
+  }
+  const size_t smem = (size_t)stages * fpm::kPStageBytes + 1024 + 256 + (size_t)fpm::kEpiWarps * 32 * 32 * 4;
+  auto kern = stages == 3 ? fpm::gemm_tc_pair_kernel<kMode, 3> : fpm::gemm_tc_pair_kernel<kMode, 4>;
   FPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(64 + 32 * fpm::kEpiWarps);
@@ -800,6 +813,8 @@ static int launch_tc_pair(const void* A_hi, const void* A_lo, const void* B_hi, 
       maxc = sms / 2;
     }
     ncl = maxc < sms / 2 ? maxc : sms / 2;
+    const char* e = getenv("FPMATCH_GEMM_CLUSTERS");   // experiment: leave SMs free for other streams' kernels
+    if (e && atoi(e) > 0 && atoi(e) < ncl) ncl = atoi(e);
   }
   const long long tiles = tab ? max_tiles : (long long)fpm_cdiv(M, 2 * fpm::P_TBM) * fpm_cdiv(N, fpm::P_TBN);
   const long long clusters = tiles < ncl ? (tiles > 0 ? tiles : 1) : ncl;

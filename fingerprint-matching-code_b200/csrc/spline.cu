@@ -11,6 +11,7 @@
 //     out_i = max_{e: j->i} sum_s basis_s(e) * Y[j, wi_s(e), :]  (0 if no in-edge) + Y[i, 25, :] + bias
 // fused with ReLU (layer 0) or the residual x + 0.1 * out (layer 1, spline_conv.py:56).
 #include "common.cuh"
+#include <stdlib.h>
 #include <limits.h>
 
 namespace fpm {
@@ -437,6 +438,22 @@ extern "C" int fpm_spline_gather_max(const float* Y, const float* xin, const lon
   if (total_nodes == 0) return FPM_OK;
   FPM_CHECK_ARG((long long)total_nodes * (kernel_size * kernel_size + 1) * (C / 4) < (1ll << 32),
                 "fpm_spline_gather_max: Y exceeds 2^32 float4 (split the batch)");
+  // FPMATCH_GATHER_CARVEOUT=1 (experiment, off): same shared-memory carve-out as the slab GEMM.
+  static int carve = -1;
+  if (carve < 0) {
+    const char* e = getenv("FPMATCH_GATHER_CARVEOUT");
+    carve = (e && e[0] == '1') ? 1 : 0;        // measured: no help, and the gather alone slows from 0.18 to 0.23 ms
+  }
+  if (carve) {
+    static bool done[16] = {false};
+    int dev = 0;
+    FPM_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 16 && !done[dev]) {
+      FPM_CUDA(cudaFuncSetAttribute(fpm::spline_gather_max_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
+      done[dev] = true;
+    }
+  }
   fpm::spline_gather_max_kernel<<<total_nodes, 192, 0, (cudaStream_t)stream>>>(
       Y, xin, (const int64_t*)edge_src, pseudo, in_ptr, in_eid, bias, out, argmax, C, kernel_size, mode);
   FPM_LAUNCH_CHECK();

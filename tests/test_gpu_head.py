@@ -215,9 +215,10 @@ def test_head_100_keypoints_matches_oracle(variant, sharpen):
         assert rec["gpu_vs_fp64"] < rec["relaxed_bar"]
     else:
         assert st["ds_mat"] < 1e-4          # north-star bar, outright, on the benchmark's own weights
-        # identical assignments, or equally optimal ones (objective equal to 1e-6 relative)
+        # identical assignments, or equally optimal ones (LAP objective equal to 1e-6 relative).  perm_mat keeps the
+        # round(k) largest entries of the assignment, so two equally optimal assignments give different (reported, not
+        # asserted) selected masses.
         assert rec["max_rel_objective_gap_of_differing_assignments"] < 1e-6, rec
-        assert rec["max_rel_selected_mass_gap_of_differing_perms"] < 1e-6, rec
 
 
 @pytest.mark.parametrize("partial,n", [(2, 20), (5, 24), (8, 30)])
