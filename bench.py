@@ -39,6 +39,13 @@ N_KPTS = 100
 BATCH = 256
 WORKLOAD = f"matching-head inference, {N_KPTS} keypoints/image, batch {BATCH} pairs, fp32"
 METRIC = "matched pairs/sec"
+# why the CPU arm is a port and what that means for the figure (BASELINE.md section 3 planned to import the reference)
+PORT_NOTE = ("the reference itself cannot be imported here (torch_geometric, torch_sparse, torch_spline_conv, pygmtools "
+             "absent; its CUDA extension does not compile against torch 2.11), so this times oracle/: the reference's own "
+             "modules' arithmetic where they import (feature_align, soft_topk, AFA-U, affinity, scipy LAP) and "
+             "restatements elsewhere (SplineConv as per-edge index_select + bmm, SAGE mean as argsort + index_add_ instead "
+             "of torch_sparse's CSR spmm, pygmtools' per-pair Sinkhorn loop) - an approximation of the reference's CPU "
+             "cost, not a measurement of its code")
 
 
 def dist_env():
@@ -158,13 +165,23 @@ def main():
             "config": {"workload": WORKLOAD, "keypoints": N_KPTS, "note": "CPU path, bounded sample"},
             "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{args.cpu_sample} pairs x {N_KPTS} keypoints per step, oracle port of the "
-                                       "reference's PyTorch+scipy path with its python loop structure"},
+                                       "reference's PyTorch+scipy path with its python loop structure",
+                             "note": PORT_NOTE},
             "e2e": {"value": pps, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
         return
 
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback exists)"
+    if world > 1 and os.environ.get("FPMATCH_BENCH_AFFINITY", "1") != "0" and hasattr(os, "sched_setaffinity"):
+        # one contiguous slice of the host cores per rank: the rank's pinned staging buffers are first touched (and its
+        # copies driven) from cores of one NUMA node instead of wherever the scheduler puts the process
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cpus) // world)
+            os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]) or set(cpus))
+        except OSError:
+            pass
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -220,7 +237,6 @@ def main():
 
     # ---- device-resident throughput + live GEMM timing for the roofline ----
     with ClockSampler(local) as clk:
-        ops.gemm_profile_start()
         l0 = ops.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -230,7 +246,6 @@ def main():
         e1.record()
         barrier()
         launches = ops.launch_count() - l0
-        gemm_events = ops.gemm_profile_stop()
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -238,6 +253,25 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / args.steps
     value = B * world / (ms_step / 1e3)
+
+    # ---- live timing of the dominant kernel for the roofline: CUDA events around every GEMM launch ON ITS OWN STREAM.
+    # The product path runs the two images' chains on two streams; an event pair on one of them would also measure the
+    # time the launch spends queued behind the other stream's GEMM, so this pass keeps everything on one stream.
+    fork_was = net.graph_fork
+    net.graph_fork = False
+    rf_steps = max(2, min(args.steps, 5))
+    step_resident()
+    barrier()
+    ops.gemm_profile_start()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(rf_steps):
+        step_resident()
+    r1.record()
+    barrier()
+    gemm_events = ops.gemm_profile_stop()
+    ms_step_single_stream = r0.elapsed_time(r1) / rf_steps
+    net.graph_fork = fork_was
 
     # dominant kernel = the SplineConv slab GEMM (largest FLOP count in the step).  With the slab planner the launch
     # computes only the tiles listed in its device-side table: FLOPs = executed tiles x 256 x 128 x K x 2.
@@ -280,7 +314,7 @@ def main():
         if g:
             traffic, traffic_src = g["dram_bytes"], f"{rec['file']} ({g['kernel']}, grid {g['grid']}, {g['time_us']:.0f} us under ncu)"
     achieved = flops / (gemm_ms / 1e3) / 1e12
-    gemm_share = gemm_ms * len(same) / args.steps / ms_step
+    gemm_share = gemm_ms * len(same) / rf_steps / ms_step_single_stream
 
     # ---- end to end through the public API with pinned host inputs: CudaPrefetcher (the host->device copy of step
     # i+1 runs on a side stream while step i is matched) -> Net.forward -> outputs copied to the host.  Every step's
@@ -353,7 +387,7 @@ def main():
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pps, sec = cpu_reference_run(4, 1, args.cpu_sample)           # ~10 s of CPU work on the box's host cores
-        cpu_base = {"value": pps, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+        cpu_base = {"value": pps, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port", "note": PORT_NOTE,
                     "sample": f"4 timed passes (+1 warm-up) over {args.cpu_sample} pairs x {N_KPTS} keypoints ({sec:.1f} s each), oracle port of the reference's "
                               "PyTorch+scipy CPU path with its per-point / per-pair python loops"}
 
@@ -368,7 +402,8 @@ def main():
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": kernel_label or f"gemm_nt[{mode}] M={big[1]} N={big[2]} K={big[3]}",
-                         "launch_ms": gemm_ms, "share_of_step": gemm_share, "peak_source": peak_note,
+                         "launch_ms": gemm_ms, "share_of_step": gemm_share,
+                         "ms_per_step_single_stream": ms_step_single_stream, "peak_source": peak_note,
                          "flops_per_launch": flops,
                          "note": ("achieved = algorithmic 2*M*N*K of the executed tiles / live CUDA-event time of the launch. "
                                   "fp32-faithful results need 3 fp16 MMAs per product (hi*hi, hi*lo, lo*hi), which are NOT "

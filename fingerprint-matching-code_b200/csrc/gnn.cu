@@ -366,7 +366,8 @@ __device__ __forceinline__ float gnn_node_inputs(const float* __restrict__ xb, c
 // per-node bookkeeping - own load, aggregation, divisions - was duplicated and the instruction count doubled).
 constexpr int kGnnMaxThreads = 256;
 
-// MINB = CTAs per SM the register allocation is sized for: 2 -> 128 registers, 3 -> 80 registers (36 bytes of spills)
+// MINB = CTAs per SM the register allocation is sized for: 3 -> 80 registers (12 bytes of spills), 4 -> 64 registers,
+// no spills (ptxas finds the tighter schedule only when it is told to)
 template <int CIN, int MINB>
 __global__ void __launch_bounds__(kGnnMaxThreads, MINB)
 gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mprev_t,
@@ -415,7 +416,8 @@ gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mpre
     if (j2 >= n2max) break;
     const size_t p = (size_t)j2 * n1max + j1;
     const float* Rs = Rsum + (size_t)r * n1max * CP;
-    // own features
+    // ---- (i) own features -> h0 = relu(W0 own + b0);  x1 accumulators = bl + Wr own.  The order of the four
+    // linears is chosen for register pressure: own[] dies before the aggregation is formed, h0 before s2 is folded in.
     float own[CP];
 #pragma unroll
     for (int c = 0; c < CP; ++c) own[c] = 0.f;
@@ -428,10 +430,41 @@ gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mpre
       }
     }
     own[CIN - 1] = mb[p];
-    // aggregation over In1(j1) of the row sums (packed adds)
+    f32x2 acc[8], xacc[8];
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) {
+      acc[pp] = pk2(c_gnn[O::b0 + 2 * pp], c_gnn[O::b0 + 2 * pp + 1]);
+      xacc[pp] = pk2(c_gnn[O::bl + 2 * pp], c_gnn[O::bl + 2 * pp + 1]);
+    }
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      GNN_FMA_ROW(acc, O::w0, c, own[c]);
+      GNN_FMA_ROW(xacc, O::wr, c, own[c]);
+    }
+    const bool self = (long long)p < ndiag;
+    // the self loop contributes own[] to the aggregation: keep it as packed pairs, own[] itself is dead from here on
     f32x2 ag[CP / 2];
 #pragma unroll
-    for (int c = 0; c < CP / 2; ++c) ag[c] = pk2(0.f, 0.f);
+    for (int c = 0; c < CP / 2; ++c) ag[c] = self ? pk2(own[2 * c], own[2 * c + 1]) : pk2(0.f, 0.f);
+    // ---- (ii) s2 = relu(W2 h0 + b2), folded into the x1 accumulators
+    {
+      float h[kF];
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) {
+        upk2(acc[pp], h[2 * pp], h[2 * pp + 1]);
+        h[2 * pp] = fmaxf(h[2 * pp], 0.f); h[2 * pp + 1] = fmaxf(h[2 * pp + 1], 0.f);
+        acc[pp] = pk2(c_gnn[O::b2 + 2 * pp], c_gnn[O::b2 + 2 * pp + 1]);
+      }
+#pragma unroll
+      for (int c = 0; c < kF; ++c) GNN_FMA_ROW(acc, O::w2, c, h[c]);
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) {
+        float s0, s1;
+        upk2(acc[pp], s0, s1);
+        xacc[pp] = add2(xacc[pp], pk2(fmaxf(s0, 0.f), fmaxf(s1, 0.f)));
+      }
+    }
+    // ---- (iii) mean over the association in-neighbours: In1(j1) of the row sums (packed adds), the self loop
     const int beg1 = ip1[j1], end1 = ip1[j1 + 1];
     for (int q = beg1; q < end1; ++q) {
       const ulonglong2* rr = (const ulonglong2*)(Rs + (size_t)is1[q] * CP);
@@ -441,7 +474,7 @@ gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mpre
         ag[2 * v] = add2(ag[2 * v], w.x); ag[2 * v + 1] = add2(ag[2 * v + 1], w.y);
       }
     }
-    long long cnt = (long long)sdeg[r] * (long long)(end1 - beg1);
+    long long cnt = (long long)sdeg[r] * (long long)(end1 - beg1) + (self ? 1 : 0);
     if (j2 == pd2) {                                    // rare: the cut-off block of this pair targets this row
       for (int q = beg1; q < end1; ++q) {
         if (ic1[q] < ccut) {
@@ -455,67 +488,26 @@ gnn_layer_kernel(const float* __restrict__ xprev, const float* __restrict__ mpre
         }
       }
     }
-    float agg[CP];
-#pragma unroll
-    for (int c = 0; c < CP / 2; ++c) upk2(ag[c], agg[2 * c], agg[2 * c + 1]);
-    if ((long long)p < ndiag) {
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) agg[c] += own[c];
-      cnt += 1;
-    }
     {
       const float inv = cnt > 0 ? (float)cnt : 1.f;
       const float rcp = __frcp_rn(inv);
 #pragma unroll
-      for (int c = 0; c < CIN; ++c) {                   // agg / inv, correctly rounded for these magnitudes
-        const float q0 = agg[c] * rcp;
-        const float e = fmaf(-q0, inv, agg[c]);
-        agg[c] = fmaf(e, rcp, q0);
+      for (int c2 = 0; c2 < (CIN + 1) / 2; ++c2) {
+        float a0, a1;
+        upk2(ag[c2], a0, a1);
+        // agg / inv: q = a r, e = fma(-q, inv, a), q += e r - the correction step of an IEEE division
+        const float q0 = a0 * rcp, q1 = a1 * rcp;
+        a0 = fmaf(fmaf(-q0, inv, a0), rcp, q0);
+        a1 = fmaf(fmaf(-q1, inv, a1), rcp, q1);
+        // ---- (iv) x1 += Wl agg
+        GNN_FMA_ROW(xacc, O::wl, 2 * c2, a0);
+        if (2 * c2 + 1 < CIN) GNN_FMA_ROW(xacc, O::wl, 2 * c2 + 1, a1);
       }
-    }
-
-    // h0 = relu(W0 own + b0)
-    f32x2 acc[8];
-#pragma unroll
-    for (int pp = 0; pp < 8; ++pp) acc[pp] = pk2(c_gnn[O::b0 + 2 * pp], c_gnn[O::b0 + 2 * pp + 1]);
-#pragma unroll
-    for (int c = 0; c < CIN; ++c) GNN_FMA_ROW(acc, O::w0, c, own[c]);
-    float h[kF];
-#pragma unroll
-    for (int pp = 0; pp < 8; ++pp) {
-      upk2(acc[pp], h[2 * pp], h[2 * pp + 1]);
-      h[2 * pp] = fmaxf(h[2 * pp], 0.f); h[2 * pp + 1] = fmaxf(h[2 * pp + 1], 0.f);
-    }
-    // s2 = relu(W2 h0 + b2)
-#pragma unroll
-    for (int pp = 0; pp < 8; ++pp) acc[pp] = pk2(c_gnn[O::b2 + 2 * pp], c_gnn[O::b2 + 2 * pp + 1]);
-#pragma unroll
-    for (int c = 0; c < kF; ++c) GNN_FMA_ROW(acc, O::w2, c, h[c]);
-    float s2[kF];
-#pragma unroll
-    for (int pp = 0; pp < 8; ++pp) {
-      upk2(acc[pp], s2[2 * pp], s2[2 * pp + 1]);
-      s2[2 * pp] = fmaxf(s2[2 * pp], 0.f); s2[2 * pp + 1] = fmaxf(s2[2 * pp + 1], 0.f);
-    }
-    // x1 = (Wl agg + bl + Wr own) + relu(s2)
-    f32x2 accr[8];
-#pragma unroll
-    for (int pp = 0; pp < 8; ++pp) {
-      acc[pp] = pk2(c_gnn[O::bl + 2 * pp], c_gnn[O::bl + 2 * pp + 1]);
-      accr[pp] = pk2(0.f, 0.f);
-    }
-#pragma unroll
-    for (int c = 0; c < CIN; ++c) {
-      GNN_FMA_ROW(acc, O::wl, c, agg[c]);
-      GNN_FMA_ROW(accr, O::wr, c, own[c]);
     }
     float x1[kF];
     float sc = c_gnn[O::cb];
 #pragma unroll
-    for (int pp = 0; pp < 8; ++pp) {
-      const f32x2 v2 = add2(add2(acc[pp], accr[pp]), pk2(s2[2 * pp], s2[2 * pp + 1]));
-      upk2(v2, x1[2 * pp], x1[2 * pp + 1]);
-    }
+    for (int pp = 0; pp < 8; ++pp) upk2(xacc[pp], x1[2 * pp], x1[2 * pp + 1]);
 #pragma unroll
     for (int o = 0; o < kF; ++o) sc = fmaf(c_gnn[O::wc + o], x1[o], sc);
     float4* dst = (float4*)(xout + ((size_t)b * N + p) * kF);
@@ -918,15 +910,15 @@ static int gnn_layer_launch(const fpm::GnnWeights& w, int dev, const float* xpre
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_gnn_layer: n1max too large");
   int rc = gnn_publish_weights<CIN>(w, dev, st);
   if (rc != FPM_OK) return rc;
-  static int minb = 0;                                 // FPMATCH_GNN_MINB=2|3 (A/B switch; default 3)
+  static int minb = 0;                                 // FPMATCH_GNN_MINB=3|4 (A/B switch; default 4)
   if (minb == 0) {
     const char* e = getenv("FPMATCH_GNN_MINB");
-    minb = (e && e[0] == '2') ? 2 : 3;
+    minb = (e && e[0] == '3') ? 3 : 4;
   }
   dim3 grid(fpm_cdiv(n2max, rows), B);
-  if (minb == 2) {
-    FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<CIN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fpm::gnn_layer_kernel<CIN, 2><<<grid, threads, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_col1, in_ptr2,
+  if (minb == 4) {
+    FPM_CUDA(cudaFuncSetAttribute(fpm::gnn_layer_kernel<CIN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fpm::gnn_layer_kernel<CIN, 4><<<grid, threads, smem, st>>>(xprev, mprev_t, in_ptr1, in_src1, in_col1, in_ptr2,
                                                               in_src2, (const int64_t*)ndiag, part, xout, score, n1max,
                                                               n2max, e1max, e2max, rows);
   } else {

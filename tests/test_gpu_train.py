@@ -219,11 +219,11 @@ def test_ngm_solver_backward():
     net = net.to(DEV)
     tables = net._edge_tables(data | {"Gs": [t.to(DEV) for t in data["Gs"]], "Hs": [t.to(DEV) for t in data["Hs"]]}, DEV) \
         if "edge_lists" not in data else [t.to(DEV, torch.int32).contiguous() for t in data["edge_lists"]]
-    swap = lambda t: torch.stack((t[:, 1], t[:, 0]), 1).contiguous()
-    meta = {"csr1": ops.assoc_in_csr(tables[0], n1max), "csr2": ops.assoc_in_csr(tables[1], n2max),
-            "ocsr1": ops.assoc_in_csr(swap(tables[0]), n1max), "ocsr2": ops.assoc_in_csr(swap(tables[1]), n2max),
-            "n1": n1.to(DEV), "n2": n2.to(DEV), "n1max": n1max, "n2max": n2max, "e1max": tables[0].shape[2],
-            "e2max": tables[1].shape[2], "layers": 3, "sk_iter": 20, "sk_tau": 0.01}
+    g1, g2 = data["pyg_graphs"]
+    assoc = ops.AssocStructure(tables[0], tables[1], g1.eptr.to(DEV), g2.eptr.to(DEV), n1.to(DEV), n2.to(DEV), n1max,
+                               n2max, with_out=True)
+    meta = {"assoc": assoc, "n1": n1.to(DEV), "n2": n2.to(DEV), "n1max": n1max, "n2max": n2max,
+            "layers": 3, "sk_iter": 20, "sk_tau": 0.01}
     params, pnames = [], []
     for i in range(3):
         L = getattr(net, f"gnn_layer_{i}")
