@@ -147,6 +147,13 @@ def main():
     ap.add_argument("--gemm", default=os.environ.get("FPMATCH_GEMM", None))
     ap.add_argument("--cpu-sample", type=int, default=32, help="pairs per step of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-inflight", type=int, default=int(os.environ.get("FPMATCH_BENCH_E2E_INFLIGHT", "1")),
+                    help="batches in flight in the end-to-end loop whose backbone maps cross PCIe every step (measured: "
+                         "one at a time is faster there - 29.1 k vs 27.6 k pairs/s - the host side of that loop is the "
+                         "limiter; the resident-maps variant uses --inflight)")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("FPMATCH_BENCH_INFLIGHT", "2")),
+                    help="batches in flight in the device-timed loop: step i is issued on stream i %% inflight, so the "
+                         "latency-bound tail of one batch (Sinkhorn, LAP, AFA-U) overlaps the tensor-bound front of the next")
     args = ap.parse_args()
     rank, world, local = dist_env()
     cores = os.cpu_count()
@@ -222,6 +229,27 @@ def main():
         with torch.no_grad():
             return net(dict(resident))    # the forward overwrites graph.x in place, as the reference does
 
+    from fpmatch.prefetch import lanes as _lanes
+    lanes = _lanes(dev, args.inflight) if args.inflight > 1 else []
+
+    def run_steps(n):
+        """n steps; with --inflight k > 1 step i runs on stream i % k (each batch's kernels stay ordered on their own
+        stream; consecutive batches are independent, as in serving).  All lanes join the current stream at the end."""
+        out = None
+        if not lanes:
+            for _ in range(n):
+                out = step_resident()
+            return out
+        cur = torch.cuda.current_stream(dev)
+        for s_ in lanes:
+            s_.wait_stream(cur)
+        for i in range(n):
+            with torch.cuda.stream(lanes[i % len(lanes)]):
+                out = step_resident()
+        for s_ in lanes:
+            cur.wait_stream(s_)
+        return out
+
     out_keys = ("ds_mat", "perm_mat", "k_prob", "cls_prob")
 
     def barrier():
@@ -233,6 +261,7 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    run_steps(2 * max(1, args.inflight))
     barrier()
 
     # ---- device-resident throughput + live GEMM timing for the roofline ----
@@ -241,8 +270,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(args.steps):
-            out = step_resident()
+        out = run_steps(args.steps)
         e1.record()
         barrier()
         launches = ops.launch_count() - l0
@@ -319,31 +347,27 @@ def main():
     # ---- end to end through the public API with pinned host inputs: CudaPrefetcher (the host->device copy of step
     # i+1 runs on a side stream while step i is matched) -> Net.forward -> outputs copied to the host.  Every step's
     # H2D and D2H happen inside the timed region; wall clock, max over ranks.
-    from fpmatch.prefetch import CudaPrefetcher, HostResultRing
+    from fpmatch.prefetch import CudaPrefetcher, HostResultRing, MatchingPipeline
     e2e_steps = max(3, min(args.steps, 10))
 
     ring = HostResultRing(device=dev)                        # pinned result buffers and device staging buffers
     feeder = CudaPrefetcher([], device=dev)                  # are allocated once and reused across steps
 
-    def e2e_run(nsteps, hb=None, extra=None, fd=None):
-        got = 0
-        fd = fd or feeder
-        fd.batches = [hb if hb is not None else host] * nsteps
-        for d in fd:
-            if extra:
-                d.update(extra)
-            with torch.no_grad():
-                o = net(d)
-            done = ring.push([o[k] for k in out_keys])       # returns the previous step's results, on the host
-            got += done is not None
-        res = ring.flush()                                   # the last step's results are on the host here
-        assert res is not None and got == nsteps - 1
+    def e2e_run(nsteps, hb=None, extra=None, fd=None, inflight=1):
+        """fpmatch.prefetch.MatchingPipeline = the public streaming API: pinned host batches in, pinned host results
+        out, `inflight` batches on the device at once."""
+        pipe = MatchingPipeline(net, [hb if hb is not None else host] * nsteps, keys=out_keys, device=dev,
+                                inflight=max(1, inflight), feeder=fd or feeder, ring=ring, extra=extra)
+        res, got = None, 0
+        for res in pipe:
+            got += 1
+        assert res is not None and got == nsteps
         return res
 
-    e2e_run(2)
+    e2e_run(3, inflight=args.e2e_inflight)
     barrier()
     t0 = time.perf_counter()
-    res = e2e_run(e2e_steps)
+    res = e2e_run(e2e_steps, inflight=args.e2e_inflight)
     barrier()
     wall = (time.perf_counter() - t0) / e2e_steps
     t = torch.tensor([wall], device=dev)
@@ -360,10 +384,10 @@ def main():
     feeder2 = CudaPrefetcher([], device=dev)
     maps_dev = {"fmaps": resident["fmaps"]}
     h2d_nomaps = sum(tensor_bytes(v) for v in host_nomaps.values())
-    e2e_run(2, host_nomaps, maps_dev, feeder2)
+    e2e_run(3, host_nomaps, maps_dev, feeder2, inflight=args.inflight)
     barrier()
     t0 = time.perf_counter()
-    e2e_run(e2e_steps, host_nomaps, maps_dev, feeder2)
+    e2e_run(e2e_steps, host_nomaps, maps_dev, feeder2, inflight=args.inflight)
     barrier()
     wall2 = (time.perf_counter() - t0) / e2e_steps
     t = torch.tensor([wall2], device=dev)
@@ -398,7 +422,12 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "keypoints": N_KPTS, "pairs_per_gpu": B, "gemm_mode": ops.gemm_mode(),
                        "l2": "inputs + intermediates per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-                       "dead_ke_computed": True, "parallelism": f"dp{world} (independent pairs, no data-path collective)"},
+                       "dead_ke_computed": True,
+                       "batches_in_flight": max(1, args.inflight),
+                       "pipeline": (f"step i issued on stream i % {args.inflight}: consecutive batches are independent, so "
+                                    "the latency-bound tail of one overlaps the tensor-bound front of the next; every "
+                                    "step is a complete forward of one 256-pair batch") if args.inflight > 1 else "one stream",
+                       "parallelism": f"dp{world} (independent pairs, no data-path collective)"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": kernel_label or f"gemm_nt[{mode}] M={big[1]} N={big[2]} K={big[3]}",
@@ -412,7 +441,8 @@ def main():
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "h2d_link_gbs_measured": h2d_gbs, "h2d_ms_per_step_at_that_rate": h2d / h2d_gbs / 1e6,
-                    "maps_resident": {"value": e2e_resident_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_nomaps,
+                    "batches_in_flight": max(1, args.e2e_inflight),
+                    "maps_resident": {"value": e2e_resident_value, "batches_in_flight": max(1, args.inflight), "unit": "pairs/s", "h2d_bytes_per_step": h2d_nomaps,
                                       "d2h_bytes_per_step": d2h,
                                       "note": "same public-API path, backbone maps produced on the device (in-process "
                                               "backbone, as in the reference's scripts); keypoints, graphs, ground "

@@ -362,7 +362,10 @@ class Net(CNN):
 
     @staticmethod
     def _ke_stream(dev, which=0):
-        key = (dev.index if dev.index is not None else torch.cuda.current_device(), which)
+        """Side stream number ``which`` OF THE CURRENT STREAM: forwards issued on different streams (two batches in
+        flight) must not share their side streams, or the second would queue behind the first."""
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), which,
+               torch.cuda.current_stream(dev).cuda_stream)
         st = _SIDE_STREAMS.get(key)
         if st is None:
             st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)

@@ -298,6 +298,31 @@ def test_head_is_deterministic():
         assert torch.equal(a, b)
 
 
+def test_batches_in_flight_give_identical_outputs():
+    """fpmatch.prefetch.MatchingPipeline keeps two batches on the device at once (batch i on stream i % 2, the two
+    images' chains of every batch on two more streams): every batch's outputs must equal, bit for bit, the outputs of
+    the same batch matched alone on the default stream - also with the association-layer weights shared through one
+    constant bank (csrc/gnn.cu: launches from different streams are serialised by an event)."""
+    from fpmatch import synth
+    from fpmatch.prefetch import MatchingPipeline
+    net = make_net().to(DEV)
+    hosts = [synth.make_batch(6, 20 + 4 * i, seed=30 + i, ragged=bool(i % 2)) for i in range(5)]
+    keys = ("ds_mat", "perm_mat", "k_prob", "cls_prob")
+    alone = []
+    for h in hosts:
+        with torch.no_grad():
+            o = net(synth.batch_to(synth.clone_batch(h), DEV))
+        alone.append([o[k].cpu().clone() for k in keys])
+    pin = lambda v: v.pin_memory() if isinstance(v, torch.Tensor) else v
+    for inflight in (2, 3):
+        got = [[t.clone() for t in res] for res in MatchingPipeline(net, hosts, keys=keys, device=DEV, inflight=inflight)]
+        assert len(got) == len(hosts)
+        for a, g in zip(alone, got):
+            for x, y in zip(a, g):
+                assert torch.equal(x, y)
+    net.check_lap_status()
+
+
 def test_head_without_dead_ke_gives_identical_outputs():
     from fpmatch import synth
     data = synth.make_batch(4, 20, seed=6)
