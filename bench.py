@@ -147,10 +147,9 @@ def main():
     ap.add_argument("--gemm", default=os.environ.get("FPMATCH_GEMM", None))
     ap.add_argument("--cpu-sample", type=int, default=32, help="pairs per step of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-inflight", type=int, default=int(os.environ.get("FPMATCH_BENCH_E2E_INFLIGHT", "1")),
-                    help="batches in flight in the end-to-end loop whose backbone maps cross PCIe every step (measured: "
-                         "one at a time is faster there - 29.1 k vs 27.6 k pairs/s - the host side of that loop is the "
-                         "limiter; the resident-maps variant uses --inflight)")
+    ap.add_argument("--e2e-inflight", type=int, default=int(os.environ.get("FPMATCH_BENCH_E2E_INFLIGHT", "2")),
+                    help="batches in flight in the end-to-end loop whose backbone maps cross PCIe every step (r2: 31.3 k "
+                         "pairs/s with 2, 29.3 k with 1); the resident-maps variant uses --inflight")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("FPMATCH_BENCH_INFLIGHT", "2")),
                     help="batches in flight in the device-timed loop: step i is issued on stream i %% inflight, so the "
                          "latency-bound tail of one batch (Sinkhorn, LAP, AFA-U) overlaps the tensor-bound front of the next")
@@ -364,7 +363,7 @@ def main():
         assert res is not None and got == nsteps
         return res
 
-    e2e_run(3, inflight=args.e2e_inflight)
+    e2e_run(6, inflight=args.e2e_inflight)       # more steps than the prefetcher has staging slots: all buffers exist
     barrier()
     t0 = time.perf_counter()
     res = e2e_run(e2e_steps, inflight=args.e2e_inflight)
@@ -384,7 +383,7 @@ def main():
     feeder2 = CudaPrefetcher([], device=dev)
     maps_dev = {"fmaps": resident["fmaps"]}
     h2d_nomaps = sum(tensor_bytes(v) for v in host_nomaps.values())
-    e2e_run(3, host_nomaps, maps_dev, feeder2, inflight=args.inflight)
+    e2e_run(6, host_nomaps, maps_dev, feeder2, inflight=args.inflight)
     barrier()
     t0 = time.perf_counter()
     e2e_run(e2e_steps, host_nomaps, maps_dev, feeder2, inflight=args.inflight)

@@ -138,15 +138,18 @@ class HostResultRing:
         return slot["bufs"]
 
 
-_LANES = {}      # (device index, k) -> k persistent compute streams shared by all pipelines on that device
+_LANES = {}      # device index -> persistent compute streams shared by all pipelines on that device
 
 
 def lanes(device, k: int):
+    """The first ``k`` compute streams of the device's persistent set (a pipeline of depth 1 reuses the first stream
+    of a pipeline of depth 2, so torch's per-stream caching allocator keeps serving the same blocks)."""
     device = torch.device(device)
-    key = (device.index if device.index is not None else torch.cuda.current_device(), int(k))
-    if key not in _LANES:
-        _LANES[key] = [torch.cuda.Stream(device=device) for _ in range(max(1, int(k)))]
-    return _LANES[key]
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    pool = _LANES.setdefault(key, [])
+    while len(pool) < max(1, int(k)):
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:max(1, int(k))]
 
 
 class MatchingPipeline:
