@@ -228,7 +228,7 @@ def main():
         with torch.no_grad():
             return net(dict(resident))    # the forward overwrites graph.x in place, as the reference does
 
-    from fpmatch.prefetch import lanes as _lanes
+    from fpmatch.prefetch import MatchingPipeline, lanes as _lanes
     lanes = _lanes(dev, args.inflight) if args.inflight > 1 else []
 
     def run_steps(n):
@@ -242,9 +242,11 @@ def main():
         cur = torch.cuda.current_stream(dev)
         for s_ in lanes:
             s_.wait_stream(cur)
+        ops.set_gemm_max_clusters(MatchingPipeline.GEMM_CLUSTERS_IN_FLIGHT)      # as the streaming API does
         for i in range(n):
             with torch.cuda.stream(lanes[i % len(lanes)]):
                 out = step_resident()
+        ops.set_gemm_max_clusters(0)
         for s_ in lanes:
             cur.wait_stream(s_)
         return out

@@ -36,6 +36,7 @@ SIGNATURES = {
     "fpm_gemm_nt_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fpm_gemm_set_trace": (_I, [_P, _I]),
     "fpm_gemm_set_pair": (_I, [_I]),
+    "fpm_gemm_set_max_clusters": (_I, [_I]),
     "fpm_f16_split_rows": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "fpm_gemm_nt_f16x3": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fpm_gemm_nt_f16x3_tiles": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _LL, _I, _P]),

@@ -46,6 +46,12 @@ def set_gemm_pair(on: bool) -> None:
     _GEMM_PAIR = bool(on)
 
 
+def set_gemm_max_clusters(n: int) -> None:
+    """Cap on the SM pairs the persistent slab GEMM occupies (0 = all 74).  Pipelines with several batches in flight
+    leave a few SMs to the other batch's tail kernels (fpmatch.prefetch.MatchingPipeline sets 70)."""
+    _lib.check(_lib.lib().fpm_gemm_set_max_clusters(int(n)), "fpm_gemm_set_max_clusters")
+
+
 def gemm_pair_enabled() -> bool:
     return _GEMM_PAIR
 
@@ -1077,7 +1083,7 @@ def add_instnorm_bwd(a: Tensor, other: Optional[Tensor], gamma: Tensor, dy: Opti
 def _install_device_guards():
     import types
     g = globals()
-    skip = {"set_gemm_mode", "gemm_mode", "set_affinity_tc", "set_gemm_pair", "gemm_pair_enabled", "set_slab_plan", "slab_plan_enabled",
+    skip = {"set_gemm_mode", "gemm_mode", "set_affinity_tc", "set_gemm_pair", "set_gemm_max_clusters", "gemm_pair_enabled", "set_slab_plan", "slab_plan_enabled",
             "launch_count", "gemm_profile_start", "gemm_profile_stop", "on_tensor_device"}
     for name, obj in list(g.items()):
         if name.startswith("_") or name in skip:

@@ -175,10 +175,20 @@ class MatchingPipeline:
         self.ring = ring if ring is not None else HostResultRing(device=self.device, lag=len(self.lanes))
         self.ring.set_lag(len(self.lanes))
 
+    GEMM_CLUSTERS_IN_FLIGHT = 70     # of 74 SM pairs: the rest stay free for the other batch's tail kernels (r2n)
+
     def __iter__(self):
+        from . import ops
         cur = torch.cuda.current_stream(self.device)
         for s in self.lanes:
             s.wait_stream(cur)
+        ops.set_gemm_max_clusters(self.GEMM_CLUSTERS_IN_FLIGHT if len(self.lanes) > 1 else 0)
+        try:
+            yield from self._run(cur)
+        finally:
+            ops.set_gemm_max_clusters(0)
+
+    def _run(self, cur):
         it = iter(self.feeder)
         i = 0
         while True:

@@ -83,6 +83,7 @@ int fpm_gemm_nt_f16x3(const void* A_hi, const void* A_lo, const float* inv_a, co
  * 256x128 tiles, TMEM double-buffered so the epilogue of one tile overlaps the main loop of the next), 0 = one 128x256
  * tile per CTA.  Also settable with the environment variable FPMATCH_GEMM_PAIR=0/1 before the first call. */
 int fpm_gemm_set_pair(int on);
+int fpm_gemm_set_max_clusters(int clusters);   /* cap on the SM pairs the persistent GEMM occupies (0 = all) */
 
 /* Tile-table form of fpm_gemm_nt_f16x3 (persistent CTA-pair kernel): computes only the *tab_count C blocks listed in
  * tab (device, 4 ints per tile: first A row of a 256-row block, first Bt row of a 128-row block, first C column, row-map
