@@ -264,3 +264,36 @@ def test_dense_gnn_layer_oracle_equals_einsum():
         x1 = mlp("n_func", x)
         ref = torch.einsum("bij,bijc,bjc->bic", An, W.expand(b, N, N, F_), x1) + mlp("n_self_func", x)
         assert (out - ref).abs().max() < 1e-5
+
+
+def test_index_lists_and_common_len_cut_match_the_reference_golden():
+    """tests/golden/kron_partial.pt was produced by the reference's own kronecker_sparse / CSCMatrix3d /
+    construct_sparse_aff_mat (make_kron_golden.py) for complete and PARTIAL ground-truth permutations.  Checked here:
+    the generator's KGHs_sparse restatement (fpmatch.synth.add_kron), the [idx; diag] lists with the ngm.py:339 cut as
+    oracle/head.py forms them, and the effective factorised structure the CUDA path derives from the edge tables."""
+    from fpmatch import synth
+    fx = torch.load(GOLD / "kron_partial.pt")
+    for tag, c in fx.items():
+        kw = c["kw"]
+        d = synth.make_batch(4, kw["n"], seed=kw["seed"], partial=kw["partial"], imposter_every=3, with_kron=True)
+        g1, g2 = d["pyg_graphs"]
+        n1max = d["Ps"][0].shape[1]
+        for b in range(4):
+            idxG, idxH = d["KGHs_sparse"][b]
+            assert torch.equal(idxG.int(), c["idxG"][b]) and torch.equal(idxH.int(), c["idxH"][b]), (tag, b)
+            n1b, n2b = int(d["ns"][0][b]), int(d["ns"][1][b])
+            e1b, e2b = int(g1.eptr[b + 1] - g1.eptr[b]), int(g2.eptr[b + 1] - g2.eptr[b])
+            diag = torch.arange(n1b * n2b)
+            row, col = torch.cat((idxG, diag)), torch.cat((idxH, diag))
+            common = min(row.numel(), col.numel(), e1b * e2b + n1b * n2b)       # oracle/head.py
+            assert common == c["common_len"][b], (tag, b)
+            assert torch.equal(row[:common].int(), c["row"][b]) and torch.equal(col[:common].int(), c["col"][b])
+            # the effective structure reproduces the reference's (row, col) multiset exactly
+            eff1, eff2, part, ndiag = effective_structure(d["edge_lists"][0][b], d["edge_lists"][1][b], e1b, e2b, n1b, n2b)
+            pairs = [(s2 * n1max + s1, d2 * n1max + d1) for (s2, d2) in eff2 for (s1, d1) in eff1]
+            if part is not None:
+                ps2, pd2, ccut = part
+                pairs += [(ps2 * n1max + s1, pd2 * n1max + d1) for (s1, d1) in eff1[:ccut]]
+            pairs += [(p, p) for p in range(ndiag)]
+            ref_pairs = list(zip(c["row"][b].tolist(), c["col"][b].tolist()))
+            assert sorted(pairs) == sorted(ref_pairs), (tag, b)
