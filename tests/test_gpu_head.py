@@ -211,7 +211,10 @@ def test_head_100_keypoints_matches_oracle(variant, sharpen):
     assert st["k_prob"] < 1e-4 and st["k_int_equal"] and st["cls_prob"] < 1e-4
     assert solver_exact
     if sharpen:
-        assert st["perm_pairs_equal"] == st["pairs"] and hung_equal
+        # perm_mat bit-exact; the full assignment may differ only between equally optimal solutions (the scores of the
+        # 100 - k unselected rows stay nearly flat even with the sharpened weights)
+        assert st["perm_pairs_equal"] == st["pairs"]
+        assert rec["max_rel_objective_gap_of_differing_assignments"] < 1e-6, rec
         assert rec["gpu_vs_fp64"] < rec["relaxed_bar"]
     else:
         assert st["ds_mat"] < 1e-4          # north-star bar, outright, on the benchmark's own weights
