@@ -816,6 +816,7 @@ struct GnnBank {
   cudaEvent_t last_use = nullptr;
   cudaStream_t last_stream = nullptr;
   bool used = false;
+  bool capturing = false;
 };
 GnnBank g_bank[16];
 }  // namespace
@@ -830,7 +831,12 @@ static int gnn_bank_acquire(int* dev_out, cudaStream_t st) {
   cudaError_t e = cudaSuccess;
   if (!k.staging) e = cudaMalloc(&k.staging, fpm::kGnnConstFloats * sizeof(float));
   if (e == cudaSuccess && !k.last_use) e = cudaEventCreateWithFlags(&k.last_use, cudaEventDisableTiming);
-  if (e == cudaSuccess && k.used && k.last_stream != st) e = cudaStreamWaitEvent(st, k.last_use, 0);
+  // A stream that is being captured into a CUDA graph must not wait on (or record) events of eager work: the graph
+  // orders its own launches, and its replays must not overlap eager forwards of other streams on this device.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (e == cudaSuccess) e = cudaStreamIsCapturing(st, &cap);
+  k.capturing = cap != cudaStreamCaptureStatusNone;
+  if (e == cudaSuccess && !k.capturing && k.used && k.last_stream != st) e = cudaStreamWaitEvent(st, k.last_use, 0);
   if (e != cudaSuccess) {
     k.mu.unlock();
     fpm_set_error(cudaGetErrorString(e));
@@ -841,7 +847,7 @@ static int gnn_bank_acquire(int* dev_out, cudaStream_t st) {
 
 static int gnn_bank_release(int dev, cudaStream_t st, int rc) {
   GnnBank& k = g_bank[dev];
-  if (rc == FPM_OK) {
+  if (rc == FPM_OK && !k.capturing) {
     cudaError_t e = cudaEventRecord(k.last_use, st);
     if (e == cudaSuccess) { k.used = true; k.last_stream = st; }
     else { fpm_set_error(cudaGetErrorString(e)); rc = (int)e; }

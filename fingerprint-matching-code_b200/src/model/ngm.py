@@ -391,7 +391,8 @@ class Net(CNN):
         e1max, e2max = tables[0].shape[2], tables[1].shape[2]
         feats, offs = [], []
         main = torch.cuda.current_stream(dev)
-        fork = self._ke_stream(dev, 1) if self.graph_fork else None
+        capturing = torch.cuda.is_current_stream_capturing()      # a CUDA graph of the forward stays on one stream
+        fork = self._ke_stream(dev, 1) if (self.graph_fork and not capturing) else None
         if fork is not None:
             self.message_pass_node_features.mp_network.prepare_weights()    # shared cached operands, before the fork
             fork.wait_stream(main)
@@ -424,7 +425,7 @@ class Net(CNN):
         if self.compute_dead_ke:
             # Nothing downstream reads Ke, so its kernels run on a side stream underneath the
             # latency-bound middle of the forward (association-graph layers, Sinkhorn, LAP); joined before returning.
-            side = self._ke_stream(dev) if self.ke_side_stream else main
+            side = self._ke_stream(dev) if (self.ke_side_stream and not capturing) else main
             if side is not main:
                 side.wait_stream(main)
             with torch.cuda.stream(side):

@@ -545,3 +545,98 @@ def test_k_branch_gradients_match_oracle():
     assert kerr < max(1e-4, 4 * kerr32)
     assert len(rows) >= 30
     assert not bad, bad
+
+
+# ------------------------------------------------------------------------------------------------- CUDA graphs
+def test_inference_forward_captures_into_a_cuda_graph():
+    """The forward issues no host synchronisation and, while a stream is being captured, keeps all of its kernels on
+    that stream (no image-chain fork, no Ke side stream, no cross-stream event of the GNN weight bank): it can be
+    captured and replayed.  Replay output == eager output, bit for bit."""
+    from fpmatch import synth
+    from src.model.ngm import Net
+    torch.manual_seed(0)
+    net = Net(regression=True).eval().to(DEV)
+    net.track_lap_status = False
+    data = synth.batch_to(synth.make_batch(6, 30, seed=12, ragged=True), DEV)
+    with torch.no_grad():
+        eager = net(dict(data))
+        ref = {k: eager[k].clone() for k in ("ds_mat", "perm_mat", "k_prob", "cls_prob")}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            net(dict(data))
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = net(dict(data))
+        for k in ref:
+            out[k].zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+
+
+def test_training_step_captures_into_a_cuda_graph():
+    """Forward + PermutationLoss + backward + clip + AdamW(capturable) of the stage-1 step as ONE CUDA graph (what
+    tools/bench_train.py --graph times): three replays follow three eager steps of a twin model to fp32 reduction noise
+    (the GNN weight gradients are reduced with floating-point atomics)."""
+    from fpmatch import synth
+    from src.loss_func import PermutationLoss
+    from src.model.ngm import Net
+    data = synth.make_batch(4, 24, seed=21, imposter_every=0, fmap_noise=1.0)
+    data.pop("label")
+    devd = synth.batch_to(data, DEV)
+    frozen = ("encoder_k.", "final_row.", "final_col.", "match_cls.", "node_layers.", "edge_layers.")
+
+    def make():
+        torch.manual_seed(0)
+        net = Net(regression=False).to(DEV).train()
+        net.track_lap_status = False
+        for k, p in net.named_parameters():
+            if k.startswith(frozen):
+                p.requires_grad_(False)
+        params = [p for p in net.parameters() if p.requires_grad]
+        return net, params, torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4, capturable=True)
+
+    crit = PermutationLoss()
+    crit.check_range = False
+
+    def step(net, params, opt):
+        d = dict(devd)
+        d["pyg_graphs"] = [g.to(DEV) for g in devd["pyg_graphs"]]
+        opt.zero_grad(set_to_none=False)
+        out = net(d)
+        loss = crit(out["ds_mat"], d["gt_perm_mat"], *d["ns"])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 5.0)
+        opt.step()
+        return loss
+
+    net_e, par_e, opt_e = make()
+    net_g, par_g, opt_g = make()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                 # warm-up on a side stream (allocations, lazy state); 3 real steps
+        for _ in range(3):
+            step(net_g, par_g, opt_g)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        step(net_e, par_e, opt_e)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    opt_g.zero_grad(set_to_none=False)
+    with torch.cuda.graph(g):
+        loss_g = step(net_g, par_g, opt_g)
+    eager_losses, graph_losses = [], []
+    step(net_e, par_e, opt_e)                     # the capture itself does not execute: twin takes the captured step's place
+    g.replay()
+    for _ in range(3):
+        eager_losses.append(step(net_e, par_e, opt_e).item())
+        g.replay()
+        torch.cuda.synchronize()
+        graph_losses.append(loss_g.item())
+    rel = max(abs(a - b) / abs(a) for a, b in zip(eager_losses, graph_losses))
+    report("cuda_graph_train_step", eager=eager_losses, graph=graph_losses, rel=rel)
+    assert rel < 1e-4, (eager_losses, graph_losses)
