@@ -441,7 +441,7 @@ def affinity_nodes(XA: Tensor, XB: Tensor, coeff: Tensor, ptrA: Tensor, ptrB: Te
         rc = L.fpm_f16_split_rows_scaled(_chk(XA, "XA"), _chk(coeff, "coeff"), _chk(ptrA, "ptrA", torch.int64), B,
                                          a_hi.data_ptr(), a_lo.data_ptr(), a_inv.data_ptr(), XA.shape[0], K, _stream())
         _lib.check(rc, "fpm_f16_split_rows_scaled"); _count()
-        b_hi, b_lo, b_inv = f16_split_rows(XB)
+        b_hi, b_lo, b_inv = f16_split_rows(XB, cache=True)      # Kp and the raw products for Ke share X2's split
         ntile = B * tA * tB
         tab = torch.empty((ntile, 4), dtype=torch.int32, device=dev)
         meta = torch.empty((1,), dtype=torch.int32, device=dev)

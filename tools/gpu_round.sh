@@ -24,5 +24,8 @@ if [[ "$*" != *noncu* ]]; then
   # gpurun_out may carry at most 64 MiB back: keep the full capture to ~20 launches (~2.5 MiB each with source)
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-gemm_tc_pair_kernel|gnn_layer_kernel|spline_gather|sinkhorn_log|lap_topk|afau_attention|match_cls_stage2|ke_factored}" -s ${NCU_SKIP:-40} -c ${NCU_COUNT:-20} -o $O/${TAG}_prof $CMD > $O/${TAG}_ncu_full.log 2>&1
   echo "ncu full rc=$?"; ls -la $O/${TAG}_prof.ncu-rep
+  # the association-graph layer kernels in their own small capture (the window above rarely reaches them)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gnn_layer_kernel" -s 6 -c 3 -o $O/${TAG}_prof_gnn $CMD > $O/${TAG}_ncu_full_gnn.log 2>&1
+  echo "ncu gnn rc=$?"
 fi
 ls -la $O | tail -12

@@ -56,12 +56,19 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 
 
 def full():
-    rep = GO / f"{tag}_prof.ncu-rep"
-    if not rep.exists():
+    reps = sorted(GO.glob(f"{tag}_prof*.ncu-rep"))       # one or several captures of the same build (different kernel sets)
+    if not reps:
         return
-    r = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True)
-    rows = list(csv.reader(io.StringIO(r.stdout)))
-    hdr, units, data = rows[0], rows[1], rows[2:]
+    hdr, units, data = None, None, []
+    for rep in reps:
+        r = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True)
+        rows = list(csv.reader(io.StringIO(r.stdout)))
+        if hdr is None:
+            hdr, units = rows[0], rows[1]
+        elif rows[0] != hdr:                                # same ncu, same --set: the columns agree; be safe anyway
+            pos = {h: i for i, h in enumerate(rows[0])}
+            rows = rows[:2] + [[d[pos[h]] if h in pos else "" for h in hdr] for d in rows[2:]]
+        data += rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
     cols = [m for m in METRICS if m in idx]
     out = [f"# ncu --set full, one launch of each hot kernel inside bench.py (B=256, n=100) - {tag}", "",
