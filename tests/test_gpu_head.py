@@ -76,6 +76,11 @@ def compare(tag, ref, out, data):
     # margin of the k rounding: distance of k*min_pts to the nearest half-integer
     ks = inter["k_scaled"].cpu()
     stats["k_round_margin"] = (ks - ks.floor() - 0.5).abs().min().item()
+    stats["ds_mat_strict_1e-4_ok"] = bool(stats["ds_mat"] < 1e-4)
+    if "hungarian" in ref and "k_int" in ref:          # would the reference's unstable argsort matter here?
+        ties = tie_stats(ref, data["ns"][0], data["ns"][1])
+        stats["tie_positive_straddle_pairs"] = ties["tie_positive_straddle_pairs"]
+        stats["tie_zero_tail_pairs"] = ties["tie_zero_tail_pairs"]
     report(tag, **stats)
     return stats
 
