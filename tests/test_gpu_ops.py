@@ -107,7 +107,14 @@ def test_fused_node_features(ops, oo):
 # -------------------------------------------------------------------------------------------- Sinkhorn
 @pytest.mark.parametrize("R,C,dummy,it,tau", [(20, 20, True, 20, 0.01), (17, 23, True, 10, 0.01),
                                               (23, 17, True, 10, 0.05), (12, 12, False, 10, 1.0),
-                                              (100, 100, True, 20, 0.01), (64, 100, True, 10, 0.01)])
+                                              (100, 100, True, 20, 0.01), (64, 100, True, 10, 0.01),
+                                              # register-resident kernel: its four row-per-warp variants and frame edges
+                                              (32, 31, False, 10, 0.05), (50, 64, True, 10, 0.05),
+                                              (112, 101, True, 20, 0.05), (128, 128, True, 10, 0.05),
+                                              (113, 120, False, 10, 0.05),
+                                              # one CTA, matrix in shared memory (128 < n <= 224)
+                                              (129, 129, True, 10, 0.05), (150, 140, True, 10, 0.05),
+                                              (200, 180, False, 10, 0.05)])
 def test_sinkhorn_vs_oracle(ops, oo, R, C, dummy, it, tau):
     g = torch.Generator().manual_seed(R * 100 + C)
     B = 9
