@@ -6,6 +6,7 @@
 // /root/reference/src/model/ngm.py:402-412.  The q/k/v, combine and feed-forward projections are plain
 // dense GEMMs and go through gemm_*.cu.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fpm {
 
@@ -103,6 +104,107 @@ afau_attention_kernel(const float* __restrict__ q, const float* __restrict__ k, 
     op[t] = make_float4(acc[t * 4] / den, acc[t * 4 + 1] / den, acc[t * 4 + 2] / den, acc[t * 4 + 3] / den);
 }
 
+// The row block of Net.forward (ngm.py:392: the row embedding is all zeros, so q = 0 and the score of (i, j) is the
+// mixing MLP of cost[i, j] alone).  CTA per (pair, kZh heads): the pair's cost tile and the heads' values are staged
+// in shared memory once; thread = one (head, query row).  The 16-unit MLP runs on packed fp32: 8 FFMA2 form the hidden
+// pairs (c * w1b + b1, one rounding instead of the generic kernel's two), 16 FMNMX, 8 FFMA2 fold them with w2; the 16
+// value accumulators are 8 FFMA2.  Scores are kept in the log2 domain (s * log2 e) so a softmax weight is one FFMA +
+// one EX2.  ~55 instructions per (i, j, head) against ~140 in the generic kernel, and the cost row is read from
+// shared memory (odd row pitch: conflict-free) instead of 32 cache lines per warp load.
+constexpr int kZh = 2;
+
+__global__ void __launch_bounds__(256, 3)
+afau_attention_qzero_kernel(const float* __restrict__ v, const float* __restrict__ cost, long long cs_b, long long cs_r,
+                            long long cs_c, const float* __restrict__ mix1_w, const float* __restrict__ mix1_b,
+                            const float* __restrict__ mix2_w, const float* __restrict__ mix2_b,
+                            float* __restrict__ out, int nr, int nc) {
+  extern __shared__ float sm[];
+  const int ldc = nc | 1;
+  float* cs = sm;                                   // [nr][ldc]
+  float* vs = sm + (((size_t)nr * ldc + 3) & ~(size_t)3);   // [kZh][nc][16], 16-byte aligned
+  const int b = blockIdx.y, h0 = blockIdx.x * kZh;
+  const int E = kHeads * kQkv;
+  const float* cb = cost + (size_t)b * cs_b;
+  if (cs_c == 1) {
+    for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
+      const int i = idx / nc, j = idx - i * nc;
+      cs[i * ldc + j] = cb[(size_t)i * cs_r + j];
+    }
+  } else {                                          // transposed cost: walk the source rows so the reads stay coalesced
+    for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
+      const int j = idx / nr, i = idx - j * nr;
+      cs[i * ldc + j] = cb[(size_t)i * cs_r + (size_t)j * cs_c];
+    }
+  }
+  for (int idx = threadIdx.x; idx < kZh * nc * kQkv; idx += blockDim.x) {
+    const int hl = idx / (nc * kQkv), rem = idx - hl * nc * kQkv;
+    const int j = rem / kQkv, d = rem - j * kQkv;
+    vs[idx] = v[((size_t)b * nc + j) * E + (h0 + hl) * kQkv + d];
+  }
+  __syncthreads();
+  const int hl = threadIdx.x / nr, i = threadIdx.x - hl * nr;
+  if (hl >= kZh) return;
+  const int h = h0 + hl;
+
+  constexpr float kL2e = 1.4426950408889634f;
+  f32x2 w1[kMs / 2], bb[kMs / 2], w2[kMs / 2];
+#pragma unroll
+  for (int m = 0; m < kMs / 2; ++m) {
+    w1[m] = pk2(mix1_w[(h * 2 + 1) * kMs + 2 * m], mix1_w[(h * 2 + 1) * kMs + 2 * m + 1]);
+    bb[m] = pk2(mix1_b[h * kMs + 2 * m], mix1_b[h * kMs + 2 * m + 1]);
+    w2[m] = pk2(mix2_w[h * kMs + 2 * m] * kL2e, mix2_w[h * kMs + 2 * m + 1] * kL2e);
+  }
+  const float b2 = mix2_b[h] * kL2e;
+  const float* crow = cs + i * ldc;
+  const float4* vh = (const float4*)(vs + (size_t)hl * nc * kQkv);
+
+  float mx = kNegInf, den = 0.f;
+  f32x2 acc[kQkv / 2];
+#pragma unroll
+  for (int d = 0; d < kQkv / 2; ++d) acc[d] = pk2(0.f, 0.f);
+  for (int j = 0; j < nc; ++j) {
+    const float c = crow[j];
+    const f32x2 cc = pk2(c, c);
+    f32x2 s2 = pk2(b2, 0.f);
+#pragma unroll
+    for (int m = 0; m < kMs / 2; ++m) {
+      float h0v, h1v;
+      upk2(fma2(cc, w1[m], bb[m]), h0v, h1v);
+      s2 = fma2(pk2(fmaxf(h0v, 0.f), fmaxf(h1v, 0.f)), w2[m], s2);
+    }
+    float sa, sb;
+    upk2(s2, sa, sb);
+    const float sj = sa + sb;                         // score * log2 e
+    if (sj > mx) {                                    // a row does this ~ln(nc) times
+      float r;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(mx - sj));     // 2^-inf = 0 on the first column
+      den *= r;
+      const f32x2 rr = pk2(r, r);
+#pragma unroll
+      for (int d = 0; d < kQkv / 2; ++d) acc[d] = fma2(acc[d], rr, pk2(0.f, 0.f));
+      mx = sj;
+    }
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(sj - mx));
+    den += e;
+    const f32x2 ee = pk2(e, e);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float4 x = vh[j * 4 + t];
+      acc[2 * t] = fma2(ee, pk2(x.x, x.y), acc[2 * t]);
+      acc[2 * t + 1] = fma2(ee, pk2(x.z, x.w), acc[2 * t + 1]);
+    }
+  }
+  float4* op = (float4*)(out + ((size_t)b * nr + i) * E + h * kQkv);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float a0, a1, a2, a3;
+    upk2(acc[2 * t], a0, a1);
+    upk2(acc[2 * t + 1], a2, a3);
+    op[t] = make_float4(a0 / den, a1 / den, a2 / den, a3 / den);
+  }
+}
+
 // out[b, r, e] = InstanceNorm over r of (a + other)[b, :, e] * gamma[e] + beta[e]; other_mode: 0 none,
 // 1 tensor [B, n, E], 2 row vector [E].  Optionally rowmax[b, e] = max_r out[b, r, e] (the
 // "pad to 600 rows with -inf, MaxPool1d(600)" of ngm.py:402-405).  Thread per channel, coalesced along E.
@@ -182,6 +284,97 @@ add_instnorm_reg_kernel(const float* __restrict__ a, const float* __restrict__ o
     }
   }
   if (rowmax) rowmax[(size_t)b * E + e] = mxv;
+}
+
+// The kernel the matching head runs (n <= kWarps * kRows rows, E % 4 == 0): CTA per (pair, 128 channels).  A lane
+// owns four adjacent channels (one 128-bit load per row, a warp reads 512 contiguous bytes of the row), a warp owns
+// rows w, w+kWarps, ...; the per-channel sums over rows are folded across the warps through shared memory (mean, then
+// the centred second moment - the two-pass form of torch's InstanceNorm, so near-constant channels stay accurate).
+// The thread-per-channel kernels above kept a whole column (104 values, 168 registers) per thread: 17 % occupancy,
+// 128-byte row segments, 16 % of the DRAM peak.  `out` may be null when only the row maximum is wanted (the second
+// normalisation of an AFA-U block feeds nothing but the max-pool, ngm.py:402-405).
+template <int kWarps, int kRows, int kMode>
+__global__ void __launch_bounds__(32 * kWarps, 1024 / (32 * kWarps))
+add_instnorm_tile_kernel(const float* __restrict__ a, const float* __restrict__ other,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
+                         float* __restrict__ rowmax, int n, int E, float eps) {
+  __shared__ float4 red[kWarps][32];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * 128 + 4 * lane;
+  const bool live = e < E;
+  const size_t base = (size_t)b * n * E + e;
+  float4 x[kRows];
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    const int r = warp + kWarps * k;
+    x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live && r < n) x[k] = *(const float4*)(a + base + (size_t)r * E);
+  }
+  if (kMode == 1) {
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int r = warp + kWarps * k;
+      if (live && r < n) {
+        const float4 o = *(const float4*)(other + base + (size_t)r * E);
+        x[k].x += o.x; x[k].y += o.y; x[k].z += o.z; x[k].w += o.w;
+      }
+    }
+  } else if (kMode == 2) {
+    float4 ov = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) ov = *(const float4*)(other + e);
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) { x[k].x += ov.x; x[k].y += ov.y; x[k].z += ov.z; x[k].w += ov.w; }
+  }
+  auto fold = [&](float4 p, bool is_max) -> float4 {      // combine the warps' partials, same order in every thread
+    __syncthreads();                                       // the previous fold's reads are done
+    red[warp][lane] = p;
+    __syncthreads();
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) {
+      const float4 q = red[w][lane];
+      if (is_max) { t.x = fmaxf(t.x, q.x); t.y = fmaxf(t.y, q.y); t.z = fmaxf(t.z, q.z); t.w = fmaxf(t.w, q.w); }
+      else { t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+    }
+    return t;
+  };
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < kRows; ++k)
+    if (warp + kWarps * k < n) { sum.x += x[k].x; sum.y += x[k].y; sum.z += x[k].z; sum.w += x[k].w; }
+  sum = fold(sum, false);
+  const float fn = (float)n;
+  const float4 mean = make_float4(sum.x / fn, sum.y / fn, sum.z / fn, sum.w / fn);
+  float4 vs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    x[k].x -= mean.x; x[k].y -= mean.y; x[k].z -= mean.z; x[k].w -= mean.w;
+    if (warp + kWarps * k < n) {
+      vs.x = fmaf(x[k].x, x[k].x, vs.x); vs.y = fmaf(x[k].y, x[k].y, vs.y);
+      vs.z = fmaf(x[k].z, x[k].z, vs.z); vs.w = fmaf(x[k].w, x[k].w, vs.w);
+    }
+  }
+  vs = fold(vs, false);
+  const float4 inv = make_float4(1.0f / sqrtf(vs.x / fn + eps), 1.0f / sqrtf(vs.y / fn + eps),
+                                 1.0f / sqrtf(vs.z / fn + eps), 1.0f / sqrtf(vs.w / fn + eps));
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f), bt = g;
+  if (live) { g = *(const float4*)(gamma + e); bt = *(const float4*)(beta + e); }
+  float4 mx = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    const int r = warp + kWarps * k;
+    if (live && r < n) {
+      float4 y;
+      y.x = x[k].x * inv.x * g.x + bt.x; y.y = x[k].y * inv.y * g.y + bt.y;
+      y.z = x[k].z * inv.z * g.z + bt.z; y.w = x[k].w * inv.w * g.w + bt.w;
+      if (out) *(float4*)(out + base + (size_t)r * E) = y;
+      mx.x = fmaxf(mx.x, y.x); mx.y = fmaxf(mx.y, y.y); mx.z = fmaxf(mx.z, y.z); mx.w = fmaxf(mx.w, y.w);
+    }
+  }
+  if (rowmax) {
+    mx = fold(mx, true);
+    if (warp == 0 && live) *(float4*)(rowmax + (size_t)b * E + e) = mx;
+  }
 }
 
 // k[b, j, o] = j < n[b] ? W[o, j] : 0 : the projection of a one-hot embedding (ngm.py:396-399) is a
@@ -434,6 +627,21 @@ extern "C" int fpm_afau_attention(const float* q, const float* k, const float* v
   FPM_CHECK_ARG(B >= 0 && nr > 0 && nc > 0, "fpm_afau_attention: bad sizes");
   if (B == 0) return FPM_OK;
   FPM_CHECK_ARG(B <= 65535, "fpm_afau_attention: batch too large");
+  static const bool qzero_path = [] {
+    const char* e = getenv("FPMATCH_AFAU_QZERO");              // 0: the generic kernel also for q == 0 (A/B runs)
+    return !(e && e[0] == '0');
+  }();
+  const size_t zsmem = ((((size_t)nr * (nc | 1) + 3) & ~(size_t)3) + (size_t)fpm::kZh * nc * fpm::kQkv) * sizeof(float);
+  if (q_zero && qzero_path && fpm::kZh * nr <= 256 && zsmem <= 72 * 1024) {
+    FPM_CUDA(cudaFuncSetAttribute(fpm::afau_attention_qzero_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)zsmem));
+    dim3 zgrid(fpm::kHeads / fpm::kZh, B);
+    const int threads = (fpm::kZh * nr + 31) / 32 * 32;
+    fpm::afau_attention_qzero_kernel<<<zgrid, threads, zsmem, (cudaStream_t)stream>>>(
+        v, cost, cs_b, cs_r, cs_c, mix1_w, mix1_b, mix2_w, mix2_b, out, nr, nc);
+    FPM_LAUNCH_CHECK();
+    return FPM_OK;
+  }
   const size_t smem = (size_t)2 * nc * fpm::kQkv * sizeof(float);
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_afau_attention: too many columns");
   FPM_CUDA(cudaFuncSetAttribute(fpm::afau_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -448,13 +656,33 @@ extern "C" int fpm_afau_attention(const float* q, const float* k, const float* v
 extern "C" int fpm_add_instnorm(const float* a, const float* other, int other_mode, const float* gamma,
                                 const float* beta, float* out, float* rowmax, int B, int n, int E, float eps,
                                 void* stream) {
-  FPM_CHECK_ARG(a && gamma && beta && out, "fpm_add_instnorm: null tensor");
+  FPM_CHECK_ARG(a && gamma && beta && (out || rowmax), "fpm_add_instnorm: null tensor");
   FPM_CHECK_ARG(other_mode == 0 || other, "fpm_add_instnorm: other tensor missing");
   FPM_CHECK_ARG(other_mode >= 0 && other_mode <= 2, "fpm_add_instnorm: bad mode");
   FPM_CHECK_ARG(B >= 0 && n > 0 && E > 0, "fpm_add_instnorm: bad sizes");
   if (B == 0) return FPM_OK;
   FPM_CHECK_ARG(B <= 65535, "fpm_add_instnorm: batch too large");
   dim3 grid(fpm_cdiv(E, 128), B);
+  const bool aligned = E % 4 == 0 && ((uintptr_t)a | (uintptr_t)other | (uintptr_t)gamma | (uintptr_t)beta |
+                                      (uintptr_t)out | (uintptr_t)rowmax) % 16 == 0;
+  static const bool tile_path = [] {
+    const char* e = getenv("FPMATCH_INSTNORM_TILE");           // 0: thread-per-channel kernels (A/B runs)
+    return !(e && e[0] == '0');
+  }();
+  if (tile_path && aligned && n <= 112) {
+#define FPM_INSTNORM(W, MODE)                                                                                   \
+  fpm::add_instnorm_tile_kernel<W, 7, MODE><<<grid, 32 * W, 0, (cudaStream_t)stream>>>(a, other, gamma, beta, out, \
+                                                                                        rowmax, n, E, eps)
+    if (n <= 56) {
+      if (other_mode == 0) FPM_INSTNORM(8, 0); else if (other_mode == 1) FPM_INSTNORM(8, 1); else FPM_INSTNORM(8, 2);
+    } else {
+      if (other_mode == 0) FPM_INSTNORM(16, 0); else if (other_mode == 1) FPM_INSTNORM(16, 1); else FPM_INSTNORM(16, 2);
+    }
+#undef FPM_INSTNORM
+    FPM_LAUNCH_CHECK();
+    return FPM_OK;
+  }
+  FPM_CHECK_ARG(out, "fpm_add_instnorm: this shape needs the out tensor");
   if (n <= 104)
     fpm::add_instnorm_reg_kernel<104><<<grid, 128, 0, (cudaStream_t)stream>>>(a, other, other_mode, gamma, beta, out,
                                                                                rowmax, n, E, eps);

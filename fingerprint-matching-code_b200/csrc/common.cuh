@@ -41,6 +41,21 @@ static inline int fpm_cdiv(long long a, long long b) { return (int)((a + b - 1) 
 namespace fpm {
 
 constexpr int kWarp = 32;
+// ---- packed fp32 arithmetic of sm_100: one instruction, two lanes (FFMA2 / FADD2) --------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+
 constexpr float kNegInf = -INFINITY;
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -213,20 +213,6 @@ __global__ void gnn_pack_weights_kernel(GnnWeights w, float* __restrict__ stagin
   if (tid == 0) staging[O::cb] = w.cls_b[0];
 }
 
-// ---- packed fp32 arithmetic of sm_100: one instruction, two lanes (FFMA2 / FADD2) --------------------------------
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
-  f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-  f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
-}
 // acc[0..7] (output channel pairs (0,1) .. (14,15)) += WT[c][0..15] * x   - 8 FFMA2 with the weight pair as a
 // uniform-register operand and x broadcast to both lanes
 #define GNN_FMA_ROW(acc, base, c, x)                                                      \

@@ -642,13 +642,17 @@ def afau_attention(q: Tensor, k: Tensor, v: Tensor, cost: Tensor, transposed_cos
 
 
 def add_instnorm(a: Tensor, other: Optional[Tensor], gamma: Tensor, beta: Tensor, want_rowmax: bool = False,
-                 eps: float = 1e-5):
+                 eps: float = 1e-5, want_out: bool = True):
+    """``want_out=False`` (with ``want_rowmax``): only the per-channel maximum over rows is produced and the normalised
+    tensor is never written (returned as None)."""
     B, n, E = a.shape
-    out = torch.empty_like(a)
+    if not want_rowmax or n > 112 or E % 4 or os.environ.get("FPMATCH_INSTNORM_TILE") == "0":
+        want_out = True
+    out = torch.empty_like(a) if want_out else None
     rowmax = torch.empty((B, E), dtype=torch.float32, device=a.device) if want_rowmax else None
     mode = 0 if other is None else (2 if other.dim() == 1 else 1)
     rc = _lib.lib().fpm_add_instnorm(_chk(a, "a"), _chk(other, "other"), mode, _chk(gamma, "norm.weight"),
-                                     _chk(beta, "norm.bias"), out.data_ptr(),
+                                     _chk(beta, "norm.bias"), out.data_ptr() if want_out else None,
                                      rowmax.data_ptr() if want_rowmax else None, B, n, E, float(eps), _stream())
     _lib.check(rc, "fpm_add_instnorm"); _count()
     return (out, rowmax) if want_rowmax else out

@@ -144,7 +144,7 @@ class EncodingBlock(nn.Module):
         mh = _lin(att, self.multi_head_combine.weight, self.multi_head_combine.bias)
         out1 = self.add_n_normalization_1(mh, None)            # row_emb + mh with row_emb = 0
         out2 = self.feed_forward(out1)
-        _, rowmax = self.add_n_normalization_2(out1, out2, want_rowmax=True)
+        _, rowmax = self.add_n_normalization_2(out1, out2, want_rowmax=True, want_out=False)
         return rowmax
 
     def forward_onehot_rows_zero_cols(self, n2, n2max):
@@ -156,7 +156,7 @@ class EncodingBlock(nn.Module):
         onehot = ops.onehot_proj(torch.eye(emb, dtype=torch.float32, device=dev), n2, n2max)
         out1 = self.add_n_normalization_1(onehot, self.multi_head_combine.bias.detach().contiguous())
         out2 = self.feed_forward(out1)
-        _, rowmax = self.add_n_normalization_2(out1, out2, want_rowmax=True)
+        _, rowmax = self.add_n_normalization_2(out1, out2, want_rowmax=True, want_out=False)
         return rowmax
 
 
@@ -194,10 +194,10 @@ class AddAndInstanceNormalization(nn.Module):
         embedding_dim = model_params['embedding_dim']
         self.norm = nn.InstanceNorm1d(embedding_dim, affine=True, track_running_stats=False)
 
-    def forward(self, input1, input2, want_rowmax=False):
+    def forward(self, input1, input2, want_rowmax=False, want_out=True):
         return ops.add_instnorm(input1.contiguous(), None if input2 is None else input2.contiguous(),
                                 self.norm.weight.detach().contiguous(), self.norm.bias.detach().contiguous(),
-                                want_rowmax=want_rowmax, eps=self.norm.eps)
+                                want_rowmax=want_rowmax, eps=self.norm.eps, want_out=want_out)
 
 
 class FeedForward(nn.Module):

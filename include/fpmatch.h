@@ -197,7 +197,7 @@ int fpm_soft_topk(const float* scores, const float* ks, const long long* n1, con
  * fpm_afau_attention replaces CrossSet_MultiHeadAttention.forward (src/model/afau.py:231-300): q [B,nr,256],
  * k,v [B,nc,256], cost addressed cost[b*cs_b + i*cs_r + j*cs_c] -> out [B,nr,256].
  * fpm_add_instnorm replaces AddAndInstanceNormalization.forward (afau.py:154-176) (+ optional max over rows,
- * ngm.py:402-405).  fpm_onehot_proj: projection of the one-hot column embedding of ngm.py:396-399.
+ * ngm.py:402-405; `out` may be NULL when only that maximum is wanted, for n <= 112 and E % 4 == 0).  fpm_onehot_proj: projection of the one-hot column embedding of ngm.py:396-399.
  * fpm_k_head replaces final_row/final_col + sigmoid (ngm.py:406-412); weights (8 pointers): final_row.0.weight,
  * .0.bias, .2.weight, .2.bias, final_col.0.weight, .0.bias, .2.weight, .2.bias.
  */

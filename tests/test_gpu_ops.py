@@ -533,6 +533,57 @@ def test_afau_encoder_golden_and_structured(ops, oo):
     assert er < 3e-4 and ec < 3e-4
 
 
+@pytest.mark.parametrize("nr,nc,transposed", [(100, 100, False), (100, 100, True), (37, 52, False), (52, 37, True),
+                                              (128, 90, False), (140, 140, False)])
+def test_afau_attention_zero_query_kernel(ops, nr, nc, transposed):
+    """The row block's dedicated kernel (q = 0: packed-fp32 score MLP, cost tile in shared memory) against a float64
+    evaluation of afau.py:253-297 and against the generic kernel fed with an explicit zero q."""
+    g = torch.Generator().manual_seed(nr * 100 + nc)
+    B, E = 3, 256
+    k = torch.randn(B, nc, E, generator=g); v = torch.randn(B, nc, E, generator=g)
+    cost = torch.rand(B, nc, nr, generator=g) if transposed else torch.rand(B, nr, nc, generator=g)
+    m1w = (torch.rand(16, 2, 16, generator=g) - 0.5); m1b = (torch.rand(16, 16, generator=g) - 0.5)
+    m2w = (torch.rand(16, 16, 1, generator=g) - 0.5) * 8; m2b = (torch.rand(16, 1, generator=g) - 0.5)
+    q = torch.zeros(B, nr, E)
+    d = lambda t: t.to(DEV)
+    fast = ops.afau_attention(d(q), d(k), d(v), d(cost), transposed, d(m1w), d(m1b), d(m2w), d(m2b), q_zero=True)
+    slow = ops.afau_attention(d(q), d(k), d(v), d(cost), transposed, d(m1w), d(m1b), d(m2w), d(m2b), q_zero=False)
+    c = (cost.transpose(1, 2) if transposed else cost).double()                      # [B, nr, nc]
+    hid = torch.relu(c[:, None, :, :, None] * m1w[None, :, 1, None, None, :].double() + m1b[None, :, None, None, :].double())
+    sc = (hid * m2w[None, :, None, None, :, 0].double()).sum(-1) + m2b[None, :, None, :].double()      # [B, H, nr, nc]
+    w = torch.softmax(sc, dim=-1)
+    ref = torch.einsum("bhij,bjhd->bihd", w, v.double().reshape(B, nc, 16, 16)).reshape(B, nr, E)
+    e_fast, e_slow = (fast.cpu().double() - ref).abs().max().item(), (slow.cpu().double() - ref).abs().max().item()
+    report("afau_attention_qzero", nr=nr, nc=nc, transposed=transposed, fast=e_fast, generic=e_slow)
+    assert e_fast < 5e-6 and e_slow < 5e-6
+
+
+@pytest.mark.parametrize("n,E", [(30, 600), (100, 600), (112, 600), (101, 88), (150, 600), (40, 130)])
+def test_add_instnorm_forward(ops, n, E):
+    """AddAndInstanceNormalization (afau.py:154-176) + the max over rows, every kernel variant: 8 / 16 warps per
+    128-channel tile, the thread-per-channel fallbacks (n > 112, E % 4 != 0), the three kinds of second operand and
+    the rowmax-only form."""
+    g = torch.Generator().manual_seed(n * 1000 + E)
+    B = 5
+    a = torch.randn(B, n, E, generator=g); o3 = torch.randn(B, n, E, generator=g); o1 = torch.randn(E, generator=g)
+    gamma, beta = torch.rand(E, generator=g) + 0.5, torch.randn(E, generator=g)
+    worst = 0.0
+    for other in (None, o3, o1):
+        x = (a if other is None else a + other).double()
+        ref = torch.nn.functional.instance_norm(x.transpose(1, 2), weight=gamma.double(), bias=beta.double(),
+                                                eps=1e-5).transpose(1, 2)
+        od = None if other is None else other.to(DEV)
+        out, rowmax = ops.add_instnorm(a.to(DEV), od, gamma.to(DEV), beta.to(DEV), want_rowmax=True)
+        none, rowmax2 = ops.add_instnorm(a.to(DEV), od, gamma.to(DEV), beta.to(DEV), want_rowmax=True, want_out=False)
+        plain = ops.add_instnorm(a.to(DEV), od, gamma.to(DEV), beta.to(DEV))
+        worst = max(worst, (out.cpu().double() - ref).abs().max().item())
+        assert torch.equal(plain, out)
+        assert torch.equal(rowmax, out.max(1).values) and torch.equal(rowmax2, rowmax)
+        assert (none is None) == (n <= 112 and E % 4 == 0)
+    report("add_instnorm_fwd", n=n, E=E, max_abs=worst)
+    assert worst < 5e-6
+
+
 # ---------------------------------------------------------------------------------------------- loss / metrics
 def test_permutation_loss_and_matching_metrics_golden():
     """PermutationLoss (value + gradient) and matching_recall / precision / accuracy against vectors produced by the
