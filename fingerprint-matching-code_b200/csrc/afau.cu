@@ -292,12 +292,14 @@ add_instnorm_reg_kernel(const float* __restrict__ a, const float* __restrict__ o
 // the centred second moment - the two-pass form of torch's InstanceNorm, so near-constant channels stay accurate).
 // The thread-per-channel kernels above kept a whole column (104 values, 168 registers) per thread: 17 % occupancy,
 // 128-byte row segments, 16 % of the DRAM peak.  `out` may be null when only the row maximum is wanted (the second
-// normalisation of an AFA-U block feeds nothing but the max-pool, ngm.py:402-405).
+// normalisation of an AFA-U block feeds nothing but the max-pool, ngm.py:402-405).  kMode: second operand none /
+// tensor / row vector as above; 3 = row vector AND `a` is the one-hot column embedding of ngm.py:396-399 given by its
+// row count hot[b] (never materialised).
 template <int kWarps, int kRows, int kMode>
 __global__ void __launch_bounds__(32 * kWarps, 1024 / (32 * kWarps))
 add_instnorm_tile_kernel(const float* __restrict__ a, const float* __restrict__ other,
                          const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
-                         float* __restrict__ rowmax, int n, int E, float eps) {
+                         float* __restrict__ rowmax, int n, int E, float eps, const int64_t* __restrict__ hot) {
   __shared__ float4 red[kWarps][32];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * 128 + 4 * lane;
@@ -308,7 +310,14 @@ add_instnorm_tile_kernel(const float* __restrict__ a, const float* __restrict__ 
   for (int k = 0; k < kRows; ++k) {
     const int r = warp + kWarps * k;
     x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live && r < n) x[k] = *(const float4*)(a + base + (size_t)r * E);
+    if (kMode == 3) {                                      // a = one-hot rows: a[b, r, c] = (c == r && r < hot[b])
+      if (r < (int)hot[b] && (r >> 2) == (e >> 2)) {
+        x[k].x = (r & 3) == 0 ? 1.f : 0.f; x[k].y = (r & 3) == 1 ? 1.f : 0.f;
+        x[k].z = (r & 3) == 2 ? 1.f : 0.f; x[k].w = (r & 3) == 3 ? 1.f : 0.f;
+      }
+    } else if (live && r < n) {
+      x[k] = *(const float4*)(a + base + (size_t)r * E);
+    }
   }
   if (kMode == 1) {
 #pragma unroll
@@ -319,7 +328,7 @@ add_instnorm_tile_kernel(const float* __restrict__ a, const float* __restrict__ 
         x[k].x += o.x; x[k].y += o.y; x[k].z += o.z; x[k].w += o.w;
       }
     }
-  } else if (kMode == 2) {
+  } else if (kMode == 2 || kMode == 3) {
     float4 ov = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) ov = *(const float4*)(other + e);
 #pragma unroll
@@ -672,7 +681,7 @@ extern "C" int fpm_add_instnorm(const float* a, const float* other, int other_mo
   if (tile_path && aligned && n <= 112) {
 #define FPM_INSTNORM(W, MODE)                                                                                   \
   fpm::add_instnorm_tile_kernel<W, 7, MODE><<<grid, 32 * W, 0, (cudaStream_t)stream>>>(a, other, gamma, beta, out, \
-                                                                                        rowmax, n, E, eps)
+                                                                                        rowmax, n, E, eps, nullptr)
     if (n <= 56) {
       if (other_mode == 0) FPM_INSTNORM(8, 0); else if (other_mode == 1) FPM_INSTNORM(8, 1); else FPM_INSTNORM(8, 2);
     } else {
@@ -689,6 +698,27 @@ extern "C" int fpm_add_instnorm(const float* a, const float* other, int other_mo
   else
     fpm::add_instnorm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, other, other_mode, gamma, beta, out,
                                                                       rowmax, n, E, eps);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+// add_instnorm of (one-hot rows [B, n, E] with hot[b] ones on the diagonal) + vec: the first normalisation of the
+// AFA-U column block (ngm.py:396-399 feeds afau.py:154-176) without materialising the embedding.
+extern "C" int fpm_onehot_instnorm(const long long* hot, const float* vec, const float* gamma, const float* beta,
+                                   float* out, float* rowmax, int B, int n, int E, float eps, void* stream) {
+  FPM_CHECK_ARG(hot && vec && gamma && beta && (out || rowmax), "fpm_onehot_instnorm: null tensor");
+  FPM_CHECK_ARG(B >= 0 && n > 0 && n <= 112 && E > 0 && E % 4 == 0, "fpm_onehot_instnorm: needs n <= 112, E % 4 == 0");
+  FPM_CHECK_ARG((((uintptr_t)vec | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)out | (uintptr_t)rowmax) & 15) == 0,
+                "fpm_onehot_instnorm: 16-byte alignment required");
+  if (B == 0) return FPM_OK;
+  FPM_CHECK_ARG(B <= 65535, "fpm_onehot_instnorm: batch too large");
+  dim3 grid(fpm_cdiv(E, 128), B);
+  if (n <= 56)
+    fpm::add_instnorm_tile_kernel<8, 7, 3><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        nullptr, vec, gamma, beta, out, rowmax, n, E, eps, (const int64_t*)hot);
+  else
+    fpm::add_instnorm_tile_kernel<16, 7, 3><<<grid, 512, 0, (cudaStream_t)stream>>>(
+        nullptr, vec, gamma, beta, out, rowmax, n, E, eps, (const int64_t*)hot);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

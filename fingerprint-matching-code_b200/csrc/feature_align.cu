@@ -72,38 +72,44 @@ __global__ void feature_align_kernel(const float* __restrict__ fmap, const float
 }
 
 // NCHW raw -> NHWC divided by the channel L2 norm (normalize_over_channels, ngm.py:65-67).
-// One CTA per (32-position tile, image); 256 threads; the tile [C][33] is staged in shared memory.
-// Optionally also reduces the per-channel max over positions of the RAW map (AdaptiveMaxPool2d(1,1),
-// feature_extractor.py:54) through ordered-int atomics into gmax_bits (pre-filled with INT_MIN).
+// One CTA per (kTp-position tile, image); 256 threads; the tile [C][kTp + 1] is staged in shared memory: a warp load
+// covers 32 / kTp channels x kTp consecutive positions (eight loads in flight per thread), the stores walk the
+// channels of one position (coalesced rows of the NHWC map).  kTp = 16 for the small maps (8 x 10 positions: a
+// 32-wide tile left 3 CTAs per image, the last one half empty, and 68 KB of shared memory per CTA at 512 channels).
+template <int kTp>
 __global__ void __launch_bounds__(256)
 fmap_prep_kernel(const float* __restrict__ fmap, float* __restrict__ out, int C, int HW) {
-  extern __shared__ float tile[];              // [C][33]
-  __shared__ float part[8][33];
-  __shared__ float norm[32];
-  const int b = blockIdx.y, p0 = blockIdx.x * 32;
+  extern __shared__ float tile[];              // [C][kTp + 1]
+  constexpr int kCpw = 32 / kTp;               // channels per warp load
+  constexpr int kLd = kTp + 1;
+  __shared__ float part[8 * kCpw][kLd];
+  __shared__ float norm[kTp];
+  const int b = blockIdx.y, p0 = blockIdx.x * kTp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int p = p0 + lane;
+  const int lp = lane % kTp, csub = lane / kTp;
+  const int p = p0 + lp;
   const float* src = fmap + (size_t)b * C * HW;
   float ss = 0.f;
-  for (int c = warp; c < C; c += 8) {
+#pragma unroll 8
+  for (int c = warp * kCpw + csub; c < C; c += 8 * kCpw) {
     const float v = (p < HW) ? src[(size_t)c * HW + p] : 0.f;
-    tile[c * 33 + lane] = v;
+    tile[c * kLd + lp] = v;
     ss = fmaf(v, v, ss);
   }
-  part[warp][lane] = ss;
+  part[warp * kCpw + csub][lp] = ss;
   __syncthreads();
-  if (warp == 0) {
+  if (threadIdx.x < kTp) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += part[w][lane];
-    norm[lane] = sqrtf(t);
+    for (int w = 0; w < 8 * kCpw; ++w) t += part[w][threadIdx.x];
+    norm[threadIdx.x] = sqrtf(t);
   }
   __syncthreads();
   float* dst = out + ((size_t)b * HW + p0) * C;
-  const int npos = min(32, HW - p0);
+  const int npos = min(kTp, HW - p0);
   for (int q = 0; q < npos; ++q) {
     const float nq = norm[q];
-    for (int c = threadIdx.x; c < C; c += 256) dst[(size_t)q * C + c] = tile[c * 33 + q] / nq;
+    for (int c = threadIdx.x; c < C; c += 256) dst[(size_t)q * C + c] = tile[c * kLd + q] / nq;
   }
 }
 
@@ -300,13 +306,17 @@ extern "C" int fpm_fmap_prep(const float* fmap, float* out_nhwc, int B, int C, i
   FPM_CHECK_ARG(B >= 0 && C > 0 && Hf > 0 && Wf > 0, "fpm_fmap_prep: bad sizes");
   if (B == 0) return FPM_OK;
   const int HW = Hf * Wf;
-  const size_t smem = (size_t)C * 33 * sizeof(float);
+  const bool narrow = HW <= 128;               // small maps: 16-position tiles
+  const size_t smem = (size_t)C * (narrow ? 17 : 33) * sizeof(float);
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_fmap_prep: channel count too large");
   FPM_CHECK_ARG(B <= 65535, "fpm_fmap_prep: batch too large");
-  FPM_CUDA(cudaFuncSetAttribute(fpm::fmap_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-  dim3 grid(fpm_cdiv(HW, 32), B);
-  fpm::fmap_prep_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(fmap, out_nhwc, C, HW);
+  if (narrow) {
+    FPM_CUDA(cudaFuncSetAttribute(fpm::fmap_prep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fpm::fmap_prep_kernel<16><<<dim3(fpm_cdiv(HW, 16), B), 256, smem, (cudaStream_t)stream>>>(fmap, out_nhwc, C, HW);
+  } else {
+    FPM_CUDA(cudaFuncSetAttribute(fpm::fmap_prep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fpm::fmap_prep_kernel<32><<<dim3(fpm_cdiv(HW, 32), B), 256, smem, (cudaStream_t)stream>>>(fmap, out_nhwc, C, HW);
+  }
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

@@ -747,10 +747,11 @@ lap_validate_kernel(const float* __restrict__ ds, const int64_t* __restrict__ n1
   const int nr = n1 ? (int)n1[b] : R, nc = n2 ? (int)n2[b] : C;
   const float* s = ds + (size_t)b * R * C;
   int bad = 0;
-  for (int i = threadIdx.x; i < nr * nc; i += blockDim.x) {
-    const float v = s[(size_t)(i / nc) * C + (i % nc)];
-    bad |= (v != v) || (v == INFINITY);
-  }
+  for (int r = threadIdx.x >> 5; r < nr; r += blockDim.x >> 5)        // warp per row: no integer division
+    for (int c = threadIdx.x & 31; c < nc; c += 32) {
+      const float v = s[(size_t)r * C + c];
+      bad |= (v != v) || (v == INFINITY);
+    }
   bad = __syncthreads_or(bad);
   if (!bad) return;
   if (threadIdx.x == 0) status[b] = 1;

@@ -35,10 +35,11 @@ match_cls_stage1_kernel(const float* __restrict__ s, const float* __restrict__ p
   __shared__ float sw[kC1 * 9], sb[kC1], ssc[kC1], ssh[kC1];
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-    // second conv's weights [32][16][3][3] -> [16 ic][32 oc][12] for stage 2 (one CTA, 24 KB)
-    for (int idx = tid; idx < kC1 * kC2 * 12; idx += 256) {
-      const int ic = idx / (kC2 * 12), oc = (idx / 12) % kC2, k = idx % 12;
-      wpack[idx] = k < 9 ? w2[((size_t)oc * kC1 + ic) * 9 + k] : 0.f;
+    // second conv's weights [32][16][3][3] -> [16 ic][16 oc pairs][10 taps (9 used)][2] for stage 2 (one CTA, 20 KB):
+    // the two output channels of a pair sit side by side, ready to be the 64-bit operand of a packed FMA
+    for (int idx = tid; idx < kC1 * (kC2 / 2) * 20; idx += 256) {
+      const int ic = idx / ((kC2 / 2) * 20), op = (idx / 20) % (kC2 / 2), k = (idx % 20) >> 1, u = idx & 1;
+      wpack[idx] = k < 9 ? w2[((size_t)(2 * op + u) * kC1 + ic) * 9 + k] : 0.f;
     }
   }
   if (tid < kC1 * 9) sw[tid] = w1[tid];
@@ -86,20 +87,23 @@ match_cls_stage1_kernel(const float* __restrict__ s, const float* __restrict__ p
 }
 
 // grid (cdiv(H2 * W2, 64), B), block 64: thread = one pooled output pixel (pixels taken in raster order, so that
-// only the last chunk of a map has idle threads), 32 channels x 4 pre-pool positions = 128 accumulators.  The 4 x 4
-// input patch of every channel comes straight from P1 (L1 / L2 resident; neighbouring threads share most of it); the
-// weights are copied from the [ic][oc][12] repack stage 1 left in the workspace and read back as 128-bit broadcasts.
+// only the last chunk of a map has idle threads), 32 channels x 4 pre-pool positions = 128 accumulators held as 64
+// packed pairs (two adjacent output channels).  The 4 x 4 input patch of every channel comes straight from P1 (L1 / L2
+// resident; neighbouring threads share most of it); the weights are copied from the [ic][oc pair][10][2] repack stage 1
+// left in the workspace and read back as 128-bit broadcasts (two taps of a channel pair each).  The 36 FMAs of an
+// (input channel, output channel) are 36 FFMA2 per channel PAIR: half the issue slots of the scalar form
+// (0.24 -> 0.14 ms at 256 pairs x 100 x 100).
 constexpr int kChunk = 64;                   // pooled pixels per CTA
-constexpr int kWpad = 12;                    // 9 taps padded to 12 floats (three 128-bit loads)
+constexpr int kWpad = 20;                    // floats per (ic, oc pair): 9 taps x 2 channels, padded to five 128-bit loads
 
 __global__ void __launch_bounds__(kChunk)
 match_cls_stage2_kernel(const float* __restrict__ p1, const float* __restrict__ wpack, const float* __restrict__ b2,
                         BnParams bn2, float eps, float* __restrict__ partial, int H1, int W1, int H2, int W2) {
   extern __shared__ __align__(16) float sm2[];
-  float* sw = sm2;                                     // [16 ic][32 oc][kWpad]
-  float* red = sw + kC1 * kC2 * kWpad;                 // [2 warps][32]
+  float* sw = sm2;                                     // [16 ic][16 oc pairs][kWpad]
+  float* red = sw + kC1 * (kC2 / 2) * kWpad;           // [2 warps][32]
   const int tid = threadIdx.x, b = blockIdx.y;
-  for (int idx = tid; idx < kC1 * kC2 * kWpad / 4; idx += kChunk)
+  for (int idx = tid; idx < kC1 * (kC2 / 2) * kWpad / 4; idx += kChunk)
     reinterpret_cast<float4*>(sw)[idx] = reinterpret_cast<const float4*>(wpack)[idx];
   __syncthreads();
 
@@ -113,29 +117,35 @@ match_cls_stage2_kernel(const float* __restrict__ p1, const float* __restrict__ 
   const bool top = y0 >= 0, bottom = y0 + 3 < H1, left = x0 >= 0, right = x0 + 3 < W1;
   const float* base = p1 + (size_t)b * kC1 * H1 * W1 + (size_t)(y0 + 1) * W1 + (x0 + 1);
 
-  float acc[kC2][4];
+  f32x2 acc[kC2 / 2][4];
 #pragma unroll
-  for (int oc = 0; oc < kC2; ++oc)
+  for (int op = 0; op < kC2 / 2; ++op)
 #pragma unroll
-    for (int d = 0; d < 4; ++d) acc[oc][d] = 0.f;
+    for (int d = 0; d < 4; ++d) acc[op][d] = pk2(0.f, 0.f);
 
   for (int ic = 0; ic < kC1; ++ic) {
     const float* t = base + (size_t)ic * H1 * W1;      // patch element (1, 1)
-    float p[4][4];
+    f32x2 p[4][4];                                     // patch values broadcast to both lanes
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const bool rok = (r == 0) ? top : (r == 3) ? bottom : true;
       const float* row = t + (r - 1) * W1;
-      p[r][0] = (rok && left) ? __ldg(row - 1) : 0.f;
-      p[r][1] = rok ? __ldg(row) : 0.f;
-      p[r][2] = rok ? __ldg(row + 1) : 0.f;
-      p[r][3] = (rok && right) ? __ldg(row + 2) : 0.f;
+      const float a0 = (rok && left) ? __ldg(row - 1) : 0.f;
+      const float a1 = rok ? __ldg(row) : 0.f;
+      const float a2 = rok ? __ldg(row + 1) : 0.f;
+      const float a3 = (rok && right) ? __ldg(row + 2) : 0.f;
+      p[r][0] = pk2(a0, a0); p[r][1] = pk2(a1, a1); p[r][2] = pk2(a2, a2); p[r][3] = pk2(a3, a3);
     }
-    const float4* wv = reinterpret_cast<const float4*>(sw + ic * kC2 * kWpad);
+    const float4* wv = reinterpret_cast<const float4*>(sw + ic * (kC2 / 2) * kWpad);
 #pragma unroll
-    for (int oc = 0; oc < kC2; ++oc) {
-      const float4 w0 = wv[oc * 3], w1 = wv[oc * 3 + 1], w2_ = wv[oc * 3 + 2];
-      const float w[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2_.x};
+    for (int op = 0; op < kC2 / 2; ++op) {
+      f32x2 w[10];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const float4 x = wv[op * 5 + q];
+        w[2 * q] = pk2(x.x, x.y);
+        w[2 * q + 1] = pk2(x.z, x.w);
+      }
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -144,22 +154,29 @@ match_cls_stage2_kernel(const float* __restrict__ p1, const float* __restrict__ 
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
-              acc[oc][dy * 2 + dx] = fmaf(p[dy + ky][dx + kx], w[ky * 3 + kx], acc[oc][dy * 2 + dx]);
+              acc[op][dy * 2 + dx] = fma2(p[dy + ky][dx + kx], w[ky * 3 + kx], acc[op][dy * 2 + dx]);
     }
   }
 
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-  for (int oc = 0; oc < kC2; ++oc) {
-    float scale, shift;
-    bn_affine(bn2, oc, eps, scale, shift);
-    const float bias = b2[oc];
-    float best = -INFINITY;
+  for (int op = 0; op < kC2 / 2; ++op) {
+    float a[4][2];
 #pragma unroll
-    for (int d = 0; d < 4; ++d) best = fmaxf(best, fmaxf(acc[oc][d] + bias, 0.f) * scale + shift);
-    float v = valid ? best : 0.f;
-    v = warp_sum(v);
-    if (lane == 0) red[warp * kC2 + oc] = v;
+    for (int d = 0; d < 4; ++d) upk2(acc[op][d], a[d][0], a[d][1]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int oc = 2 * op + u;
+      float scale, shift;
+      bn_affine(bn2, oc, eps, scale, shift);
+      const float bias = b2[oc];
+      float best = -INFINITY;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) best = fmaxf(best, fmaxf(a[d][u] + bias, 0.f) * scale + shift);
+      float v = valid ? best : 0.f;
+      v = warp_sum(v);
+      if (lane == 0) red[warp * kC2 + oc] = v;
+    }
   }
   __syncthreads();
   if (tid < kC2) partial[((size_t)b * gridDim.x + blockIdx.x) * kC2 + tid] = red[tid] + red[kC2 + tid];
@@ -188,7 +205,7 @@ static inline long long match_cls_chunks(int H, int W) {
 extern "C" long long fpm_match_classifier_workspace_floats(int B, int H, int W) {
   const long long H1 = H / 2, W1 = W / 2;
   return (long long)B * fpm::kC1 * H1 * W1 + (long long)B * match_cls_chunks(H, W) * fpm::kC2 +
-         (long long)fpm::kC1 * fpm::kC2 * fpm::kWpad;
+         (long long)fpm::kC1 * (fpm::kC2 / 2) * fpm::kWpad;
 }
 
 extern "C" int fpm_match_classifier(const float* s, const float* perm, const float* w1, const float* b1,
@@ -210,7 +227,7 @@ extern "C" int fpm_match_classifier(const float* s, const float* perm, const flo
   fpm::match_cls_stage1_kernel<<<dim3(fpm_cdiv(W1, 32), fpm_cdiv(H1, 8), B), dim3(32, 8), 0, st>>>(
       s, perm, w1, b1, q1, eps, p1, H, W, H1, W1, w2, wpack);
   FPM_LAUNCH_CHECK();
-  const size_t smem2 = sizeof(float) * ((size_t)fpm::kC1 * fpm::kC2 * fpm::kWpad + 2 * fpm::kC2);
+  const size_t smem2 = sizeof(float) * ((size_t)fpm::kC1 * (fpm::kC2 / 2) * fpm::kWpad + 2 * fpm::kC2);
   fpm::match_cls_stage2_kernel<<<dim3(chunks, B), fpm::kChunk, smem2, st>>>(p1, wpack, b2, q2, eps, partial, H1, W1,
                                                                           H2, W2);
   FPM_LAUNCH_CHECK();

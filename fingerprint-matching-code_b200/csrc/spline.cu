@@ -11,6 +11,7 @@
 //     out_i = max_{e: j->i} sum_s basis_s(e) * Y[j, wi_s(e), :]  (0 if no in-edge) + Y[i, 25, :] + bias
 // fused with ReLU (layer 0) or the residual x + 0.1 * out (layer 1, spline_conv.py:56).
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <limits.h>
 
@@ -100,6 +101,7 @@ spline_gather_max_kernel(const float* __restrict__ Y, const float* __restrict__ 
                          const int64_t* __restrict__ edge_src, const float* __restrict__ pseudo,
                          const int* __restrict__ in_ptr, const int* __restrict__ in_eid,
                          const float* __restrict__ bias, float* __restrict__ out, int* __restrict__ argmax,
+                         __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_inv,
                          int C, int KS, int mode) {
   __shared__ int s_e[kGatherChunk];
   __shared__ unsigned s_off[kGatherChunk][4];  // float4 offset of the slab row inside Y: (j * NS + wi) * C / 4
@@ -184,18 +186,49 @@ spline_gather_max_kernel(const float* __restrict__ Y, const float* __restrict__ 
       }
     }
   }
-  if (!live) return;
-  if (argmax) *(int4*)(argmax + (size_t)i * C + c4 * 4) = arg;
-  if (e_beg == e_end) best = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 v;
-  v.x = best.x + r.x + bi.x; v.y = best.y + r.y + bi.y;
-  v.z = best.z + r.z + bi.z; v.w = best.w + r.w + bi.w;
-  if (mode == 0) {
-    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-  } else if (mode == 1) {
-    v.x = x0.x + 0.1f * v.x; v.y = x0.y + 0.1f * v.y; v.z = x0.z + 0.1f * v.z; v.w = x0.w + 0.1f * v.w;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    if (argmax) *(int4*)(argmax + (size_t)i * C + c4 * 4) = arg;
+    if (e_beg == e_end) best = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = best.x + r.x + bi.x; v.y = best.y + r.y + bi.y;
+    v.z = best.z + r.z + bi.z; v.w = best.w + r.w + bi.w;
+    if (mode == 0) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    } else if (mode == 1) {
+      v.x = x0.x + 0.1f * v.x; v.y = x0.y + 0.1f * v.y; v.z = x0.z + 0.1f * v.z; v.w = x0.w + 0.1f * v.w;
+    }
+    if (out) *(float4*)(out + (size_t)i * C + c4 * 4) = v;
   }
-  *(float4*)(out + (size_t)i * C + c4 * 4) = v;
+  if (out_hi) {
+    // The row is the A operand of the next layer's slab GEMM: emit its error-compensated fp16 split here (the same
+    // arithmetic as f16_split_rows_kernel, gemm_tcgen05.cu) instead of writing fp32 and re-reading it in a split pass.
+    __shared__ float s_amax[8];
+    float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    amax = warp_max(amax);
+    __syncthreads();                                  // the edge chunks' shared arrays are not read any more
+    if ((threadIdx.x & 31) == 0) s_amax[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = s_amax[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) amax = fmaxf(amax, s_amax[w]);
+    int e = 0;
+    if (amax > 0.f && amax < INFINITY) frexpf(amax, &e);
+    e = max(-100, min(100, e));
+    const float sc = ldexpf(1.f, -e);
+    if (threadIdx.x == 0) out_inv[i] = ldexpf(1.f, e);
+    if (live) {
+      const float x[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
+      __half hh[4], ll[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hh[j] = __float2half_rn(x[j]);
+        ll[j] = __float2half_rn((x[j] - __half2float(hh[j])) * 2048.f);
+      }
+      __half2* h2 = (__half2*)(out_hi + (size_t)i * C + c4 * 4);
+      __half2* l2 = (__half2*)(out_lo + (size_t)i * C + c4 * 4);
+      h2[0] = __halves2half2(hh[0], hh[1]); h2[1] = __halves2half2(hh[2], hh[3]);
+      l2[0] = __halves2half2(ll[0], ll[1]); l2[1] = __halves2half2(ll[2], ll[3]);
+    }
+  }
 }
 
 // Backward of the gather/max: dY[j, k, :] = sum over out-edges e = (j -> i) whose message won the max at
@@ -325,26 +358,41 @@ __global__ void __launch_bounds__(kPlanThreads)
 slab_plan_kernel(const unsigned* __restrict__ mask, int T, int KS, int C, int* __restrict__ meta,
                  int4* __restrict__ tab, int max_tiles) {
   const int NS = KS * KS + 1;
-  __shared__ int cnt[32], dense[32], off[33], dlist[32];
+  __shared__ int cnt[32], dense[32], off[33], dlist[32], tstart[33];
   __shared__ int nd, total_sparse;
   const int tid = threadIdx.x;
   if (tid < 32) cnt[tid] = 0;
   __syncthreads();
-  for (int j = tid; j < T; j += kPlanThreads) {
-    unsigned m = mask[j];
-    while (m) { const int k = __ffs(m) - 1; m &= m - 1; atomicAdd(&cnt[k], 1); }
+  {
+    // nodes per slab: lane k of every warp counts slab k with one ballot per (32 nodes, slab) - the first version
+    // issued one shared-memory atomic per (node, slab) on 26 addresses: 220 k serialised atomics, 39 us at T = 25 600
+    const int lane = tid & 31;
+    int mine = 0;
+    for (int j0 = tid - lane; j0 < T; j0 += kPlanThreads) {
+      const unsigned m = (j0 + lane < T) ? mask[j0 + lane] : 0u;
+      for (int k = 0; k < NS; ++k) {
+        const int c = __popc(__ballot_sync(0xffffffffu, (m >> k) & 1u));
+        if (lane == k) mine += c;
+      }
+    }
+    if (lane < NS && mine) atomicAdd(&cnt[lane], mine);
   }
   __syncthreads();
   if (tid == 0) {
     cnt[NS - 1] = T;                                  // the root slab serves every node
-    int n = 0, run = 0;
+    int n = 0, run = 0, trun = 0;
     for (int k = 0; k < NS; ++k) {
       dense[k] = (k == NS - 1) || (4LL * cnt[k] >= (long long)T && cnt[k] > 0);
       if (dense[k]) dlist[n++] = k;
       off[k] = run;
-      if (!dense[k]) run += (cnt[k] + kTileM - 1) / kTileM * kTileM;
+      tstart[k] = trun;                               // first sparse tile of slab k (after the dense tiles)
+      if (!dense[k]) {
+        run += (cnt[k] + kTileM - 1) / kTileM * kTileM;
+        trun += (cnt[k] + kTileM - 1) / kTileM * (C / kTileN);
+      }
     }
     off[NS] = run;
+    tstart[NS] = trun;
     nd = n; total_sparse = run;
   }
   __syncthreads();
@@ -360,16 +408,17 @@ slab_plan_kernel(const unsigned* __restrict__ mask, int T, int KS, int C, int* _
     const int k = dlist[sn / ntn], nt = sn % ntn;
     tab[t] = make_int4(mi * kTileM, k * C + nt * kTileN, k * C + nt * kTileN, -1);
   }
-  if (tid == 0) {
-    int t = total_dense;
-    for (int k = 0; k < NS; ++k) {
-      if (dense[k] || cnt[k] == 0) continue;
-      const int mt = (cnt[k] + kTileM - 1) / kTileM;
-      for (int nt = 0; nt < ntn; ++nt)
-        for (int m = 0; m < mt && t < max_tiles; ++m, ++t)
-          tab[t] = make_int4(T_pad + off[k] + m * kTileM, k * C + nt * kTileN, k * C + nt * kTileN, off[k] + m * kTileM);
+  for (int k = 0; k < NS; ++k) {
+    if (dense[k] || cnt[k] == 0) continue;
+    const int mt = (cnt[k] + kTileM - 1) / kTileM;
+    for (int i = tid; i < mt * ntn; i += kPlanThreads) {
+      const int nt = i / mt, m = i - nt * mt, t = total_dense + tstart[k] + i;
+      if (t < max_tiles)
+        tab[t] = make_int4(T_pad + off[k] + m * kTileM, k * C + nt * kTileN, k * C + nt * kTileN, off[k] + m * kTileM);
     }
-    meta[0] = t;
+  }
+  if (tid == 0) {
+    meta[0] = min(total_dense + tstart[NS], max_tiles);
     meta[1] = total_sparse;
   }
   if (tid < NS) { meta[2 + tid] = dense[tid]; meta[2 + 2 * NS + 1 + tid] = 0; }
@@ -430,9 +479,13 @@ extern "C" int fpm_csr_by_dst(const long long* edge_dst, const long long* ptr, c
 
 extern "C" int fpm_spline_gather_max(const float* Y, const float* xin, const long long* edge_src,
                                      const float* pseudo, const int* in_ptr, const int* in_eid,
-                                     const float* bias, float* out, int* argmax, int total_nodes, int C,
-                                     int kernel_size, int mode, void* stream) {
-  FPM_CHECK_ARG(Y && edge_src && pseudo && in_ptr && in_eid && bias && out, "fpm_spline_gather_max: null tensor");
+                                     const float* bias, float* out, int* argmax, void* out_hi, void* out_lo,
+                                     float* out_inv, int total_nodes, int C, int kernel_size, int mode,
+                                     void* stream) {
+  FPM_CHECK_ARG(Y && edge_src && pseudo && in_ptr && in_eid && bias && (out || out_hi),
+                "fpm_spline_gather_max: null tensor");
+  FPM_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr) && (out_hi == nullptr) == (out_inv == nullptr),
+                "fpm_spline_gather_max: the fp16 split needs hi, lo and inv");
   FPM_CHECK_ARG(mode == 0 || mode == 2 || (mode == 1 && xin), "fpm_spline_gather_max: bad mode / residual mode needs xin");
   FPM_CHECK_ARG(C % 4 == 0 && C <= 768, "fpm_spline_gather_max: C must be a multiple of 4, at most 768");
   if (total_nodes == 0) return FPM_OK;
@@ -455,7 +508,8 @@ extern "C" int fpm_spline_gather_max(const float* Y, const float* xin, const lon
     }
   }
   fpm::spline_gather_max_kernel<<<total_nodes, 192, 0, (cudaStream_t)stream>>>(
-      Y, xin, (const int64_t*)edge_src, pseudo, in_ptr, in_eid, bias, out, argmax, C, kernel_size, mode);
+      Y, xin, (const int64_t*)edge_src, pseudo, in_ptr, in_eid, bias, out, argmax, (__half*)out_hi, (__half*)out_lo,
+      out_inv, C, kernel_size, mode);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

@@ -43,7 +43,7 @@ SIGNATURES = {
     "fpm_spline_plan": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "fpm_spline_gather_rows": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_csr_by_dst": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
-    "fpm_spline_gather_max": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "fpm_spline_gather_max": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_affinity": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "fpm_f16_split_rows_scaled": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P]),
     "fpm_affinity_tiles": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
@@ -59,6 +59,7 @@ SIGNATURES = {
     "fpm_soft_topk": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "fpm_afau_attention": (_I, [_P, _P, _P, _P, _LL, _LL, _LL, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_add_instnorm": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "fpm_onehot_instnorm": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "fpm_onehot_proj": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_k_head": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "fpm_lap_topk": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),

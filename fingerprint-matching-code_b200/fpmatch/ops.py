@@ -365,17 +365,41 @@ class _PlanInfo:
         return int(self.meta[0].item())
 
 
-def spline_slab_gemm(x: Tensor, packed: Tensor, plan: SlabPlan) -> Tensor:
-    """Y [total, NS*C] = x @ packed^T restricted to the (node, slab) blocks of ``plan`` (other blocks are left
-    uninitialised: no edge reads them).  Error-compensated fp16 on the persistent CTA-pair kernel."""
-    T, K = x.shape
-    assert T == plan.T and packed.shape[0] == plan.NS * plan.C
-    dev = x.device
+_GATHER_SPLIT = os.environ.get("FPMATCH_GATHER_SPLIT", "1") != "0"
+
+
+def gather_split_enabled() -> bool:
+    """True (default): the hidden layer of an SConv is written by the gather kernel directly as the fp16 operand of the
+    next slab GEMM; FPMATCH_GATHER_SPLIT=0 keeps the fp32 tensor + split pass (A/B runs)."""
+    return _GATHER_SPLIT
+
+
+def slab_operand_buffers(plan: "SlabPlan", K: int, device):
+    """Uninitialised A-operand buffers (fp16 hi, lo, fp32 row scales) of ``spline_slab_gemm`` for ``plan``: the dense
+    node rows first, the compacted rows of the sparse slabs behind them."""
     rows = plan.T_pad + plan.rowmap_cap
-    a_hi = torch.empty((rows, K), dtype=torch.float16, device=dev)
-    a_lo = torch.empty((rows, K), dtype=torch.float16, device=dev)
-    a_inv = torch.empty((rows,), dtype=torch.float32, device=dev)
-    f16_split_rows(x, out=(a_hi, a_lo, a_inv))
+    return (torch.empty((rows, K), dtype=torch.float16, device=device),
+            torch.empty((rows, K), dtype=torch.float16, device=device),
+            torch.empty((rows,), dtype=torch.float32, device=device))
+
+
+def spline_slab_gemm(x: Optional[Tensor], packed: Tensor, plan: SlabPlan, presplit=None) -> Tensor:
+    """Y [total, NS*C] = x @ packed^T restricted to the (node, slab) blocks of ``plan`` (other blocks are left
+    uninitialised: no edge reads them).  Error-compensated fp16 on the persistent CTA-pair kernel.  ``presplit`` =
+    buffers from ``slab_operand_buffers`` whose first T rows already hold the split of x (written by the previous
+    layer's ``spline_gather_max``): the split pass over x is skipped."""
+    K = packed.shape[1]
+    T = plan.T
+    assert packed.shape[0] == plan.NS * plan.C
+    dev = packed.device
+    rows = plan.T_pad + plan.rowmap_cap
+    if presplit is None:
+        assert x.shape == (T, K)
+        a_hi, a_lo, a_inv = slab_operand_buffers(plan, K, dev)
+        f16_split_rows(x, out=(a_hi, a_lo, a_inv))
+    else:
+        a_hi, a_lo, a_inv = presplit
+        assert a_hi.shape == (rows, K) and a_lo.shape == (rows, K) and a_inv.shape == (rows,)
     L = _lib.lib()
     rc = L.fpm_spline_gather_rows(plan.meta.data_ptr(), plan.rowmap.data_ptr(), a_hi.data_ptr(), a_lo.data_ptr(),
                                   a_inv.data_ptr(), plan.T_pad, K, plan.rowmap_cap, _stream())
@@ -398,15 +422,28 @@ def spline_slab_gemm(x: Tensor, packed: Tensor, plan: SlabPlan) -> Tensor:
 
 
 def spline_gather_max(Y: Tensor, xin: Optional[Tensor], edge_index: Tensor, pseudo: Tensor, in_ptr: Tensor,
-                      in_eid: Tensor, bias: Tensor, mode: int, kernel_size: int = 5, want_argmax: bool = False):
+                      in_eid: Tensor, bias: Tensor, mode: int, kernel_size: int = 5, want_argmax: bool = False,
+                      split_out=None, want_out: bool = True):
+    """``split_out`` = (hi, lo, inv) from ``slab_operand_buffers``: the result rows are also written as the
+    error-compensated fp16 operand of the next layer's slab GEMM (bit-identical to ``f16_split_rows`` of the fp32
+    result); with ``want_out=False`` the fp32 tensor is then not written at all (returned as None)."""
     total, Cc = Y.shape[0], bias.shape[0]
-    out = torch.empty((total, Cc), dtype=torch.float32, device=Y.device)
+    want_out = want_out or split_out is None
+    out = torch.empty((total, Cc), dtype=torch.float32, device=Y.device) if want_out else None
     arg = torch.empty((total, Cc), dtype=torch.int32, device=Y.device) if want_argmax else None
+    if split_out is not None:
+        hi, lo, inv = split_out
+        assert hi.shape[1] == Cc and hi.shape[0] >= total and hi.dtype == torch.float16 and hi.is_contiguous()
+        assert lo.shape == hi.shape and lo.is_contiguous() and inv.shape[0] == hi.shape[0]
     rc = _lib.lib().fpm_spline_gather_max(_chk(Y, "Y"), _chk(xin, "xin"), _chk(edge_index[0], "edge_index[0]", torch.int64),
                                           _chk(pseudo, "pseudo"), _chk(in_ptr, "in_ptr", torch.int32),
-                                          _chk(in_eid, "in_eid", torch.int32), _chk(bias, "bias"), out.data_ptr(),
-                                          arg.data_ptr() if want_argmax else None, total, Cc, kernel_size, mode,
-                                          _stream())
+                                          _chk(in_eid, "in_eid", torch.int32), _chk(bias, "bias"),
+                                          out.data_ptr() if want_out else None,
+                                          arg.data_ptr() if want_argmax else None,
+                                          hi.data_ptr() if split_out is not None else None,
+                                          lo.data_ptr() if split_out is not None else None,
+                                          inv.data_ptr() if split_out is not None else None,
+                                          total, Cc, kernel_size, mode, _stream())
     _lib.check(rc, "fpm_spline_gather_max"); _count()
     return (out, arg) if want_argmax else out
 
@@ -656,6 +693,17 @@ def add_instnorm(a: Tensor, other: Optional[Tensor], gamma: Tensor, beta: Tensor
                                      rowmax.data_ptr() if want_rowmax else None, B, n, E, float(eps), _stream())
     _lib.check(rc, "fpm_add_instnorm"); _count()
     return (out, rowmax) if want_rowmax else out
+
+
+def onehot_instnorm(hot: Tensor, nmax: int, vec: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tensor:
+    """``add_instnorm(onehot, vec)`` for the one-hot column embedding ``onehot[b, r, c] = (c == r and r < hot[b])`` of
+    ngm.py:396-399 without materialising it ([B, nmax, E] with E = len(vec))."""
+    B, E = hot.shape[0], vec.shape[0]
+    out = torch.empty((B, nmax, E), dtype=torch.float32, device=vec.device)
+    rc = _lib.lib().fpm_onehot_instnorm(_chk(_i64(hot), "hot", torch.int64), _chk(vec, "vec"), _chk(gamma, "norm.weight"),
+                                        _chk(beta, "norm.bias"), out.data_ptr(), None, B, nmax, E, float(eps), _stream())
+    _lib.check(rc, "fpm_onehot_instnorm"); _count()
+    return out
 
 
 def onehot_proj(W: Tensor, n: Tensor, nmax: int) -> Tensor:

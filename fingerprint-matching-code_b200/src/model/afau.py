@@ -153,8 +153,13 @@ class EncodingBlock(nn.Module):
         B = n2.shape[0]
         dev = n2.device
         emb = self.Wq.in_features
-        onehot = ops.onehot_proj(torch.eye(emb, dtype=torch.float32, device=dev), n2, n2max)
-        out1 = self.add_n_normalization_1(onehot, self.multi_head_combine.bias.detach().contiguous())
+        norm = self.add_n_normalization_1.norm
+        if n2max <= 112 and emb % 4 == 0 and n2max <= emb:
+            out1 = ops.onehot_instnorm(n2, n2max, self.multi_head_combine.bias.detach().contiguous(),
+                                       norm.weight.detach().contiguous(), norm.bias.detach().contiguous(), norm.eps)
+        else:
+            onehot = ops.onehot_proj(torch.eye(emb, dtype=torch.float32, device=dev), n2, n2max)
+            out1 = self.add_n_normalization_1(onehot, self.multi_head_combine.bias.detach().contiguous())
         out2 = self.feed_forward(out1)
         _, rowmax = self.add_n_normalization_2(out1, out2, want_rowmax=True, want_out=False)
         return rowmax

@@ -60,27 +60,33 @@ class SplineConv(torch.nn.Module):
             self._packed = (key, w.permute(0, 2, 1).reshape(-1, self.in_channels).contiguous())
         return self._packed[1]
 
-    def forward(self, x, edge_index, pseudo, csr=None, ptr=None, eptr=None, mode=None, residual=None, plan=None):
+    def forward(self, x, edge_index, pseudo, csr=None, ptr=None, eptr=None, mode=None, residual=None, plan=None,
+                presplit=None, split_out=None):
         """``csr`` = in-edge lists from ``ops.csr_by_dst``; built on the fly when missing.  ``mode``:
         None / 2 = plain conv output, 0 = relu(out), 1 = residual + 0.1 * out.  ``plan`` = ``ops.SlabPlan`` of the
-        graph (shared by the layers of an SConv): only the (node, slab) products some edge reads are computed."""
-        total = x.shape[0]
+        graph (shared by the layers of an SConv): only the (node, slab) products some edge reads are computed.
+        ``split_out`` (with a plan): operand buffers of the NEXT layer's slab GEMM; the result is written there as its
+        fp16 split and not as an fp32 tensor (returns None).  ``presplit``: such buffers holding THIS layer's input
+        (``x`` is then unused)."""
+        total = x.shape[0] if x is not None else plan.T
         if csr is None:
             if ptr is None:
-                ptr = torch.tensor([0, total], dtype=torch.int64, device=x.device)
-                eptr = torch.tensor([0, edge_index.shape[1]], dtype=torch.int64, device=x.device)
+                ptr = torch.tensor([0, total], dtype=torch.int64, device=edge_index.device)
+                eptr = torch.tensor([0, edge_index.shape[1]], dtype=torch.int64, device=edge_index.device)
             max_e = int((eptr[1:] - eptr[:-1]).max())
             csr = ops.csr_by_dst(edge_index.contiguous(), ptr, eptr, total, max_e)
         if plan is None and slab_plan_enabled() and self.out_channels % 128 == 0 and self.in_channels % 8 == 0:
             plan = ops.SlabPlan(edge_index.contiguous(), pseudo.contiguous(), total, self.out_channels, self.kernel_size)
         if plan is not None:
-            Y = ops.spline_slab_gemm(x.detach().contiguous(), self.packed_weight(), plan)
+            Y = ops.spline_slab_gemm(None if presplit is not None else x.detach().contiguous(), self.packed_weight(),
+                                     plan, presplit=presplit)
         else:
+            assert presplit is None and split_out is None
             Y = ops.gemm_nt(x.detach().contiguous(), self.packed_weight(), weight_operand=True)
         bias = self.bias.detach().contiguous()
         mode = 2 if mode is None else mode
         return ops.spline_gather_max(Y, residual, edge_index, pseudo.contiguous(), csr[0], csr[1], bias, mode,
-                                     self.kernel_size)
+                                     self.kernel_size, split_out=split_out, want_out=split_out is None)
 
 
 class SConv(torch.nn.Module):
@@ -128,10 +134,16 @@ class SConv(torch.nn.Module):
         c0 = self.convs[0]
         if slab_plan_enabled() and c0.out_channels % 128 == 0 and c0.in_channels % 8 == 0:
             plan = ops.SlabPlan(edge_index, edge_attr, x.shape[0], c0.out_channels, c0.kernel_size)
-        h = self.convs[0](x, edge_index, edge_attr, csr=csr, mode=0, plan=plan)
+        # with a plan the hidden layer only ever exists as the fp16 operand of the second layer's slab GEMM: the first
+        # layer's gather writes it in that form (no fp32 tensor, no separate split pass)
+        mid = None
+        if plan is not None and ops.gather_split_enabled() and c0.out_channels == self.convs[1].in_channels:
+            mid = ops.slab_operand_buffers(plan, c0.out_channels, x.device)
+        h = self.convs[0](x, edge_index, edge_attr, csr=csr, mode=0, plan=plan, split_out=mid)
         if residual_scale_input is not None:
-            return self.convs[1](h, edge_index, edge_attr, csr=csr, mode=1, residual=residual_scale_input, plan=plan)
-        return self.convs[1](h, edge_index, edge_attr, csr=csr, mode=2, plan=plan)
+            return self.convs[1](h, edge_index, edge_attr, csr=csr, mode=1, residual=residual_scale_input, plan=plan,
+                                 presplit=mid)
+        return self.convs[1](h, edge_index, edge_attr, csr=csr, mode=2, plan=plan, presplit=mid)
 
 
 class SiameseSConvOnNodes(torch.nn.Module):

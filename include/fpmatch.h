@@ -117,8 +117,12 @@ int fpm_csr_by_dst(const long long* edge_dst, const long long* ptr, const long l
                    int* in_eid, int B, int total_nodes, int max_edges_per_graph, void* stream);
 int fpm_spline_gather_max(const float* Y, const float* xin, const long long* edge_src, const float* pseudo,
                           const int* in_ptr, const int* in_eid, const float* bias, float* out, int* argmax,
-                          int total_nodes, int C, int kernel_size, int mode, void* stream);
-                          /* argmax (optional, training): [total_nodes,C] int32 winning edge id per channel */
+                          void* out_hi, void* out_lo, float* out_inv, int total_nodes, int C, int kernel_size,
+                          int mode, void* stream);
+                          /* argmax (optional, training): [total_nodes,C] int32 winning edge id per channel.
+                           * out_hi / out_lo / out_inv (optional, all or none): the result rows also (or, with out =
+                           * NULL, only) as the fp16 hi / lo halves + row scales of fpm_f16_split_rows, i.e. directly
+                           * as the A operand of the next layer's fpm_gemm_nt_f16x3_tiles */
 
 /* ---- (2) affinities --------------------------------------------------------------------------------------
  * Replaces InnerProductWithWeightsAffinity.forward (src/model/affinity_layer.py:11-22) for Kp (node mode:
@@ -209,6 +213,10 @@ int fpm_add_instnorm(const float* a, const float* other, int other_mode, const f
                      float* out, float* rowmax, int B, int n, int E, float eps, void* stream);
 int fpm_onehot_proj(const float* W, const long long* n, float* out, int B, int nmax, int OUT, int IN,
                     void* stream);
+/* add_instnorm(onehot, vec) where onehot[b, r, c] = (c == r && r < hot[b]) is the column embedding of ngm.py:396-399,
+ * never materialised (n <= 112, E % 4 == 0). */
+int fpm_onehot_instnorm(const long long* hot, const float* vec, const float* gamma, const float* beta, float* out,
+                        float* rowmax, int B, int n, int E, float eps, void* stream);
 int fpm_k_head(const float* g_row, const float* g_col, const float* const* weights, const long long* n1,
                const long long* n2, float* ks, float* k_scaled, int B, int E, int Hd, int mean_k, void* stream);
 

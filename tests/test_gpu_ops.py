@@ -379,6 +379,48 @@ def test_spline_conv_slab_plan(ops, oo, pseudo_kind):
     assert tiles <= dense_tiles + 26 and (pseudo_kind == "uniform" or tiles < dense_tiles)
 
 
+def test_sconv_hidden_layer_as_fp16_operand(ops):
+    """SConv (spline_conv.py:28-58): the first layer's gather writes the hidden features directly as the fp16 hi / lo
+    operand of the second layer's slab GEMM.  The split is the same arithmetic as the separate pass, so the module
+    output is bit-identical with the fusion on and off, with and without the residual form."""
+    from src.model.spline_conv import SConv
+    torch.manual_seed(11)
+    data = _small_graph_batch(9, 37, 23)
+    graph = data["pyg_graphs"][0]
+    net = SConv(128, 128).to(DEV)
+    with torch.no_grad():
+        for c in net.convs:
+            c.bias.uniform_(-0.1, 0.1)
+    x = torch.randn(graph.x.shape[0], 128).to(DEV)
+    assert ops.gather_split_enabled()
+    outs = {}
+    for fused in (True, False):
+        ops._GATHER_SPLIT = fused
+        try:
+            for resid in (False, True):
+                g = graph.to(DEV)
+                g.x = x.clone()
+                outs[(fused, resid)] = net(g, residual_scale_input=x if resid else None)
+        finally:
+            ops._GATHER_SPLIT = True
+    for resid in (False, True):
+        assert torch.equal(outs[(True, resid)], outs[(False, resid)])
+    # the kernel-level contract: split rows written by the gather == f16_split_rows of its fp32 output
+    ei, ea = graph.edge_index.to(DEV), graph.edge_attr.to(DEV).float().contiguous()
+    plan = ops.SlabPlan(ei, ea, x.shape[0], 128, 5)
+    csr = ops.csr_by_dst(ei, graph.ptr.to(DEV), graph.eptr.to(DEV), x.shape[0], int((graph.eptr[1:] - graph.eptr[:-1]).max()))
+    Y = ops.spline_slab_gemm(x, net.convs[0].packed_weight(), plan)
+    bias = net.convs[0].bias.detach()
+    bufs = ops.slab_operand_buffers(plan, 128, DEV)
+    full = ops.spline_gather_max(Y, None, ei, ea, csr[0], csr[1], bias, 0, 5)
+    both = ops.spline_gather_max(Y, None, ei, ea, csr[0], csr[1], bias, 0, 5, split_out=bufs, want_out=True)
+    none = ops.spline_gather_max(Y, None, ei, ea, csr[0], csr[1], bias, 0, 5, split_out=bufs, want_out=False)
+    hi, lo, inv = ops.f16_split_rows(full)
+    T = x.shape[0]
+    assert none is None and torch.equal(both, full)
+    assert torch.equal(bufs[0][:T], hi) and torch.equal(bufs[1][:T], lo) and torch.equal(bufs[2][:T], inv)
+
+
 def test_spline_conv_vs_oracle(ops, oo):
     from src.model.spline_conv import SplineConv
     from fpmatch import synth
@@ -582,6 +624,13 @@ def test_add_instnorm_forward(ops, n, E):
         assert (none is None) == (n <= 112 and E % 4 == 0)
     report("add_instnorm_fwd", n=n, E=E, max_abs=worst)
     assert worst < 5e-6
+    if n <= 112 and E % 4 == 0 and n <= E:
+        # the column block's one-hot embedding (ngm.py:396-399) given by its row counts instead of as a tensor
+        hot = torch.randint(1, n + 1, (B,), generator=g); hot[0] = n
+        dense = ops.onehot_proj(torch.eye(E, device=DEV), hot.to(DEV), n)
+        want = ops.add_instnorm(dense, o1.to(DEV), gamma.to(DEV), beta.to(DEV))
+        got = ops.onehot_instnorm(hot.to(DEV), n, o1.to(DEV), gamma.to(DEV), beta.to(DEV))
+        assert torch.equal(got, want)
 
 
 # ---------------------------------------------------------------------------------------------- loss / metrics
