@@ -125,21 +125,29 @@ afau_attention_qzero_kernel(const float* __restrict__ v, const float* __restrict
   const int b = blockIdx.y, h0 = blockIdx.x * kZh;
   const int E = kHeads * kQkv;
   const float* cb = cost + (size_t)b * cs_b;
+  // staging: a warp per cost row (or per column when the caller passes cost^T), lanes along the contiguous index, four
+  // loads in flight; the first version walked a flat index with a division and ONE load in flight per thread - 30 %
+  // of the kernel was the store waiting for that load
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   if (cs_c == 1) {
-    for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
-      const int i = idx / nc, j = idx - i * nc;
-      cs[i * ldc + j] = cb[(size_t)i * cs_r + j];
+    for (int i = warp; i < nr; i += nwarps) {
+      const float* src = cb + (size_t)i * cs_r;
+#pragma unroll 4
+      for (int j = lane; j < nc; j += 32) cs[i * ldc + j] = src[j];
     }
-  } else {                                          // transposed cost: walk the source rows so the reads stay coalesced
-    for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
-      const int j = idx / nr, i = idx - j * nr;
-      cs[i * ldc + j] = cb[(size_t)i * cs_r + (size_t)j * cs_c];
+  } else {
+    for (int j = warp; j < nc; j += nwarps) {
+      const float* src = cb + (size_t)j * cs_c;
+#pragma unroll 4
+      for (int i = lane; i < nr; i += 32) cs[i * ldc + j] = src[(size_t)i * cs_r];
     }
   }
-  for (int idx = threadIdx.x; idx < kZh * nc * kQkv; idx += blockDim.x) {
-    const int hl = idx / (nc * kQkv), rem = idx - hl * nc * kQkv;
-    const int j = rem / kQkv, d = rem - j * kQkv;
-    vs[idx] = v[((size_t)b * nc + j) * E + (h0 + hl) * kQkv + d];
+#pragma unroll
+  for (int hl = 0; hl < kZh; ++hl) {
+    const float* src = v + (size_t)b * nc * E + (h0 + hl) * kQkv;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < nc * kQkv; e += blockDim.x)
+      vs[hl * nc * kQkv + e] = src[(size_t)(e >> 4) * E + (e & 15)];
   }
   __syncthreads();
   const int hl = threadIdx.x / nr, i = threadIdx.x - hl * nr;
@@ -301,6 +309,7 @@ add_instnorm_tile_kernel(const float* __restrict__ a, const float* __restrict__ 
                          const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
                          float* __restrict__ rowmax, int n, int E, float eps, const int64_t* __restrict__ hot) {
   __shared__ float4 red[kWarps][32];
+  __shared__ float4 stat[32];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * 128 + 4 * lane;
   const bool live = e < E;
@@ -334,26 +343,36 @@ add_instnorm_tile_kernel(const float* __restrict__ a, const float* __restrict__ 
 #pragma unroll
     for (int k = 0; k < kRows; ++k) { x[k].x += ov.x; x[k].y += ov.y; x[k].z += ov.z; x[k].w += ov.w; }
   }
-  auto fold = [&](float4 p, bool is_max) -> float4 {      // combine the warps' partials, same order in every thread
-    __syncthreads();                                       // the previous fold's reads are done
+  // Combine the warps' partials: thread c < 128 owns channel c of the tile, adds the kWarps partials in warp order and
+  // finishes the statistic (one division / square root per channel and CTA, not per thread), everybody reads it back.
+  // kind 0: mean = sum / n;  1: 1 / sqrt(sum / n + eps);  2: max, written to rowmax by the owner (no read-back).
+  const float fn = (float)n;
+  auto fold = [&](float4 p, int kind) -> float4 {
     red[warp][lane] = p;
     __syncthreads();
-    float4 t = red[0][lane];
+    if (threadIdx.x < 128) {
+      const float* rf = reinterpret_cast<const float*>(&red[0][0]) + threadIdx.x;
+      float t = rf[0];
 #pragma unroll
-    for (int w = 1; w < kWarps; ++w) {
-      const float4 q = red[w][lane];
-      if (is_max) { t.x = fmaxf(t.x, q.x); t.y = fmaxf(t.y, q.y); t.z = fmaxf(t.z, q.z); t.w = fmaxf(t.w, q.w); }
-      else { t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+      for (int w = 1; w < kWarps; ++w) t = kind == 2 ? fmaxf(t, rf[w * 128]) : t + rf[w * 128];
+      if (kind == 0) t = t / fn;
+      if (kind == 1) t = 1.0f / sqrtf(t / fn + eps);
+      if (kind == 2) {
+        const int ec = blockIdx.x * 128 + threadIdx.x;
+        if (ec < E) rowmax[(size_t)b * E + ec] = t;
+      } else {
+        reinterpret_cast<float*>(&stat[0])[threadIdx.x] = t;
+      }
     }
-    return t;
+    if (kind == 2) return p;
+    __syncthreads();
+    return stat[lane];
   };
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < kRows; ++k)
     if (warp + kWarps * k < n) { sum.x += x[k].x; sum.y += x[k].y; sum.z += x[k].z; sum.w += x[k].w; }
-  sum = fold(sum, false);
-  const float fn = (float)n;
-  const float4 mean = make_float4(sum.x / fn, sum.y / fn, sum.z / fn, sum.w / fn);
+  const float4 mean = fold(sum, 0);
   float4 vs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < kRows; ++k) {
@@ -363,9 +382,7 @@ add_instnorm_tile_kernel(const float* __restrict__ a, const float* __restrict__ 
       vs.z = fmaf(x[k].z, x[k].z, vs.z); vs.w = fmaf(x[k].w, x[k].w, vs.w);
     }
   }
-  vs = fold(vs, false);
-  const float4 inv = make_float4(1.0f / sqrtf(vs.x / fn + eps), 1.0f / sqrtf(vs.y / fn + eps),
-                                 1.0f / sqrtf(vs.z / fn + eps), 1.0f / sqrtf(vs.w / fn + eps));
+  const float4 inv = fold(vs, 1);
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f), bt = g;
   if (live) { g = *(const float4*)(gamma + e); bt = *(const float4*)(beta + e); }
   float4 mx = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
@@ -380,10 +397,7 @@ add_instnorm_tile_kernel(const float* __restrict__ a, const float* __restrict__ 
       mx.x = fmaxf(mx.x, y.x); mx.y = fmaxf(mx.y, y.y); mx.z = fmaxf(mx.z, y.z); mx.w = fmaxf(mx.w, y.w);
     }
   }
-  if (rowmax) {
-    mx = fold(mx, true);
-    if (warp == 0 && live) *(float4*)(rowmax + (size_t)b * E + e) = mx;
-  }
+  if (rowmax) fold(mx, 2);
 }
 
 // k[b, j, o] = j < n[b] ? W[o, j] : 0 : the projection of a one-hot embedding (ngm.py:396-399) is a
@@ -632,7 +646,8 @@ extern "C" int fpm_afau_attention(const float* q, const float* k, const float* v
                                   long long cs_b, long long cs_r, long long cs_c, const float* mix1_w,
                                   const float* mix1_b, const float* mix2_w, const float* mix2_b, float* out,
                                   int B, int nr, int nc, int q_zero, void* stream) {
-  FPM_CHECK_ARG(q && k && v && cost && mix1_w && mix1_b && mix2_w && mix2_b && out, "fpm_afau_attention: null tensor");
+  FPM_CHECK_ARG(v && cost && mix1_w && mix1_b && mix2_w && mix2_b && out, "fpm_afau_attention: null tensor");
+  FPM_CHECK_ARG(q_zero || (q && k), "fpm_afau_attention: q and k may only be omitted with q_zero");
   FPM_CHECK_ARG(B >= 0 && nr > 0 && nc > 0, "fpm_afau_attention: bad sizes");
   if (B == 0) return FPM_OK;
   FPM_CHECK_ARG(B <= 65535, "fpm_afau_attention: batch too large");
@@ -651,6 +666,7 @@ extern "C" int fpm_afau_attention(const float* q, const float* k, const float* v
     FPM_LAUNCH_CHECK();
     return FPM_OK;
   }
+  FPM_CHECK_ARG(q && k, "fpm_afau_attention: this shape runs the generic kernel, which reads q and k");
   const size_t smem = (size_t)2 * nc * fpm::kQkv * sizeof(float);
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_afau_attention: too many columns");
   FPM_CUDA(cudaFuncSetAttribute(fpm::afau_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -120,6 +120,13 @@ __device__ __forceinline__ float softplus_torch(float x) {   // beta = 1, thresh
 
 // softplus for values nobody reads back at full precision (the dead edge affinities Ke): fast exp / log, absolute
 // error < 3e-6 (x > 8: x + log1p(e^-x) by its series; tiny e^x: series; otherwise log(1 + e^x) with __logf).
+// log(1 + e^x) = max(x, 0) + log1p(e^-|x|), branch-free on ex2.approx / lg2.approx: absolute error < 3e-7
+__device__ __forceinline__ float softplus_sfu(float x) {
+  float t, l;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-fabsf(x) * 1.4426950408889634f));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + t));
+  return fmaf(l, 0.6931471805599453f, fmaxf(x, 0.f));
+}
 __device__ __forceinline__ float softplus_fast(float x) {
   if (x > 8.f) { const float u = __expf(-x); return x + u * (1.f - 0.5f * u); }
   const float t = __expf(x);

@@ -247,11 +247,13 @@ ke_factored_kernel(const float* __restrict__ P, const int64_t* __restrict__ eidx
     ends[threadIdx.x] = r < nrow ? (int)(eidxA[(size_t)which * EA + ea0 + k1_0 + r] - pa) : 0;
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < kKeRows * Cn; idx += blockDim.x) {
-    const int r = idx / Cn, j = idx - r * Cn;
-    float d = 0.f;
-    if (r < nrow) d = Pb[(size_t)ends[2 * r] * Cn + j] - Pb[(size_t)ends[2 * r + 1] * Cn + j];
-    Dt[j * kKeLd + r] = d;
+  // warp per edge row, lanes along the node columns: coalesced row reads, several loads in flight, no division
+  for (int r = threadIdx.x >> 5; r < kKeRows; r += blockDim.x >> 5) {
+    const float* ps = Pb + (size_t)ends[2 * r] * Cn;
+    const float* pd = Pb + (size_t)ends[2 * r + 1] * Cn;
+    const bool on = r < nrow;
+#pragma unroll 4
+    for (int j = threadIdx.x & 31; j < Cn; j += 32) Dt[j * kKeLd + r] = on ? ps[j] - pd[j] : 0.f;
   }
   __syncthreads();
   const int64_t pb = ptrB[b], eb0 = eptrB[b];
@@ -270,8 +272,9 @@ ke_factored_kernel(const float* __restrict__ P, const int64_t* __restrict__ eidx
       for (int t = 0; t < 4; ++t) {
         const int r = 4 * q + t;
         if (k1_0 + r < e1max) {
-          // Ke feeds nothing: fast softplus, |error| < 2e-6
-          const float v = (col_ok && r < nrow) ? scale * (softplus_fast(dot[t]) - 0.5f) : 0.f;
+          // Ke feeds nothing: branch-free softplus = max(x, 0) + log1p(e^-|x|) on the two
+          // SFU approximations, |error| < 2e-6 (the log1p argument is formed as 1 + t: absolute, not relative, accuracy)
+          const float v = (col_ok && r < nrow) ? scale * (softplus_sfu(dot[t]) - 0.5f) : 0.f;
           ob[(size_t)r * e2max] = v;
         }
       }

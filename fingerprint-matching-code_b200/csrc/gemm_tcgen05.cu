@@ -782,15 +782,16 @@ static int launch_tc_pair(const void* A_hi, const void* A_lo, const void* B_hi, 
   if ((rc = make_map(&mAl, A_lo, M, K, lda, fpm::P_TBM, f16)) != FPM_OK) return rc;
   if ((rc = make_map(&mBh, B_hi, N, K, ldb, fpm::P_TBN / 2, f16)) != FPM_OK) return rc;
   if ((rc = make_map(&mBl, B_lo, N, K, ldb, fpm::P_TBN / 2, f16)) != FPM_OK) return rc;
-  // FPMATCH_GEMM_STAGES=3|4.  Default 3: measured as fast as 4 on the slab GEMM (0.751 vs 0.757 ms per launch, r2d) and
+  // FPMATCH_GEMM_STAGES=2|3|4.  Default 3: measured as fast as 4 on the slab GEMM (0.751 vs 0.757 ms per launch, r2d) and
   // it leaves 46 KB of shared memory to CTAs of other streams' kernels.
   static int stages = 0;
   if (stages == 0) {
     const char* e = getenv("FPMATCH_GEMM_STAGES");
-    stages = (e && e[0] == '4') ? 4 : 3;
+    stages = (e && e[0] == '4') ? 4 : (e && e[0] == '2') ? 2 : 3;
   }
   const size_t smem = (size_t)stages * fpm::kPStageBytes + 1024 + 256 + (size_t)fpm::kEpiWarps * 32 * 32 * 4;
-  auto kern = stages == 3 ? fpm::gemm_tc_pair_kernel<kMode, 3> : fpm::gemm_tc_pair_kernel<kMode, 4>;
+  auto kern = stages == 3 ? fpm::gemm_tc_pair_kernel<kMode, 3>
+                          : stages == 2 ? fpm::gemm_tc_pair_kernel<kMode, 2> : fpm::gemm_tc_pair_kernel<kMode, 4>;
   FPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(64 + 32 * fpm::kEpiWarps);

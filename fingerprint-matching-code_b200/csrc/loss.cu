@@ -64,6 +64,60 @@ matching_stats_kernel(const float* __restrict__ pred, const float* __restrict__ 
   if (threadIdx.x == 0) { stats[b * 3] = hit; stats[b * 3 + 1] = ngt; stats[b * 3 + 2] = npred; }
 }
 
+// The scalar tail of Net.forward in eval mode (ngm.py:456-469): cls_prob = sigmoid(logits), the BCE-with-logits mean
+// against the pair labels, the k-regression MSE (x k_factor) and L1 error against gt_ks = sum(gt_perm_mat) and
+// min(n1, n2).  Stock torch spends ~17 launches of 1-CTA kernels on these 4 x B numbers.  CTA per pair (it sums its
+// ground-truth matrix); the last CTA to finish adds the per-pair terms in a fixed order (deterministic) and rearms the
+// ticket counter.  scalars: [0] cls_loss (0 without labels), [1] ks_loss, [2] ks_error.
+__global__ void __launch_bounds__(256)
+head_losses_kernel(const float* __restrict__ logits, const float* __restrict__ label, const float* __restrict__ ks,
+                   const float* __restrict__ gt_perm, const int64_t* __restrict__ n1, const int64_t* __restrict__ n2,
+                   float k_factor, float* __restrict__ cls_prob, float* __restrict__ terms, int* __restrict__ counter,
+                   float* __restrict__ scalars, int B, int RC) {
+  __shared__ float red[32];
+  __shared__ int last;
+  const int b = blockIdx.x;
+  const float* g = gt_perm + (size_t)b * RC;
+  float cnt = 0.f;
+  for (int i = threadIdx.x; i < RC; i += blockDim.x) cnt += g[i];
+  cnt = block_sum(cnt, red);
+  if (threadIdx.x == 0) {
+    const float x = logits[b];
+    cls_prob[b] = 1.0f / (1.0f + expf(-x));
+    float bce = 0.f;
+    if (label) {                                     // (1 - y) x + max(-x, 0) + log(exp(-max) + exp(-x - max))
+      const float mv = fmaxf(-x, 0.f);
+      bce = (1.0f - label[b]) * x + mv + logf(expf(-mv) + expf(-x - mv));
+    }
+    float mse = 0.f, l1 = 0.f;
+    if (ks) {
+      const float mp = (float)min(n1[b], n2[b]);
+      const float d = ks[b] - cnt / mp;
+      mse = d * d;
+      l1 = fabsf(ks[b] * mp - cnt);
+    }
+    terms[b * 3] = bce; terms[b * 3 + 1] = mse; terms[b * 3 + 2] = l1;
+    __threadfence();
+    last = atomicAdd(counter, 1) == B - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const volatile float* t = terms + (size_t)i * 3;
+    acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) acc[k] = block_sum(acc[k], red);
+  if (threadIdx.x == 0) {
+    scalars[0] = acc[0] / (float)B;
+    scalars[1] = acc[1] / (float)B * k_factor;
+    scalars[2] = acc[2] / (float)B;
+    *counter = 0;
+  }
+}
+
 }  // namespace fpm
 
 extern "C" int fpm_permutation_loss(const float* pred, const float* gt, const long long* n1, const long long* n2,
@@ -92,6 +146,19 @@ extern "C" int fpm_matching_stats(const float* pred, const float* gt, const long
   FPM_CHECK_ARG(pred && gt && ns && stats, "fpm_matching_stats: null tensor");
   if (B == 0) return FPM_OK;
   fpm::matching_stats_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pred, gt, (const int64_t*)ns, stats, R, C);
+  FPM_LAUNCH_CHECK();
+  return FPM_OK;
+}
+
+// workspace: 3 * B floats + one int (zero before the first use; the kernel rearms it), 16-byte aligned.
+extern "C" int fpm_head_losses(const float* logits, const float* label, const float* ks, const float* gt_perm,
+                               const long long* n1, const long long* n2, float k_factor, float* cls_prob,
+                               float* workspace, float* scalars, int B, int R, int C, void* stream) {
+  FPM_CHECK_ARG(logits && gt_perm && n1 && n2 && cls_prob && workspace && scalars, "fpm_head_losses: null tensor");
+  FPM_CHECK_ARG(B > 0 && R > 0 && C > 0, "fpm_head_losses: bad sizes");
+  fpm::head_losses_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, label, ks, gt_perm, (const int64_t*)n1,
+                                                              (const int64_t*)n2, k_factor, cls_prob, workspace,
+                                                              (int*)(workspace + (size_t)3 * B), scalars, B, R * C);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

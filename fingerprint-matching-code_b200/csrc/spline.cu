@@ -353,30 +353,39 @@ __global__ void slab_mask_kernel(const int64_t* __restrict__ edge_src, const flo
 }
 
 // meta (ints): [0] tile count, [1] sparse rows in use, [2 .. 2+NS) dense flag per slab, [2+NS .. 2+2NS] sparse row
-// offset per slab (+ total), [2+2NS+1 .. ) cursors.  One CTA.
+// offset per slab (+ total), [2+2NS+1 .. 2+3NS+1) cursors, then 33 ints of scratch the caller zero-fills (per-slab node
+// counts + a ticket).  The node counts are taken by all CTAs of the grid (one ballot per (32 nodes, slab), one global
+// atomic per (warp, slab)); the LAST CTA to finish then lays out the tile table alone.  (First version: one CTA did
+// everything, counting with one shared-memory atomic per (node, slab): 39 us at T = 25 600; with ballots in that one
+// CTA still 57 us - 8 k instructions per warp on a single SM.)
 __global__ void __launch_bounds__(kPlanThreads)
 slab_plan_kernel(const unsigned* __restrict__ mask, int T, int KS, int C, int* __restrict__ meta,
                  int4* __restrict__ tab, int max_tiles) {
   const int NS = KS * KS + 1;
   __shared__ int cnt[32], dense[32], off[33], dlist[32], tstart[33];
-  __shared__ int nd, total_sparse;
+  __shared__ int nd, total_sparse, is_last;
   const int tid = threadIdx.x;
-  if (tid < 32) cnt[tid] = 0;
-  __syncthreads();
+  int* gcnt = meta + 2 + 3 * NS + 2;
+  int* ticket = gcnt + 32;
   {
-    // nodes per slab: lane k of every warp counts slab k with one ballot per (32 nodes, slab) - the first version
-    // issued one shared-memory atomic per (node, slab) on 26 addresses: 220 k serialised atomics, 39 us at T = 25 600
     const int lane = tid & 31;
     int mine = 0;
-    for (int j0 = tid - lane; j0 < T; j0 += kPlanThreads) {
+    for (int j0 = blockIdx.x * kPlanThreads + tid - lane; j0 < T; j0 += gridDim.x * kPlanThreads) {
       const unsigned m = (j0 + lane < T) ? mask[j0 + lane] : 0u;
       for (int k = 0; k < NS; ++k) {
         const int c = __popc(__ballot_sync(0xffffffffu, (m >> k) & 1u));
         if (lane == k) mine += c;
       }
     }
-    if (lane < NS && mine) atomicAdd(&cnt[lane], mine);
+    if (lane < NS && mine) atomicAdd(&gcnt[lane], mine);
   }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid < 32) cnt[tid] = tid < NS ? *((volatile int*)gcnt + tid) : 0;
   __syncthreads();
   if (tid == 0) {
     cnt[NS - 1] = T;                                  // the root slab serves every node
@@ -549,7 +558,8 @@ extern "C" int fpm_spline_scatter_bwd_compact(const float* G, const int* argmax,
 }
 
 // Builds the slab plan of one graph batch (see the planner comment above).  mask [T] uint32 and rowmap [rowmap_cap]
-// int32 are scratch the caller zero- / -1-fills; meta needs 2 + 3*(KS*KS+1) + 2 ints; tab holds max_tiles int4.
+// int32 are scratch the caller zero- / -1-fills; meta needs 2 + 3*(KS*KS+1) + 2 + 33 ints, ZERO-FILLED; tab holds
+// max_tiles int4.
 extern "C" int fpm_spline_plan(const long long* edge_src, const float* pseudo, unsigned* mask, int* meta, int* tab,
                                int* rowmap, int T, int E, int C, int kernel_size, int max_tiles, int rowmap_cap,
                                void* stream) {
@@ -561,7 +571,8 @@ extern "C" int fpm_spline_plan(const long long* edge_src, const float* pseudo, u
     fpm::slab_mask_kernel<<<fpm_cdiv(E, 256), 256, 0, st>>>((const int64_t*)edge_src, pseudo, mask, E, kernel_size);
     FPM_LAUNCH_CHECK();
   }
-  fpm::slab_plan_kernel<<<1, fpm::kPlanThreads, 0, st>>>(mask, T, kernel_size, C, meta, (int4*)tab, max_tiles);
+  const int plan_ctas = fpm_cdiv(T, fpm::kPlanThreads) < 64 ? fpm_cdiv(T, fpm::kPlanThreads) : 64;
+  fpm::slab_plan_kernel<<<plan_ctas, fpm::kPlanThreads, 0, st>>>(mask, T, kernel_size, C, meta, (int4*)tab, max_tiles);
   FPM_LAUNCH_CHECK();
   fpm::slab_compact_kernel<<<fpm_cdiv(T, 256), 256, 0, st>>>(mask, T, kernel_size, meta, rowmap, rowmap_cap);
   FPM_LAUNCH_CHECK();

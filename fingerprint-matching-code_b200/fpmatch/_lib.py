@@ -68,6 +68,7 @@ SIGNATURES = {
     "fpm_permutation_loss": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_permutation_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_matching_stats": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "fpm_head_losses": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),
     # batched CSR / CSC containers + dense FGM affinity
     "fpm_csr_dot_diag": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "fpm_csr_dot_csc_dense": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),

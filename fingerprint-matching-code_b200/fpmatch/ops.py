@@ -342,7 +342,7 @@ class SlabPlan:
         self.rowmap_cap = (NS - 1) * ((total // 4 + 255) // 256 * 256 + 256)
         self.max_tiles = tiles_m * NS * ntn + (self.rowmap_cap // 256) * ntn
         self.mask = torch.zeros((total,), dtype=torch.int32, device=dev)
-        self.meta = torch.zeros((2 + 3 * NS + 2,), dtype=torch.int32, device=dev)
+        self.meta = torch.zeros((2 + 3 * NS + 2 + 33,), dtype=torch.int32, device=dev)    # + planner scratch
         self.tab = torch.empty((self.max_tiles, 4), dtype=torch.int32, device=dev)
         self.rowmap = torch.full((self.rowmap_cap,), -1, dtype=torch.int32, device=dev)
         src = edge_index[0]
@@ -657,13 +657,27 @@ def soft_topk(scores: Tensor, ks: Tensor, n1: Optional[Tensor], n2: Optional[Ten
 # ---------------------------------------------------------------------------------------------------
 # AFA-U
 # ---------------------------------------------------------------------------------------------------
-def afau_attention(q: Tensor, k: Tensor, v: Tensor, cost: Tensor, transposed_cost: bool, mix1_w: Tensor,
-                   mix1_b: Tensor, mix2_w: Tensor, mix2_b: Tensor, q_zero: bool = False) -> Tensor:
-    """cost is the ORIGINAL [B, n1, n2] matrix; ``transposed_cost`` makes the kernel read cost^T."""
-    B, nr, E = q.shape
-    nc = k.shape[1]
-    out = torch.empty((B, nr, E), dtype=torch.float32, device=q.device)
+def afau_zero_query_kernel_fits(nr: int, nc: int) -> bool:
+    """True when ``afau_attention(..., q_zero=True)`` runs the dedicated zero-query kernel (csrc/afau.cu), which reads
+    neither q nor k: they may then be passed as None."""
+    if os.environ.get("FPMATCH_AFAU_QZERO") == "0":
+        return False
+    smem = (((nr * (nc | 1) + 3) & ~3) + 2 * nc * 16) * 4
+    return 2 * nr <= 256 and smem <= 72 * 1024
+
+
+def afau_attention(q: Optional[Tensor], k: Optional[Tensor], v: Tensor, cost: Tensor, transposed_cost: bool,
+                   mix1_w: Tensor, mix1_b: Tensor, mix2_w: Tensor, mix2_b: Tensor, q_zero: bool = False) -> Tensor:
+    """cost is the ORIGINAL [B, n1, n2] matrix; ``transposed_cost`` makes the kernel read cost^T.  With ``q_zero`` (the
+    caller guarantees q == 0) and ``afau_zero_query_kernel_fits`` q and k may be None."""
+    B, nc, E = v.shape
     R, Cc = cost.shape[1], cost.shape[2]
+    nr = Cc if transposed_cost else R
+    if q is not None:
+        assert q.shape == (B, nr, E) and k.shape == v.shape
+    else:
+        assert q_zero and k is None and afau_zero_query_kernel_fits(nr, nc)
+    out = torch.empty((B, nr, E), dtype=torch.float32, device=v.device)
     if transposed_cost:
         assert (nr, nc) == (Cc, R)
         cs_b, cs_r, cs_c = R * Cc, 1, Cc
@@ -1035,6 +1049,24 @@ def matching_stats(pred: Tensor, gt: Tensor, ns: Tensor) -> Tensor:
                                        B, R, Cc, _stream())
     _lib.check(rc, "fpm_matching_stats"); _count()
     return out
+
+
+def head_losses(logits: Tensor, label: Optional[Tensor], ks: Optional[Tensor], gt_perm: Tensor, n1: Tensor, n2: Tensor,
+                k_factor: float):
+    """The scalar tail of ``Net.forward`` in eval mode (ngm.py:456-469) in one launch.  Returns ``(cls_prob [B],
+    cls_loss, ks_loss, ks_error)``, the three losses as 0-dim views of one tensor; ``label`` / ``ks`` None -> the
+    corresponding losses are 0."""
+    B, R, Cc = gt_perm.shape
+    dev = logits.device
+    ws = torch.zeros((3 * B + 4,), dtype=torch.float32, device=dev)       # per-pair terms + the ticket counter
+    cls_prob = torch.empty((B,), dtype=torch.float32, device=dev)
+    scalars = torch.empty((3,), dtype=torch.float32, device=dev)
+    rc = _lib.lib().fpm_head_losses(_chk(logits, "cls_logits"), _chk(label, "label"), _chk(ks, "ks"),
+                                    _chk(gt_perm, "gt_perm_mat"), _chk(_i64(n1), "n1", torch.int64),
+                                    _chk(_i64(n2), "n2", torch.int64), float(k_factor), cls_prob.data_ptr(),
+                                    ws.data_ptr(), scalars.data_ptr(), B, R, Cc, _stream())
+    _lib.check(rc, "fpm_head_losses"); _count()
+    return cls_prob, scalars[0], scalars[1], scalars[2]
 
 
 def fgm_aggregate(A: Tensor, W: Tensor, X: Tensor, norm: bool = True, trans: bool = False,

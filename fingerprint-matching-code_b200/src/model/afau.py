@@ -137,9 +137,12 @@ class EncodingBlock(nn.Module):
         B = cost_mat.shape[0]
         dev = cost_mat.device
         E = self.Wq.out_features
-        q = torch.zeros((B, n1max, E), dtype=torch.float32, device=dev)
-        k = ops.onehot_proj(self.Wk.weight.detach().contiguous(), n2, n2max)
         v = ops.onehot_proj(self.Wv.weight.detach().contiguous(), n2, n2max)
+        if ops.afau_zero_query_kernel_fits(n1max, n2max):
+            q = k = None                                   # the zero-query kernel reads neither
+        else:
+            q = torch.zeros((B, n1max, E), dtype=torch.float32, device=dev)
+            k = ops.onehot_proj(self.Wk.weight.detach().contiguous(), n2, n2max)
         att = self.mixed_score_MHA(q, k, v, cost_mat, transposed_cost=False, q_zero=True)
         mh = _lin(att, self.multi_head_combine.weight, self.multi_head_combine.bias)
         out1 = self.add_n_normalization_1(mh, None)            # row_emb + mh with row_emb = 0
@@ -234,10 +237,12 @@ class CrossSet_MultiHeadAttention(nn.Module):
     def forward(self, q, k, v, cost_mat, transposed_cost=False, q_zero=False):
         """q [B, nr, 256] (heads concatenated), k/v [B, nc, 256]; returns [B, nr, 256].  ``q_zero``: the caller
         guarantees q == 0, the kernel then skips the q.k products (identical result)."""
-        if q.dim() == 4:      # reference layout [B, H, n, d]
+        if q is not None and q.dim() == 4:      # reference layout [B, H, n, d]
             q, k, v = (t.transpose(1, 2).reshape(t.shape[0], t.shape[2], -1) for t in (q, k, v))
         d = lambda t: t.detach().contiguous()
-        return ops.afau_attention(q.contiguous(), k.contiguous(), v.contiguous(), d(cost_mat), transposed_cost,
+        if q is not None:
+            q, k = q.contiguous(), k.contiguous()
+        return ops.afau_attention(q, k, v.contiguous(), d(cost_mat), transposed_cost,
                                   d(self.mix1_weight), d(self.mix1_bias), d(self.mix2_weight), d(self.mix2_bias),
                                   q_zero=q_zero)
 

@@ -452,9 +452,12 @@ class Net(CNN):
         ss = ops.sinkhorn_log(s, n1, n2, self.sinkhorn.max_iter, self.sinkhorn.tau, True)      # :371
 
         # ---- k (ngm.py:374-416)
-        min_point_tensor = torch.minimum(n1, n2).to(torch.float32)
         gt_perm = data_dict['gt_perm_mat'].to(dev)
-        gt_ks = gt_perm.sum(dim=(1, 2)).to(torch.float32)
+        fused_tail = gt_perm.dtype == torch.float32 and gt_perm.is_contiguous()
+        if not (fused_tail and self.regression and not self.training):
+            # with the k head in eval mode only the losses need these two, and ops.head_losses derives them itself
+            min_point_tensor = torch.minimum(n1, n2).to(torch.float32)
+            gt_ks = gt_perm.sum(dim=(1, 2)).to(torch.float32)
         if self.regression:
             assert self.univ_size - n1max >= 0 and self.univ_size - n2max >= 0
             g_row, g_col = self.encoder_k.forward_k_inputs(ss, n2, n1max, n2max)
@@ -476,18 +479,29 @@ class Net(CNN):
 
         # ---- genuine / imposter classifier and losses (ngm.py:451-469)
         cls_logits = self.match_cls.forward_product(s, x)
-        cls_prob = torch.sigmoid(cls_logits)
-        cls_loss = torch.zeros((), device=dev)          # a fill kernel: torch.tensor(0.0, device=...) is a blocking host copy
-        if 'label' in data_dict:
-            label_tensor = data_dict['label'].to(dev).view(-1).float()
-            cls_loss = torch.nn.functional.binary_cross_entropy_with_logits(cls_logits, label_tensor)
-        supervised_ks = gt_ks / min_point_tensor
-        if self.regression:
-            ks_loss = torch.nn.functional.mse_loss(ks, supervised_ks) * self.k_factor
-            ks_error = torch.nn.functional.l1_loss(ks * min_point_tensor, gt_ks)
+        label_tensor = data_dict['label'].to(dev).view(-1).float().contiguous() if 'label' in data_dict else None
+        if fused_tail and cls_logits.dim() == 1 and not cls_logits.requires_grad:
+            # sigmoid, BCE, the k-regression MSE / L1 and gt_ks = sum(gt_perm) in one launch (stock torch: ~17)
+            cls_prob, cls_loss, ks_loss, ks_error = ops.head_losses(
+                cls_logits.contiguous(), label_tensor, ks.contiguous() if self.regression else None, gt_perm, n1, n2,
+                self.k_factor)
+            if not self.regression:
+                ks_loss, ks_error = 0.0, 0.0
         else:
-            ks_loss = 0.0
-            ks_error = 0.0
+            if self.regression and not self.training and fused_tail:
+                min_point_tensor = torch.minimum(n1, n2).to(torch.float32)
+                gt_ks = gt_perm.sum(dim=(1, 2)).to(torch.float32)
+            cls_prob = torch.sigmoid(cls_logits)
+            cls_loss = torch.zeros((), device=dev)      # a fill kernel: torch.tensor(0.0, device=...) is a blocking host copy
+            if label_tensor is not None:
+                cls_loss = torch.nn.functional.binary_cross_entropy_with_logits(cls_logits, label_tensor)
+            supervised_ks = gt_ks / min_point_tensor
+            if self.regression:
+                ks_loss = torch.nn.functional.mse_loss(ks, supervised_ks) * self.k_factor
+                ks_error = torch.nn.functional.l1_loss(ks * min_point_tensor, gt_ks)
+            else:
+                ks_loss = 0.0
+                ks_error = 0.0
 
         if ke_join is not None:
             torch.cuda.current_stream(dev).wait_stream(ke_join)

@@ -107,7 +107,8 @@ int fpm_gemm_set_trace(void* buf, int cap);
 /* Slab planner (device side, no host round trip): marks the (node, weight slab) products the gather will read and emits
  * the tile table for fpm_gemm_nt_f16x3_tiles - slabs needed by >= 1/4 of the nodes are computed for all nodes, the
  * others only for their nodes, compacted behind the dense rows of the A buffer (fpm_spline_gather_rows copies the
- * fp16 halves there).  mask [T] u32 zero-filled, rowmap [rowmap_cap] i32 filled with -1, meta [2 + 3*(KS*KS+1) + 2] i32
+ * fp16 halves there).  mask [T] u32 zero-filled, rowmap [rowmap_cap] i32 filled with -1, meta [2 + 3*(KS*KS+1) + 2 + 33] i32
+ * zero-filled
  * (meta[0] = tile count, meta[1] = compact rows in use), tab [max_tiles] int4. */
 int fpm_spline_plan(const long long* edge_src, const float* pseudo, unsigned* mask, int* meta, int* tab, int* rowmap,
                     int T, int E, int C, int kernel_size, int max_tiles, int rowmap_cap, void* stream);
@@ -246,6 +247,13 @@ int fpm_permutation_loss_bwd(const float* pred, const float* gt, const long long
                              const float* gscale, float* grad, int B, int R, int C, void* stream);
 int fpm_matching_stats(const float* pred, const float* gt, const long long* ns, float* stats, int B, int R, int C,
                        void* stream);
+/* The scalar tail of Net.forward in eval mode (ngm.py:456-469) in one launch: cls_prob [B] = sigmoid(logits);
+ * scalars[0] = BCE-with-logits mean against label [B] (0 if label is NULL), scalars[1] = k_factor * mse(ks, gt_ks / min(n1, n2)),
+ * scalars[2] = l1(ks * min(n1, n2), gt_ks) with gt_ks = sum(gt_perm [B,R,C]) (both 0 if ks is NULL).
+ * workspace: 3*B floats + 1 int, the int zero before the first call (the kernel rearms it); one call at a time per workspace. */
+int fpm_head_losses(const float* logits, const float* label, const float* ks, const float* gt_perm, const long long* n1,
+                    const long long* n2, float k_factor, float* cls_prob, float* workspace, float* scalars, int B,
+                    int R, int C, void* stream);
 
 /* ---- (A14) batched CSR / CSC products, dense factorised-graph-matching affinity ------------------------------------
  * Replace the reference's JIT extension (src/extension/sparse_dot/sparse_dot.cpp:191-331, bilinear_diag.cpp:303-326)

@@ -598,6 +598,34 @@ def test_afau_attention_zero_query_kernel(ops, nr, nc, transposed):
     e_fast, e_slow = (fast.cpu().double() - ref).abs().max().item(), (slow.cpu().double() - ref).abs().max().item()
     report("afau_attention_qzero", nr=nr, nc=nc, transposed=transposed, fast=e_fast, generic=e_slow)
     assert e_fast < 5e-6 and e_slow < 5e-6
+    if ops.afau_zero_query_kernel_fits(nr, nc):         # that kernel reads neither q nor k: they may be omitted
+        bare = ops.afau_attention(None, None, d(v), d(cost), transposed, d(m1w), d(m1b), d(m2w), d(m2b), q_zero=True)
+        assert torch.equal(bare, fast)
+    else:
+        assert nr > 128
+
+
+def test_head_losses_kernel(ops):
+    """The scalar tail of Net.forward in eval mode (ngm.py:456-469) in one launch vs the stock torch expressions."""
+    g = torch.Generator().manual_seed(21)
+    B, R, Cc = 37, 19, 23
+    logits = torch.randn(B, generator=g) * 3; label = (torch.rand(B, generator=g) > 0.5).float()
+    ks = torch.rand(B, generator=g)
+    n1 = torch.randint(5, R + 1, (B,), generator=g); n2 = torch.randint(5, Cc + 1, (B,), generator=g)
+    gt = (torch.rand(B, R, Cc, generator=g) > 0.9).float()
+    F = torch.nn.functional
+    mp = torch.minimum(n1, n2).float(); gt_ks = gt.sum((1, 2))
+    want = (torch.sigmoid(logits), F.binary_cross_entropy_with_logits(logits, label),
+            F.mse_loss(ks, gt_ks / mp) * 2.5, F.l1_loss(ks * mp, gt_ks))
+    d = lambda t: t.to(DEV)
+    for lab, kk in ((label, ks), (None, ks), (label, None)):
+        got = ops.head_losses(d(logits), None if lab is None else d(lab), None if kk is None else d(kk), d(gt), d(n1),
+                              d(n2), 2.5)
+        assert (got[0].cpu() - want[0]).abs().max() < 1e-6
+        exp = (want[1] if lab is not None else torch.zeros(()), want[2] if kk is not None else torch.zeros(()),
+               want[3] if kk is not None else torch.zeros(()))
+        for a, b in zip(got[1:], exp):
+            assert a.dim() == 0 and abs(a.item() - b.item()) <= 2e-6 * max(1.0, abs(b.item()))
 
 
 @pytest.mark.parametrize("n,E", [(30, 600), (100, 600), (112, 600), (101, 88), (150, 600), (40, 130)])
