@@ -76,7 +76,7 @@ __global__ void feature_align_kernel(const float* __restrict__ fmap, const float
 // covers 32 / kTp channels x kTp consecutive positions (eight loads in flight per thread), the stores walk the
 // channels of one position (coalesced rows of the NHWC map).  kTp = 16 for the small maps (8 x 10 positions: a
 // 32-wide tile left 3 CTAs per image, the last one half empty, and 68 KB of shared memory per CTA at 512 channels).
-template <int kTp>
+template <int kTp, int kCpt>                   // kCpt = C / 256 when that is exact (channels per thread), else 0
 __global__ void __launch_bounds__(256)
 fmap_prep_kernel(const float* __restrict__ fmap, float* __restrict__ out, int C, int HW) {
   extern __shared__ float tile[];              // [C][kTp + 1]
@@ -109,14 +109,30 @@ fmap_prep_kernel(const float* __restrict__ fmap, float* __restrict__ out, int C,
   __syncthreads();
   float* dst = out + ((size_t)b * HW + p0) * C;
   const int npos = min(kTp, HW - p0);
-  for (int q = 0; q < npos; ++q) {
-    // v / n from the position's correctly rounded reciprocal and one FMA correction (Markstein): three FMA-pipe
-    // instructions per element instead of a full IEEE division sequence in every thread
-    const float nq = norm[q], rq = rnorm[q];
-    for (int c = threadIdx.x; c < C; c += 256) {
-      const float v = tile[c * kLd + q];
-      const float d = v * rq;
-      dst[(size_t)q * C + c] = fmaf(fmaf(-d, nq, v), rq, d);
+  // v / n from the position's correctly rounded reciprocal and one FMA correction (Markstein): three FMA-pipe
+  // instructions per element instead of a full IEEE division sequence in every thread.  With the channel count a
+  // multiple of 256 a thread owns fixed channels and walks the positions, four in flight (the generic loop spends
+  // ~80 instructions of control per position for one or two elements).
+  if (kCpt > 0) {
+    float* d0 = dst + threadIdx.x;
+#pragma unroll 4
+    for (int q = 0; q < npos; ++q) {
+      const float nq = norm[q], rq = rnorm[q];
+#pragma unroll
+      for (int u = 0; u < kCpt; ++u) {
+        const float v = tile[(threadIdx.x + 256 * u) * kLd + q];
+        const float d = v * rq;
+        d0[(size_t)q * C + 256 * u] = fmaf(fmaf(-d, nq, v), rq, d);
+      }
+    }
+  } else {
+    for (int q = 0; q < npos; ++q) {
+      const float nq = norm[q], rq = rnorm[q];
+      for (int c = threadIdx.x; c < C; c += 256) {
+        const float v = tile[c * kLd + q];
+        const float d = v * rq;
+        dst[(size_t)q * C + c] = fmaf(fmaf(-d, nq, v), rq, d);
+      }
     }
   }
 }
@@ -318,13 +334,20 @@ extern "C" int fpm_fmap_prep(const float* fmap, float* out_nhwc, int B, int C, i
   const size_t smem = (size_t)C * (narrow ? 17 : 33) * sizeof(float);
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_fmap_prep: channel count too large");
   FPM_CHECK_ARG(B <= 65535, "fpm_fmap_prep: batch too large");
+  const int cpt = (C % 256 == 0 && C <= 512) ? C / 256 : 0;
+#define FPM_FMAP_PREP(TP, CPT)                                                                                     \
+  do {                                                                                                             \
+    FPM_CUDA(cudaFuncSetAttribute(fpm::fmap_prep_kernel<TP, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                  (int)smem));                                                                     \
+    fpm::fmap_prep_kernel<TP, CPT><<<dim3(fpm_cdiv(HW, TP), B), 256, smem, (cudaStream_t)stream>>>(fmap, out_nhwc, \
+                                                                                                   C, HW);         \
+  } while (0)
   if (narrow) {
-    FPM_CUDA(cudaFuncSetAttribute(fpm::fmap_prep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fpm::fmap_prep_kernel<16><<<dim3(fpm_cdiv(HW, 16), B), 256, smem, (cudaStream_t)stream>>>(fmap, out_nhwc, C, HW);
+    if (cpt == 1) FPM_FMAP_PREP(16, 1); else if (cpt == 2) FPM_FMAP_PREP(16, 2); else FPM_FMAP_PREP(16, 0);
   } else {
-    FPM_CUDA(cudaFuncSetAttribute(fpm::fmap_prep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fpm::fmap_prep_kernel<32><<<dim3(fpm_cdiv(HW, 32), B), 256, smem, (cudaStream_t)stream>>>(fmap, out_nhwc, C, HW);
+    if (cpt == 1) FPM_FMAP_PREP(32, 1); else if (cpt == 2) FPM_FMAP_PREP(32, 2); else FPM_FMAP_PREP(32, 0);
   }
+#undef FPM_FMAP_PREP
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

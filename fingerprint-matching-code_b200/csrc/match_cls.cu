@@ -123,29 +123,19 @@ match_cls_stage2_kernel(const float* __restrict__ p1, const float* __restrict__ 
 #pragma unroll
     for (int d = 0; d < 4; ++d) acc[op][d] = pk2(0.f, 0.f);
 
-  // the 4 x 4 patch of the NEXT input channel is fetched while the current one is multiplied (two warps per
-  // scheduler cannot hide a dependent global load otherwise)
-  auto load_patch = [&](int ic, float (&a)[4][4]) {
+  for (int ic = 0; ic < kC1; ++ic) {
     const float* t = base + (size_t)ic * H1 * W1;      // patch element (1, 1)
+    f32x2 p[4][4];                                     // patch values broadcast to both lanes
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const bool rok = (r == 0) ? top : (r == 3) ? bottom : true;
       const float* row = t + (r - 1) * W1;
-      a[r][0] = (rok && left) ? __ldg(row - 1) : 0.f;
-      a[r][1] = rok ? __ldg(row) : 0.f;
-      a[r][2] = rok ? __ldg(row + 1) : 0.f;
-      a[r][3] = (rok && right) ? __ldg(row + 2) : 0.f;
+      const float a0 = (rok && left) ? __ldg(row - 1) : 0.f;
+      const float a1 = rok ? __ldg(row) : 0.f;
+      const float a2 = rok ? __ldg(row + 1) : 0.f;
+      const float a3 = (rok && right) ? __ldg(row + 2) : 0.f;
+      p[r][0] = pk2(a0, a0); p[r][1] = pk2(a1, a1); p[r][2] = pk2(a2, a2); p[r][3] = pk2(a3, a3);
     }
-  };
-  float nxt[4][4];
-  load_patch(0, nxt);
-  for (int ic = 0; ic < kC1; ++ic) {
-    f32x2 p[4][4];                                     // patch values broadcast to both lanes
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) p[r][c] = pk2(nxt[r][c], nxt[r][c]);
-    if (ic + 1 < kC1) load_patch(ic + 1, nxt);
     const float4* wv = reinterpret_cast<const float4*>(sw + ic * (kC2 / 2) * kWpad);
 #pragma unroll
     for (int op = 0; op < kC2 / 2; ++op) {

@@ -83,6 +83,20 @@ def plain(n=6):
     return (time.perf_counter() - t0) / n * 1e3
 plain(2)
 res["synchronous_reference_style_loop"] = plain()
+# host cost of ENQUEUEING one forward (python + ctypes + allocator + launches): a 2-pair batch keeps the GPU far ahead of
+# the host, so the wall clock per step is the host's alone; it does not depend on the batch size
+tiny = synth.batch_to(synth.make_batch(2, 100, seed=5, with_dense_gh=False), dev)
+def enqueue(n=30):
+    for _ in range(5):
+        with torch.no_grad():
+            net(synth.clone_batch(tiny))
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(n):
+        with torch.no_grad():
+            net(synth.clone_batch(tiny))
+    t1 = time.perf_counter(); torch.cuda.synchronize()
+    return (t1 - t0) / n * 1e3
+res["host_enqueue_ms_per_forward"] = enqueue()
 print(json.dumps(res, indent=1))
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
 (ROOT / "gpurun_out" / "e2e_probe.json").write_text(json.dumps(res))
