@@ -105,41 +105,44 @@ afau_attention_kernel(const float* __restrict__ q, const float* __restrict__ k, 
 }
 
 // The row block of Net.forward (ngm.py:392: the row embedding is all zeros, so q = 0 and the score of (i, j) is the
-// mixing MLP of cost[i, j] alone).  CTA per (pair, kZh heads): the pair's cost tile and the heads' values are staged
-// in shared memory once; thread = one (head, query row).  The 16-unit MLP runs on packed fp32: 8 FFMA2 form the hidden
-// pairs (c * w1b + b1, one rounding instead of the generic kernel's two), 16 FMNMX, 8 FFMA2 fold them with w2; the 16
-// value accumulators are 8 FFMA2.  Scores are kept in the log2 domain (s * log2 e) so a softmax weight is one FFMA +
-// one EX2.  ~55 instructions per (i, j, head) against ~140 in the generic kernel, and the cost row is read from
-// shared memory (odd row pitch: conflict-free) instead of 32 cache lines per warp load.
+// mixing MLP of cost[i, j] alone).  CTA per (pair, kZh heads), thread = one (head, query row); the heads' values are
+// staged in shared memory.  The 16-unit MLP runs on packed fp32: 8 FFMA2 form the hidden pairs (c * w1b + b1, one
+// rounding instead of the generic kernel's two), 16 FMNMX, 8 FFMA2 fold them with w2; the 16 value accumulators are
+// 8 FFMA2.  Scores are kept in the log2 domain (s * log2 e) so a softmax weight is one FFMA + one EX2.
+// kStage = false (cost addressed with unit ROW stride, i.e. the caller holds cost^T - Net.forward passes the
+// transposed copy the Sinkhorn kernel writes anyway): the threads of a warp read one column of their rows with a
+// single coalesced load, four columns prefetched ahead, and the CTA needs only 13 KB of shared memory - it fits
+// beside a GEMM CTA of another stream.  kStage = true: the pair's cost tile goes through shared memory first
+// (odd row pitch: conflict-free), by warp-per-row loops with four loads in flight.
 constexpr int kZh = 2;
 
-__global__ void __launch_bounds__(256, 3)
+template <bool kStage>
+__global__ void __maxnreg__(96)       // 3 CTAs of 7 warps per SM; two of its warps fit a sub-partition beside a GEMM CTA
 afau_attention_qzero_kernel(const float* __restrict__ v, const float* __restrict__ cost, long long cs_b, long long cs_r,
                             long long cs_c, const float* __restrict__ mix1_w, const float* __restrict__ mix1_b,
                             const float* __restrict__ mix2_w, const float* __restrict__ mix2_b,
                             float* __restrict__ out, int nr, int nc) {
   extern __shared__ float sm[];
   const int ldc = nc | 1;
-  float* cs = sm;                                   // [nr][ldc]
-  float* vs = sm + (((size_t)nr * ldc + 3) & ~(size_t)3);   // [kZh][nc][16], 16-byte aligned
+  float* cs = sm;                                                           // [nr][ldc] (kStage only)
+  float* vs = kStage ? sm + (((size_t)nr * ldc + 3) & ~(size_t)3) : sm;     // [kZh][nc][16], 16-byte aligned
   const int b = blockIdx.y, h0 = blockIdx.x * kZh;
   const int E = kHeads * kQkv;
   const float* cb = cost + (size_t)b * cs_b;
-  // staging: a warp per cost row (or per column when the caller passes cost^T), lanes along the contiguous index, four
-  // loads in flight; the first version walked a flat index with a division and ONE load in flight per thread - 30 %
-  // of the kernel was the store waiting for that load
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  if (cs_c == 1) {
-    for (int i = warp; i < nr; i += nwarps) {
-      const float* src = cb + (size_t)i * cs_r;
+  if (kStage) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (cs_c == 1) {
+      for (int i = warp; i < nr; i += nwarps) {
+        const float* src = cb + (size_t)i * cs_r;
 #pragma unroll 4
-      for (int j = lane; j < nc; j += 32) cs[i * ldc + j] = src[j];
-    }
-  } else {
-    for (int j = warp; j < nc; j += nwarps) {
-      const float* src = cb + (size_t)j * cs_c;
+        for (int j = lane; j < nc; j += 32) cs[i * ldc + j] = src[j];
+      }
+    } else {
+      for (int j = warp; j < nc; j += nwarps) {
+        const float* src = cb + (size_t)j * cs_c;
 #pragma unroll 4
-      for (int i = lane; i < nr; i += 32) cs[i * ldc + j] = src[(size_t)i * cs_r];
+        for (int i = lane; i < nr; i += 32) cs[i * ldc + j] = src[(size_t)i * cs_r];
+      }
     }
   }
 #pragma unroll
@@ -163,21 +166,18 @@ afau_attention_qzero_kernel(const float* __restrict__ v, const float* __restrict
     w2[m] = pk2(mix2_w[h * kMs + 2 * m] * kL2e, mix2_w[h * kMs + 2 * m + 1] * kL2e);
   }
   const float b2 = mix2_b[h] * kL2e;
-  const float* crow = cs + i * ldc;
   const float4* vh = (const float4*)(vs + (size_t)hl * nc * kQkv);
 
   float mx = kNegInf, den = 0.f;
   f32x2 acc[kQkv / 2];
 #pragma unroll
   for (int d = 0; d < kQkv / 2; ++d) acc[d] = pk2(0.f, 0.f);
-  for (int j = 0; j < nc; ++j) {
-    const float c = crow[j];
-    const f32x2 cc = pk2(c, c);
+  auto column = [&](int j, float c) {
     f32x2 s2 = pk2(b2, 0.f);
 #pragma unroll
     for (int m = 0; m < kMs / 2; ++m) {
       float h0v, h1v;
-      upk2(fma2(cc, w1[m], bb[m]), h0v, h1v);
+      upk2(fma2(pk2(c, c), w1[m], bb[m]), h0v, h1v);
       s2 = fma2(pk2(fmaxf(h0v, 0.f), fmaxf(h1v, 0.f)), w2[m], s2);
     }
     float sa, sb;
@@ -201,6 +201,25 @@ afau_attention_qzero_kernel(const float* __restrict__ v, const float* __restrict
       const float4 x = vh[j * 4 + t];
       acc[2 * t] = fma2(ee, pk2(x.x, x.y), acc[2 * t]);
       acc[2 * t + 1] = fma2(ee, pk2(x.z, x.w), acc[2 * t + 1]);
+    }
+  };
+  if (kStage) {
+    const float* crow = cs + i * ldc;
+    for (int j = 0; j < nc; ++j) column(j, crow[j]);
+  } else {
+    const float* crow = cb + (size_t)i * cs_r;        // cs_r == 1: lanes = consecutive rows, one line per column
+    float nxt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) nxt[u] = u < nc ? __ldg(crow + (size_t)u * cs_c) : 0.f;
+    for (int j0 = 0; j0 < nc; j0 += 4) {
+      float cur[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nxt[u] = j0 + 4 + u < nc ? __ldg(crow + (size_t)(j0 + 4 + u) * cs_c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < nc) column(j0 + u, cur[u]);
     }
   }
   float4* op = (float4*)(out + ((size_t)b * nr + i) * E + h * kQkv);
@@ -655,14 +674,23 @@ extern "C" int fpm_afau_attention(const float* q, const float* k, const float* v
     const char* e = getenv("FPMATCH_AFAU_QZERO");              // 0: the generic kernel also for q == 0 (A/B runs)
     return !(e && e[0] == '0');
   }();
-  const size_t zsmem = ((((size_t)nr * (nc | 1) + 3) & ~(size_t)3) + (size_t)fpm::kZh * nc * fpm::kQkv) * sizeof(float);
+  const bool direct = cs_r == 1;                             // cost^T: coalesced column reads, nothing staged
+  const size_t vbytes = (size_t)fpm::kZh * nc * fpm::kQkv * sizeof(float);
+  const size_t zsmem = direct ? vbytes : (((size_t)nr * (nc | 1) + 3) & ~(size_t)3) * sizeof(float) + vbytes;
   if (q_zero && qzero_path && fpm::kZh * nr <= 256 && zsmem <= 72 * 1024) {
-    FPM_CUDA(cudaFuncSetAttribute(fpm::afau_attention_qzero_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)zsmem));
     dim3 zgrid(fpm::kHeads / fpm::kZh, B);
     const int threads = (fpm::kZh * nr + 31) / 32 * 32;
-    fpm::afau_attention_qzero_kernel<<<zgrid, threads, zsmem, (cudaStream_t)stream>>>(
-        v, cost, cs_b, cs_r, cs_c, mix1_w, mix1_b, mix2_w, mix2_b, out, nr, nc);
+    if (direct) {
+      FPM_CUDA(cudaFuncSetAttribute(fpm::afau_attention_qzero_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
+      fpm::afau_attention_qzero_kernel<false><<<zgrid, threads, zsmem, (cudaStream_t)stream>>>(
+          v, cost, cs_b, cs_r, cs_c, mix1_w, mix1_b, mix2_w, mix2_b, out, nr, nc);
+    } else {
+      FPM_CUDA(cudaFuncSetAttribute(fpm::afau_attention_qzero_kernel<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
+      fpm::afau_attention_qzero_kernel<true><<<zgrid, threads, zsmem, (cudaStream_t)stream>>>(
+          v, cost, cs_b, cs_r, cs_c, mix1_w, mix1_b, mix2_w, mix2_b, out, nr, nc);
+    }
     FPM_LAUNCH_CHECK();
     return FPM_OK;
   }

@@ -427,8 +427,8 @@ struct PairTile { int a_row0, b_row0, c_col0, rowmap_off; };
 // warps are dealt to them round-robin; at the 160 registers ptxas takes when left alone the fullest sub-partition
 // (3 of the 10 warps) keeps 1 K registers free and no warp of any other kernel fits beside the GEMM CTA.  At 128
 // (no spills) it keeps 4 K: two warps of the 56-register gather kernel.
-template <int kMode, int kPStages>
-__global__ void __maxnreg__(128)
+template <int kMode, int kPStages, int kRegs>
+__global__ void __maxnreg__(kRegs)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const float* __restrict__ inv_a, const float* __restrict__ inv_b,
@@ -790,8 +790,16 @@ static int launch_tc_pair(const void* A_hi, const void* A_lo, const void* B_hi, 
     stages = (e && e[0] == '4') ? 4 : (e && e[0] == '2') ? 2 : 3;
   }
   const size_t smem = (size_t)stages * fpm::kPStageBytes + 1024 + 256 + (size_t)fpm::kEpiWarps * 32 * 32 * 4;
-  auto kern = stages == 3 ? fpm::gemm_tc_pair_kernel<kMode, 3>
-                          : stages == 2 ? fpm::gemm_tc_pair_kernel<kMode, 2> : fpm::gemm_tc_pair_kernel<kMode, 4>;
+  // FPMATCH_GEMM_REGS=96: the 3-stage kernel capped at 96 registers per thread (104 bytes of spill in the epilogue)
+  // so that more of the other streams' CTAs fit beside it.
+  static int regs = 0;
+  if (regs == 0) {
+    const char* e = getenv("FPMATCH_GEMM_REGS");
+    regs = (e && atoi(e) == 96) ? 96 : 128;
+  }
+  auto kern = stages == 3 ? (regs == 96 ? fpm::gemm_tc_pair_kernel<kMode, 3, 96> : fpm::gemm_tc_pair_kernel<kMode, 3, 128>)
+                          : stages == 2 ? fpm::gemm_tc_pair_kernel<kMode, 2, 128>
+                                        : fpm::gemm_tc_pair_kernel<kMode, 4, 128>;
   FPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(64 + 32 * fpm::kEpiWarps);

@@ -167,7 +167,7 @@ __device__ __forceinline__ float sk_warp_max(float v) {
 }
 
 template <int kRpw, bool kFast>
-__global__ void __launch_bounds__(kSkRegWarps * 32, 2)
+__global__ void __maxnreg__(kRpw <= 7 ? 48 : 56)   // 4 warps per sub-partition beside a 96-register GEMM CTA
 sinkhorn_log_reg_kernel(const float* __restrict__ s, const int64_t* __restrict__ n1, const int64_t* __restrict__ n2,
                         float* __restrict__ out, float* __restrict__ out_t, int R, int C, int max_iter, float tau,
                         int dummy_row) {

@@ -40,12 +40,14 @@ class Encoder(nn.Module):
             row_emb, col_emb = layer(row_emb, col_emb, cost_mat)
         return row_emb, col_emb
 
-    def forward_k_inputs(self, cost_mat, n2, n1max, n2max):
+    def forward_k_inputs(self, cost_mat, n2, n1max, n2max, cost_t=None):
         """(max over rows of row block output [B,600], max over rows of col block output [B,600]) for
-        row_emb = 0 [B,n1max,600] and col_emb = one-hot(j < n2_b) [B,n2max,600]."""
+        row_emb = 0 [B,n1max,600] and col_emb = one-hot(j < n2_b) [B,n2max,600].  ``cost_t`` = the contiguous
+        transposed copy of ``cost_mat`` when the caller has one (the Sinkhorn kernel writes it for free): the attention
+        kernel then reads a column of 32 rows with one coalesced load and stages nothing."""
         assert len(self.layers) == 1
         layer = self.layers[0]
-        g_row = layer.row_encoding_block.forward_zero_rows(cost_mat, n2, n1max, n2max)
+        g_row = layer.row_encoding_block.forward_zero_rows(cost_mat, n2, n1max, n2max, cost_t=cost_t)
         g_col = layer.col_encoding_block.forward_onehot_rows_zero_cols(n2, n2max)
         return g_row, g_col
 
@@ -132,7 +134,7 @@ class EncodingBlock(nn.Module):
         return self._tail(row_emb, att)
 
     # ---- structured forms used by Net.forward --------------------------------------------------
-    def forward_zero_rows(self, cost_mat, n2, n1max, n2max):
+    def forward_zero_rows(self, cost_mat, n2, n1max, n2max, cost_t=None):
         """Row block with row_emb = 0 and col_emb = one-hot: q = 0, k/v = weight columns."""
         B = cost_mat.shape[0]
         dev = cost_mat.device
@@ -143,7 +145,10 @@ class EncodingBlock(nn.Module):
         else:
             q = torch.zeros((B, n1max, E), dtype=torch.float32, device=dev)
             k = ops.onehot_proj(self.Wk.weight.detach().contiguous(), n2, n2max)
-        att = self.mixed_score_MHA(q, k, v, cost_mat, transposed_cost=False, q_zero=True)
+        if cost_t is not None and q is None:
+            att = self.mixed_score_MHA(q, k, v, cost_t, transposed_cost=True, q_zero=True)
+        else:
+            att = self.mixed_score_MHA(q, k, v, cost_mat, transposed_cost=False, q_zero=True)
         mh = _lin(att, self.multi_head_combine.weight, self.multi_head_combine.bias)
         out1 = self.add_n_normalization_1(mh, None)            # row_emb + mh with row_emb = 0
         out2 = self.feed_forward(out1)

@@ -449,7 +449,9 @@ class Net(CNN):
             xprev, _, m_t = layer.forward_factorised(xprev, m_t, assoc, n1, n2)
         s = ops.final_classifier(xprev, m_t, self.classifier.weight.detach().reshape(-1).contiguous(),
                                  self.classifier.bias.detach().contiguous(), n1max, n2max)     # :368-369
-        ss = ops.sinkhorn_log(s, n1, n2, self.sinkhorn.max_iter, self.sinkhorn.tau, True)      # :371
+        ss = ops.sinkhorn_log(s, n1, n2, self.sinkhorn.max_iter, self.sinkhorn.tau, True,
+                              want_t=self.regression)                                          # :371
+        ss, ss_t = ss if self.regression else (ss, None)       # the k head's attention reads the transposed copy
 
         # ---- k (ngm.py:374-416)
         gt_perm = data_dict['gt_perm_mat'].to(dev)
@@ -460,7 +462,7 @@ class Net(CNN):
             gt_ks = gt_perm.sum(dim=(1, 2)).to(torch.float32)
         if self.regression:
             assert self.univ_size - n1max >= 0 and self.univ_size - n2max >= 0
-            g_row, g_col = self.encoder_k.forward_k_inputs(ss, n2, n1max, n2max)
+            g_row, g_col = self.encoder_k.forward_k_inputs(ss, n2, n1max, n2max, cost_t=ss_t)
             d = lambda t: t.detach().contiguous()
             hw = [d(self.final_row[0].weight), d(self.final_row[0].bias), d(self.final_row[2].weight).reshape(-1),
                   d(self.final_row[2].bias), d(self.final_col[0].weight), d(self.final_col[0].bias),

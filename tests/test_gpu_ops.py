@@ -601,6 +601,10 @@ def test_afau_attention_zero_query_kernel(ops, nr, nc, transposed):
     if ops.afau_zero_query_kernel_fits(nr, nc):         # that kernel reads neither q nor k: they may be omitted
         bare = ops.afau_attention(None, None, d(v), d(cost), transposed, d(m1w), d(m1b), d(m2w), d(m2b), q_zero=True)
         assert torch.equal(bare, fast)
+        # the other orientation of the same cost (staged tile <-> direct coalesced column reads): same numbers
+        other = ops.afau_attention(None, None, d(v), d(cost.transpose(1, 2).contiguous()), not transposed, d(m1w),
+                                   d(m1b), d(m2w), d(m2b), q_zero=True)
+        assert torch.equal(other, fast)
     else:
         assert nr > 128
 
