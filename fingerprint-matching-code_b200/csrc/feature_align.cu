@@ -137,16 +137,33 @@ fmap_prep_kernel(const float* __restrict__ fmap, float* __restrict__ out, int C,
   }
 }
 
-// global[b, c] = max over positions of the raw map; one warp per (b, c).
-__global__ void global_max_kernel(const float* __restrict__ fmap, float* __restrict__ out, int BC, int HW,
-                                  int out_stride, int out_offset, int C) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= BC) return;
-  const float* src = fmap + (size_t)w * HW;
+// global[b, c] = max over positions of the raw map (AdaptiveMaxPool2d(1, 1), feature_extractor.py:54).  The (b, c)
+// rows are contiguous, so kG lanes share a row with 128-bit loads (kG = 8 for the 8 x 10 maps: a warp then reads four
+// whole rows = 1280 contiguous bytes with three independent loads per lane); HW % 4 != 0 takes the scalar
+// warp-per-row loop.  (First version: always one warp per row with scalar loads - 131 k warps of 320 bytes each,
+// 1.4 TB/s.)
+template <int kG>
+__global__ void __launch_bounds__(256)
+global_max_kernel(const float* __restrict__ fmap, float* __restrict__ out, int BC, int HW, int out_stride,
+                  int out_offset, int C, int vec) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = t / kG, sub = t % kG;
   float m = kNegInf;
-  for (int i = lane; i < HW; i += 32) m = fmaxf(m, src[i]);
-  m = warp_max(m);
-  if (lane == 0) out[(size_t)(w / C) * out_stride + out_offset + (w % C)] = m;
+  if (w < BC) {
+    if (vec) {
+      const float4* src = (const float4*)(fmap + (size_t)w * HW);
+      for (int i = sub; i < HW / 4; i += kG) {
+        const float4 v = src[i];
+        m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+      }
+    } else {
+      const float* src = fmap + (size_t)w * HW;
+      for (int i = sub; i < HW; i += kG) m = fmaxf(m, src[i]);
+    }
+  }
+#pragma unroll
+  for (int o = kG / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (w < BC && sub == 0) out[(size_t)(w / C) * out_stride + out_offset + (w % C)] = m;
 }
 
 // Fused gather: X[ptr[b] + i, 0:C1] = align(nodes_nhwc), X[.., C1:C1+C2] = align(edges_nhwc).
@@ -356,9 +373,16 @@ extern "C" int fpm_global_max(const float* fmap, float* out, int B, int C, int H
                               int out_offset, void* stream) {
   FPM_CHECK_ARG(fmap && out, "fpm_global_max: null tensor");
   if (B == 0) return FPM_OK;
-  const long long warps = (long long)B * C;
-  fpm::global_max_kernel<<<fpm_cdiv(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      fmap, out, (int)warps, HW, out_stride, out_offset, C);
+  const long long rows = (long long)B * C;
+  const int vec = (HW % 4 == 0 && ((uintptr_t)fmap & 15) == 0) ? 1 : 0;
+  const int per_row = vec ? HW / 4 : HW;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (per_row <= 24)
+    fpm::global_max_kernel<8><<<fpm_cdiv(rows * 8, 256), 256, 0, st>>>(fmap, out, (int)rows, HW, out_stride, out_offset, C, vec);
+  else if (per_row <= 48)
+    fpm::global_max_kernel<16><<<fpm_cdiv(rows * 16, 256), 256, 0, st>>>(fmap, out, (int)rows, HW, out_stride, out_offset, C, vec);
+  else
+    fpm::global_max_kernel<32><<<fpm_cdiv(rows * 32, 256), 256, 0, st>>>(fmap, out, (int)rows, HW, out_stride, out_offset, C, vec);
   FPM_LAUNCH_CHECK();
   return FPM_OK;
 }

@@ -96,32 +96,29 @@ assoc_effective_kernel(const int* __restrict__ edges1, const int* __restrict__ e
 }
 
 // In-neighbour lists from per-pair edge tables [B, 2, emax] (int32, -1 padded; row 0 = G-node (source), row 1 =
-// H-node (target) of every column; a column counts only if BOTH ends are present).  One CTA per pair, one WARP per
-// destination node: the edge table is walked 32 columns at a time and the hits are compacted in column order with a
-// ballot -> deterministic, ascending column ids inside every list.
+// H-node (target) of every column; a column counts only if BOTH ends are present).  One CTA per pair, a counting sort
+// in shared memory: in-degree counts by atomics, scan, scatter of the column ids through atomic cursors, then one
+// thread per node sorts its (short) list -> deterministic, ascending column ids inside every list whatever order the
+// atomics produced.  (Before: one warp per destination node walked the whole edge table twice, O(n e): 23 us.)
 // in_ptr: [B, nmax + 1] (offsets local to the pair), in_src: [B, emax], in_col (optional): [B, emax] column ids.
 constexpr int kAssocThreads = 512;
 __global__ void __launch_bounds__(kAssocThreads)
 assoc_in_csr_kernel(const int* __restrict__ edges, int* __restrict__ in_ptr, int* __restrict__ in_src,
                     int* __restrict__ in_col, int nmax, int emax) {
-  extern __shared__ int sh[];            // [2 * emax] edge table, then [nmax + 1] counts
-  int* ssrc = sh; int* sdst = sh + emax; int* cnt = sh + 2 * emax;
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  extern __shared__ int sh[];            // [3 * emax] sources, targets, sorted column ids; [2 * (nmax + 1)] cursors, offsets
+  int* ssrc = sh; int* sdst = sh + emax; int* slist = sh + 2 * emax;
+  int* cnt = sh + 3 * emax; int* off = cnt + nmax + 1;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int* eb = edges + (size_t)b * 2 * emax;
+  for (int j = threadIdx.x; j <= nmax; j += blockDim.x) cnt[j] = 0;
   for (int k = threadIdx.x; k < emax; k += blockDim.x) {
     const int s_ = eb[k], d_ = eb[emax + k];
     ssrc[k] = s_;
-    sdst[k] = (s_ >= 0 && s_ < nmax) ? d_ : -1;      // a column without a valid source end is no edge
+    sdst[k] = (s_ >= 0 && s_ < nmax && d_ >= 0 && d_ < nmax) ? d_ : -1;   // a column without two valid ends is no edge
   }
   __syncthreads();
-  for (int j = warp; j < nmax; j += nwarps) {
-    int c = 0;
-    for (int k0 = 0; k0 < emax; k0 += 32) {
-      const int k = k0 + lane;
-      c += __popc(__ballot_sync(0xffffffffu, k < emax && sdst[k] == j));
-    }
-    if (lane == 0) cnt[j] = c;
-  }
+  for (int k = threadIdx.x; k < emax; k += blockDim.x)
+    if (sdst[k] >= 0) atomicAdd(&cnt[sdst[k]], 1);
   __syncthreads();
   if (warp == 0) {                       // exclusive scan, 32 nodes at a time
     int base = 0;
@@ -134,26 +131,31 @@ assoc_in_csr_kernel(const int* __restrict__ edges, int* __restrict__ in_ptr, int
         const int t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
       }
-      if (j < nmax) cnt[j] = base + inc - c;
+      if (j < nmax) { cnt[j] = base + inc - c; off[j] = base + inc - c; }
       base += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) cnt[nmax] = base;
+    if (lane == 0) { cnt[nmax] = base; off[nmax] = base; }
   }
   __syncthreads();
-  for (int j = threadIdx.x; j <= nmax; j += blockDim.x) in_ptr[(size_t)b * (nmax + 1) + j] = cnt[j];
-  for (int j = warp; j < nmax; j += nwarps) {
-    int w = cnt[j];
-    for (int k0 = 0; k0 < emax; k0 += 32) {
-      const int k = k0 + lane;
-      const bool hit = k < emax && sdst[k] == j;
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const size_t o = (size_t)b * emax + w + __popc(m & ((1u << lane) - 1u));
-        in_src[o] = ssrc[k];
-        if (in_col) in_col[o] = k;
-      }
-      w += __popc(m);
+  for (int j = threadIdx.x; j <= nmax; j += blockDim.x) in_ptr[(size_t)b * (nmax + 1) + j] = off[j];
+  for (int k = threadIdx.x; k < emax; k += blockDim.x)
+    if (sdst[k] >= 0) slist[atomicAdd(&cnt[sdst[k]], 1)] = k;
+  __syncthreads();
+  for (int j = threadIdx.x; j < nmax; j += blockDim.x) {
+    const int beg = off[j], end = off[j + 1];
+    for (int a = beg + 1; a < end; ++a) {            // insertion sort: in-degrees are a handful
+      const int key = slist[a];
+      int q = a - 1;
+      while (q >= beg && slist[q] > key) { slist[q + 1] = slist[q]; --q; }
+      slist[q + 1] = key;
     }
+  }
+  __syncthreads();
+  const int total = off[nmax];
+  for (int p = threadIdx.x; p < total; p += blockDim.x) {
+    const int k = slist[p];
+    in_src[(size_t)b * emax + p] = ssrc[k];
+    if (in_col) in_col[(size_t)b * emax + p] = k;
   }
 }
 
@@ -876,7 +878,7 @@ extern "C" int fpm_assoc_in_csr(const int* edges, int* in_ptr, int* in_src, int*
   FPM_CHECK_ARG(edges && in_ptr && in_src, "fpm_assoc_in_csr: null tensor");
   FPM_CHECK_ARG(B >= 0 && nmax > 0 && emax >= 0, "fpm_assoc_in_csr: bad sizes");
   if (B == 0) return FPM_OK;
-  const size_t smem = (size_t)(2 * emax + nmax + 1) * sizeof(int);
+  const size_t smem = (size_t)(3 * emax + 2 * (nmax + 1)) * sizeof(int);
   FPM_CHECK_ARG(smem <= 200 * 1024, "fpm_assoc_in_csr: graph too large for one CTA");
   FPM_CUDA(cudaFuncSetAttribute(fpm::assoc_in_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));

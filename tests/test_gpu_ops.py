@@ -104,6 +104,18 @@ def test_fused_node_features(ops, oo):
     assert torch.equal(gm[:, :512].cpu(), edges.amax(dim=(2, 3)))
 
 
+@pytest.mark.parametrize("shape", [(5, 48, 8, 10), (3, 40, 15, 20), (4, 33, 7, 9), (2, 16, 4, 40), (1, 8, 1, 1)])
+def test_global_max_kernel_variants(ops, shape):
+    """AdaptiveMaxPool2d(1, 1) of the raw maps (feature_extractor.py:54): 8 / 16 / 32 lanes per (b, c) row with 128-bit
+    loads, and the scalar path for H * W not a multiple of 4."""
+    g = torch.Generator().manual_seed(sum(shape))
+    fm = torch.randn(*shape, generator=g)
+    out = torch.full((shape[0], shape[1] + 7), -5.0, device=DEV)
+    ops.global_max_into(fm.to(DEV), out, 3)
+    assert torch.equal(out[:, 3:3 + shape[1]].cpu(), fm.amax(dim=(2, 3)))
+    assert (out[:, :3] == -5).all() and (out[:, 3 + shape[1]:] == -5).all()
+
+
 # -------------------------------------------------------------------------------------------- Sinkhorn
 @pytest.mark.parametrize("R,C,dummy,it,tau", [(20, 20, True, 20, 0.01), (17, 23, True, 10, 0.01),
                                               (23, 17, True, 10, 0.05), (12, 12, False, 10, 1.0),
