@@ -11,6 +11,8 @@ state); CUDA events order "copy into set j" after "the step that last read set j
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from utils.data_to_cuda import data_to_cuda
@@ -174,6 +176,9 @@ class MatchingPipeline:
         self.lanes = lanes(self.device, inflight)
         self.ring = ring if ring is not None else HostResultRing(device=self.device, lag=len(self.lanes))
         self.ring.set_lag(len(self.lanes))
+        # stagger: batch i + 1's SplineConv front waits for batch i's front (Net.front_gate / front_done), so the tail of
+        # one batch runs under the GEMMs of the next instead of both batches marching in lockstep
+        self.stagger = os.environ.get("FPMATCH_STAGGER", "1") != "0"
 
     GEMM_CLUSTERS_IN_FLIGHT = 70     # of 74 SM pairs: the rest stay free for the other batch's tail kernels (r2n)
 
@@ -199,6 +204,8 @@ class MatchingPipeline:
                     break
                 if self.extra:
                     d.update(self.extra)
+                if self.stagger and len(self.lanes) > 1:
+                    self.net.front_gate = getattr(self.net, "front_done", None) if i else None
                 with torch.no_grad():
                     out = self.net(d)
                 prev = self.ring.push([out[k] for k in self.keys])

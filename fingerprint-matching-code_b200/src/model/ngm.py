@@ -392,6 +392,12 @@ class Net(CNN):
         feats, offs = [], []
         main = torch.cuda.current_stream(dev)
         capturing = torch.cuda.is_current_stream_capturing()      # a CUDA graph of the forward stays on one stream
+        gate, self.front_gate = getattr(self, "front_gate", None), None
+        if gate is not None and not capturing:
+            # batches in flight (fpmatch.prefetch.MatchingPipeline): this batch's tensor-bound front (SplineConv slab
+            # GEMMs) starts when the PREVIOUS batch's front is done, so that fronts and latency-bound tails of
+            # consecutive batches alternate instead of running in lockstep
+            main.wait_event(gate)
         fork = self._ke_stream(dev, 1) if (self.graph_fork and not capturing) else None
         if fork is not None:
             self.message_pass_node_features.mp_network.prepare_weights()    # shared cached operands, before the fork
@@ -416,6 +422,9 @@ class Net(CNN):
             main.wait_stream(fork)
             for t in (feats[1], offs[1][0], offs[1][1]):            # allocated on the fork stream, read on main from here on
                 t.record_stream(main)
+        if not capturing:
+            self.front_done = torch.cuda.Event()
+            self.front_done.record(main)
 
         # ---- affinities (ngm.py:262-287, 317-321)
         coeff_v = self.vertex_affinity.fused_coefficients(gcat)
