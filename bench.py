@@ -152,6 +152,9 @@ def main():
     ap.add_argument("--gemm", default=os.environ.get("FPMATCH_GEMM", None))
     ap.add_argument("--cpu-sample", type=int, default=32, help="pairs per step of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace-ops", action="store_true",
+                    help="diagnostic: report the largest host-side gaps between op launches of the timed loop")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: no NVML sampling thread")
     ap.add_argument("--e2e-inflight", type=int, default=int(os.environ.get("FPMATCH_BENCH_E2E_INFLIGHT", "2")),
                     help="batches in flight in the end-to-end loop whose backbone maps cross PCIe every step (r2: 31.3 k "
                          "pairs/s with 2, 29.3 k with 1); the resident-maps variant uses --inflight")
@@ -244,19 +247,41 @@ def main():
         """n steps; with --inflight k > 1 step i runs on stream i % k (each batch's kernels stay ordered on their own
         stream; consecutive batches are independent, as in serving).  All lanes join the current stream at the end."""
         out = None
+        # The host enqueues a step in ~3 ms, the device needs ~6.5: left alone the host runs the whole loop ahead and the
+        # caching allocator has to find fresh 2 GB blocks for every step still in flight (cudaMalloc inside the timed
+        # region, and - once, on a fresh box - an allocator retry that drained the device: 20-80 ms gaps in
+        # submission, 8.5 / 19 ms per step instead of 6.4).  A serving loop reads its results, which bounds the
+        # run-ahead (MatchingPipeline: the result ring); the device-timed loop bounds it the same way: at most
+        # `depth` steps are in flight, the host waits for the oldest one's completion event before it issues the next.
+        depth = max(1, len(lanes)) + 1
+        pending = []
+
+        def throttle():
+            if len(pending) >= depth:
+                pending.pop(0).synchronize()
+
+        def issued():
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append(ev)
+
         if not lanes:
             for _ in range(n):
+                throttle()
                 out = step_resident()
+                issued()
             return out
         cur = torch.cuda.current_stream(dev)
         for s_ in lanes:
             s_.wait_stream(cur)
         ops.set_gemm_max_clusters(MatchingPipeline.GEMM_CLUSTERS_IN_FLIGHT)      # as the streaming API does
         for i in range(n):
+            throttle()
             with torch.cuda.stream(lanes[i % len(lanes)]):
                 if stagger:                                  # as MatchingPipeline does: fronts of consecutive batches in turn
                     net.front_gate = getattr(net, "front_done", None) if i else None
                 out = step_resident()
+                issued()
                 if step_marks is not None:
                     ev = torch.cuda.Event(enable_timing=True); ev.record(); step_marks.append(ev)
                     enqueue_marks.append(time.perf_counter())
@@ -275,9 +300,11 @@ def main():
             torch.cuda.synchronize()
 
     sampler = ClockSampler(local)                # NVML is initialised and queried once before any timing
+    if args.no_clock_sampler:
+        sampler.nv = None
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    run_steps(2 * max(1, args.inflight))
+    run_steps(4 * max(1, args.inflight) + 2)     # the throttled steady state of run_steps, long enough for the allocator
     barrier()
     # the collector is parked for the timed regions (as timeit does): a generation-2 pass over the process's objects
     # takes several milliseconds of host time in the middle of a 65 ms measurement
@@ -293,7 +320,15 @@ def main():
         e0.record()
         step_marks = []
         t_host0 = time.perf_counter()
+        if args.trace_ops:
+            ops.op_trace_start()
         out = run_steps(args.steps)
+        if args.trace_ops:
+            tr = ops.op_trace_stop()
+            gaps = sorted(((tr[i + 1][0] - tr[i][0]) * 1e3, tr[i][1], tr[i + 1][1], (tr[i][0] - t_host0) * 1e3)
+                          for i in range(len(tr) - 1))[-6:]
+            print("host gaps (ms, after op, before op, at ms):", [(round(g, 2), a, b_, round(t_, 1)) for g, a, b_, t_ in gaps],
+                  file=sys.stderr)
         marks, step_marks = step_marks, None
         e1.record()
         barrier()

@@ -71,9 +71,27 @@ def launch_count() -> int:
     return _LAUNCHES
 
 
+_OP_TRACE = None        # diagnostic (bench.py --trace-ops): host time + name of every wrapper that launched something
+
+
+def op_trace_start() -> None:
+    global _OP_TRACE
+    _OP_TRACE = []
+
+
+def op_trace_stop():
+    global _OP_TRACE
+    t, _OP_TRACE = _OP_TRACE, None
+    return t
+
+
 def _count(n: int = 1) -> None:
     global _LAUNCHES
     _LAUNCHES += n
+    if _OP_TRACE is not None:
+        import sys as _sys
+        import time as _time
+        _OP_TRACE.append((_time.perf_counter(), _sys._getframe(1).f_code.co_name))
 
 
 def _stream() -> int:
