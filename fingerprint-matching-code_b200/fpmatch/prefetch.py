@@ -180,7 +180,8 @@ class MatchingPipeline:
         # one batch runs under the GEMMs of the next instead of both batches marching in lockstep
         self.stagger = os.environ.get("FPMATCH_STAGGER", "1") != "0"
 
-    GEMM_CLUSTERS_IN_FLIGHT = 70     # of 74 SM pairs: the rest stay free for the other batch's tail kernels (r2n)
+    # of 74 SM pairs: the rest stay free for the other batch's tail kernels (r2n; FPMATCH_INFLIGHT_CLUSTERS overrides)
+    GEMM_CLUSTERS_IN_FLIGHT = int(os.environ.get("FPMATCH_INFLIGHT_CLUSTERS", "70"))
 
     def __iter__(self):
         from . import ops
