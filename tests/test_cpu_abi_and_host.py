@@ -310,3 +310,22 @@ def test_pygnn_layer_edge_emb_creates_the_unused_edge_mlp():
     extra = sorted(set(a.state_dict()) - set(b.state_dict()))
     assert extra == ["e_func.0.bias", "e_func.0.weight", "e_func.2.bias", "e_func.2.weight"]
     assert a.e_func[0].in_features == 16 + 17 and a.e_func[0].out_features == 16
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on a 2-pair sample: one JSON line with the
+    contract's keys, `impl: reference`, a `cpu_baseline` describing the run and a zero-copy `e2e` equal to the value."""
+    import json
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample", "2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "matched pairs/sec" and line["unit"] == "pairs/s"
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["value"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and "sample" in cb and cb["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
